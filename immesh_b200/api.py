@@ -1,0 +1,296 @@
+"""ctypes binding of include/immesh_b200.h (test / bench harness; no compute happens in Python)."""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libimmesh_b200.so")
+_lib_cache: dict[str, C.CDLL] = {}
+
+STATE_DOUBLES = 348
+
+
+class _LioCfg(C.Structure):
+    _fields_ = [
+        ("voxel_size", C.c_double), ("max_layer", C.c_int), ("layer_init_size", C.c_int * 5), ("max_points_size", C.c_int),
+        ("min_eigen_value", C.c_double), ("dept_err", C.c_double), ("beam_err", C.c_double),
+        ("ext_R", C.c_double * 9), ("ext_T", C.c_double * 3), ("max_iteration", C.c_int), ("calib_laser", C.c_int),
+        ("hash_capacity_log2", C.c_int), ("max_nodes", C.c_int), ("max_chunks", C.c_int), ("max_scan_points", C.c_int),
+    ]
+
+
+class _MeshCfg(C.Structure):
+    _fields_ = [
+        ("points_minimum_scale", C.c_double), ("voxel_resolution", C.c_double), ("number_of_pts_append_to_map", C.c_int),
+        ("max_vertices", C.c_int), ("max_triangles", C.c_int), ("max_voxels", C.c_int), ("max_frame_points", C.c_int),
+    ]
+
+
+@dataclasses.dataclass
+class LioConfig:
+    """Hot-path parameters of Voxel_mapping (config/*.yaml of the reference)."""
+    voxel_size: float = 0.5
+    max_layer: int = 2
+    layer_init_size: tuple = (5, 5, 5, 5, 5)
+    max_points_size: int = 100
+    min_eigen_value: float = 0.01
+    dept_err: float = 0.02
+    beam_err: float = 0.05
+    ext_R: tuple = (1, 0, 0, 0, 1, 0, 0, 0, 1)
+    ext_T: tuple = (0.04165, 0.02326, -0.0284)
+    max_iteration: int = 4
+    calib_laser: int = 0
+    filter_size_surf: float = 0.4   # leaf of the down-sampling step before the path
+    hash_capacity_log2: int = 0
+    max_nodes: int = 0
+    max_chunks: int = 0
+    max_scan_points: int = 0
+
+
+@dataclasses.dataclass
+class MeshConfig:
+    points_minimum_scale: float = 0.1
+    voxel_resolution: float = 0.4
+    number_of_pts_append_to_map: int = 10000
+    max_vertices: int = 0
+    max_triangles: int = 0
+    max_voxels: int = 0
+    max_frame_points: int = 0
+
+
+AVIA = LioConfig()  # config/avia.yaml
+VELODYNE = LioConfig(voxel_size=3.0, max_layer=4, max_points_size=1000, dept_err=0.04, beam_err=0.1, ext_T=(0, 0, 0),
+                     max_iteration=3, calib_laser=0, filter_size_surf=0.5)  # config/velodyne.yaml (calib_laser applied upstream)
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """Load the C-ABI shared library.  There is no fallback: a missing CUDA build is an error."""
+    path = path or _LIB_PATH
+    if path in _lib_cache:
+        return _lib_cache[path]
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()')")
+    lib = C.CDLL(path)
+    vp, ip, dp, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_float)
+    lib.immesh_lio_create.argtypes = [C.POINTER(_LioCfg), C.POINTER(vp)]
+    lib.immesh_lio_destroy.argtypes = [vp]
+    lib.immesh_lio_set_state.argtypes = [vp, dp]
+    lib.immesh_lio_get_state.argtypes = [vp, dp]
+    lib.immesh_lio_predict.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    lib.immesh_voxelmap_build.argtypes = [vp, fp, C.c_int]
+    lib.immesh_lio_estimate.argtypes = [vp, fp, C.c_int, ip]
+    lib.immesh_voxelmap_update.argtypes = [vp]
+    lib.immesh_lio_iter_stats.argtypes = [vp, C.c_int, dp]
+    lib.immesh_lio_matches.argtypes = [vp, ip, C.c_int]
+    lib.immesh_voxelmap_dump.argtypes = [vp, dp, C.c_int64]
+    lib.immesh_voxelmap_dump.restype = C.c_int64
+    lib.immesh_voxelmap_counts.argtypes = [vp, C.POINTER(C.c_int64)]
+    for name, args in (
+        ("immesh_lio_step", [vp, fp, C.c_int, C.c_double, C.c_double, C.c_double, dp, ip]),
+        ("immesh_residual_build", [vp, fp, C.c_int, ip, dp, C.c_int, ip]),
+        ("immesh_lio_last_timing", [vp, dp]),
+        ("immesh_mesh_create", [C.POINTER(_MeshCfg), C.POINTER(vp)]),
+        ("immesh_mesh_destroy", [vp]),
+        ("immesh_mesh_push_frame", [vp, fp, C.c_int, dp, C.c_int]),
+        ("immesh_mesh_counts", [vp, C.POINTER(C.c_int64)]),
+        ("immesh_mesh_snapshot", [vp, fp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+        ("immesh_knn", [vp, fp, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int32), fp]),
+        ("immesh_mesh_last_timing", [vp, dp]),
+    ):
+        if hasattr(lib, name):
+            getattr(lib, name).argtypes = args
+    if hasattr(lib, "immesh_last_error"):
+        lib.immesh_last_error.restype = C.c_char_p
+    if hasattr(lib, "immesh_version"):
+        lib.immesh_version.restype = C.c_char_p
+    _lib_cache[path] = lib
+    return lib
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _check(lib, rc, what):
+    if rc != 0:
+        msg = lib.immesh_last_error().decode() if hasattr(lib, "immesh_last_error") else ""
+        raise RuntimeError(f"{what} failed with code {rc}: {msg}")
+
+
+class Lio:
+    """Mirror of the reference's Voxel_mapping hot-path methods (voxel_map_init / lio_state_estimation /
+    map_incremental_grow) on the device-resident VoxelMap."""
+
+    def __init__(self, cfg: LioConfig = AVIA, lib: Optional[C.CDLL] = None):
+        self.lib = lib or load_library()
+        self.cfg = cfg
+        c = _LioCfg()
+        c.voxel_size = cfg.voxel_size
+        c.max_layer = cfg.max_layer
+        for i in range(5):
+            c.layer_init_size[i] = cfg.layer_init_size[i]
+        c.max_points_size = cfg.max_points_size
+        c.min_eigen_value = cfg.min_eigen_value
+        c.dept_err, c.beam_err = cfg.dept_err, cfg.beam_err
+        for i in range(9):
+            c.ext_R[i] = cfg.ext_R[i]
+        for i in range(3):
+            c.ext_T[i] = cfg.ext_T[i]
+        c.max_iteration, c.calib_laser = cfg.max_iteration, cfg.calib_laser
+        c.hash_capacity_log2, c.max_nodes, c.max_chunks, c.max_scan_points = cfg.hash_capacity_log2, cfg.max_nodes, cfg.max_chunks, cfg.max_scan_points
+        self._h = C.c_void_p()
+        _check(self.lib, self.lib.immesh_lio_create(C.byref(c), C.byref(self._h)), "immesh_lio_create")
+
+    def close(self):
+        if self._h:
+            self.lib.immesh_lio_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- state
+    def get_state(self) -> np.ndarray:
+        s = np.zeros(STATE_DOUBLES)
+        _check(self.lib, self.lib.immesh_lio_get_state(self._h, s.ctypes.data_as(C.POINTER(C.c_double))), "get_state")
+        return s
+
+    def set_state(self, s):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        assert s.size == STATE_DOUBLES
+        _check(self.lib, self.lib.immesh_lio_set_state(self._h, s.ctypes.data_as(C.POINTER(C.c_double))), "set_state")
+
+    def set_pose(self, R, t):
+        s = self.get_state()
+        s[0:9] = np.asarray(R, dtype=np.float64).reshape(9)
+        s[9:12] = t
+        self.set_state(s)
+
+    # --- reference-named operations
+    def predict(self, dt, cov_gyr=0.1, cov_acc=0.1):
+        _check(self.lib, self.lib.immesh_lio_predict(self._h, dt, cov_gyr, cov_acc), "predict")
+
+    def voxel_map_init(self, body_full):
+        a, p = _f32(body_full)
+        _check(self.lib, self.lib.immesh_voxelmap_build(self._h, p, a.shape[0]), "voxelmap_build")
+
+    def lio_state_estimation(self, body_ds) -> int:
+        a, p = _f32(body_ds)
+        it = C.c_int(0)
+        _check(self.lib, self.lib.immesh_lio_estimate(self._h, p, a.shape[0], C.byref(it)), "lio_estimate")
+        self._last_n = a.shape[0]
+        return it.value
+
+    def map_incremental_grow(self):
+        _check(self.lib, self.lib.immesh_voxelmap_update(self._h), "voxelmap_update")
+
+    def step(self, body_ds, dt=0.0, cov_gyr=0.1, cov_acc=0.1):
+        a, p = _f32(body_ds)
+        it = C.c_int(0)
+        s = np.zeros(STATE_DOUBLES)
+        _check(self.lib, self.lib.immesh_lio_step(self._h, p, a.shape[0], dt, cov_gyr, cov_acc, s.ctypes.data_as(C.POINTER(C.c_double)), C.byref(it)), "lio_step")
+        self._last_n = a.shape[0]
+        return s, it.value
+
+    def residual_build(self, body_ds):
+        a, p = _f32(body_ds)
+        n = a.shape[0]
+        il = np.zeros((n, 2), dtype=np.int32)
+        vals = np.zeros((n, 31))
+        m = C.c_int(0)
+        _check(self.lib, self.lib.immesh_residual_build(self._h, p, n, il.ctypes.data_as(C.POINTER(C.c_int)), vals.ctypes.data_as(C.POINTER(C.c_double)), n, C.byref(m)), "residual_build")
+        return il[: m.value], vals[: m.value]
+
+    # --- diagnostics
+    def iter_stats(self, it):
+        o = np.zeros(63)
+        _check(self.lib, self.lib.immesh_lio_iter_stats(self._h, it, o.ctypes.data_as(C.POINTER(C.c_double))), "iter_stats")
+        return dict(HTH=o[:36].reshape(6, 6).copy(), HTz=o[36:42].copy(), n_match=int(o[42]), total_residual=o[43], solution=o[44:62].copy(), converged=int(o[62]))
+
+    def matches(self, n=None):
+        n = n or self._last_n
+        o = np.zeros(n, dtype=np.int32)
+        _check(self.lib, self.lib.immesh_lio_matches(self._h, o.ctypes.data_as(C.POINTER(C.c_int)), n), "matches")
+        return o
+
+    def dump_map(self) -> np.ndarray:
+        rows = self.lib.immesh_voxelmap_dump(self._h, None, 0)
+        out = np.zeros((rows, 45))
+        r2 = self.lib.immesh_voxelmap_dump(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), rows)
+        assert r2 == rows
+        return out
+
+    def counts(self):
+        o = np.zeros(4, dtype=np.int64)
+        self.lib.immesh_voxelmap_counts(self._h, o.ctypes.data_as(C.POINTER(C.c_int64)))
+        return dict(roots=int(o[0]), nodes=int(o[1]), chunks=int(o[2]), err=int(o[3]))
+
+    def last_timing(self):
+        o = np.zeros(3)
+        self.lib.immesh_lio_last_timing(self._h, o.ctypes.data_as(C.POINTER(C.c_double)))
+        return o
+
+
+class Mesh:
+    """Mirror of incremental_mesh_reconstruction + Global_map/Triangle_manager snapshot + KD_TREE::Nearest_Search."""
+
+    def __init__(self, cfg: MeshConfig = MeshConfig(), lib: Optional[C.CDLL] = None):
+        self.lib = lib or load_library()
+        self.cfg = cfg
+        c = _MeshCfg(cfg.points_minimum_scale, cfg.voxel_resolution, cfg.number_of_pts_append_to_map, cfg.max_vertices, cfg.max_triangles,
+                     cfg.max_voxels, cfg.max_frame_points)
+        self._h = C.c_void_p()
+        _check(self.lib, self.lib.immesh_mesh_create(C.byref(c), C.byref(self._h)), "immesh_mesh_create")
+
+    def close(self):
+        if self._h:
+            self.lib.immesh_mesh_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push_frame(self, world_xyz, pose_t, frame_idx=0):
+        a, p = _f32(world_xyz)
+        t = np.ascontiguousarray(pose_t, dtype=np.float64)
+        _check(self.lib, self.lib.immesh_mesh_push_frame(self._h, p, a.shape[0], t.ctypes.data_as(C.POINTER(C.c_double)), frame_idx), "mesh_push_frame")
+
+    def counts(self):
+        o = np.zeros(8, dtype=np.int64)
+        _check(self.lib, self.lib.immesh_mesh_counts(self._h, o.ctypes.data_as(C.POINTER(C.c_int64))), "mesh_counts")
+        keys = ["n_vertices", "n_triangles", "frame_new_vertices", "frame_voxels_meshed", "frame_added", "frame_removed", "n_voxels", "n_activated"]
+        return dict(zip(keys, (int(v) for v in o)))
+
+    def snapshot(self):
+        c = self.counts()
+        v = np.zeros((c["n_vertices"], 3), dtype=np.float32)
+        t = np.zeros((c["n_triangles"], 3), dtype=np.int32)
+        f = np.zeros(c["n_triangles"], dtype=np.int32)
+        _check(self.lib, self.lib.immesh_mesh_snapshot(self._h, v.ctypes.data_as(C.POINTER(C.c_float)), t.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                     f.ctypes.data_as(C.POINTER(C.c_int32))), "mesh_snapshot")
+        return v, t, f
+
+    def knn(self, q, k, max_dist=float("inf")):
+        a, p = _f32(q)
+        nq = a.shape[0]
+        idx = np.zeros((nq, k), dtype=np.int32)
+        d2 = np.zeros((nq, k), dtype=np.float32)
+        _check(self.lib, self.lib.immesh_knn(self._h, p, nq, k, max_dist, idx.ctypes.data_as(C.POINTER(C.c_int32)), d2.ctypes.data_as(C.POINTER(C.c_float))), "knn")
+        return idx, d2
+
+    def last_timing(self):
+        o = np.zeros(4)
+        self.lib.immesh_mesh_last_timing(self._h, o.ctypes.data_as(C.POINTER(C.c_double)))
+        return o

@@ -1,0 +1,472 @@
+// immesh_b200 -- CUDA kernels (sm_100a) and C-ABI host orchestration of the localization path.
+// Kernel bodies live in lio_core.cuh / voxelmap.cuh; this file adds the launch geometry, the
+// block-level integer reduction of the normal equations, stream/event plumbing and the C ABI.
+// There is no CPU path: every entry point needs a CUDA device and fails loudly without one.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/immesh_b200.h"
+#include "common_host.hpp"
+#include "lio_core.cuh"
+#include "map_dump.hpp"
+
+using namespace immesh;
+
+// ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(128) k_prepare(LioParams P, ScanBuf sb, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) prepare_point(P, sb, i);
+}
+
+__global__ void k_reset_scan(ScanBuf sb, LioCtrl* ctrl, int copy_prop) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nt = gridDim.x * blockDim.x;
+    unsigned long long* acc = &ctrl->acc[0][0];
+    for (int i = tid; i < IM_MAX_ITER * IM_NTERMS * 2; i += nt) acc[i] = 0ull;
+    if (copy_prop)
+        for (int i = tid; i < IM_STATE_DOUBLES; i += nt) ctrl->state_prop[i] = ctrl->state[i];
+    if (tid == 0) {
+        ctrl->stop = 0;
+        ctrl->iters_run = 0;
+        ctrl->rematch_num = 0;
+    }
+}
+
+// K2+K3: one thread per scan point; the block's 30 fixed-point sums are reduced with warp shuffles
+// (integer adds: exact, order-free) and folded into the iteration's global accumulators with 60 atomics.
+#define RES_THREADS 128
+__global__ void __launch_bounds__(RES_THREADS) k_residual(VoxelMapDev map, LioParams P, ScanBuf sb, LioCtrl* ctrl, int iter, int n) {
+    __shared__ double s_state[24 + 6 * 18];
+    __shared__ long long s_part[RES_THREADS / 32][IM_NTERMS];
+    if (ctrl->stop) return;
+    // stage rot/pos and the 6x6 pose block of the covariance (the only parts of the state this pass reads)
+    for (int i = threadIdx.x; i < 24 + 6 * 18; i += blockDim.x) s_state[i] = ctrl->state[i];
+    __syncthreads();
+    long long acc[IM_NTERMS];
+#pragma unroll
+    for (int k = 0; k < IM_NTERMS; ++k) acc[k] = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        long long t[IM_NTERMS];
+        if (residual_point(map, P, sb, s_state, i, t, map.err)) {
+#pragma unroll
+            for (int k = 0; k < IM_NTERMS; ++k) acc[k] += t[k];
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < IM_NTERMS - 1; ++k) {
+        long long v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < IM_NTERMS - 1) {
+        long long v = 0;
+        for (int w = 0; w < RES_THREADS / 32; ++w) v += s_part[w][threadIdx.x];
+        if (v != 0) {
+            atomicAdd(&ctrl->acc[iter][2 * threadIdx.x], (unsigned long long)(v >> 32));
+            atomicAdd(&ctrl->acc[iter][2 * threadIdx.x + 1], (unsigned long long)(v & 0xffffffffLL));
+        }
+    }
+}
+
+#define SOLVE_THREADS 352
+__global__ void __launch_bounds__(SOLVE_THREADS) k_solve(LioParams P, LioCtrl* ctrl, int iter) {
+    __shared__ SolveScratch S;
+    ieskf_solve(P, ctrl, iter, &S, threadIdx.x, blockDim.x);
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS) k_predict(LioCtrl* ctrl, double dt, double cov_gyr, double cov_acc) {
+    __shared__ double T[324], Fx[324];
+    predict_const_vel(ctrl->state, dt, cov_gyr, cov_acc, T, Fx, threadIdx.x, blockDim.x);
+}
+
+__global__ void __launch_bounds__(128) k_grow_point(VoxelMapDev map, LioParams P, ScanBuf sb, LioCtrl* ctrl, int n, int mode) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) grow_point(map, P, sb, ctrl->state, i, mode);
+}
+__global__ void __launch_bounds__(128) k_grow_segment(ScanBuf sb) {
+    const int nt = *sb.n_touched;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) grow_segment(sb, t);
+}
+__global__ void __launch_bounds__(128) k_grow_scatter(ScanBuf sb, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) grow_scatter(sb, i);
+}
+// one warp per touched root voxel, voxels claimed dynamically (their cost varies by orders of magnitude)
+__global__ void __launch_bounds__(128) k_grow_voxel(VoxelMapDev map, LioParams P, ScanBuf sb, int mode, int* sorted_scratch, int* work_counter) {
+    const int lane = threadIdx.x & 31;
+    const int nt = *sb.n_touched;
+    while (true) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(work_counter, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= nt) break;
+        grow_voxel(map, P, sb, t, mode, lane, 32, sorted_scratch);
+    }
+}
+__global__ void k_grow_finish(VoxelMapDev map, ScanBuf sb, int* work_counter) {
+    recycle_chunks(map, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0) {
+        *sb.n_touched = 0;
+        *sb.seg_top = 0;
+        *work_counter = 0;
+    }
+}
+// ptpl payload of every matched point (diagnostic / drop-in immesh_residual_build)
+__global__ void k_gather_ptpl(VoxelMapDev map, ScanBuf sb, int n, double* out /*[n][31]*/) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int nd = sb.match_node[i];
+        if (nd < 0) continue;
+        const PlaneRec& pl = map.planes[nd];
+        double* o = out + (size_t)i * 31;
+        for (int j = 0; j < 3; ++j) { o[j] = (double)sb.body[i * 3 + j]; o[3 + j] = pl.normal[j]; o[6 + j] = pl.center[j]; }
+        o[9] = (double)pl.d;
+        for (int j = 0; j < 21; ++j) o[10 + j] = pl.pv[j];
+    }
+}
+
+// ------------------------------------------------------------------ host side
+struct immesh_lio {
+    LioParams P;
+    VoxelMapDev map;
+    ScanBuf sb;
+    LioCtrl* d_ctrl = nullptr;
+    int* d_counters = nullptr;  // node_count, chunk_bump, avail_top, pending_n, err, n_roots, n_touched, seg_top, work_counter
+    int* d_sorted = nullptr;
+    double* d_ptpl = nullptr;
+    float* h_body = nullptr;   // pinned staging
+    double* h_state = nullptr; // pinned
+    int* h_ints = nullptr;     // pinned
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t cap = 0;
+    int max_nodes = 0, max_chunks = 0, max_scan = 0;
+    int n_sm = 148;
+    int last_n = 0;
+    double last_ms[3] = {0, 0, 0};
+    std::vector<void*> allocs;
+};
+
+static void fill_params(const immesh_lio_config* c, LioParams& P) {
+    P.voxel_size = c->voxel_size;
+    P.voxel_size_f = (float)c->voxel_size;
+    P.voxel_size_ins = (double)P.voxel_size_f;
+    P.max_layer = c->max_layer;
+    for (int i = 0; i < 5; ++i) P.layer_init[i] = c->layer_init_size[i];
+    P.max_points = c->max_points_size;
+    P.planer_threshold = (float)c->min_eigen_value;
+    P.dept_err = (float)c->dept_err;
+    // DEG2RAD is PCL's macro ((x)*0.017453293); the squared sine is a per-configuration constant
+    const float be = (float)c->beam_err;
+    const double s = std::sin((double)be * 0.017453293);
+    P.dir_var = s * s;
+    const double sc = std::sin((double)(float)0.01 * 0.017453293);  // CALIB_ANGLE_COV, include/common_lib.h:41
+    P.dir_var_calib = sc * sc;
+    P.calib_laser = c->calib_laser;
+    P.max_iter = c->max_iteration;
+    for (int i = 0; i < 9; ++i) P.extR[i] = c->ext_R[i];
+    for (int i = 0; i < 3; ++i) P.extT[i] = c->ext_T[i];
+}
+
+template <class T>
+static cudaError_t dev_alloc(immesh_lio* h, T** p, size_t count, int memset_byte = -1) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    if (memset_byte >= 0) e = cudaMemset(q, memset_byte, count * sizeof(T));
+    return e;
+}
+
+static int grid_for(const immesh_lio* h, int n, int threads, int max_waves = 8) {
+    int g = (n + threads - 1) / threads;
+    const int cap = h->n_sm * max_waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return g;
+}
+
+extern "C" {
+
+int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
+    if (!cfg || !out) return im_fail(IMMESH_E_INVALID, "null argument");
+    if (cfg->max_iteration < 1 || cfg->max_iteration > IM_MAX_ITER) return im_fail(IMMESH_E_INVALID, "max_iteration must be in [1,8]");
+    if (cfg->max_layer < 0 || cfg->max_layer > 4) return im_fail(IMMESH_E_INVALID, "max_layer must be in [0,4]");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return im_fail(IMMESH_E_NO_DEVICE, "no CUDA device: immesh_b200 has no CPU path");
+    immesh_lio* h = new immesh_lio();
+    fill_params(cfg, h->P);
+    const int caplog = cfg->hash_capacity_log2 ? cfg->hash_capacity_log2 : 22;
+    h->cap = (size_t)1 << caplog;
+    h->max_nodes = cfg->max_nodes ? cfg->max_nodes : (4 << 20);
+    h->max_chunks = cfg->max_chunks ? cfg->max_chunks : (4 << 20);
+    h->max_scan = cfg->max_scan_points ? cfg->max_scan_points : (2 << 20);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
+    IM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) IM_CUDA(cudaEventCreate(&e));
+    VoxelMapDev& m = h->map;
+    IM_CUDA(dev_alloc(h, &m.keys, h->cap, 0xFF));
+    IM_CUDA(dev_alloc(h, &m.root_node, h->cap, 0xFF));
+    m.cap_mask = (unsigned)(h->cap - 1);
+    IM_CUDA(dev_alloc(h, &m.nodes, (size_t)h->max_nodes));
+    IM_CUDA(dev_alloc(h, &m.planes, (size_t)h->max_nodes));
+    IM_CUDA(dev_alloc(h, &m.chunks, (size_t)h->max_chunks));
+    IM_CUDA(dev_alloc(h, &m.avail, (size_t)h->max_chunks));
+    IM_CUDA(dev_alloc(h, &m.pending, (size_t)h->max_chunks));
+    IM_CUDA(dev_alloc(h, &h->d_counters, 16, 0));
+    m.node_count = h->d_counters + 0; m.chunk_bump = h->d_counters + 1; m.avail_top = h->d_counters + 2; m.pending_n = h->d_counters + 3;
+    m.err = h->d_counters + 4; m.n_roots = h->d_counters + 5;
+    m.max_nodes = h->max_nodes; m.max_chunks = h->max_chunks;
+    ScanBuf& sb = h->sb;
+    const size_t ms = (size_t)h->max_scan;
+    float* d_body = nullptr;
+    IM_CUDA(dev_alloc(h, &d_body, ms * 3));
+    sb.body = d_body;
+    IM_CUDA(dev_alloc(h, &sb.body_cov, ms * 6));
+    IM_CUDA(dev_alloc(h, &sb.p_imu, ms * 3));
+    IM_CUDA(dev_alloc(h, &sb.match_node, ms, 0xFF));
+    IM_CUDA(dev_alloc(h, &sb.match_layer, ms, 0));
+    IM_CUDA(dev_alloc(h, &sb.pw, ms * 3));
+    IM_CUDA(dev_alloc(h, &sb.var, ms * 6));
+    IM_CUDA(dev_alloc(h, &sb.sortkey, ms));
+    IM_CUDA(dev_alloc(h, &sb.slot, ms));
+    IM_CUDA(dev_alloc(h, &sb.seg, ms));
+    IM_CUDA(dev_alloc(h, &h->d_sorted, ms));
+    IM_CUDA(dev_alloc(h, &sb.touched, ms));
+    IM_CUDA(dev_alloc(h, &sb.slot_count, h->cap, 0));
+    IM_CUDA(dev_alloc(h, &sb.slot_offset, h->cap, 0));
+    IM_CUDA(dev_alloc(h, &sb.slot_cursor, h->cap, 0));
+    sb.n_touched = h->d_counters + 6; sb.seg_top = h->d_counters + 7;
+    sb.n = 0;
+    IM_CUDA(dev_alloc(h, &h->d_ctrl, 1, 0));
+    IM_CUDA(cudaMallocHost((void**)&h->h_body, ms * 3 * sizeof(float)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_state, (IM_STATE_DOUBLES + 64) * sizeof(double)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_ints, 64 * sizeof(int)));
+    // StatesGroup(): identity rotation, cov = INIT_COV * I  (include/common_lib.h:201-211)
+    std::memset(h->h_state, 0, IM_STATE_DOUBLES * sizeof(double));
+    h->h_state[0] = h->h_state[4] = h->h_state[8] = 1.0;
+    for (int i = 0; i < 18; ++i) h->h_state[24 + i * 18 + i] = 0.0000001;
+    IM_CUDA(cudaMemcpy(h->d_ctrl->state, h->h_state, IM_STATE_DOUBLES * sizeof(double), cudaMemcpyHostToDevice));
+    IM_CUDA(cudaDeviceSynchronize());
+    *out = h;
+    return IMMESH_OK;
+}
+
+int immesh_lio_destroy(immesh_lio_t* h) {
+    if (!h) return IMMESH_OK;
+    cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->h_body) cudaFreeHost(h->h_body);
+    if (h->h_state) cudaFreeHost(h->h_state);
+    if (h->h_ints) cudaFreeHost(h->h_ints);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return IMMESH_OK;
+}
+
+int immesh_lio_set_state(immesh_lio_t* h, const double* s) {
+    if (!h || !s) return im_fail(IMMESH_E_INVALID, "null argument");
+    std::memcpy(h->h_state, s, IM_STATE_DOUBLES * sizeof(double));
+    IM_CUDA(cudaMemcpyAsync(h->d_ctrl->state, h->h_state, IM_STATE_DOUBLES * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    return IMMESH_OK;
+}
+int immesh_lio_get_state(immesh_lio_t* h, double* s) {
+    if (!h || !s) return im_fail(IMMESH_E_INVALID, "null argument");
+    IM_CUDA(cudaMemcpyAsync(h->h_state, h->d_ctrl->state, IM_STATE_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    std::memcpy(s, h->h_state, IM_STATE_DOUBLES * sizeof(double));
+    return IMMESH_OK;
+}
+
+static int upload_scan(immesh_lio* h, const float* body, int n) {
+    if (!body || n < 0) return im_fail(IMMESH_E_INVALID, "bad scan");
+    if (n > h->max_scan) return im_fail(IMMESH_E_CAPACITY, "scan larger than max_scan_points");
+    std::memcpy(h->h_body, body, (size_t)n * 3 * sizeof(float));
+    IM_CUDA(cudaMemcpyAsync((void*)h->sb.body, h->h_body, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    h->sb.n = n;
+    h->last_n = n;
+    return IMMESH_OK;
+}
+static int check_flags(immesh_lio* h) {
+    IM_CUDA(cudaMemcpyAsync(h->h_ints, h->d_counters, 16 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    const int err = h->h_ints[4];
+    if (err & (IM_ERR_NODE_POOL | IM_ERR_CHUNK_POOL | IM_ERR_HASH_FULL | IM_ERR_SEG_POOL)) return im_fail(IMMESH_E_CAPACITY, "device pool overflow (raise the capacities in immesh_lio_config)");
+    if (err & (IM_ERR_KEY_RANGE | IM_ERR_FX_RANGE)) return im_fail(IMMESH_E_RANGE, "coordinate / normal-equation term outside the representable range");
+    return IMMESH_OK;
+}
+static void launch_grow(immesh_lio* h, int n, int mode) {
+    if (n <= 0) return;
+    k_grow_point<<<grid_for(h, n, 128), 128, 0, h->stream>>>(h->map, h->P, h->sb, h->d_ctrl, n, mode);
+    k_grow_segment<<<grid_for(h, n, 128, 2), 128, 0, h->stream>>>(h->sb);
+    k_grow_scatter<<<grid_for(h, n, 128), 128, 0, h->stream>>>(h->sb, n);
+    k_grow_voxel<<<h->n_sm * 4, 128, 0, h->stream>>>(h->map, h->P, h->sb, mode, h->d_sorted, h->d_counters + 8);
+    k_grow_finish<<<1, 256, 0, h->stream>>>(h->map, h->sb, h->d_counters + 8);
+}
+static void launch_estimate(immesh_lio* h, int n) {
+    k_reset_scan<<<2, 256, 0, h->stream>>>(h->sb, h->d_ctrl, 1);
+    if (n <= 0) return;
+    k_prepare<<<grid_for(h, n, 128), 128, 0, h->stream>>>(h->P, h->sb, n);
+    const int g = grid_for(h, n, RES_THREADS, 4);
+    for (int it = 0; it < h->P.max_iter; ++it) {
+        k_residual<<<g, RES_THREADS, 0, h->stream>>>(h->map, h->P, h->sb, h->d_ctrl, it, n);
+        k_solve<<<1, SOLVE_THREADS, 0, h->stream>>>(h->P, h->d_ctrl, it);
+    }
+}
+
+int immesh_lio_predict(immesh_lio_t* h, double dt, double cov_gyr, double cov_acc) {
+    if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
+    k_predict<<<1, SOLVE_THREADS, 0, h->stream>>>(h->d_ctrl, dt, cov_gyr, cov_acc);
+    IM_CUDA(cudaGetLastError());
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    return IMMESH_OK;
+}
+
+int immesh_voxelmap_build(immesh_lio_t* h, const float* body, int n) {
+    if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
+    int rc = upload_scan(h, body, n);
+    if (rc) return rc;
+    launch_grow(h, n, 1);
+    IM_CUDA(cudaGetLastError());
+    return check_flags(h);
+}
+
+int immesh_lio_estimate(immesh_lio_t* h, const float* body, int n, int* iters_run) {
+    if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
+    int rc = upload_scan(h, body, n);
+    if (rc) return rc;
+    launch_estimate(h, n);
+    IM_CUDA(cudaGetLastError());
+    IM_CUDA(cudaMemcpyAsync(h->h_ints + 32, &h->d_ctrl->iters_run, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    rc = check_flags(h);
+    if (iters_run) *iters_run = h->h_ints[32];
+    return rc;
+}
+
+int immesh_voxelmap_update(immesh_lio_t* h) {
+    if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
+    launch_grow(h, h->last_n, 0);
+    IM_CUDA(cudaGetLastError());
+    return check_flags(h);
+}
+
+int immesh_lio_step(immesh_lio_t* h, const float* body, int n, double dt, double cov_gyr, double cov_acc, double* state_out, int* iters_run) {
+    if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
+    IM_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    int rc = upload_scan(h, body, n);
+    if (rc) return rc;
+    if (dt > 0) k_predict<<<1, SOLVE_THREADS, 0, h->stream>>>(h->d_ctrl, dt, cov_gyr, cov_acc);
+    IM_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    launch_estimate(h, n);
+    IM_CUDA(cudaEventRecord(h->ev[2], h->stream));
+    launch_grow(h, n, 0);
+    IM_CUDA(cudaGetLastError());
+    IM_CUDA(cudaMemcpyAsync(h->h_state, h->d_ctrl->state, IM_STATE_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaMemcpyAsync(h->h_ints + 32, &h->d_ctrl->iters_run, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaEventRecord(h->ev[3], h->stream));
+    rc = check_flags(h);
+    if (state_out) std::memcpy(state_out, h->h_state, IM_STATE_DOUBLES * sizeof(double));
+    if (iters_run) *iters_run = h->h_ints[32];
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, h->ev[0], h->ev[3]);
+    cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&c, h->ev[2], h->ev[3]);
+    h->last_ms[0] = a; h->last_ms[1] = b; h->last_ms[2] = c;
+    return rc;
+}
+
+int immesh_lio_last_timing(immesh_lio_t* h, double* ms) {
+    if (!h || !ms) return im_fail(IMMESH_E_INVALID, "null argument");
+    ms[0] = h->last_ms[0]; ms[1] = h->last_ms[1]; ms[2] = h->last_ms[2];
+    return IMMESH_OK;
+}
+
+int immesh_residual_build(immesh_lio_t* h, const float* body, int n, int* index_layer, double* ptpl, int cap, int* n_out) {
+    if (!h || !n_out) return im_fail(IMMESH_E_INVALID, "null argument");
+    int rc = upload_scan(h, body, n);
+    if (rc) return rc;
+    if (!h->d_ptpl) IM_CUDA(dev_alloc(h, &h->d_ptpl, (size_t)h->max_scan * 31));
+    k_reset_scan<<<2, 256, 0, h->stream>>>(h->sb, h->d_ctrl, 0);
+    *n_out = 0;
+    if (n == 0) return IMMESH_OK;
+    k_prepare<<<grid_for(h, n, 128), 128, 0, h->stream>>>(h->P, h->sb, n);
+    k_residual<<<grid_for(h, n, RES_THREADS, 4), RES_THREADS, 0, h->stream>>>(h->map, h->P, h->sb, h->d_ctrl, 0, n);
+    k_gather_ptpl<<<grid_for(h, n, 128), 128, 0, h->stream>>>(h->map, h->sb, n, h->d_ptpl);
+    IM_CUDA(cudaGetLastError());
+    std::vector<int> node(n), layer(n);
+    std::vector<double> vals((size_t)n * 31);
+    IM_CUDA(cudaMemcpyAsync(node.data(), h->sb.match_node, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaMemcpyAsync(layer.data(), h->sb.match_layer, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaMemcpyAsync(vals.data(), h->d_ptpl, (size_t)n * 31 * 8, cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        if (node[i] < 0) continue;
+        if (m < cap) {
+            if (index_layer) { index_layer[2 * m] = i; index_layer[2 * m + 1] = layer[i]; }
+            if (ptpl) std::memcpy(ptpl + (size_t)m * 31, vals.data() + (size_t)i * 31, 31 * 8);
+        }
+        ++m;
+    }
+    *n_out = m;
+    return check_flags(h);
+}
+
+int immesh_lio_iter_stats(immesh_lio_t* h, int it, double* out) {
+    if (!h || !out || it < 0 || it >= IM_MAX_ITER) return im_fail(IMMESH_E_INVALID, "bad argument");
+    IterStats s;
+    IM_CUDA(cudaMemcpyAsync(&s, &h->d_ctrl->stats[it], sizeof(IterStats), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    std::memcpy(out, s.HTH, 36 * 8);
+    std::memcpy(out + 36, s.HTz, 6 * 8);
+    out[42] = s.n_match; out[43] = s.total_residual;
+    std::memcpy(out + 44, s.solution, 18 * 8);
+    out[62] = s.converged;
+    return IMMESH_OK;
+}
+
+int immesh_lio_matches(immesh_lio_t* h, int* plane_layer, int n) {
+    if (!h || !plane_layer || n > h->max_scan) return im_fail(IMMESH_E_INVALID, "bad argument");
+    std::vector<int> node(n), layer(n);
+    IM_CUDA(cudaMemcpyAsync(node.data(), h->sb.match_node, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaMemcpyAsync(layer.data(), h->sb.match_layer, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; ++i) plane_layer[i] = node[i] >= 0 ? layer[i] : -1;
+    return IMMESH_OK;
+}
+
+int64_t immesh_voxelmap_dump(immesh_lio_t* h, double* rows, int64_t cap_rows) {
+    if (!h) return -1;
+    int counters[16];
+    if (cudaMemcpy(counters, h->d_counters, sizeof(counters), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    const int nn = counters[0] < h->max_nodes ? counters[0] : h->max_nodes;
+    std::vector<unsigned long long> keys(h->cap);
+    std::vector<int> roots(h->cap);
+    std::vector<NodeRec> nodes(nn > 0 ? nn : 1);
+    std::vector<PlaneRec> planes(nn > 0 ? nn : 1);
+    cudaMemcpy(keys.data(), h->map.keys, h->cap * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(roots.data(), h->map.root_node, h->cap * 4, cudaMemcpyDeviceToHost);
+    if (nn > 0) {
+        cudaMemcpy(nodes.data(), h->map.nodes, (size_t)nn * sizeof(NodeRec), cudaMemcpyDeviceToHost);
+        cudaMemcpy(planes.data(), h->map.planes, (size_t)nn * sizeof(PlaneRec), cudaMemcpyDeviceToHost);
+    }
+    return dump_voxelmap(keys.data(), roots.data(), h->cap, nodes.data(), planes.data(), rows, cap_rows);
+}
+
+int immesh_voxelmap_counts(immesh_lio_t* h, int64_t* out) {
+    if (!h || !out) return im_fail(IMMESH_E_INVALID, "null argument");
+    int counters[16];
+    IM_CUDA(cudaMemcpy(counters, h->d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
+    out[0] = counters[5]; out[1] = counters[0]; out[2] = counters[1]; out[3] = counters[4];
+    return IMMESH_OK;
+}
+
+}  // extern "C"

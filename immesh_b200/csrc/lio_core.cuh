@@ -1,0 +1,479 @@
+// immesh_b200 -- per-scan localization path on the device-resident VoxelMap:
+//   K1 scan preparation        (m_body_cov_list / m_cross_mat_list, voxel_mapping.cpp:1302-1316)
+//   K2+K3 residual + Jacobian row + normal-equation terms, one thread per scan point
+//                              (voxel_mapping.cpp:1344-1392, :1487-1586)
+//   K4 IESKF solve             (voxel_mapping.cpp:1586-1650), one thread block
+//   K5 map growth              (ImMesh_mesh_reconstruction.cpp:387-408 + updateVoxelMap)
+// The bodies are __host__ __device__ so that tests/emu can execute the very same source on the
+// CPU (single lane / single thread) for logic tests; the product only ever runs them on the GPU.
+#pragma once
+#include "voxelmap.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define IM_SYNCBLOCK() __syncthreads()
+#else
+#define IM_SYNCBLOCK()
+#endif
+
+namespace immesh {
+
+#define IM_MAX_ITER 8
+#define IM_STATE_DOUBLES 348  // rot 9, pos 3, vel 3, bg 3, ba 3, grav 3, cov 324
+#define IM_NTERMS 30          // 21 HTH + 6 HTz + sum|r| + match count + spare
+
+struct IterStats {
+    double HTH[36];
+    double HTz[6];
+    double n_match;
+    double total_residual;
+    double solution[18];
+    double converged;
+};
+
+struct LioCtrl {
+    double state[IM_STATE_DOUBLES];
+    double state_prop[IM_STATE_DOUBLES];
+    double G[324];
+    unsigned long long acc[IM_MAX_ITER][IM_NTERMS * 2];  // (hi, lo) pairs, two's complement sums
+    IterStats stats[IM_MAX_ITER];
+    int stop;
+    int iters_run;
+    int rematch_num;
+    int pad_;
+};
+
+struct ScanBuf {
+    int n;
+    const float* body;   // [n][3] body-frame (LiDAR) points, float like pcl::PointXYZI
+    double* body_cov;    // [n][6]
+    double* p_imu;       // [n][3]  R_ext p + t_ext (z==0 -> 0.001 rule applied first, :1305-1312)
+    int* match_node;     // [n] plane node of the accepted match, -1 otherwise (last residual pass)
+    int* match_layer;    // [n]
+    float* pw;           // [n][3] world points of the growth pass
+    double* var;         // [n][6]
+    double* sortkey;     // [n]
+    int* slot;           // [n]
+    int* seg;            // [n] point indices grouped by root voxel
+    // per-slot scratch (size = hash capacity)
+    int* slot_count;
+    int* slot_offset;
+    int* slot_cursor;
+    // touched root voxels of this scan
+    int* touched;
+    int* n_touched;
+    int* seg_top;
+};
+
+// ------------------------------------------------------------------ K1
+IM_HDN inline void prepare_point(const LioParams& P, const ScanBuf& sb, int i) {
+    double p[3] = {(double)sb.body[i * 3 + 0], (double)sb.body[i * 3 + 1], (double)sb.body[i * 3 + 2]};
+    if (p[2] == 0) p[2] = 0.001;
+    calc_body_var(p, P.dept_err, P.dir_var, sb.body_cov + (size_t)i * 6);
+    double q[3];
+    m3_vec(P.extR, p, q);
+    sb.p_imu[(size_t)i * 3 + 0] = q[0] + P.extT[0];
+    sb.p_imu[(size_t)i * 3 + 1] = q[1] + P.extT[1];
+    sb.p_imu[(size_t)i * 3 + 2] = q[2] + P.extT[2];
+}
+
+// world covariance for matching: R S_b R^T + (-[p]x) S_R (-[p]x)^T + S_t   (voxel_mapping.cpp:1356)
+IM_HDN inline void world_cov(const double* A, const double* body_cov6, const double* p_imu, const double* cov18, double* out6) {
+    double Sb[9], C[9], nC[9], rot_var[9], T1[6], T2[6];
+    s6_full(body_cov6, Sb);
+    congr6(A, Sb, T1);
+    skew3(p_imu, C);
+    for (int k = 0; k < 9; ++k) nC[k] = -C[k];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) rot_var[a * 3 + b] = cov18[a * 18 + b];
+    congr6(nC, rot_var, T2);
+    for (int a = 0; a < 3; ++a)
+        for (int b = a; b < 3; ++b) out6[s6(a, b)] = (T1[s6(a, b)] + T2[s6(a, b)]) + cov18[(3 + a) * 18 + (3 + b)];
+}
+
+// ------------------------------------------------------------------ K2 + K3 (one scan point)
+// terms[0..20] = upper triangle of w h h^T, [21..26] = w h z, [27] = |r|, [28] = 1 (match count); as 2^-20 fixed point.
+// returns true when the point is matched.
+IM_HDN inline bool residual_point(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, long long* terms, int* err) {
+    const double* R = state;
+    const double* t = state + 9;
+    const double* cov = state + 24;
+    const double pb[3] = {(double)sb.body[i * 3 + 0], (double)sb.body[i * 3 + 1], (double)sb.body[i * 3 + 2]};
+    double pwd[3], pw[3], var6[6];
+    body_to_world(P, R, t, pb, pwd);
+    pw[0] = (double)(float)pwd[0]; pw[1] = (double)(float)pwd[1]; pw[2] = (double)(float)pwd[2];
+    world_cov(R, sb.body_cov + (size_t)i * 6, sb.p_imu + (size_t)i * 3, cov, var6);
+    const MatchResult mr = match_point(map, P, pw, var6);
+    sb.match_node[i] = mr.node;
+    sb.match_layer[i] = mr.layer;
+    if (mr.node < 0) return false;
+    const PlaneRec& pl = map.planes[mr.node];
+    // float-rounded normal / residual through the PCL point structs (voxel_mapping.cpp:1377-1389)
+    const float nf[3] = {(float)pl.normal[0], (float)pl.normal[1], (float)pl.normal[2]};
+    const float dis = (float)(((pwd[0] * (double)nf[0] + pwd[1] * (double)nf[1]) + pwd[2] * (double)nf[2]) + (double)pl.d);
+    // Jacobian row and weight (voxel_mapping.cpp:1496-1569)
+    double p_imu[3];
+    m3_vec(P.extR, pb, p_imu);
+    p_imu[0] = p_imu[0] + P.extT[0]; p_imu[1] = p_imu[1] + P.extT[1]; p_imu[2] = p_imu[2] + P.extT[2];
+    double C[9];
+    skew3(p_imu, C);
+    const double nv[3] = {(double)nf[0], (double)nf[1], (double)nf[2]};
+    double pw2[3];
+    m3_vec(R, p_imu, pw2);
+    pw2[0] = pw2[0] + t[0]; pw2[1] = pw2[1] + t[1]; pw2[2] = pw2[2] + t[2];
+    double bv[6], Sb[9], RRe[9], wv[6];
+    double pv3[3] = {p_imu[0], p_imu[1], p_imu[2]};
+    calc_body_var(pv3, P.dept_err, P.calib_laser ? P.dir_var_calib : P.dir_var, bv);  // evaluated at the IMU-frame point (:1498-1521)
+    s6_full(bv, Sb);
+    m3_mul(R, P.extR, RRe);
+    congr6(RRe, Sb, wv);
+    const double sigma_l = plane_sigma(pw2, pl.center, pl.normal, pl.pv);
+    const double R_inv = 1.0 / (sigma_l + quad6(nv, wv));
+    double CRt[9], A[3];
+    m3_mul_bt(C, R, CRt);
+    m3_vec(CRt, nv, A);
+    const double h[6] = {A[0], A[1], A[2], nv[0], nv[1], nv[2]};
+    const double z = -(double)dis;
+    double hw[6];
+    for (int a = 0; a < 6; ++a) hw[a] = h[a] * R_inv;
+    int e = 0;
+    bool range_ok = true;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b, ++e) {
+            const double term = hw[a] * h[b];
+            if (!(fabs(term) < 1.0e10)) range_ok = false;
+            terms[e] = im_llrint(term * IM_FX_SCALE);
+        }
+    for (int a = 0; a < 6; ++a) {
+        const double term = hw[a] * z;
+        if (!(fabs(term) < 1.0e10)) range_ok = false;
+        terms[21 + a] = im_llrint(term * IM_FX_SCALE);
+    }
+    terms[27] = im_llrint(fabs((double)dis) * IM_FX_SCALE);
+    terms[28] = 1;
+    terms[29] = 0;
+    if (!range_ok) {
+        im_atomic_or(err, IM_ERR_FX_RANGE);
+        for (int k = 0; k < IM_NTERMS; ++k) terms[k] = 0;
+        return false;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------ K4: 18x18 LU inverse, cooperative
+// a: 18x18 working copy (shared), piv: 18 ints (shared), inv: 18x18 output.  Same elimination order as a
+// textbook serial partial-pivot LU, every element's update sequence is serial in k.
+IM_HDN inline void lu_inverse18(double* a, int* piv, double* inv, int tid, int nthreads) {
+    for (int i = tid; i < 18; i += nthreads) piv[i] = i;
+    IM_SYNCBLOCK();
+    for (int k = 0; k < 18; ++k) {
+        if (tid == 0) {
+            int best = k;
+            double bv = fabs(a[k * 18 + k]);
+            for (int i = k + 1; i < 18; ++i) {
+                const double v = fabs(a[i * 18 + k]);
+                if (v > bv) { bv = v; best = i; }
+            }
+            if (best != k) {
+                for (int j = 0; j < 18; ++j) { const double tv = a[k * 18 + j]; a[k * 18 + j] = a[best * 18 + j]; a[best * 18 + j] = tv; }
+                const int tp = piv[k]; piv[k] = piv[best]; piv[best] = tp;
+            }
+        }
+        IM_SYNCBLOCK();
+        const double pivv = a[k * 18 + k];
+        IM_SYNCBLOCK();
+        for (int i = k + 1 + tid; i < 18; i += nthreads) a[i * 18 + k] = a[i * 18 + k] / pivv;
+        IM_SYNCBLOCK();
+        for (int idx = tid; idx < 324; idx += nthreads) {
+            const int i = idx / 18, j = idx % 18;
+            if (i > k && j > k) a[i * 18 + j] = a[i * 18 + j] - a[i * 18 + k] * a[k * 18 + j];
+        }
+        IM_SYNCBLOCK();
+    }
+    for (int c = tid; c < 18; c += nthreads) {
+        double y[18];
+        for (int i = 0; i < 18; ++i) {
+            double s = (piv[i] == c) ? 1.0 : 0.0;
+            for (int j = 0; j < i; ++j) s = s - a[i * 18 + j] * y[j];
+            y[i] = s;
+        }
+        for (int i = 17; i >= 0; --i) {
+            double s = y[i];
+            for (int j = i + 1; j < 18; ++j) s = s - a[i * 18 + j] * y[j];
+            y[i] = s / a[i * 18 + i];
+        }
+        for (int i = 0; i < 18; ++i) inv[i * 18 + c] = y[i];
+    }
+    IM_SYNCBLOCK();
+}
+
+struct SolveScratch {
+    double a[324];
+    double Pinv[324];
+    double K1[324];
+    double ncov[324];
+    double HTH[36];
+    double HTz[6];
+    double vec[18];
+    double sol[18];
+    int piv[18];
+    int flags[4];
+};
+
+// state_propagat (-) state, include/common_lib.h:249-260
+IM_HDN inline void state_minus(const double* a, const double* b, double* out) {
+    double rotd[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) rotd[i * 3 + j] = (b[0 * 3 + i] * a[0 * 3 + j] + b[1 * 3 + i] * a[1 * 3 + j]) + b[2 * 3 + i] * a[2 * 3 + j];
+    so3_log3(rotd, out);
+    for (int i = 0; i < 15; ++i) out[3 + i] = a[9 + i] - b[9 + i];
+}
+// state (+)= delta, include/common_lib.h:238-247
+IM_HDN inline void state_plus(double* s, const double* add) {
+    double E[9], Rn[9];
+    so3_exp3(add[0], add[1], add[2], E);
+    m3_mul(s, E, Rn);
+    for (int i = 0; i < 9; ++i) s[i] = Rn[i];
+    for (int i = 0; i < 15; ++i) s[9 + i] = s[9 + i] + add[3 + i];
+}
+
+// one IESKF update (voxel_mapping.cpp:1586-1650) executed by one thread block
+IM_HDN inline void ieskf_solve(const LioParams& P, LioCtrl* ctrl, int iter, SolveScratch* S, int tid, int nthreads) {
+    if (ctrl->stop) return;  // block-uniform
+    double* state = ctrl->state;
+    double* cov = state + 24;
+    // normal equations from the fixed-point accumulators
+    for (int e = tid; e < 29; e += nthreads) {
+        const long long hi = (long long)ctrl->acc[iter][2 * e], lo = (long long)ctrl->acc[iter][2 * e + 1];
+        // hi/lo were accumulated from block sums: total = hi * 2^32 + lo (two's complement, exact)
+        const double v = fx_value(hi, lo);
+        if (e < 21) {
+            int ei = 0, base = 0;
+            while (e >= base + (6 - ei)) { base += 6 - ei; ++ei; }
+            const int ej = ei + (e - base);
+            S->HTH[ei * 6 + ej] = v;
+            S->HTH[ej * 6 + ei] = v;
+        } else if (e < 27) {
+            S->HTz[e - 21] = v;
+        } else if (e == 27) {
+            ctrl->stats[iter].total_residual = v;
+        } else {
+            ctrl->stats[iter].n_match = (double)((hi << 32) + lo);
+        }
+    }
+    for (int i = tid; i < 324; i += nthreads) S->a[i] = cov[i];
+    IM_SYNCBLOCK();
+    lu_inverse18(S->a, S->piv, S->Pinv, tid, nthreads);
+    for (int idx = tid; idx < 324; idx += nthreads) {
+        const int i = idx / 18, j = idx % 18;
+        const double hth = (i < 6 && j < 6) ? S->HTH[i * 6 + j] : 0.0;
+        S->a[idx] = hth + S->Pinv[idx];
+    }
+    IM_SYNCBLOCK();
+    lu_inverse18(S->a, S->piv, S->K1, tid, nthreads);
+    // G[:, :6] = K1[:, :6] * HTH
+    for (int idx = tid; idx < 18 * 6; idx += nthreads) {
+        const int i = idx / 6, j = idx % 6;
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) s = s + S->K1[i * 18 + k] * S->HTH[k * 6 + j];
+        ctrl->G[i * 18 + j] = s;
+    }
+    if (tid == 0) state_minus(ctrl->state_prop, state, S->vec);
+    IM_SYNCBLOCK();
+    for (int i = tid; i < 18; i += nthreads) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = 0; k < 6; ++k) s1 = s1 + S->K1[i * 18 + k] * S->HTz[k];
+        for (int k = 0; k < 6; ++k) s2 = s2 + ctrl->G[i * 18 + k] * S->vec[k];
+        S->sol[i] = (s1 + S->vec[i]) - s2;
+    }
+    IM_SYNCBLOCK();
+    if (tid == 0) {
+        state_plus(state, S->sol);
+        const double* sol = S->sol;
+        const double rn = sqrt((sol[0] * sol[0] + sol[1] * sol[1]) + sol[2] * sol[2]);
+        const double tn = sqrt((sol[3] * sol[3] + sol[4] * sol[4]) + sol[5] * sol[5]);
+        const int converged = ((rn * 57.3 < 0.01) && (tn * 100 < 0.015)) ? 1 : 0;
+        IterStats& st = ctrl->stats[iter];
+        for (int i = 0; i < 36; ++i) st.HTH[i] = S->HTH[i];
+        for (int i = 0; i < 6; ++i) st.HTz[i] = S->HTz[i];
+        for (int i = 0; i < 18; ++i) st.solution[i] = sol[i];
+        st.converged = converged;
+        ctrl->iters_run = iter + 1;
+        int rematch = ctrl->rematch_num;
+        if (converged || ((rematch == 0) && (iter == P.max_iter - 2))) rematch++;
+        ctrl->rematch_num = rematch;
+        S->flags[0] = (rematch >= 2 || iter == P.max_iter - 1) ? 1 : 0;
+    }
+    IM_SYNCBLOCK();
+    if (S->flags[0]) {
+        // cov = (I - G) * cov
+        for (int idx = tid; idx < 324; idx += nthreads) {
+            const int i = idx / 18, j = idx % 18;
+            double s = 0.0;
+            for (int k = 0; k < 18; ++k) {
+                const double ig = ((i == k) ? 1.0 : 0.0) - ((k < 6) ? ctrl->G[i * 18 + k] : 0.0);
+                s = s + ig * cov[k * 18 + j];
+            }
+            S->ncov[idx] = s;
+        }
+        IM_SYNCBLOCK();
+        for (int idx = tid; idx < 324; idx += nthreads) cov[idx] = S->ncov[idx];
+        if (tid == 0) ctrl->stop = 1;
+    }
+    IM_SYNCBLOCK();
+}
+
+// Forward_without_imu (constant-velocity prediction), src/IMU_Processing.cpp:486-553
+IM_HDN inline void predict_const_vel(double* state, double dt, double cov_gyr, double cov_acc, double* T /*324*/, double* Fx /*324*/, int tid, int nthreads) {
+    double* cov = state + 24;
+    if (tid == 0) {
+        for (int i = 0; i < 324; ++i) Fx[i] = 0.0;
+        for (int i = 0; i < 18; ++i) Fx[i * 18 + i] = 1.0;
+        double En[9];
+        so3_exp_dt(state + 15, -dt, En);
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) Fx[a * 18 + b] = En[a * 3 + b];
+        for (int a = 0; a < 3; ++a) { Fx[a * 18 + 9 + a] = dt; Fx[(3 + a) * 18 + 6 + a] = dt; }
+    }
+    IM_SYNCBLOCK();
+    for (int idx = tid; idx < 324; idx += nthreads) {
+        const int i = idx / 18, j = idx % 18;
+        double s = 0.0;
+        for (int k = 0; k < 18; ++k) s = s + Fx[i * 18 + k] * cov[k * 18 + j];
+        T[idx] = s;
+    }
+    IM_SYNCBLOCK();
+    for (int idx = tid; idx < 324; idx += nthreads) {
+        const int i = idx / 18, j = idx % 18;
+        double s = 0.0;
+        for (int k = 0; k < 18; ++k) s = s + T[i * 18 + k] * Fx[j * 18 + k];
+        double cw = 0.0;
+        if (i == j && i >= 9 && i < 12) cw = cov_gyr * dt * dt;
+        if (i == j && i >= 6 && i < 9) cw = cov_acc * dt * dt;
+        cov[idx] = s + cw;
+    }
+    IM_SYNCBLOCK();
+    if (tid == 0) {
+        double Ef[9], Rn[9];
+        so3_exp_dt(state + 15, dt, Ef);
+        m3_mul(state, Ef, Rn);
+        for (int i = 0; i < 9; ++i) state[i] = Rn[i];
+        for (int i = 0; i < 3; ++i) state[9 + i] = state[9 + i] + state[12 + i] * dt;
+    }
+    IM_SYNCBLOCK();
+}
+
+// ------------------------------------------------------------------ K5: map growth
+// pass 1 (thread / point): world point + covariance with the converged state, sort key, root-voxel insert, count
+//   mode 0: map_incremental_grow (ImMesh_mesh_reconstruction.cpp:393-404)   cov uses (R R_ext) and [p_imu]x
+//   mode 1: voxel_map_init       (voxel_mapping.cpp:1249-1265)              cov uses R and [p_lidar]x, input order kept
+IM_HDN inline void grow_point(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, int mode) {
+    const double* R = state;
+    const double* t = state + 9;
+    const double* cov = state + 24;
+    const double pb[3] = {(double)sb.body[i * 3 + 0], (double)sb.body[i * 3 + 1], (double)sb.body[i * 3 + 2]};
+    double pwd[3];
+    body_to_world(P, R, t, pb, pwd);
+    const float wx = (float)pwd[0], wy = (float)pwd[1], wz = (float)pwd[2];
+    sb.pw[(size_t)i * 3 + 0] = wx; sb.pw[(size_t)i * 3 + 1] = wy; sb.pw[(size_t)i * 3 + 2] = wz;
+    double* v6 = sb.var + (size_t)i * 6;
+    if (mode == 0) {
+        double RRe[9];
+        m3_mul(R, P.extR, RRe);
+        world_cov(RRe, sb.body_cov + (size_t)i * 6, sb.p_imu + (size_t)i * 3, cov, v6);
+        sb.sortkey[i] = sqrt((v6[0] * v6[0] + v6[3] * v6[3]) + v6[5] * v6[5]);  // var_contrast, voxel_mapping.cpp:49
+    } else {
+        double pt[3] = {pb[0], pb[1], pb[2]};
+        double bv[6];
+        calc_body_var(pt, P.dept_err, P.dir_var, bv);
+        world_cov(R, bv, pt, cov, v6);
+        sb.sortkey[i] = (double)i;
+    }
+    const double pw[3] = {(double)wx, (double)wy, (double)wz};
+    long long k[3];
+    sb.slot[i] = -1;
+    if (!voxel_key3(pw, P.voxel_size_ins, k)) { im_atomic_or(map.err, IM_ERR_KEY_RANGE); return; }
+    int created = 0;
+    const unsigned long long key = pack_key(k[0], k[1], k[2]);
+    const int slot = hash_insert(map, key, &created);
+    if (slot < 0) return;
+    if (created) {
+        map.root_node[slot] = make_root(map, P, key, slot);
+        im_atomic_add(map.n_roots, 1);
+    }
+    sb.slot[i] = slot;
+    if (im_atomic_add(&sb.slot_count[slot], 1) == 0) {
+        const int ti = im_atomic_add(sb.n_touched, 1);
+        sb.touched[ti] = slot;
+    }
+}
+// pass 2 (thread / touched voxel): claim a segment
+IM_HD void grow_segment(const ScanBuf& sb, int ti) {
+    const int slot = sb.touched[ti];
+    sb.slot_offset[slot] = im_atomic_add(sb.seg_top, sb.slot_count[slot]);
+    sb.slot_cursor[slot] = 0;
+}
+// pass 3 (thread / point): scatter point indices into the voxel's segment
+IM_HD void grow_scatter(const ScanBuf& sb, int i) {
+    const int slot = sb.slot[i];
+    if (slot < 0) return;
+    const int pos = sb.slot_offset[slot] + im_atomic_add(&sb.slot_cursor[slot], 1);
+    sb.seg[pos] = i;
+}
+// pass 4 (warp / touched voxel): order the segment like std::sort(var_contrast) would, then apply the points
+IM_HDN inline void grow_voxel(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, int ti, int mode, int lane, int nlanes, int* sorted_scratch) {
+    const int slot = sb.touched[ti];
+    const int cnt = sb.slot_count[slot];
+    const int off = sb.slot_offset[slot];
+    // rank sort on (key, index): rank = number of strictly smaller elements
+    for (int a = lane; a < cnt; a += nlanes) {
+        const int ia = sb.seg[off + a];
+        const double ka = sb.sortkey[ia];
+        int rank = 0;
+        for (int b = 0; b < cnt; ++b) {
+            const int ib = sb.seg[off + b];
+            const double kb = sb.sortkey[ib];
+            if (kb < ka || (kb == ka && ib < ia)) ++rank;
+        }
+        sorted_scratch[off + rank] = ia;
+    }
+    IM_SYNCWARP();
+    const int root = map.root_node[slot];
+    if (root >= 0) {
+        if (mode == 0) {
+            for (int a = 0; a < cnt; ++a) {
+                const int i = sorted_scratch[off + a];
+                update_octo_tree(map, P, root, sb.pw[(size_t)i * 3 + 0], sb.pw[(size_t)i * 3 + 1], sb.pw[(size_t)i * 3 + 2], sb.var + (size_t)i * 6, lane, nlanes);
+            }
+        } else {
+            // buildVoxelMap: append everything, then one init_octo_tree (voxel_mapping.cpp:115-150)
+            if (lane == 0) {
+                for (int a = 0; a < cnt; ++a) {
+                    const int i = sorted_scratch[off + a];
+                    node_append(map, root, sb.pw[(size_t)i * 3 + 0], sb.pw[(size_t)i * 3 + 1], sb.pw[(size_t)i * 3 + 2], sb.var + (size_t)i * 6);
+                    map.nodes[root].new_points += 1;
+                }
+            }
+            IM_SYNCWARP();
+            init_octo_tree(map, P, root, lane, nlanes);
+        }
+    }
+    IM_SYNCWARP();
+    if (lane == 0) {
+        sb.slot_count[slot] = 0;
+        sb.slot_cursor[slot] = 0;
+    }
+}
+// between scans: recycle chunks freed during the scan
+IM_HD void recycle_chunks(const VoxelMapDev& map, int tid, int nthreads) {
+    int top = *map.avail_top;
+    if (top < 0) top = 0;
+    const int np = *map.pending_n < map.max_chunks ? *map.pending_n : map.max_chunks;
+    for (int i = tid; i < np; i += nthreads) map.avail[top + i] = map.pending[i];
+    IM_SYNCBLOCK();
+    if (tid == 0) {
+        *map.avail_top = top + np;
+        *map.pending_n = 0;
+    }
+}
+
+}  // namespace immesh

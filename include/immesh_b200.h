@@ -1,0 +1,135 @@
+/* immesh_b200 -- C ABI of the B200-native ImMesh localization + meshing hot path.
+ *
+ * The reference (hku-mars/ImMesh) has no plugin / FFI layer; this header cuts the drop-in
+ * boundary at the C++ seams its ROS node calls.  Every entry point names the reference
+ * function it replaces (paths relative to the reference repository).  All buffers are plain
+ * caller-owned host arrays (row-major); handles own all device memory; no exceptions cross the
+ * boundary; every function returns 0 on success or a negative IMMESH_E_* code.  Calls on one
+ * handle must be serialised by the caller (exactly as the reference serialises its LIO thread
+ * and its mesh frames); different handles may be used concurrently.
+ */
+#ifndef IMMESH_B200_H_
+#define IMMESH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMMESH_OK 0
+#define IMMESH_E_INVALID (-1)  /* bad argument */
+#define IMMESH_E_CUDA (-2)     /* CUDA runtime failure (see immesh_last_error) */
+#define IMMESH_E_CAPACITY (-3) /* a device pool / hash table overflowed */
+#define IMMESH_E_NO_DEVICE (-4)
+#define IMMESH_E_RANGE (-5)    /* coordinate outside the representable key range */
+
+#define IMMESH_STATE_DOUBLES 348 /* rot_end[9] pos_end[3] vel_end[3] bias_g[3] bias_a[3] gravity[3] cov[18*18]
+                                    = StatesGroup, include/common_lib.h:199-288 */
+#define IMMESH_ITER_STATS_DOUBLES 63 /* HTH[36] HTz[6] n_match total_residual solution[18] converged */
+#define IMMESH_MAP_DUMP_COLS 45
+#define IMMESH_PTPL_DOUBLES 31 /* point[3] normal[3] center[3] d plane_var_upper[21]  (struct ptpl, src/voxel_loc.hpp:63-73) */
+
+typedef struct immesh_lio immesh_lio_t;
+typedef struct immesh_mesh immesh_mesh_t;
+
+/* Parameters of Voxel_mapping that the path reads (src/voxel_mapping.hpp:149-191,
+ * read_ros_parameters src/voxel_mapping_common.cpp:625-707). */
+typedef struct immesh_lio_config {
+    double voxel_size;         /* voxel/voxel_size -> m_max_voxel_size */
+    int max_layer;             /* voxel/max_layer */
+    int layer_init_size[5];    /* voxel/layer_init_size */
+    int max_points_size;       /* voxel/max_points_size */
+    double min_eigen_value;    /* voxel/min_eigen_value */
+    double dept_err, beam_err; /* voxel/dept_err, voxel/beam_err */
+    double ext_R[9], ext_T[3]; /* mapping/extrinsic_R, extrinsic_T (LiDAR -> IMU) */
+    int max_iteration;         /* max_iteration (NUM_MAX_ITERATIONS), <= 8 */
+    int calib_laser;           /* preprocess/calib_laser */
+    /* capacities of the device-resident map (0 = defaults) */
+    int hash_capacity_log2;    /* root-voxel hash slots = 2^this          (default 22) */
+    int max_nodes;             /* octree node / plane records              (default 4 Mi) */
+    int max_chunks;            /* 8-point storage chunks (512 B each)      (default 4 Mi) */
+    int max_scan_points;       /* largest scan handed to any call          (default 2 Mi) */
+} immesh_lio_config;
+
+/* ---- localization handle: owns the VoxelMap (m_feat_map) and the filter state ------------------------ */
+int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out);
+int immesh_lio_destroy(immesh_lio_t* h);
+int immesh_lio_set_state(immesh_lio_t* h, const double* state /*[348]*/);
+int immesh_lio_get_state(immesh_lio_t* h, double* state /*[348]*/);
+
+/* ImuProcess::Forward_without_imu (src/IMU_Processing.cpp:486-553): constant-velocity prediction of the
+ * state and its covariance, used when imu_en is false. */
+int immesh_lio_predict(immesh_lio_t* h, double dt, double cov_gyr, double cov_acc);
+
+/* Voxel_mapping::voxel_map_init + buildVoxelMap (src/voxel_mapping.cpp:1243-1281, :110-151):
+ * first-scan map construction from the full-resolution body-frame scan, at the current state. */
+int immesh_voxelmap_build(immesh_lio_t* h, const float* body_xyz /*[n][3]*/, int n);
+
+/* Voxel_mapping::lio_state_estimation (src/voxel_mapping.cpp:1284-1652): all IESKF iterations on the
+ * down-sampled body-frame scan; the propagated state is the handle's state on entry.  The whole loop
+ * (BuildResidualListOMP + Jacobian + H^T R^-1 H reduction + 18x18 solve + convergence logic) runs on the
+ * device without host round trips. */
+int immesh_lio_estimate(immesh_lio_t* h, const float* body_xyz /*[n][3]*/, int n, int* iters_run);
+
+/* Voxel_mapping::map_incremental_grow, VoxelMap part (src/ImMesh_mesh_reconstruction.cpp:387-408 ->
+ * updateVoxelMap src/voxel_mapping.cpp:320-354) on the scan last given to immesh_lio_estimate. */
+int immesh_voxelmap_update(immesh_lio_t* h);
+
+/* predict + estimate + update for one scan in one call (one H2D copy, one stream, no intermediate sync).
+ * dt <= 0 skips the prediction.  state_out may be NULL. */
+int immesh_lio_step(immesh_lio_t* h, const float* body_xyz, int n, double dt, double cov_gyr, double cov_acc,
+                    double* state_out /*[348] or NULL*/, int* iters_run /*or NULL*/);
+
+/* BuildResidualListOMP (src/voxel_mapping.hpp:103-105, src/voxel_mapping.cpp:153-245) as a stand-alone call at
+ * the current state: fills, for every accepted match in scan order, its scan index, octree layer and the ptpl
+ * payload.  Returns the number of matches in *n_out (written entries are capped by cap). */
+int immesh_residual_build(immesh_lio_t* h, const float* body_xyz, int n, int* index_layer /*[cap][2]*/,
+                          double* ptpl /*[cap][31]*/, int cap, int* n_out);
+
+/* diagnostics used by the parity tests */
+int immesh_lio_iter_stats(immesh_lio_t* h, int iter, double* out /*[63]*/);
+int immesh_lio_matches(immesh_lio_t* h, int* plane_layer /*[n] layer or -1*/, int n);
+/* canonical dump of the VoxelMap (roots by ascending key, nodes in pre-order), 45 doubles per node */
+int64_t immesh_voxelmap_dump(immesh_lio_t* h, double* rows, int64_t cap_rows);
+int immesh_voxelmap_counts(immesh_lio_t* h, int64_t* out /*[4]: roots, nodes, chunks_in_use, error_flags*/);
+/* device time (ms, CUDA events on the handle's stream) of the stages of the last immesh_lio_step call:
+ * [0] whole step incl. H2D, [1] residual+solve iterations, [2] map update */
+int immesh_lio_last_timing(immesh_lio_t* h, double* ms /*[3]*/);
+
+/* ---- meshing handle: Global_map + Triangle_manager of the voxel-wise mesher ---------------------------- */
+typedef struct immesh_mesh_config {
+    double points_minimum_scale; /* meshing/points_minimum_scale * distance_scale -> m_minimum_pts_size */
+    double voxel_resolution;     /* meshing/voxel_resolution * distance_scale -> m_voxel_resolution */
+    int number_of_pts_append_to_map; /* appending_pts_frame (src/ImMesh_node.cpp:93-98) */
+    int max_vertices;            /* capacities (0 = defaults) */
+    int max_triangles;
+    int max_voxels;
+    int max_frame_points;
+} immesh_mesh_config;
+
+int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out);
+int immesh_mesh_destroy(immesh_mesh_t* h);
+/* incremental_mesh_reconstruction(frame_pts, pose_q, pose_t, frame_idx) (src/ImMesh_mesh_reconstruction.cpp:92-267):
+ * append vertices, find activated voxels, per voxel retrieve + dilate + project + 2-D Delaunay + pull/commit,
+ * then push.  world_xyz is the full-resolution scan already in the world frame (float, as pcl::PointXYZI). */
+int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz /*[n][3]*/, int n, const double* pose_t /*[3]*/, int frame_idx);
+/* counts: [n_vertices, n_live_triangles, frame_new_vertices, frame_voxels_meshed, frame_added, frame_removed, n_voxels, n_activated] */
+int immesh_mesh_counts(immesh_mesh_t* h, int64_t* out /*[8]*/);
+/* Triangle_manager::get_all_triangle_list (src/meshing/r3live/triangle.cpp:12-33) + the vertex array:
+ * live triangles as ascending sorted (i<j<k) id triples with their m_index_flip. */
+int immesh_mesh_snapshot(immesh_mesh_t* h, float* vertices /*[nv][3] or NULL*/, int32_t* triangles /*[nt][3] or NULL*/,
+                         int32_t* flips /*[nt] or NULL*/);
+/* KD_TREE::Nearest_Search(point, k, ..., max_dist) (include/ikd-Tree/ikd_Tree.h:306) over the mesh vertices:
+ * exact k nearest by float squared distance, ascending, ties by lower id; idx = -1 / d2 = inf when fewer exist. */
+int immesh_knn(immesh_mesh_t* h, const float* query_xyz /*[nq][3]*/, int nq, int k, double max_dist, int32_t* idx /*[nq][k]*/,
+               float* d2 /*[nq][k]*/);
+int immesh_mesh_last_timing(immesh_mesh_t* h, double* ms /*[4]: whole frame incl. H2D, append, per-voxel, push*/);
+
+const char* immesh_last_error(void);
+const char* immesh_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMMESH_B200_H_ */

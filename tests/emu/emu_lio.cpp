@@ -1,0 +1,176 @@
+// TEST INFRASTRUCTURE (not product code): executes the __host__ __device__ bodies of the CUDA
+// localization path (immesh_b200/csrc/*.cuh) on the CPU, one lane / one thread at a time, so
+// that the host-side logic (state machines, pool bookkeeping, numerics contract) can be checked
+// against the oracle in the CPU-only test tier.  The shipped library (libimmesh_b200.so) never
+// links or calls this; it has no CPU path.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/immesh_b200.h"
+#include "../../immesh_b200/csrc/lio_core.cuh"
+
+using namespace immesh;
+
+struct immesh_lio {
+    LioParams P;
+    VoxelMapDev map;
+    ScanBuf sb;
+    LioCtrl ctrl;
+    std::vector<unsigned long long> keys;
+    std::vector<int> root_node, avail, pending, ints;
+    std::vector<NodeRec> nodes;
+    std::vector<PlaneRec> planes;
+    std::vector<Chunk> chunks;
+    std::vector<float> body, pw;
+    std::vector<double> body_cov, p_imu, var, sortkey;
+    std::vector<int> match_node, match_layer, slot, seg, seg2, slot_count, slot_offset, slot_cursor, touched;
+    int counters[16];
+    int max_scan;
+};
+
+static void fill_params(const immesh_lio_config* c, LioParams& P) {
+    P.voxel_size = c->voxel_size;
+    P.voxel_size_f = (float)c->voxel_size;
+    P.voxel_size_ins = (double)P.voxel_size_f;
+    P.max_layer = c->max_layer;
+    for (int i = 0; i < 5; ++i) P.layer_init[i] = c->layer_init_size[i];
+    P.max_points = c->max_points_size;
+    P.planer_threshold = (float)c->min_eigen_value;
+    P.dept_err = (float)c->dept_err;
+    const float be = (float)c->beam_err;
+    const double s = std::sin((double)be * 0.017453293);
+    P.dir_var = s * s;
+    const double sc = std::sin((double)(float)0.01 * 0.017453293);
+    P.dir_var_calib = sc * sc;
+    P.calib_laser = c->calib_laser;
+    P.max_iter = c->max_iteration;
+    for (int i = 0; i < 9; ++i) P.extR[i] = c->ext_R[i];
+    for (int i = 0; i < 3; ++i) P.extT[i] = c->ext_T[i];
+}
+
+extern "C" {
+int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
+    immesh_lio* h = new immesh_lio();
+    fill_params(cfg, h->P);
+    const int caplog = cfg->hash_capacity_log2 ? cfg->hash_capacity_log2 : 18;
+    const int max_nodes = cfg->max_nodes ? cfg->max_nodes : (1 << 18);
+    const int max_chunks = cfg->max_chunks ? cfg->max_chunks : (1 << 19);
+    h->max_scan = cfg->max_scan_points ? cfg->max_scan_points : (1 << 20);
+    const size_t cap = (size_t)1 << caplog;
+    h->keys.assign(cap, IM_EMPTY_KEY);
+    h->root_node.assign(cap, -1);
+    h->nodes.resize(max_nodes);
+    h->planes.resize(max_nodes);
+    h->chunks.resize(max_chunks);
+    h->avail.assign(max_chunks, 0);
+    h->pending.assign(max_chunks, 0);
+    std::memset(h->counters, 0, sizeof(h->counters));
+    VoxelMapDev& m = h->map;
+    m.keys = h->keys.data(); m.root_node = h->root_node.data(); m.cap_mask = (unsigned)(cap - 1);
+    m.nodes = h->nodes.data(); m.planes = h->planes.data(); m.node_count = &h->counters[0]; m.max_nodes = max_nodes;
+    m.chunks = h->chunks.data(); m.chunk_bump = &h->counters[1]; m.max_chunks = max_chunks;
+    m.avail = h->avail.data(); m.avail_top = &h->counters[2]; m.pending = h->pending.data(); m.pending_n = &h->counters[3];
+    m.err = &h->counters[4]; m.n_roots = &h->counters[5];
+    const int ms = h->max_scan;
+    h->body.resize((size_t)ms * 3); h->pw.resize((size_t)ms * 3);
+    h->body_cov.resize((size_t)ms * 6); h->p_imu.resize((size_t)ms * 3); h->var.resize((size_t)ms * 6); h->sortkey.resize(ms);
+    h->match_node.assign(ms, -1); h->match_layer.assign(ms, 0); h->slot.resize(ms); h->seg.resize(ms); h->seg2.resize(ms); h->touched.resize(ms);
+    h->slot_count.assign(cap, 0); h->slot_offset.assign(cap, 0); h->slot_cursor.assign(cap, 0);
+    ScanBuf& sb = h->sb;
+    sb.n = 0; sb.body = h->body.data(); sb.body_cov = h->body_cov.data(); sb.p_imu = h->p_imu.data();
+    sb.match_node = h->match_node.data(); sb.match_layer = h->match_layer.data(); sb.pw = h->pw.data(); sb.var = h->var.data();
+    sb.sortkey = h->sortkey.data(); sb.slot = h->slot.data(); sb.seg = h->seg.data();
+    sb.slot_count = h->slot_count.data(); sb.slot_offset = h->slot_offset.data(); sb.slot_cursor = h->slot_cursor.data();
+    sb.touched = h->touched.data(); sb.n_touched = &h->counters[6]; sb.seg_top = &h->counters[7];
+    std::memset(&h->ctrl, 0, sizeof(LioCtrl));
+    double* s = h->ctrl.state;
+    s[0] = s[4] = s[8] = 1.0;
+    for (int i = 0; i < 18; ++i) s[24 + i * 18 + i] = 0.0000001;
+    *out = h;
+    return 0;
+}
+int immesh_lio_destroy(immesh_lio_t* h) { delete h; return 0; }
+int immesh_lio_set_state(immesh_lio_t* h, const double* s) { std::memcpy(h->ctrl.state, s, 348 * 8); return 0; }
+int immesh_lio_get_state(immesh_lio_t* h, double* s) { std::memcpy(s, h->ctrl.state, 348 * 8); return 0; }
+int immesh_lio_predict(immesh_lio_t* h, double dt, double cg, double ca) {
+    std::vector<double> T(324), Fx(324);
+    predict_const_vel(h->ctrl.state, dt, cg, ca, T.data(), Fx.data(), 0, 1);
+    return 0;
+}
+static void load_scan(immesh_lio* h, const float* body, int n) {
+    std::memcpy(h->body.data(), body, (size_t)n * 12);
+    h->sb.n = n;
+}
+static void grow(immesh_lio* h, int mode) {
+    const int n = h->sb.n;
+    *h->sb.n_touched = 0;
+    *h->sb.seg_top = 0;
+    for (int i = 0; i < n; ++i) grow_point(h->map, h->P, h->sb, h->ctrl.state, i, mode);
+    const int nt = *h->sb.n_touched;
+    for (int t = 0; t < nt; ++t) grow_segment(h->sb, t);
+    for (int i = 0; i < n; ++i) grow_scatter(h->sb, i);
+    for (int t = 0; t < nt; ++t) grow_voxel(h->map, h->P, h->sb, t, mode, 0, 1, h->seg2.data());
+    recycle_chunks(h->map, 0, 1);
+}
+int immesh_voxelmap_build(immesh_lio_t* h, const float* body, int n) {
+    load_scan(h, body, n);
+    grow(h, 1);
+    return (*h->map.err) ? IMMESH_E_CAPACITY : 0;
+}
+int immesh_lio_estimate(immesh_lio_t* h, const float* body, int n, int* iters_run) {
+    load_scan(h, body, n);
+    LioCtrl& c = h->ctrl;
+    std::memcpy(c.state_prop, c.state, 348 * 8);
+    std::memset(c.acc, 0, sizeof(c.acc));
+    c.stop = 0; c.iters_run = 0; c.rematch_num = 0;
+    for (int i = 0; i < n; ++i) prepare_point(h->P, h->sb, i);
+    SolveScratch S;
+    for (int it = 0; it < h->P.max_iter && !c.stop; ++it) {
+        long long sum[IM_NTERMS];
+        for (int k = 0; k < IM_NTERMS; ++k) sum[k] = 0;
+        for (int i = 0; i < n; ++i) {
+            long long t[IM_NTERMS];
+            if (residual_point(h->map, h->P, h->sb, c.state, i, t, h->map.err))
+                for (int k = 0; k < IM_NTERMS; ++k) sum[k] += t[k];
+        }
+        for (int k = 0; k < IM_NTERMS; ++k) {
+            c.acc[it][2 * k] += (unsigned long long)(sum[k] >> 32);
+            c.acc[it][2 * k + 1] += (unsigned long long)(sum[k] & 0xffffffffLL);
+        }
+        ieskf_solve(h->P, &c, it, &S, 0, 1);
+    }
+    if (iters_run) *iters_run = c.iters_run;
+    return 0;
+}
+int immesh_voxelmap_update(immesh_lio_t* h) {
+    grow(h, 0);
+    return (*h->map.err) ? IMMESH_E_CAPACITY : 0;
+}
+int immesh_lio_iter_stats(immesh_lio_t* h, int it, double* out) {
+    const IterStats& s = h->ctrl.stats[it];
+    std::memcpy(out, s.HTH, 36 * 8);
+    std::memcpy(out + 36, s.HTz, 6 * 8);
+    out[42] = s.n_match; out[43] = s.total_residual;
+    std::memcpy(out + 44, s.solution, 18 * 8);
+    out[62] = s.converged;
+    return 0;
+}
+int immesh_lio_matches(immesh_lio_t* h, int* plane_layer, int n) {
+    for (int i = 0; i < n; ++i) plane_layer[i] = h->match_node[i] >= 0 ? h->match_layer[i] : -1;
+    return 0;
+}
+}  // extern "C"
+
+// canonical dump shared with the CUDA library's host-side dump (same traversal on host copies of the pools)
+#include "../../immesh_b200/csrc/map_dump.hpp"
+extern "C" {
+int64_t immesh_voxelmap_dump(immesh_lio_t* h, double* rows, int64_t cap_rows) {
+    return dump_voxelmap(h->keys.data(), h->root_node.data(), h->keys.size(), h->nodes.data(), h->planes.data(), rows, cap_rows);
+}
+int immesh_voxelmap_counts(immesh_lio_t* h, int64_t* out) {
+    out[0] = h->counters[5]; out[1] = h->counters[0]; out[2] = h->counters[1]; out[3] = h->counters[4];
+    return 0;
+}
+}
