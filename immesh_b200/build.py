@@ -56,7 +56,10 @@ def build_emu(force=False):
     src = _sources(emu_dir, (".cpp",))
     deps = src + _sources(CSRC, (".cuh", ".hpp"))
     if force or _newer(EMU, deps):
-        subprocess.check_call([GXX, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-x", "c++", "-shared", "-o", EMU, *src])
+        cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include", "-shared", "-o", EMU]
+        for s in src:
+            cmd += ["-x", "c++", s]
+        subprocess.check_call(cmd)
     return EMU
 
 

@@ -1,0 +1,504 @@
+// immesh_b200 -- CUDA kernels (sm_100a) and C-ABI host orchestration of the voxel-wise incremental mesher.
+// Kernel bodies live in mesh_core.cuh / mesh_voxel.cuh.  No CPU path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/immesh_b200.h"
+#include "common_host.hpp"
+#include "mesh_voxel.cuh"
+
+using namespace immesh;
+
+// ------------------------------------------------------------------ kernels
+__global__ void k_frame_begin(MeshDev M, FrameBuf F) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (unsigned int i = tid; i <= F.cmask; i += nt) { F.ckeys[i] = IM_EMPTY_KEY; F.chead[i] = -1; }
+    if (tid == 0) {
+        for (int k = 5; k <= 10; ++k) M.cnt[k] = 0;
+        M.cnt[18] = 0;
+    }
+}
+__global__ void __launch_bounds__(128) k_cand_init(MeshDev M, MeshParams P, FrameBuf F) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F.m; c += gridDim.x * blockDim.x) cand_init(M, P, F, c);
+}
+__global__ void __launch_bounds__(128) k_cand_conflicts(MeshDev M, MeshParams P, FrameBuf F) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F.m; c += gridDim.x * blockDim.x) cand_conflicts(M, P, F, c);
+}
+// Priority polling: candidate c waits only on candidates with a smaller index.  Blocks take tickets so that the
+// block holding the smallest undecided candidate is always resident; a poll cap turns a (never observed) livelock
+// into an error flag instead of a hang.
+__global__ void __launch_bounds__(128) k_cand_resolve(MeshDev M, MeshParams P, FrameBuf F) {
+    __shared__ int s_ticket;
+    const int nblocks = (F.m + blockDim.x - 1) / blockDim.x;
+    while (true) {
+        if (threadIdx.x == 0) s_ticket = atomicAdd(&M.cnt[18], 1);
+        __syncthreads();
+        const int b = s_ticket;
+        __syncthreads();
+        if (b >= nblocks) break;
+        const int c = b * blockDim.x + threadIdx.x;
+        if (c < F.m && F.cand_status[c] == CAND_UNDECIDED) {
+            int polls = 0;
+            while (!cand_poll(M, P, F, c)) {
+                if (++polls > (1 << 22)) { atomicOr(&M.cnt[3], IM_MERR_LIST_CAP); atomicAdd(&M.cnt[9], 1); break; }
+                __nanosleep(64);
+            }
+            __threadfence();
+        }
+    }
+}
+// exclusive scan of the accept flags by one block (m is ~1e4 per frame)
+__global__ void __launch_bounds__(1024) k_cand_scan(MeshDev M, FrameBuf F) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < F.m; base += 1024) {
+        const int c = base + threadIdx.x;
+        const int f = (c < F.m && F.cand_status[c] == CAND_ACCEPT) ? 1 : 0;
+        int v = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        if (lane == 31) s_warp[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int wv = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, wv, o);
+                if (lane >= o) wv += u;
+            }
+            s_warp[lane] = wv;
+        }
+        __syncthreads();
+        const int prefix = s_carry + (warp ? s_warp[warp - 1] : 0) + v - f;
+        if (c < F.m) F.cand_scan[c] = prefix;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = prefix + f;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(128) k_cand_commit(MeshDev M, MeshParams P, FrameBuf F) {
+    const int base = M.cnt[0];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F.m; c += gridDim.x * blockDim.x) cand_commit(M, P, F, c, base);
+}
+__global__ void __launch_bounds__(128) k_voxel_select(MeshDev M, FrameBuf F) {
+    const int na = min(M.cnt[5], F.max_act);
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < na; a += gridDim.x * blockDim.x) voxel_select(M, F, a);
+}
+__global__ void __launch_bounds__(128) k_voxel_dilate(MeshDev M, MeshParams P, FrameBuf F) {
+    __shared__ DilateSmem S;
+    const int nw = min(M.cnt[6], F.max_work);
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        voxel_dilate(M, P, F, w, &S, threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
+}
+template <int MAXD>
+__global__ void __launch_bounds__(128) k_voxel_mesh(MeshDev M, MeshParams P, FrameBuf F, int lo) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MeshSmem<MAXD>* S = reinterpret_cast<MeshSmem<MAXD>*>(smem_raw);
+    const int nw = min(M.cnt[6], F.max_work);
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const int n = F.work_n_ids[w];
+        if (n > lo && n <= MAXD) voxel_mesh<MAXD>(M, P, F, w, S, threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(128) k_push_remove(MeshDev M, FrameBuf F) {
+    const int n = min(M.cnt[8], F.max_list);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) tri_remove(M, F.rem_tri[e]);
+}
+__global__ void __launch_bounds__(128) k_push_add(MeshDev M, FrameBuf F) {
+    const int n = min(M.cnt[7], F.max_list);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+        tri_add(M, F.add_tri[(size_t)e * 3 + 0], F.add_tri[(size_t)e * 3 + 1], F.add_tri[(size_t)e * 3 + 2], F.add_flip[e]);
+}
+__global__ void k_frame_end(MeshDev M) {
+    M.cnt[0] += M.cnt[10];
+}
+// snapshot: compact live triangles
+__global__ void __launch_bounds__(128) k_snapshot(MeshDev M, int n_alloc, int* out_tri, int* out_flip, int* out_n) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_alloc; t += gridDim.x * blockDim.x) {
+        const int4 r = M.tri[t];
+        if (!r.w) continue;
+        const int k = atomicAdd(out_n, 1);
+        out_tri[(size_t)k * 3 + 0] = r.x; out_tri[(size_t)k * 3 + 1] = r.y; out_tri[(size_t)k * 3 + 2] = r.z;
+        out_flip[k] = (int)(M.tri_flip[t] & 1ull);
+    }
+}
+
+// exact kNN over the mesh vertices for arbitrary queries (KD_TREE::Nearest_Search): one warp per query, ring
+// expansion over the mesh-voxel hash, per-lane sorted top-k lists merged with warp shuffles.
+#define KNN_KMAX 32
+__global__ void __launch_bounds__(128) k_knn(MeshDev M, MeshParams P, const float* q, int nq, int k, double max_dist, int* out_idx, float* out_d2) {
+    const int lane = threadIdx.x & 31;
+    const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const double max_d2 = max_dist * max_dist;
+    for (int qi = wglobal; qi < nq; qi += nw) {
+        const float qx = q[qi * 3 + 0], qy = q[qi * 3 + 1], qz = q[qi * 3 + 2];
+        const int cx = round_key(qx, P.res), cy = round_key(qy, P.res), cz = round_key(qz, P.res);
+        float ld[KNN_KMAX];
+        int lid[KNN_KMAX];
+        int ln = 0;
+        int far = 0;
+        if (M.cnt[4] > 0) {
+            far = max(far, max(abs(cx - M.cnt[11]), abs(cx - M.cnt[14])));
+            far = max(far, max(abs(cy - M.cnt[12]), abs(cy - M.cnt[15])));
+            far = max(far, max(abs(cz - M.cnt[13]), abs(cz - M.cnt[16])));
+        } else {
+            far = -1;
+        }
+        float kth = INFINITY;
+        int total = 0;
+        for (int ring = 0; ring <= far; ++ring) {
+            if (ring >= 1) {
+                const double lb = (double)(ring - 1) * P.res;
+                if (lb > max_dist) break;
+                if (total >= k && (double)kth < lb * lb * 0.999999) break;
+            }
+            const int side = 2 * ring + 1;
+            for (int c = lane; c < side * side * side; c += 32) {
+                const int dx = c / (side * side) - ring, dy = (c / side) % side - ring, dz = c % side - ring;
+                if (max(abs(dx), max(abs(dy), abs(dz))) != ring) continue;
+                if (!ikey_ok(cx + dx, cy + dy, cz + dz)) continue;
+                const int s = table_find(M.vkeys, M.vmask, pack_ikey(cx + dx, cy + dy, cz + dz));
+                if (s < 0) continue;
+                for (int v = M.vox_head[s]; v >= 0; v = M.v_next[v]) {
+                    const float4 p = M.vpos[v];
+                    const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                    if (!((double)d2 <= max_d2)) continue;
+                    // insert (d2, v) into this lane's ascending list, keeping at most k
+                    if (ln == k && !(d2 < ld[ln - 1] || (d2 == ld[ln - 1] && v < lid[ln - 1]))) continue;
+                    int pos = ln < k ? ln : k - 1;
+                    while (pos > 0 && (d2 < ld[pos - 1] || (d2 == ld[pos - 1] && v < lid[pos - 1]))) {
+                        ld[pos] = ld[pos - 1]; lid[pos] = lid[pos - 1];
+                        --pos;
+                    }
+                    ld[pos] = d2; lid[pos] = v;
+                    if (ln < k) ++ln;
+                }
+            }
+            // k-th smallest over the warp: merge the lane lists (non-destructively)
+            int cur = 0;
+            total = 0;
+            kth = INFINITY;
+            for (int r = 0; r < k; ++r) {
+                float bd = cur < ln ? ld[cur] : INFINITY;
+                int bid = cur < ln ? lid[cur] : 0x7fffffff;
+                int who = lane;
+                warp_min_pair(&bd, &bid, &who);
+                if (bid == 0x7fffffff) break;
+                if (who == lane) ++cur;
+                kth = bd;
+                ++total;
+            }
+        }
+        int cur = 0;
+        for (int r = 0; r < k; ++r) {
+            float bd = cur < ln ? ld[cur] : INFINITY;
+            int bid = cur < ln ? lid[cur] : 0x7fffffff;
+            int who = lane;
+            warp_min_pair(&bd, &bid, &who);
+            if (bid != 0x7fffffff && who == lane) ++cur;
+            if (lane == 0) {
+                out_idx[(size_t)qi * k + r] = bid == 0x7fffffff ? -1 : bid;
+                out_d2[(size_t)qi * k + r] = bid == 0x7fffffff ? INFINITY : bd;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+struct immesh_mesh {
+    MeshParams P;
+    MeshDev M;
+    FrameBuf F;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* d_pts = nullptr;
+    float* h_pts = nullptr;  // pinned
+    int* h_cnt = nullptr;    // pinned
+    int* d_snap_tri = nullptr;
+    int* d_snap_flip = nullptr;
+    int* d_snap_n = nullptr;
+    int max_frame_points = 0;
+    int frame_counter = 0;
+    int n_sm = 148;
+    size_t ccap = 0;
+    double last_ms[4] = {0, 0, 0, 0};
+    int last_cnt[32];
+    std::vector<void*> allocs;
+};
+
+template <class T>
+static cudaError_t mdev_alloc(immesh_mesh* h, T** p, size_t count, int memset_byte = -1) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    if (memset_byte >= 0) e = cudaMemset(q, memset_byte, count * sizeof(T));
+    return e;
+}
+static size_t pow2_at_least(size_t v) {
+    size_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+extern "C" {
+
+int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
+    if (!cfg || !out) return im_fail(IMMESH_E_INVALID, "null argument");
+    if (!(cfg->points_minimum_scale > 0) || !(cfg->voxel_resolution > 0) || cfg->number_of_pts_append_to_map < 1) return im_fail(IMMESH_E_INVALID, "bad mesh configuration");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return im_fail(IMMESH_E_NO_DEVICE, "no CUDA device: immesh_b200 has no CPU path");
+    immesh_mesh* h = new immesh_mesh();
+    MeshParams& P = h->P;
+    P.xi = cfg->points_minimum_scale;
+    P.res = cfg->voxel_resolution;
+    P.accept = cfg->voxel_resolution * 1.25;
+    P.knn_max = P.accept * 2 * 1.000001;
+    P.inv_q = 4194304.0 / cfg->voxel_resolution;
+    P.append_target = cfg->number_of_pts_append_to_map;
+    const int max_v = cfg->max_vertices ? cfg->max_vertices : (8 << 20);
+    const int max_t = cfg->max_triangles ? cfg->max_triangles : (32 << 20);
+    const int max_vox = cfg->max_voxels ? cfg->max_voxels : (2 << 20);
+    h->max_frame_points = cfg->max_frame_points ? cfg->max_frame_points : (2 << 20);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
+    IM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) IM_CUDA(cudaEventCreate(&e));
+    MeshDev& M = h->M;
+    M.max_v = max_v;
+    M.max_t = max_t;
+    IM_CUDA(mdev_alloc(h, &M.vpos, (size_t)max_v));
+    IM_CUDA(mdev_alloc(h, &M.vsmooth, (size_t)max_v * 3));
+    IM_CUDA(mdev_alloc(h, &M.v_next, (size_t)max_v, 0xFF));
+    IM_CUDA(mdev_alloc(h, &M.v_tri_head, (size_t)max_v, 0xFF));
+    const size_t gcap = pow2_at_least((size_t)max_v * 2);
+    IM_CUDA(mdev_alloc(h, &M.gkeys, gcap, 0xFF));
+    IM_CUDA(mdev_alloc(h, &M.gval, gcap, 0xFF));
+    M.gmask = (unsigned)(gcap - 1);
+    const size_t vcap = pow2_at_least((size_t)max_vox * 2);
+    IM_CUDA(mdev_alloc(h, &M.vkeys, vcap, 0xFF));
+    M.vmask = (unsigned)(vcap - 1);
+    IM_CUDA(mdev_alloc(h, &M.vox_head, vcap, 0xFF));
+    IM_CUDA(mdev_alloc(h, &M.vox_count, vcap, 0));
+    IM_CUDA(mdev_alloc(h, &M.vox_meshing_times, vcap, 0));
+    IM_CUDA(mdev_alloc(h, &M.vox_new_added, vcap, 0));
+    IM_CUDA(mdev_alloc(h, &M.vox_frame, vcap, 0xFF));
+    M.vox_short_axis = nullptr;
+    IM_CUDA(mdev_alloc(h, &M.tri, (size_t)max_t));
+    IM_CUDA(mdev_alloc(h, &M.tri_next, (size_t)max_t * 3));
+    IM_CUDA(mdev_alloc(h, &M.tri_flip, (size_t)max_t));
+    const size_t tcap = pow2_at_least((size_t)max_t * 2);
+    IM_CUDA(mdev_alloc(h, &M.thash, tcap, 0xFF));
+    M.tmask = (unsigned)(tcap - 1);
+    IM_CUDA(mdev_alloc(h, &M.cnt, 32, 0));
+    {
+        int init[32];
+        std::memset(init, 0, sizeof(init));
+        init[11] = init[12] = init[13] = 0x7fffffff;
+        init[14] = init[15] = init[16] = -0x7fffffff;
+        IM_CUDA(cudaMemcpy(M.cnt, init, sizeof(init), cudaMemcpyHostToDevice));
+    }
+    FrameBuf& F = h->F;
+    const size_t mc = (size_t)h->max_frame_points;  // candidates <= points
+    F.max_cand = (int)mc;
+    F.max_work = max_vox < (1 << 16) ? max_vox : (1 << 16);
+    F.max_act = (int)std::min<size_t>((size_t)max_vox, mc);
+    F.max_list = 4 << 20;
+    IM_CUDA(mdev_alloc(h, &h->d_pts, mc * 3));
+    F.pts = h->d_pts;
+    IM_CUDA(mdev_alloc(h, &F.cand_gkey, mc));
+    IM_CUDA(mdev_alloc(h, &F.cand_vslot, mc));
+    IM_CUDA(mdev_alloc(h, &F.cand_status, mc));
+    IM_CUDA(mdev_alloc(h, &F.cand_scan, mc));
+    IM_CUDA(mdev_alloc(h, &F.cand_conf, mc * IM_CONF_K));
+    IM_CUDA(mdev_alloc(h, &F.cand_nconf, mc));
+    IM_CUDA(mdev_alloc(h, &F.cand_next, mc));
+    h->ccap = pow2_at_least(mc * 2);
+    IM_CUDA(mdev_alloc(h, &F.ckeys, h->ccap));
+    IM_CUDA(mdev_alloc(h, &F.chead, h->ccap));
+    F.scan_block = nullptr;
+    IM_CUDA(mdev_alloc(h, &F.act, (size_t)F.max_act));
+    IM_CUDA(mdev_alloc(h, &F.work, (size_t)F.max_work));
+    IM_CUDA(mdev_alloc(h, &F.work_n_ids, (size_t)F.max_work));
+    IM_CUDA(mdev_alloc(h, &F.work_ids, (size_t)F.max_work * IM_MAXD));
+    IM_CUDA(mdev_alloc(h, &F.add_tri, (size_t)F.max_list * 3));
+    IM_CUDA(mdev_alloc(h, &F.add_flip, (size_t)F.max_list));
+    IM_CUDA(mdev_alloc(h, &F.rem_tri, (size_t)F.max_list));
+    IM_CUDA(cudaMallocHost((void**)&h->h_pts, mc * 3 * sizeof(float)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_cnt, 32 * sizeof(int)));
+    IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<1024>)));
+    IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<256>)));
+    std::memset(h->last_cnt, 0, sizeof(h->last_cnt));
+    IM_CUDA(cudaDeviceSynchronize());
+    *out = h;
+    return IMMESH_OK;
+}
+
+int immesh_mesh_destroy(immesh_mesh_t* h) {
+    if (!h) return IMMESH_OK;
+    cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->h_pts) cudaFreeHost(h->h_pts);
+    if (h->h_cnt) cudaFreeHost(h->h_cnt);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return IMMESH_OK;
+}
+
+static int mesh_grid(const immesh_mesh* h, int n, int threads, int waves = 8) {
+    int g = (n + threads - 1) / threads;
+    if (g > h->n_sm * waves) g = h->n_sm * waves;
+    return g < 1 ? 1 : g;
+}
+
+int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, const double* pose_t, int frame_idx) {
+    (void)frame_idx;
+    if (!h || (!world_xyz && n > 0) || !pose_t || n < 0) return im_fail(IMMESH_E_INVALID, "bad argument");
+    if (n > h->max_frame_points) return im_fail(IMMESH_E_CAPACITY, "frame larger than max_frame_points");
+    FrameBuf& F = h->F;
+    const MeshParams& P = h->P;
+    // append_point_step = max(1, round(N / appending_pts_frame)), integer division first (ImMesh_mesh_reconstruction.cpp:111)
+    const int step = std::max(1, (int)std::lround((double)(n / P.append_target)));
+    F.n = n;
+    F.step = step;
+    F.m = n > 0 ? (n + step - 1) / step : 0;
+    F.frame = ++h->frame_counter;
+    for (int j = 0; j < 3; ++j) {
+        F.pose_t[j] = pose_t[j];
+        F.prio_origin[j] = (long long)std::floor(pose_t[j] / P.res) - 1024;
+    }
+    F.cmask = (unsigned)(pow2_at_least((size_t)std::max(F.m, 1) * 2) - 1);
+    cudaStream_t st = h->stream;
+    IM_CUDA(cudaEventRecord(h->ev[0], st));
+    if (n > 0) {
+        std::memcpy(h->h_pts, world_xyz, (size_t)n * 3 * sizeof(float));
+        IM_CUDA(cudaMemcpyAsync(h->d_pts, h->h_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    k_frame_begin<<<mesh_grid(h, (int)F.cmask + 1, 256), 256, 0, st>>>(h->M, F);
+    IM_CUDA(cudaEventRecord(h->ev[1], st));
+    if (F.m > 0) {
+        const int g = mesh_grid(h, F.m, 128);
+        k_cand_init<<<g, 128, 0, st>>>(h->M, P, F);
+        k_cand_conflicts<<<g, 128, 0, st>>>(h->M, P, F);
+        k_cand_resolve<<<mesh_grid(h, F.m, 128, 16), 128, 0, st>>>(h->M, P, F);
+        k_cand_scan<<<1, 1024, 0, st>>>(h->M, F);
+        k_cand_commit<<<g, 128, 0, st>>>(h->M, P, F);
+        k_voxel_select<<<mesh_grid(h, F.m, 128), 128, 0, st>>>(h->M, F);
+    }
+    IM_CUDA(cudaEventRecord(h->ev[2], st));
+    if (F.m > 0) {
+        k_voxel_dilate<<<h->n_sm * 4, 128, 0, st>>>(h->M, P, F);
+        k_voxel_mesh<256><<<h->n_sm * 6, 128, sizeof(MeshSmem<256>), st>>>(h->M, P, F, 0);
+        k_voxel_mesh<1024><<<h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st>>>(h->M, P, F, 256);
+    }
+    IM_CUDA(cudaEventRecord(h->ev[3], st));
+    if (F.m > 0) {
+        k_push_remove<<<h->n_sm * 2, 128, 0, st>>>(h->M, F);
+        k_push_add<<<h->n_sm * 2, 128, 0, st>>>(h->M, F);
+    }
+    k_frame_end<<<1, 1, 0, st>>>(h->M);
+    IM_CUDA(cudaGetLastError());
+    IM_CUDA(cudaMemcpyAsync(h->h_cnt, h->M.cnt, 32 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    IM_CUDA(cudaEventRecord(h->ev[4], st));
+    IM_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(h->last_cnt, h->h_cnt, 32 * sizeof(int));
+    float a = 0, b = 0, c = 0, d = 0;
+    cudaEventElapsedTime(&a, h->ev[0], h->ev[4]);
+    cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&c, h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&d, h->ev[3], h->ev[4]);
+    h->last_ms[0] = a; h->last_ms[1] = b; h->last_ms[2] = c; h->last_ms[3] = d;
+    const int err = h->last_cnt[3];
+    if (err & (IM_MERR_VERT_POOL | IM_MERR_TRI_POOL | IM_MERR_HASH_FULL | IM_MERR_LIST_CAP | IM_MERR_VOXEL_CAP)) return im_fail(IMMESH_E_CAPACITY, "mesh pool / per-voxel working-set overflow");
+    if (err & (IM_MERR_KEY_RANGE | IM_MERR_PRIO_RANGE)) return im_fail(IMMESH_E_RANGE, "mesh key out of range");
+    return IMMESH_OK;
+}
+
+int immesh_mesh_counts(immesh_mesh_t* h, int64_t* out) {
+    if (!h || !out) return im_fail(IMMESH_E_INVALID, "null argument");
+    const int* c = h->last_cnt;
+    out[0] = c[0]; out[1] = c[2]; out[2] = c[10]; out[3] = c[6]; out[4] = c[7]; out[5] = c[8]; out[6] = c[4]; out[7] = c[5];
+    return IMMESH_OK;
+}
+
+int immesh_mesh_snapshot(immesh_mesh_t* h, float* vertices, int32_t* triangles, int32_t* flips) {
+    if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
+    int cnt[32];
+    IM_CUDA(cudaMemcpy(cnt, h->M.cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
+    const int nv = cnt[0], nalloc = std::min(cnt[1], h->M.max_t), nlive = cnt[2];
+    if (vertices && nv > 0) {
+        std::vector<float4> v(nv);
+        IM_CUDA(cudaMemcpy(v.data(), h->M.vpos, (size_t)nv * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nv; ++i) { vertices[i * 3] = v[i].x; vertices[i * 3 + 1] = v[i].y; vertices[i * 3 + 2] = v[i].z; }
+    }
+    if ((triangles || flips) && nlive > 0) {
+        int *d_tri = nullptr, *d_flip = nullptr, *d_n = nullptr;
+        IM_CUDA(cudaMalloc(&d_tri, (size_t)nlive * 3 * sizeof(int)));
+        IM_CUDA(cudaMalloc(&d_flip, (size_t)nlive * sizeof(int)));
+        IM_CUDA(cudaMalloc(&d_n, sizeof(int)));
+        IM_CUDA(cudaMemset(d_n, 0, sizeof(int)));
+        k_snapshot<<<mesh_grid(h, nalloc, 128), 128, 0, h->stream>>>(h->M, nalloc, d_tri, d_flip, d_n);
+        std::vector<int> t((size_t)nlive * 3), f(nlive);
+        IM_CUDA(cudaMemcpyAsync(t.data(), d_tri, (size_t)nlive * 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        IM_CUDA(cudaMemcpyAsync(f.data(), d_flip, (size_t)nlive * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        IM_CUDA(cudaStreamSynchronize(h->stream));
+        cudaFree(d_tri); cudaFree(d_flip); cudaFree(d_n);
+        std::vector<int> order(nlive);
+        for (int i = 0; i < nlive; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int a, int b) {
+            for (int j = 0; j < 3; ++j)
+                if (t[(size_t)a * 3 + j] != t[(size_t)b * 3 + j]) return t[(size_t)a * 3 + j] < t[(size_t)b * 3 + j];
+            return false;
+        });
+        for (int i = 0; i < nlive; ++i) {
+            if (triangles)
+                for (int j = 0; j < 3; ++j) triangles[(size_t)i * 3 + j] = t[(size_t)order[i] * 3 + j];
+            if (flips) flips[i] = f[order[i]];
+        }
+    }
+    return IMMESH_OK;
+}
+
+int immesh_knn(immesh_mesh_t* h, const float* query_xyz, int nq, int k, double max_dist, int32_t* idx, float* d2) {
+    if (!h || !query_xyz || !idx || !d2 || nq < 0 || k < 1 || k > KNN_KMAX) return im_fail(IMMESH_E_INVALID, "bad argument (k must be in [1,32])");
+    if (nq == 0) return IMMESH_OK;
+    float* dq = nullptr;
+    int* di = nullptr;
+    float* dd = nullptr;
+    IM_CUDA(cudaMalloc(&dq, (size_t)nq * 3 * sizeof(float)));
+    IM_CUDA(cudaMalloc(&di, (size_t)nq * k * sizeof(int)));
+    IM_CUDA(cudaMalloc(&dd, (size_t)nq * k * sizeof(float)));
+    IM_CUDA(cudaMemcpyAsync(dq, query_xyz, (size_t)nq * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    k_knn<<<mesh_grid(h, nq * 32, 128), 128, 0, h->stream>>>(h->M, h->P, dq, nq, k, max_dist, di, dd);
+    IM_CUDA(cudaGetLastError());
+    IM_CUDA(cudaMemcpyAsync(idx, di, (size_t)nq * k * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaMemcpyAsync(d2, dd, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(dq); cudaFree(di); cudaFree(dd);
+    return IMMESH_OK;
+}
+
+int immesh_mesh_last_timing(immesh_mesh_t* h, double* ms) {
+    if (!h || !ms) return im_fail(IMMESH_E_INVALID, "null argument");
+    for (int i = 0; i < 4; ++i) ms[i] = h->last_ms[i];
+    return IMMESH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,351 @@
+// immesh_b200 -- the two per-voxel thread-block stages of the incremental mesher:
+//   stage A  voxel_dilate : in-voxel vertices -> exact 20-NN each (ring-expanding neighbourhood gather staged
+//                           in shared memory) -> dilated vertex set + smoothed positions
+//                           (retrieve_pts_in_voxels + retrieve_neighbor_pts_kdtree)
+//   stage B  voxel_mesh   : PCA -> 2-D projection -> exact Delaunay -> 150-degree filter -> pull / commit ->
+//                           add / remove lists + orientation flags (delaunay_triangulation, triangle_compare,
+//                           correct_triangle_index)
+// Stage A of every voxel completes before stage B of any voxel starts (kernel boundary), which is the defined
+// replacement of the reference's racy smoothing / orientation interplay.
+#pragma once
+#include "mesh_core.cuh"
+
+namespace immesh {
+
+#if defined(__CUDA_ARCH__)
+#define IM_NLANES 32
+IM_HD void warp_min_pair(float* d, int* id, int* aux) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, *d, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, *id, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, *aux, o);
+        if (od < *d || (od == *d && oi < *id)) { *d = od; *id = oi; *aux = oa; }
+    }
+}
+#else
+#define IM_NLANES 1
+IM_HD void warp_min_pair(float*, int*, int*) {}
+#endif
+
+struct DilateSmem {
+    float4 cand[IM_MAXG];      // gathered neighbourhood vertices: xyz + id (bit-cast in w)
+    int flag[IM_MAXG];         // member of the dilated set
+    int q[IM_MAXIN];           // in-voxel vertex ids (the kNN queries)
+    int ids[IM_MAXD];          // output, ascending
+    int n_cand, n_q, n_out, need_more, overflow;
+};
+
+IM_HD int f2i(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(f);
+#else
+    int i; memcpy(&i, &f, 4); return i;
+#endif
+}
+IM_HD float i2f(int i) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(i);
+#else
+    float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+
+// stage A for work item w (one thread block; warps take queries round-robin)
+IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, DilateSmem* S, int tid, int nthreads) {
+    const int vs = F.work[w];
+    int kx, ky, kz;
+    unpack_ikey(M.vkeys[vs], &kx, &ky, &kz);
+    if (tid == 0) { S->n_cand = 0; S->n_q = 0; S->n_out = 0; S->overflow = 0; }
+    IM_SYNCBLOCK_M();
+    // queries = the voxel's own vertices (retrieve_pts_in_voxels); they are also ring-0 candidates
+    if (tid == 0) {
+        int n = 0;
+        for (int v = M.vox_head[vs]; v >= 0; v = M.v_next[v]) {
+            if (n < IM_MAXIN && n < IM_MAXG) {
+                S->q[n] = v;
+                const float4 p = M.vpos[v];
+                S->cand[n] = make_float4(p.x, p.y, p.z, i2f(v));
+            } else {
+                S->overflow = 1;
+            }
+            ++n;
+        }
+        if (n > IM_MAXIN) n = IM_MAXIN;
+        S->n_q = n;
+        S->n_cand = n;
+    }
+    IM_SYNCBLOCK_M();
+    const int nq = S->n_q;
+    const double max_d2 = P.knn_max * P.knn_max;
+    const int lane = tid % IM_NLANES, warp = tid / IM_NLANES, nwarps = (nthreads + IM_NLANES - 1) / IM_NLANES;
+    for (int ring = 1; ring <= 3; ++ring) {
+        // gather the shell of Chebyshev radius `ring`
+        const int side = 2 * ring + 1;
+        for (int c = tid; c < side * side * side; c += nthreads) {
+            const int dx = c / (side * side) - ring, dy = (c / side) % side - ring, dz = c % side - ring;
+            const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, az = dz < 0 ? -dz : dz;
+            if ((ax > ay ? (ax > az ? ax : az) : (ay > az ? ay : az)) != ring) continue;
+            if (!ikey_ok(kx + dx, ky + dy, kz + dz)) continue;
+            const int s = table_find(M.vkeys, M.vmask, pack_ikey(kx + dx, ky + dy, kz + dz));
+            if (s < 0) continue;
+            for (int v = M.vox_head[s]; v >= 0; v = M.v_next[v]) {
+                const int k = im_atomic_add(&S->n_cand, 1);
+                if (k < IM_MAXG) {
+                    const float4 p = M.vpos[v];
+                    S->cand[k] = make_float4(p.x, p.y, p.z, i2f(v));
+                } else {
+                    S->overflow = 1;
+                }
+            }
+        }
+        IM_SYNCBLOCK_M();
+        const int nc = S->n_cand < IM_MAXG ? S->n_cand : IM_MAXG;
+        for (int i = tid; i < nc; i += nthreads) S->flag[i] = 0;
+        if (tid == 0) S->need_more = 0;
+        IM_SYNCBLOCK_M();
+        // after gathering rings 0..ring, every unseen vertex is at least ring*res away from any query of this voxel
+        const double lb = (double)ring * P.res;
+        for (int qi = warp; qi < nq; qi += nwarps) {
+            const int qv = S->q[qi];
+            const float4 qp = M.vpos[qv];
+            float prev_d = -1.0f;
+            int prev_id = -1;
+            double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
+            int cnt = 0, found = 0;
+            float last_d = 0.f;
+            for (int r = 0; r < 20; ++r) {
+                float bd = INFINITY;
+                int bid = 0x7fffffff, bidx = -1;
+                for (int i = lane; i < nc; i += IM_NLANES) {
+                    const float4 cp = S->cand[i];
+                    const float d2 = dist2f(qp.x, qp.y, qp.z, cp.x, cp.y, cp.z);
+                    const int id = f2i(cp.w);
+                    if (!((double)d2 <= max_d2)) continue;
+                    if (d2 < prev_d || (d2 == prev_d && id <= prev_id)) continue;  // already reported
+                    if (d2 < bd || (d2 == bd && id < bid)) { bd = d2; bid = id; bidx = i; }
+                }
+                warp_min_pair(&bd, &bid, &bidx);
+                if (bidx < 0) break;
+                prev_d = bd; prev_id = bid;
+                last_d = bd;
+                ++found;
+                const float sd = sqrtf(bd);
+                if ((double)sd < P.accept && lane == 0) S->flag[bidx] = 1;
+                if ((double)sd < P.accept * 2) {
+                    ++cnt;
+                    const float4 cp = S->cand[bidx];
+                    sv0 = sv0 + (double)cp.x; sv1 = sv1 + (double)cp.y; sv2 = sv2 + (double)cp.z;
+                }
+            }
+            const bool complete = (lb > P.knn_max) || (found >= 20 && (double)last_d < lb * lb * 0.999999);
+            if (!complete) {
+                if (lane == 0) S->need_more = 1;
+            }
+            if (lane == 0) {
+                // smooth_factor = 1.0f (mesh_rec_geometry.cpp:334,367-369)
+                M.vsmooth[(size_t)qv * 3 + 0] = (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f);
+                M.vsmooth[(size_t)qv * 3 + 1] = (sv1 / (double)cnt) * (double)1.0f + (double)qp.y * (double)(1 - 1.0f);
+                M.vsmooth[(size_t)qv * 3 + 2] = (sv2 / (double)cnt) * (double)1.0f + (double)qp.z * (double)(1 - 1.0f);
+            }
+        }
+        IM_SYNCBLOCK_M();
+        if (!S->need_more) break;
+    }
+    // dilated set = flagged candidates, ascending by id (std::set<long>, ImMesh_mesh_reconstruction.cpp:157-170)
+    const int nc = S->n_cand < IM_MAXG ? S->n_cand : IM_MAXG;
+    for (int i = tid; i < nc; i += nthreads)
+        if (S->flag[i]) {
+            const int k = im_atomic_add(&S->n_out, 1);
+            if (k < IM_MAXD) S->ids[k] = f2i(S->cand[i].w); else S->overflow = 1;
+        }
+    IM_SYNCBLOCK_M();
+    int n = S->n_out < IM_MAXD ? S->n_out : IM_MAXD;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = n + tid; i < np2; i += nthreads) S->ids[i] = 0x7fffffff;
+    IM_SYNCBLOCK_M();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += nthreads) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const int a = S->ids[i], b = S->ids[l];
+                    const bool up = ((i & k) == 0);
+                    if ((a > b) == up) { S->ids[i] = b; S->ids[l] = a; }
+                }
+            }
+            IM_SYNCBLOCK_M();
+        }
+    for (int i = tid; i < n; i += nthreads) F.work_ids[(size_t)w * IM_MAXD + i] = S->ids[i];
+    if (tid == 0) {
+        F.work_n_ids[w] = n;
+        if (S->overflow) im_atomic_or(&M.cnt[3], IM_MERR_VOXEL_CAP);
+    }
+}
+
+// ------------------------------------------------------------------ stage B
+template <int MAXD>
+struct MeshSmem {
+    int ids[MAXD];
+    float pos[MAXD][3];
+    double uv[MAXD][2];
+    int2 snap[MAXD];
+    DTri tris[3 * MAXD + 8];
+    int faces[2 * MAXD][3];       // global ids, a<b<c
+    int fhash[4 * MAXD];          // open-addressed set of face indices
+    int scratch[8 + 256 + 520];
+    double axes[9];               // short, mid, long
+    double centre[3];
+    int ntri, nface;
+};
+
+template <int MAXD>
+IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, MeshSmem<MAXD>* S, int tid, int nthreads) {
+    const int n = F.work_n_ids[w];
+    if (n < 3 || n > MAXD) return;
+    const int vs = F.work[w];
+    for (int i = tid; i < n; i += nthreads) {
+        const int id = F.work_ids[(size_t)w * IM_MAXD + i];
+        S->ids[i] = id;
+        const float4 p = M.vpos[id];
+        S->pos[i][0] = p.x; S->pos[i][1] = p.y; S->pos[i][2] = p.z;
+    }
+    for (int i = tid; i < 4 * MAXD; i += nthreads) S->fhash[i] = -1;
+    if (tid == 0) S->nface = 0;
+    IM_SYNCBLOCK_M();
+    if (tid == 0) {
+        // centroid, covariance, principal axes (mesh_rec_geometry.cpp:193-213); sequential sums: bit-reproducible
+        double c[3] = {0, 0, 0};
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < 3; ++j) c[j] = c[j] + (double)S->pos[i][j];
+        for (int j = 0; j < 3; ++j) c[j] = c[j] / (double)n;
+        double cov[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < n; ++i) {
+            const double d[3] = {(double)S->pos[i][0] - c[0], (double)S->pos[i][1] - c[1], (double)S->pos[i][2] - c[2]};
+            cov[0] += d[0] * d[0]; cov[1] += d[0] * d[1]; cov[2] += d[0] * d[2];
+            cov[3] += d[1] * d[1]; cov[4] += d[1] * d[2]; cov[5] += d[2] * d[2];
+        }
+        for (int k = 0; k < 6; ++k) cov[k] = cov[k] / (double)n;
+        double ev[3], U[9];
+        jacobi3(cov, ev, U);
+        int order[3] = {0, 1, 2};  // ascending eigenvalues (SelfAdjointEigenSolver order)
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2 - a; ++b)
+                if (ev[order[b + 1]] < ev[order[b]]) { const int t = order[b]; order[b] = order[b + 1]; order[b + 1] = t; }
+        double s[3], m[3];
+        for (int j = 0; j < 3; ++j) { s[j] = U[j * 3 + order[0]]; m[j] = U[j * 3 + order[1]]; }
+        const double d0[3] = {(double)S->pos[0][0] - c[0], (double)S->pos[0][1] - c[1], (double)S->pos[0][2] - c[2]};
+        const double d1[3] = {(double)S->pos[1][0] - c[0], (double)S->pos[1][1] - c[1], (double)S->pos[1][2] - c[2]};
+        if (dot3(d0, s) < 0) { s[0] = -s[0]; s[1] = -s[1]; s[2] = -s[2]; }
+        if (dot3(d1, m) < 0) { m[0] = -m[0]; m[1] = -m[1]; m[2] = -m[2]; }
+        S->axes[0] = s[0]; S->axes[1] = s[1]; S->axes[2] = s[2];
+        S->axes[3] = m[0]; S->axes[4] = m[1]; S->axes[5] = m[2];
+        S->axes[6] = s[1] * m[2] - s[2] * m[1];
+        S->axes[7] = s[2] * m[0] - s[0] * m[2];
+        S->axes[8] = s[0] * m[1] - s[1] * m[0];
+        S->centre[0] = c[0]; S->centre[1] = c[1]; S->centre[2] = c[2];
+    }
+    IM_SYNCBLOCK_M();
+    for (int i = tid; i < n; i += nthreads) {
+        const double d[3] = {(double)S->pos[i][0] - S->centre[0], (double)S->pos[i][1] - S->centre[1], (double)S->pos[i][2] - S->centre[2]};
+        const double u = dot3(d, S->axes + 6), v = dot3(d, S->axes + 3);
+        S->uv[i][0] = u; S->uv[i][1] = v;
+        S->snap[i] = make_int2((int)im_llrint(u * P.inv_q), (int)im_llrint(v * P.inv_q));
+    }
+    IM_SYNCBLOCK_M();
+    delaunay_block(S->snap, n, S->tris, 3 * MAXD + 8, &S->ntri, S->scratch, tid, nthreads);
+    IM_SYNCBLOCK_M();
+    if (S->scratch[4] == 0) return;  // all points collinear: T.number_of_faces() == 0 (mesh_rec_geometry.cpp:257-260)
+    if (S->scratch[6]) { if (tid == 0) im_atomic_or(&M.cnt[3], IM_MERR_VOXEL_CAP); return; }
+    // finite faces passing the 150-degree filter (is_face_is_ok), as sorted global id triples
+    const int nt = S->ntri;
+    for (int t = tid; t < nt; t += nthreads) {
+        const DTri& tr = S->tris[t];
+        if (!tr.alive || tr.v[0] < 0 || tr.v[1] < 0 || tr.v[2] < 0) continue;
+        const int i0 = tr.v[0], i1 = tr.v[1], i2 = tr.v[2];
+        if (angle_bad(S->uv[i0][0], S->uv[i0][1], S->uv[i1][0], S->uv[i1][1], S->uv[i2][0], S->uv[i2][1])) continue;
+        if (angle_bad(S->uv[i1][0], S->uv[i1][1], S->uv[i2][0], S->uv[i2][1], S->uv[i0][0], S->uv[i0][1])) continue;
+        if (angle_bad(S->uv[i2][0], S->uv[i2][1], S->uv[i0][0], S->uv[i0][1], S->uv[i1][0], S->uv[i1][1])) continue;
+        int a = S->ids[i0], b = S->ids[i1], c = S->ids[i2];
+        if (a > b) { const int x = a; a = b; b = x; }
+        if (b > c) { const int x = b; b = c; c = x; }
+        if (a > b) { const int x = a; a = b; b = x; }
+        const int k = im_atomic_add(&S->nface, 1);
+        S->faces[k][0] = a; S->faces[k][1] = b; S->faces[k][2] = c;
+        unsigned int hs = tri_hash(a, b, c) & (4 * MAXD - 1);
+        while (im_atomic_cas32(&S->fhash[hs], -1, k) != -1) hs = (hs + 1) & (4 * MAXD - 1);
+    }
+    IM_SYNCBLOCK_M();
+    const int nf = S->nface;
+    // flip priority of this voxel: its key relative to the frame origin (ascending (x,y,z) order, last one wins)
+    int kx, ky, kz;
+    unpack_ikey(M.vkeys[vs], &kx, &ky, &kz);
+    const long long lx = kx - F.prio_origin[0], ly = ky - F.prio_origin[1], lz = kz - F.prio_origin[2];
+    if (lx < 0 || lx >= 2048 || ly < 0 || ly >= 2048 || lz < 0 || lz >= 2048) {
+        if (tid == 0) im_atomic_or(&M.cnt[3], IM_MERR_PRIO_RANGE);
+    }
+    const unsigned long long prio = ((unsigned long long)(lx & 2047) << 22) | ((unsigned long long)(ly & 2047) << 11) | (unsigned long long)(lz & 2047);
+    const unsigned long long word_base = ((unsigned long long)F.frame << 34) | (prio << 1);
+    // commit, faces side (triangle_compare): a face already live in the store is "existing", otherwise "to add"
+    for (int k = tid; k < nf; k += nthreads) {
+        const int a = S->faces[k][0], b = S->faces[k][1], c = S->faces[k][2];
+        const unsigned long long word = word_base | (unsigned long long)compute_flip(M, a, b, c, F.pose_t, S->axes);
+        const int t = tri_find(M, a, b, c);
+        if (t >= 0 && M.tri[t].w) {
+            im_atomic_max64(&M.tri_flip[t], word);
+        } else {
+            const int e = im_atomic_add(&M.cnt[7], 1);
+            if (e < F.max_list) {
+                F.add_tri[(size_t)e * 3 + 0] = a; F.add_tri[(size_t)e * 3 + 1] = b; F.add_tri[(size_t)e * 3 + 2] = c;
+                F.add_flip[e] = word;
+            } else {
+                im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+            }
+        }
+    }
+    // pull (find_relative_triangulation_combination) + commit, store side: live triangles with all three vertices in
+    // the dilated set that the new triangulation does not contain are removed.  Each triangle is visited from its
+    // smallest vertex only.
+    for (int i = tid; i < n; i += nthreads) {
+        const int v = S->ids[i];
+        for (int t = M.v_tri_head[v]; t >= 0;) {
+            const int4 r = M.tri[t];
+            const int slot = (r.x == v) ? 0 : ((r.y == v) ? 1 : 2);
+            const int nx = M.tri_next[(size_t)t * 3 + slot];
+            if (r.w && r.x == v) {
+                // binary search y and z in the ascending id list
+                bool in_set = true;
+                for (int pass = 0; pass < 2 && in_set; ++pass) {
+                    const int key = pass == 0 ? r.y : r.z;
+                    int lo = 0, hi = n - 1;
+                    bool hit = false;
+                    while (lo <= hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const int val = S->ids[mid];
+                        if (val == key) { hit = true; break; }
+                        if (val < key) lo = mid + 1; else hi = mid - 1;
+                    }
+                    in_set = hit;
+                }
+                if (in_set) {
+                    bool in_new = false;
+                    unsigned int hs = tri_hash(r.x, r.y, r.z) & (4 * MAXD - 1);
+                    for (int probe = 0; probe < 4 * MAXD; ++probe) {
+                        const int k = S->fhash[hs];
+                        if (k < 0) break;
+                        if (S->faces[k][0] == r.x && S->faces[k][1] == r.y && S->faces[k][2] == r.z) { in_new = true; break; }
+                        hs = (hs + 1) & (4 * MAXD - 1);
+                    }
+                    if (!in_new) {
+                        const int e = im_atomic_add(&M.cnt[8], 1);
+                        if (e < F.max_list) F.rem_tri[e] = t; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+                    }
+                }
+            }
+            t = nx;
+        }
+    }
+}
+
+}  // namespace immesh

@@ -124,15 +124,15 @@ void* orc_mesh_create(double minimum_pts, double voxel_res, int append_target, i
 }
 void orc_mesh_destroy(void* h) { delete (MeshOracle*)h; }
 void orc_mesh_push_frame(void* h, const float* pts, int n, const double* pose_t) { ((MeshOracle*)h)->push_frame(pts, n, pose_t); }
-// counts: [n_vertices, n_live_tris, frame_new_vertices, frame_voxels_meshed, frame_added, frame_removed, n_voxels, n_activated]
+// counts: [n_vertices, n_live_tris, frame_new_vertices, frame_voxels_meshed, frame_added, frame_removed (summed over voxels), n_voxels, n_activated]
 void orc_mesh_counts(void* h, long* c) {
     MeshOracle* m = (MeshOracle*)h;
     c[0] = (long)m->vpos.size();
     c[1] = (long)m->live.size();
     c[2] = m->frame_new_vertices;
     c[3] = m->frame_voxels_meshed;
-    c[4] = (long)m->frame_added.size();
-    c[5] = (long)m->frame_removed.size();
+    c[4] = m->frame_added_mult;
+    c[5] = m->frame_removed_mult;
     c[6] = (long)m->voxels.size();
     c[7] = (long)m->activated.size();
 }

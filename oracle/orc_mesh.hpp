@@ -245,6 +245,7 @@ class MeshOracle {
     // per-frame outputs
     std::vector<Tri> frame_added, frame_removed;
     int frame_new_vertices = 0, frame_voxels_meshed = 0;
+    long frame_added_mult = 0, frame_removed_mult = 0;  // summed over voxels (total_add_triangle / total_delete_triangle, :226-237)
 
     explicit MeshOracle(const MeshCfg& c) : cfg(c) {}
 
@@ -521,6 +522,9 @@ class MeshOracle {
             for (const Tri& t : r.existing) r.flip_exist.push_back(compute_flip(t, pose_t, vx.short_axis));
         }
         frame_voxels_meshed = (int)work.size();
+        frame_added_mult = 0;
+        frame_removed_mult = 0;
+        for (auto& r : res) { frame_added_mult += (long)r.to_add.size(); frame_removed_mult += (long)r.to_remove.size(); }
         for (auto& r : res)
             for (size_t i = 0; i < r.existing.size(); ++i) flip[r.existing[i]] = r.flip_exist[i];
         // ---- push: all removals, then all insertions (:228-244)

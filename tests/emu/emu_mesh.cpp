@@ -1,0 +1,132 @@
+// TEST INFRASTRUCTURE (not product code): executes the __host__ __device__ bodies of the CUDA mesher
+// (immesh_b200/csrc/mesh_core.cuh, mesh_voxel.cuh) on the CPU, one thread at a time, for the CPU-only logic
+// tests.  The shipped library never links or calls this.
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/immesh_b200.h"
+#include "../../immesh_b200/csrc/mesh_voxel.cuh"
+
+using namespace immesh;
+
+struct immesh_mesh {
+    MeshParams P;
+    MeshDev M;
+    FrameBuf F;
+    std::vector<float4> vpos;
+    std::vector<double> vsmooth;
+    std::vector<int> v_next, v_tri_head, gval, vox_head, vox_count, vox_mt, vox_na, vox_frame, tri_next, thash, cnt;
+    std::vector<unsigned long long> gkeys, vkeys, tri_flip, ckeys, cand_gkey, add_flip;
+    std::vector<int4> tri;
+    std::vector<float> pts;
+    std::vector<int> cand_vslot, cand_status, cand_scan, cand_conf, cand_nconf, cand_next, chead, act, work, work_n, work_ids, add_tri, rem_tri;
+    int frame_counter = 0;
+    int last_cnt[32];
+};
+static size_t p2(size_t v) { size_t p = 1; while (p < v) p <<= 1; return p; }
+
+extern "C" {
+int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
+    immesh_mesh* h = new immesh_mesh();
+    MeshParams& P = h->P;
+    P.xi = cfg->points_minimum_scale; P.res = cfg->voxel_resolution; P.accept = cfg->voxel_resolution * 1.25;
+    P.knn_max = P.accept * 2 * 1.000001; P.inv_q = 4194304.0 / cfg->voxel_resolution; P.append_target = cfg->number_of_pts_append_to_map;
+    const int max_v = cfg->max_vertices ? cfg->max_vertices : (1 << 20), max_t = cfg->max_triangles ? cfg->max_triangles : (1 << 22);
+    const int max_vox = cfg->max_voxels ? cfg->max_voxels : (1 << 18), mfp = cfg->max_frame_points ? cfg->max_frame_points : (1 << 20);
+    MeshDev& M = h->M;
+    M.max_v = max_v; M.max_t = max_t;
+    h->vpos.resize(max_v); h->vsmooth.resize((size_t)max_v * 3); h->v_next.assign(max_v, -1); h->v_tri_head.assign(max_v, -1);
+    const size_t gcap = p2((size_t)max_v * 2), vcap = p2((size_t)max_vox * 2), tcap = p2((size_t)max_t * 2);
+    h->gkeys.assign(gcap, IM_EMPTY_KEY); h->gval.assign(gcap, -1);
+    h->vkeys.assign(vcap, IM_EMPTY_KEY); h->vox_head.assign(vcap, -1); h->vox_count.assign(vcap, 0); h->vox_mt.assign(vcap, 0); h->vox_na.assign(vcap, 0); h->vox_frame.assign(vcap, -1);
+    h->tri.resize(max_t); h->tri_next.resize((size_t)max_t * 3); h->tri_flip.resize(max_t); h->thash.assign(tcap, -1);
+    h->cnt.assign(32, 0);
+    h->cnt[11] = h->cnt[12] = h->cnt[13] = 0x7fffffff; h->cnt[14] = h->cnt[15] = h->cnt[16] = -0x7fffffff;
+    M.vpos = h->vpos.data(); M.vsmooth = h->vsmooth.data(); M.v_next = h->v_next.data(); M.v_tri_head = h->v_tri_head.data();
+    M.gkeys = h->gkeys.data(); M.gval = h->gval.data(); M.gmask = (unsigned)(gcap - 1);
+    M.vkeys = h->vkeys.data(); M.vmask = (unsigned)(vcap - 1); M.vox_head = h->vox_head.data(); M.vox_count = h->vox_count.data();
+    M.vox_meshing_times = h->vox_mt.data(); M.vox_new_added = h->vox_na.data(); M.vox_frame = h->vox_frame.data(); M.vox_short_axis = nullptr;
+    M.tri = h->tri.data(); M.tri_next = h->tri_next.data(); M.tri_flip = h->tri_flip.data(); M.thash = h->thash.data(); M.tmask = (unsigned)(tcap - 1);
+    M.cnt = h->cnt.data();
+    FrameBuf& F = h->F;
+    const size_t mc = mfp;
+    F.max_cand = mfp; F.max_work = std::min(max_vox, 1 << 14); F.max_act = std::min<size_t>(max_vox, mc); F.max_list = 1 << 20;
+    h->pts.resize(mc * 3); h->cand_gkey.resize(mc); h->cand_vslot.resize(mc); h->cand_status.resize(mc); h->cand_scan.resize(mc);
+    h->cand_conf.resize(mc * IM_CONF_K); h->cand_nconf.resize(mc); h->cand_next.resize(mc);
+    const size_t ccap = p2(mc * 2);
+    h->ckeys.resize(ccap); h->chead.resize(ccap);
+    h->act.resize(F.max_act); h->work.resize(F.max_work); h->work_n.resize(F.max_work); h->work_ids.resize((size_t)F.max_work * IM_MAXD);
+    h->add_tri.resize((size_t)F.max_list * 3); h->add_flip.resize(F.max_list); h->rem_tri.resize(F.max_list);
+    F.pts = h->pts.data(); F.cand_gkey = h->cand_gkey.data(); F.cand_vslot = h->cand_vslot.data(); F.cand_status = h->cand_status.data();
+    F.cand_scan = h->cand_scan.data(); F.cand_conf = h->cand_conf.data(); F.cand_nconf = h->cand_nconf.data(); F.cand_next = h->cand_next.data();
+    F.ckeys = h->ckeys.data(); F.chead = h->chead.data(); F.scan_block = nullptr;
+    F.act = h->act.data(); F.work = h->work.data(); F.work_n_ids = h->work_n.data(); F.work_ids = h->work_ids.data();
+    F.add_tri = h->add_tri.data(); F.add_flip = h->add_flip.data(); F.rem_tri = h->rem_tri.data();
+    std::memset(h->last_cnt, 0, sizeof(h->last_cnt));
+    *out = h;
+    return 0;
+}
+int immesh_mesh_destroy(immesh_mesh_t* h) { delete h; return 0; }
+int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, const double* pose_t, int) {
+    FrameBuf& F = h->F;
+    MeshDev& M = h->M;
+    const MeshParams& P = h->P;
+    const int step = std::max(1, (int)std::lround((double)(n / P.append_target)));
+    F.n = n; F.step = step; F.m = n > 0 ? (n + step - 1) / step : 0; F.frame = ++h->frame_counter;
+    for (int j = 0; j < 3; ++j) { F.pose_t[j] = pose_t[j]; F.prio_origin[j] = (long long)std::floor(pose_t[j] / P.res) - 1024; }
+    F.cmask = (unsigned)(p2((size_t)std::max(F.m, 1) * 2) - 1);
+    if (n > 0) std::memcpy(h->pts.data(), world_xyz, (size_t)n * 12);
+    for (unsigned i = 0; i <= F.cmask; ++i) { F.ckeys[i] = IM_EMPTY_KEY; F.chead[i] = -1; }
+    for (int k = 5; k <= 10; ++k) M.cnt[k] = 0;
+    for (int c = 0; c < F.m; ++c) cand_init(M, P, F, c);
+    for (int c = 0; c < F.m; ++c) cand_conflicts(M, P, F, c);
+    for (int c = 0; c < F.m; ++c)
+        if (F.cand_status[c] == CAND_UNDECIDED && !cand_poll(M, P, F, c)) return -100;
+    int run = 0;
+    for (int c = 0; c < F.m; ++c) { F.cand_scan[c] = run; run += F.cand_status[c] == CAND_ACCEPT; }
+    const int base = M.cnt[0];
+    for (int c = 0; c < F.m; ++c) cand_commit(M, P, F, c, base);
+    const int na = std::min(M.cnt[5], F.max_act);
+    for (int a = 0; a < na; ++a) voxel_select(M, F, a);
+    const int nw = std::min(M.cnt[6], F.max_work);
+    DilateSmem* DS = new DilateSmem();
+    for (int w = 0; w < nw; ++w) voxel_dilate(M, P, F, w, DS, 0, 1);
+    delete DS;
+    MeshSmem<256>* S1 = new MeshSmem<256>();
+    MeshSmem<1024>* S2 = new MeshSmem<1024>();
+    for (int w = 0; w < nw; ++w) {
+        const int nd = F.work_n_ids[w];
+        if (nd <= 256) voxel_mesh<256>(M, P, F, w, S1, 0, 1); else voxel_mesh<1024>(M, P, F, w, S2, 0, 1);
+    }
+    delete S1; delete S2;
+    const int nr = std::min(M.cnt[8], F.max_list), nadd = std::min(M.cnt[7], F.max_list);
+    for (int e = 0; e < nr; ++e) tri_remove(M, F.rem_tri[e]);
+    for (int e = 0; e < nadd; ++e) tri_add(M, F.add_tri[(size_t)e * 3], F.add_tri[(size_t)e * 3 + 1], F.add_tri[(size_t)e * 3 + 2], F.add_flip[e]);
+    M.cnt[0] += M.cnt[10];
+    std::memcpy(h->last_cnt, M.cnt, 32 * sizeof(int));
+    return M.cnt[3] ? IMMESH_E_CAPACITY : 0;
+}
+int immesh_mesh_counts(immesh_mesh_t* h, int64_t* out) {
+    const int* c = h->last_cnt;
+    out[0] = c[0]; out[1] = c[2]; out[2] = c[10]; out[3] = c[6]; out[4] = c[7]; out[5] = c[8]; out[6] = c[4]; out[7] = c[5];
+    return 0;
+}
+int immesh_mesh_snapshot(immesh_mesh_t* h, float* vertices, int32_t* triangles, int32_t* flips) {
+    const MeshDev& M = h->M;
+    const int nv = M.cnt[0], nalloc = M.cnt[1];
+    if (vertices)
+        for (int i = 0; i < nv; ++i) { vertices[i * 3] = M.vpos[i].x; vertices[i * 3 + 1] = M.vpos[i].y; vertices[i * 3 + 2] = M.vpos[i].z; }
+    std::vector<std::array<int, 4>> rows;
+    for (int t = 0; t < nalloc; ++t)
+        if (M.tri[t].w) rows.push_back({M.tri[t].x, M.tri[t].y, M.tri[t].z, (int)(M.tri_flip[t] & 1ull)});
+    std::sort(rows.begin(), rows.end());
+    for (size_t i = 0; i < rows.size(); ++i) {
+        if (triangles) for (int j = 0; j < 3; ++j) triangles[i * 3 + j] = rows[i][j];
+        if (flips) flips[i] = rows[i][3];
+    }
+    return 0;
+}
+}

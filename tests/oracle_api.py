@@ -143,7 +143,7 @@ class OracleMesh:
 
     def frame_delta(self):
         c = self.counts()
-        a = np.zeros((c["frame_added"], 3), dtype=np.int32)
+        a = np.zeros((c["frame_added"], 3), dtype=np.int32)      # upper bounds (unique sets are smaller)
         r = np.zeros((c["frame_removed"], 3), dtype=np.int32)
         self.L.orc_mesh_get_frame_delta(self.h, _p(a), _p(r))
         return a, r
