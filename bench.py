@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- scans/sec of the ImMesh localization + meshing hot path on synthetic 100k-point scans.
+
+One "step" = one LiDAR scan through the whole path: constant-velocity prediction, all IESKF iterations (voxel-hash
+lookup, point-to-plane residual selection, Jacobian, H^T R^-1 H reduction, 18x18 solve), VoxelMap update, transform
+of the full-resolution scan, vertex append, per-voxel dilation / Delaunay / pull-commit, push.
+
+  python bench.py --gpus 1 --steps K --warmup W               our CUDA path (N>1: launched under torchrun)
+  python bench.py --impl reference --gpus 1 --steps K ...     the reference algorithm on the host cores (oracle port)
+
+Prints ONE JSON line (rank 0).  `value` = scans/s with the scans already resident in HBM (device-event time, L2
+flushed between scans); `e2e` = scans/s through the C ABI with host buffers (H2D of both clouds and D2H of the
+state + frame counters inside the timed region); `roofline` = the dominant kernel's algorithmic bytes / CUDA-event
+time against the measured HBM peak; `cpu_baseline` = the CPU oracle on a bounded sample of the same stream.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOAD = "synthetic 100k-pt scan stream (Livox-Avia-shape FoV, 10 Hz, 1 m/s), avia.yaml parameters: leaf 0.4 m, root voxel 0.5 m, max_layer 2, 4 IESKF iterations, mesh voxel 0.4 m, xi 0.1 m, 10000 pts appended/frame"
+METRIC = "scans/sec (synthetic 100k-pt scans) loc+mesh"
+MAP_WARM = 8          # untimed scans that densify the map before the warm-up steps (both arms)
+
+
+def get_stream(n_scans, seed=0, kind="avia100k"):
+    from immesh_b200 import api, synth
+    cfg = api.AVIA
+    sensor, scans = synth.make_stream(kind, n_scans, seed=seed, leaf=cfg.filter_size_surf, ext_T=cfg.ext_T)
+    return cfg, sensor, scans
+
+
+def init_state_vec(scans):
+    s = np.zeros(348)
+    s[0:9] = scans[0]["R_true"].reshape(9)
+    s[9:12] = scans[0]["t_true"]
+    s[12:15] = (scans[1]["t_true"] - scans[0]["t_true"]) / scans[0]["dt"]
+    for i in range(18):
+        s[24 + i * 18 + i] = 1e-7
+    return s
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def run_cpu(cfg, scans, n_warm, n_timed, threads):
+    """The reference algorithm on the host cores (oracle port): returns per-scan (t_loc, t_mesh) seconds."""
+    from immesh_b200 import api
+    from oracle_api import OracleLio, OracleMesh
+    lio = OracleLio(cfg, sum_mode=1, omp_threads=threads)
+    mesh = OracleMesh(api.MeshConfig(), threads=threads)
+    lio.set_state(init_state_vec(scans))
+    lio.voxel_map_init(scans[0]["body_full"])
+    times = []
+    for k in range(1, 1 + n_warm + n_timed):
+        sc = scans[k]
+        t0 = time.perf_counter()
+        lio.predict(sc["dt"])
+        lio.lio_state_estimation(sc["body_ds"])
+        lio.map_incremental_grow(sc["body_ds"])
+        t1 = time.perf_counter()
+        s = lio.get_state()
+        R, t = s[0:9].reshape(3, 3), s[9:12]
+        eT = np.asarray(cfg.ext_T)
+        world = ((sc["body_full"].astype(np.float64) + eT) @ R.T + t).astype(np.float32)   # transformLidar of the full scan
+        mesh.push_frame(world, t, k)
+        t2 = time.perf_counter()
+        if k > n_warm:
+            times.append((t1 - t0, t2 - t1))
+    return np.array(times)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def algorithmic_bytes(kernel, info):
+    """Compulsory bytes per launch of `kernel` from the work counters of the profiled scans."""
+    n = info["n_ds"]
+    if kernel == "k_residual":
+        # 12 B body xyz + 16 B hash slot (key + root index) per point, 240 B per distinct matched plane record, 232 B out
+        return 28.0 * n + 240.0 * info["planes_unique"] + 232.0
+    if kernel == "k_grow_voxel":
+        return 28.0 * n + info["touched"] * (96.0 * 8 + 456.0)
+    if kernel == "k_voxel_dilate":
+        # float4 per gathered kNN candidate, 27 voxel-hash probes (16 B) per voxel, smoothed position write per query, ids out
+        return 16.0 * info["gathered"] + 27 * 16.0 * info["voxels_meshed"] + 24.0 * info["queries"] + 4.0 * info["dilated"]
+    if kernel.startswith("k_voxel_mesh"):
+        # ids + float4 position per dilated vertex, 16 B triple-hash probe + 12 B emit per facet, incidence walk 16 B per facet pulled
+        return 20.0 * info["dilated"] + 44.0 * info["faces"]
+    if kernel == "k_cand_init":
+        return info["candidates"] * (12.0 + 16.0 + 27 * 16.0)
+    return None
+
+
+def run_gpu(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from immesh_b200 import api
+
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K, W = args.steps, max(args.warmup, 3)
+    n_prof = min(K, 10)
+    n_scans = 1 + MAP_WARM + W + 2 * K + n_prof + 1
+    cfg, sensor, scans = get_stream(n_scans, seed=rank if args.independent_streams else 0)
+    lib = api.load_library()
+    lio = api.Lio(cfg, lib=lib)
+    mesh = api.Mesh(api.MeshConfig(), lib=lib)
+    lio.set_state(init_state_vec(scans))
+    lio.voxel_map_init(scans[0]["body_full"])
+    dev = torch.device("cuda", local_rank)
+    d_ds = [torch.from_numpy(s["body_ds"]).to(dev) for s in scans]
+    d_full = [torch.from_numpy(s["body_full"]).to(dev) for s in scans]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_dev(k):
+        sc = scans[k]
+        lio.step_dev(d_ds[k].data_ptr(), d_ds[k].shape[0], sc["dt"])
+        mesh.push_frame_from_lio(lio, d_full[k].data_ptr(), d_full[k].shape[0], on_device=True)
+        return lio.last_timing()[0] + mesh.last_timing()[0]
+
+    def step_host(k):
+        sc = scans[k]
+        lio.step(sc["body_ds"], sc["dt"])
+        mesh.push_frame_from_lio(lio, sc["body_full"])
+
+    k = 1
+    for _ in range(MAP_WARM + W):          # untimed: map densification + warm-up steps
+        step_dev(k)
+        k += 1
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- timed region 1: K scans, inputs resident in HBM, device-event time per scan, L2 flushed between scans
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = api.launch_count(lib)
+    barrier()
+    dev_ms, stage = [], []
+    for _ in range(K):
+        flush.zero_()
+        torch.cuda.synchronize()
+        dev_ms.append(step_dev(k))
+        stage.append((lio.last_timing().copy(), mesh.last_timing().copy()))
+        k += 1
+    barrier()
+    launches = api.launch_count(lib) - launches0
+    clocks = sampler.stop()
+    total_ms = float(np.sum(dev_ms))
+    # ---- timed region 2: K scans end to end through the C ABI with host buffers (wall clock around the calls)
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(K):
+        step_host(k)
+        h2d += (scans[k]["body_ds"].nbytes + scans[k]["body_full"].nbytes)
+        d2h += 348 * 8 + 4 + 16 * 4 + 32 * 4
+        k += 1
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    # ---- profiling pass (CUDA events around every kernel; not part of any reported throughput)
+    api.profile_reset(lib)
+    api.profile_enable(True, lib)
+    info = dict(n_ds=0, planes_unique=0, touched=0, gathered=0, queries=0, dilated=0, faces=0, voxels_meshed=0, candidates=0)
+    for _ in range(n_prof):
+        flush.zero_()
+        torch.cuda.synchronize()
+        roots0 = lio.counts()["roots"]
+        step_dev(k)
+        nodes = lio.match_nodes()
+        info["n_ds"] += d_ds[k].shape[0]
+        info["planes_unique"] += int(np.unique(nodes[nodes >= 0]).size)
+        info["touched"] += int(np.unique(np.floor(scans[k]["body_ds"] / cfg.voxel_size).astype(np.int64), axis=0).shape[0])
+        ws = mesh.work_stats()
+        for key in ("gathered", "queries", "dilated", "faces", "voxels_meshed", "candidates"):
+            info[key] += ws[key]
+        k += 1
+    api.profile_enable(False, lib)
+    prof = api.profile_report(lib)
+    for key in info:
+        info[key] /= n_prof            # per scan
+    kern_ms = {name: ms / n_prof for name, (ms, cnt) in prof.items()}              # per scan
+    kern_launch_ms = {name: ms / cnt for name, (ms, cnt) in prof.items() if cnt}
+    kern_launches_per_scan = {name: cnt / n_prof for name, (ms, cnt) in prof.items()}
+    dominant = max(kern_ms, key=kern_ms.get)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    roof = None
+    b = algorithmic_bytes(dominant, info)
+    if b is not None:
+        per_launch_bytes = b / kern_launches_per_scan[dominant]
+        achieved = per_launch_bytes / (kern_launch_ms[dominant] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dominant)
+        roof = {"kernel": dominant, "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 6),
+                "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": round(per_launch_bytes), "ms_per_launch": round(kern_launch_ms[dominant], 5),
+                "share_of_step": round(kern_ms[dominant] / sum(kern_ms.values()), 4)}
+    # ---- max over ranks, aggregate
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+    scans_done = K * (world if args.independent_streams else 1)
+    out = {
+        "metric": METRIC, "value": round(scans_done / (total_ms * 1e-3), 3), "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(total_ms / K, 4), "higher_is_better": True, "scaling": "weak" if args.independent_streams else "strong",
+        "vs_baseline": None, "dtype": "f64 (f32 keys/distances, i64 fixed-point reductions)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "points_per_scan_raw": int(np.mean([s["body_full"].shape[0] for s in scans])),
+                   "points_per_scan_downsampled": int(np.mean([s["body_ds"].shape[0] for s in scans])),
+                   "l2": "flushed (256 MB write) between timed scans, excluded from the per-scan device time",
+                   "parallelism": f"{world} x replica" if args.independent_streams else ("single GPU" if world == 1 else f"map sharded over {world} GPUs"),
+                   "map_warm_scans": MAP_WARM},
+        "e2e": {"value": round(scans_done / e2e_s, 3), "unit": "scans/s", "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
+                "ms_per_step": round(e2e_s / K * 1e3, 4)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "stage_ms": {"lio_total": round(float(np.mean([s[0][0] for s in stage])), 4), "lio_iterations": round(float(np.mean([s[0][1] for s in stage])), 4),
+                     "lio_map_update": round(float(np.mean([s[0][2] for s in stage])), 4), "mesh_total": round(float(np.mean([s[1][0] for s in stage])), 4),
+                     "mesh_append": round(float(np.mean([s[1][1] for s in stage])), 4), "mesh_voxels": round(float(np.mean([s[1][2] for s in stage])), 4),
+                     "mesh_push": round(float(np.mean([s[1][3] for s in stage])), 4)},
+        "kernel_ms_per_scan": {k2: round(v, 5) for k2, v in sorted(kern_ms.items(), key=lambda kv: -kv[1])},
+        "roofline": roof,
+    }
+    if rank == 0:
+        # ---- CPU baseline on a bounded sample of the same stream (rank 0, N = 1 only)
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_s = 8
+            tt = run_cpu(cfg, scans, MAP_WARM + 2, n_s, threads)
+            per = tt.sum(axis=1)
+            out["cpu_baseline"] = {"value": round(1.0 / float(np.mean(per)), 3), "unit": "scans/s", "cores": threads, "kind": "port",
+                                   "sample": f"{n_s} scans of the same stream after {MAP_WARM + 2} untimed scans; oracle (C++ restatement, -O3, OpenMP residual loop + voxel-parallel meshing)",
+                                   "loc_ms": round(float(np.mean(tt[:, 0])) * 1e3, 3), "mesh_ms": round(float(np.mean(tt[:, 1])) * 1e3, 3),
+                                   "reference_published": "Avia 24k-pt scans on i9-10900: localization 16.6 ms, meshing 25.3 ms (T-RO Table IV)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself cannot be built here) on all host cores."""
+    if rank != 0:
+        return
+    K, W = args.steps, max(args.warmup, 3)
+    K_eff = min(K, 40)      # bounded so that the run ends within a few minutes
+    cfg, sensor, scans = get_stream(1 + MAP_WARM + W + K_eff + 1)
+    threads = os.cpu_count() or 1
+    tt = run_cpu(cfg, scans, MAP_WARM + W, K_eff, threads)
+    per = tt.sum(axis=1)
+    v = 1.0 / float(np.mean(per))
+    out = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "scans/s", "n_gpus": world, "steps": K_eff, "warmup": W,
+           "ms_per_step": round(float(np.mean(per)) * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "map_warm_scans": MAP_WARM},
+           "cpu_baseline": {"value": round(v, 3), "unit": "scans/s", "cores": threads, "kind": "port",
+                            "sample": f"{K_eff} scans (one per step); oracle port of the reference CPU path (the reference needs ROS/Eigen/PCL/CGAL and cannot be compiled here)",
+                            "loc_ms": round(float(np.mean(tt[:, 0])) * 1e3, 3), "mesh_ms": round(float(np.mean(tt[:, 1])) * 1e3, 3)},
+           "e2e": {"value": round(v, 3), "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--independent-streams", action="store_true", default=None, help="N>1: every rank runs its own scan stream (replicas)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.independent_streams is None:
+        args.independent_streams = world > 1
+    from immesh_b200 import build
+    if rank == 0:
+        build.build_oracle()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -92,7 +92,16 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.immesh_voxelmap_counts.argtypes = [vp, C.POINTER(C.c_int64)]
     for name, args in (
         ("immesh_lio_step", [vp, fp, C.c_int, C.c_double, C.c_double, C.c_double, dp, ip]),
+        ("immesh_lio_step_dev", [vp, vp, C.c_int, C.c_double, C.c_double, C.c_double, dp, ip]),
         ("immesh_residual_build", [vp, fp, C.c_int, ip, dp, C.c_int, ip]),
+        ("immesh_mesh_push_frame_dev", [vp, vp, C.c_int, dp, C.c_int]),
+        ("immesh_mesh_push_frame_from_lio", [vp, vp, vp, C.c_int, C.c_int]),
+        ("immesh_lio_match_nodes", [vp, ip, C.c_int]),
+        ("immesh_mesh_work_stats", [vp, C.POINTER(C.c_int64)]),
+        ("immesh_profile_enable", [C.c_int]),
+        ("immesh_profile_reset", []),
+        ("immesh_profile_report", [C.c_char_p, C.c_int]),
+        ("immesh_launch_count", []),
         ("immesh_lio_last_timing", [vp, dp]),
         ("immesh_mesh_create", [C.POINTER(_MeshCfg), C.POINTER(vp)]),
         ("immesh_mesh_destroy", [vp]),
@@ -104,6 +113,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     ):
         if hasattr(lib, name):
             getattr(lib, name).argtypes = args
+    if hasattr(lib, "immesh_launch_count"):
+        lib.immesh_launch_count.restype = C.c_longlong
     if hasattr(lib, "immesh_last_error"):
         lib.immesh_last_error.restype = C.c_char_p
     if hasattr(lib, "immesh_version"):
@@ -201,6 +212,14 @@ class Lio:
         self._last_n = a.shape[0]
         return s, it.value
 
+    def step_dev(self, dev_ptr, n, dt=0.0, cov_gyr=0.1, cov_acc=0.1):
+        """Same as step() with the scan already in device memory (dev_ptr: integer CUDA address of float32[n][3])."""
+        it = C.c_int(0)
+        s = np.zeros(STATE_DOUBLES)
+        _check(self.lib, self.lib.immesh_lio_step_dev(self._h, C.c_void_p(dev_ptr), n, dt, cov_gyr, cov_acc, s.ctypes.data_as(C.POINTER(C.c_double)), C.byref(it)), "lio_step_dev")
+        self._last_n = n
+        return s, it.value
+
     def residual_build(self, body_ds):
         a, p = _f32(body_ds)
         n = a.shape[0]
@@ -220,6 +239,12 @@ class Lio:
         n = n or self._last_n
         o = np.zeros(n, dtype=np.int32)
         _check(self.lib, self.lib.immesh_lio_matches(self._h, o.ctypes.data_as(C.POINTER(C.c_int)), n), "matches")
+        return o
+
+    def match_nodes(self, n=None):
+        n = n or self._last_n
+        o = np.zeros(n, dtype=np.int32)
+        _check(self.lib, self.lib.immesh_lio_match_nodes(self._h, o.ctypes.data_as(C.POINTER(C.c_int)), n), "match_nodes")
         return o
 
     def dump_map(self) -> np.ndarray:
@@ -267,10 +292,31 @@ class Mesh:
         t = np.ascontiguousarray(pose_t, dtype=np.float64)
         _check(self.lib, self.lib.immesh_mesh_push_frame(self._h, p, a.shape[0], t.ctypes.data_as(C.POINTER(C.c_double)), frame_idx), "mesh_push_frame")
 
+    def push_frame_dev(self, dev_ptr, n, pose_t, frame_idx=0):
+        t = np.ascontiguousarray(pose_t, dtype=np.float64)
+        _check(self.lib, self.lib.immesh_mesh_push_frame_dev(self._h, C.c_void_p(dev_ptr), n, t.ctypes.data_as(C.POINTER(C.c_double)), frame_idx), "mesh_push_frame_dev")
+
+    def push_frame_from_lio(self, lio: "Lio", body_full, n=None, on_device=False):
+        """map_incremental_grow's hand-off: transform the full-resolution body scan with lio's converged state on the
+        device and mesh it.  body_full: float32[n][3] host array, or an integer CUDA address when on_device."""
+        if on_device:
+            ptr = C.c_void_p(body_full)
+        else:
+            a, p = _f32(body_full)
+            n = a.shape[0]
+            ptr = C.cast(p, C.c_void_p)
+        _check(self.lib, self.lib.immesh_mesh_push_frame_from_lio(self._h, lio._h, ptr, n, 1 if on_device else 0), "mesh_push_frame_from_lio")
+
     def counts(self):
         o = np.zeros(8, dtype=np.int64)
         _check(self.lib, self.lib.immesh_mesh_counts(self._h, o.ctypes.data_as(C.POINTER(C.c_int64))), "mesh_counts")
         keys = ["n_vertices", "n_triangles", "frame_new_vertices", "frame_voxels_meshed", "frame_added", "frame_removed", "n_voxels", "n_activated"]
+        return dict(zip(keys, (int(v) for v in o)))
+
+    def work_stats(self):
+        o = np.zeros(8, dtype=np.int64)
+        _check(self.lib, self.lib.immesh_mesh_work_stats(self._h, o.ctypes.data_as(C.POINTER(C.c_int64))), "mesh_work_stats")
+        keys = ["candidates", "gathered", "queries", "dilated", "faces", "voxels_meshed", "add_entries", "remove_entries"]
         return dict(zip(keys, (int(v) for v in o)))
 
     def snapshot(self):
@@ -294,3 +340,29 @@ class Mesh:
         o = np.zeros(4)
         self.lib.immesh_mesh_last_timing(self._h, o.ctypes.data_as(C.POINTER(C.c_double)))
         return o
+
+
+def profile_enable(on: bool, lib: Optional[C.CDLL] = None):
+    lib = lib or load_library()
+    lib.immesh_profile_enable(1 if on else 0)
+
+
+def profile_reset(lib: Optional[C.CDLL] = None):
+    (lib or load_library()).immesh_profile_reset()
+
+
+def profile_report(lib: Optional[C.CDLL] = None) -> dict:
+    """{kernel: (total_ms, launches)} measured with CUDA events on the launching stream."""
+    lib = lib or load_library()
+    n = lib.immesh_profile_report(None, 0)
+    buf = C.create_string_buffer(n + 16)
+    lib.immesh_profile_report(buf, n + 16)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, cnt = line.rsplit(" ", 2)
+        out[name.strip("()")] = (float(ms), int(cnt))
+    return out
+
+
+def launch_count(lib: Optional[C.CDLL] = None) -> int:
+    return int((lib or load_library()).immesh_launch_count())

@@ -1,0 +1,55 @@
+// immesh_b200 -- handle definitions shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "lio_core.cuh"
+#include "mesh_voxel.cuh"
+
+using immesh::LioParams; using immesh::VoxelMapDev; using immesh::ScanBuf; using immesh::LioCtrl;
+using immesh::MeshParams; using immesh::MeshDev; using immesh::FrameBuf;
+
+struct immesh_lio {
+    LioParams P;
+    VoxelMapDev map;
+    ScanBuf sb;
+    LioCtrl* d_ctrl = nullptr;
+    int* d_counters = nullptr;  // node_count, chunk_bump, avail_top, pending_n, err, n_roots, n_touched, seg_top, work_counter
+    int* d_sorted = nullptr;
+    double* d_ptpl = nullptr;
+    float* d_body_own = nullptr;  // scan buffer owned by the handle (sb.body points here unless the caller passed a device pointer)
+    float* h_body = nullptr;   // pinned staging
+    double* h_state = nullptr; // pinned
+    int* h_ints = nullptr;     // pinned
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t cap = 0;
+    int max_nodes = 0, max_chunks = 0, max_scan = 0;
+    int n_sm = 148;
+    int last_n = 0;
+    double last_ms[3] = {0, 0, 0};
+    std::vector<void*> allocs;
+};
+
+struct immesh_mesh {
+    MeshParams P;
+    MeshDev M;
+    FrameBuf F;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* d_pts = nullptr;
+    float* d_body = nullptr;  // staging for body-frame scans handed over by the localization handle
+    float* h_pts = nullptr;  // pinned
+    int* h_cnt = nullptr;    // pinned
+    int* d_snap_tri = nullptr;
+    int* d_snap_flip = nullptr;
+    int* d_snap_n = nullptr;
+    int max_frame_points = 0;
+    int frame_counter = 0;
+    int n_sm = 148;
+    size_t ccap = 0;
+    double last_ms[4] = {0, 0, 0, 0};
+    int last_cnt[32];
+    std::vector<void*> allocs;
+};

@@ -11,7 +11,7 @@
 
 #include "../../include/immesh_b200.h"
 #include "common_host.hpp"
-#include "lio_core.cuh"
+#include "handles.hpp"
 #include "map_dump.hpp"
 
 using namespace immesh;
@@ -129,26 +129,6 @@ __global__ void k_gather_ptpl(VoxelMapDev map, ScanBuf sb, int n, double* out /*
 }
 
 // ------------------------------------------------------------------ host side
-struct immesh_lio {
-    LioParams P;
-    VoxelMapDev map;
-    ScanBuf sb;
-    LioCtrl* d_ctrl = nullptr;
-    int* d_counters = nullptr;  // node_count, chunk_bump, avail_top, pending_n, err, n_roots, n_touched, seg_top, work_counter
-    int* d_sorted = nullptr;
-    double* d_ptpl = nullptr;
-    float* h_body = nullptr;   // pinned staging
-    double* h_state = nullptr; // pinned
-    int* h_ints = nullptr;     // pinned
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t cap = 0;
-    int max_nodes = 0, max_chunks = 0, max_scan = 0;
-    int n_sm = 148;
-    int last_n = 0;
-    double last_ms[3] = {0, 0, 0};
-    std::vector<void*> allocs;
-};
 
 static void fill_params(const immesh_lio_config* c, LioParams& P) {
     P.voxel_size = c->voxel_size;
@@ -228,6 +208,7 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     float* d_body = nullptr;
     IM_CUDA(dev_alloc(h, &d_body, ms * 3));
     sb.body = d_body;
+    h->d_body_own = d_body;
     IM_CUDA(dev_alloc(h, &sb.body_cov, ms * 6));
     IM_CUDA(dev_alloc(h, &sb.p_imu, ms * 3));
     IM_CUDA(dev_alloc(h, &sb.match_node, ms, 0xFF));
@@ -286,11 +267,18 @@ int immesh_lio_get_state(immesh_lio_t* h, double* s) {
     return IMMESH_OK;
 }
 
-static int upload_scan(immesh_lio* h, const float* body, int n) {
-    if (!body || n < 0) return im_fail(IMMESH_E_INVALID, "bad scan");
+static int upload_scan(immesh_lio* h, const float* body, int n, int on_device = 0) {
+    if ((!body && n > 0) || n < 0) return im_fail(IMMESH_E_INVALID, "bad scan");
     if (n > h->max_scan) return im_fail(IMMESH_E_CAPACITY, "scan larger than max_scan_points");
-    std::memcpy(h->h_body, body, (size_t)n * 3 * sizeof(float));
-    IM_CUDA(cudaMemcpyAsync((void*)h->sb.body, h->h_body, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (on_device) {
+        h->sb.body = body;  // caller-owned device buffer, must stay valid until the next call on this handle
+    } else {
+        h->sb.body = h->d_body_own;
+        if (n > 0) {
+            std::memcpy(h->h_body, body, (size_t)n * 3 * sizeof(float));
+            IM_CUDA(cudaMemcpyAsync((void*)h->d_body_own, h->h_body, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        }
+    }
     h->sb.n = n;
     h->last_n = n;
     return IMMESH_OK;
@@ -305,26 +293,26 @@ static int check_flags(immesh_lio* h) {
 }
 static void launch_grow(immesh_lio* h, int n, int mode) {
     if (n <= 0) return;
-    k_grow_point<<<grid_for(h, n, 128), 128, 0, h->stream>>>(h->map, h->P, h->sb, h->d_ctrl, n, mode);
-    k_grow_segment<<<grid_for(h, n, 128, 2), 128, 0, h->stream>>>(h->sb);
-    k_grow_scatter<<<grid_for(h, n, 128), 128, 0, h->stream>>>(h->sb, n);
-    k_grow_voxel<<<h->n_sm * 4, 128, 0, h->stream>>>(h->map, h->P, h->sb, mode, h->d_sorted, h->d_counters + 8);
-    k_grow_finish<<<1, 256, 0, h->stream>>>(h->map, h->sb, h->d_counters + 8);
+    IM_LAUNCH(k_grow_point, grid_for(h, n, 128), 128, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, n, mode);
+    IM_LAUNCH(k_grow_segment, grid_for(h, n, 128, 2), 128, 0, h->stream, h->sb);
+    IM_LAUNCH(k_grow_scatter, grid_for(h, n, 128), 128, 0, h->stream, h->sb, n);
+    IM_LAUNCH(k_grow_voxel, h->n_sm * 4, 128, 0, h->stream, h->map, h->P, h->sb, mode, h->d_sorted, h->d_counters + 8);
+    IM_LAUNCH(k_grow_finish, 1, 256, 0, h->stream, h->map, h->sb, h->d_counters + 8);
 }
 static void launch_estimate(immesh_lio* h, int n) {
-    k_reset_scan<<<2, 256, 0, h->stream>>>(h->sb, h->d_ctrl, 1);
+    IM_LAUNCH(k_reset_scan, 2, 256, 0, h->stream, h->sb, h->d_ctrl, 1);
     if (n <= 0) return;
-    k_prepare<<<grid_for(h, n, 128), 128, 0, h->stream>>>(h->P, h->sb, n);
+    IM_LAUNCH(k_prepare, grid_for(h, n, 128), 128, 0, h->stream, h->P, h->sb, n);
     const int g = grid_for(h, n, RES_THREADS, 4);
     for (int it = 0; it < h->P.max_iter; ++it) {
-        k_residual<<<g, RES_THREADS, 0, h->stream>>>(h->map, h->P, h->sb, h->d_ctrl, it, n);
-        k_solve<<<1, SOLVE_THREADS, 0, h->stream>>>(h->P, h->d_ctrl, it);
+        IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n);
+        IM_LAUNCH(k_solve, 1, SOLVE_THREADS, 0, h->stream, h->P, h->d_ctrl, it);
     }
 }
 
 int immesh_lio_predict(immesh_lio_t* h, double dt, double cov_gyr, double cov_acc) {
     if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
-    k_predict<<<1, SOLVE_THREADS, 0, h->stream>>>(h->d_ctrl, dt, cov_gyr, cov_acc);
+    IM_LAUNCH(k_predict, 1, SOLVE_THREADS, 0, h->stream, h->d_ctrl, dt, cov_gyr, cov_acc);
     IM_CUDA(cudaGetLastError());
     IM_CUDA(cudaStreamSynchronize(h->stream));
     return IMMESH_OK;
@@ -358,12 +346,12 @@ int immesh_voxelmap_update(immesh_lio_t* h) {
     return check_flags(h);
 }
 
-int immesh_lio_step(immesh_lio_t* h, const float* body, int n, double dt, double cov_gyr, double cov_acc, double* state_out, int* iters_run) {
+static int lio_step_impl(immesh_lio_t* h, const float* body, int n, int on_device, double dt, double cov_gyr, double cov_acc, double* state_out, int* iters_run) {
     if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
     IM_CUDA(cudaEventRecord(h->ev[0], h->stream));
-    int rc = upload_scan(h, body, n);
+    int rc = upload_scan(h, body, n, on_device);
     if (rc) return rc;
-    if (dt > 0) k_predict<<<1, SOLVE_THREADS, 0, h->stream>>>(h->d_ctrl, dt, cov_gyr, cov_acc);
+    if (dt > 0) IM_LAUNCH(k_predict, 1, SOLVE_THREADS, 0, h->stream, h->d_ctrl, dt, cov_gyr, cov_acc);
     IM_CUDA(cudaEventRecord(h->ev[1], h->stream));
     launch_estimate(h, n);
     IM_CUDA(cudaEventRecord(h->ev[2], h->stream));
@@ -373,6 +361,7 @@ int immesh_lio_step(immesh_lio_t* h, const float* body, int n, double dt, double
     IM_CUDA(cudaMemcpyAsync(h->h_ints + 32, &h->d_ctrl->iters_run, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     IM_CUDA(cudaEventRecord(h->ev[3], h->stream));
     rc = check_flags(h);
+    if (profiler().enabled) profiler().collect();
     if (state_out) std::memcpy(state_out, h->h_state, IM_STATE_DOUBLES * sizeof(double));
     if (iters_run) *iters_run = h->h_ints[32];
     float a = 0, b = 0, c = 0;
@@ -381,6 +370,13 @@ int immesh_lio_step(immesh_lio_t* h, const float* body, int n, double dt, double
     cudaEventElapsedTime(&c, h->ev[2], h->ev[3]);
     h->last_ms[0] = a; h->last_ms[1] = b; h->last_ms[2] = c;
     return rc;
+}
+
+int immesh_lio_step(immesh_lio_t* h, const float* body, int n, double dt, double cov_gyr, double cov_acc, double* state_out, int* iters_run) {
+    return lio_step_impl(h, body, n, 0, dt, cov_gyr, cov_acc, state_out, iters_run);
+}
+int immesh_lio_step_dev(immesh_lio_t* h, const float* d_body, int n, double dt, double cov_gyr, double cov_acc, double* state_out, int* iters_run) {
+    return lio_step_impl(h, d_body, n, 1, dt, cov_gyr, cov_acc, state_out, iters_run);
 }
 
 int immesh_lio_last_timing(immesh_lio_t* h, double* ms) {
@@ -394,12 +390,12 @@ int immesh_residual_build(immesh_lio_t* h, const float* body, int n, int* index_
     int rc = upload_scan(h, body, n);
     if (rc) return rc;
     if (!h->d_ptpl) IM_CUDA(dev_alloc(h, &h->d_ptpl, (size_t)h->max_scan * 31));
-    k_reset_scan<<<2, 256, 0, h->stream>>>(h->sb, h->d_ctrl, 0);
+    IM_LAUNCH(k_reset_scan, 2, 256, 0, h->stream, h->sb, h->d_ctrl, 0);
     *n_out = 0;
     if (n == 0) return IMMESH_OK;
-    k_prepare<<<grid_for(h, n, 128), 128, 0, h->stream>>>(h->P, h->sb, n);
-    k_residual<<<grid_for(h, n, RES_THREADS, 4), RES_THREADS, 0, h->stream>>>(h->map, h->P, h->sb, h->d_ctrl, 0, n);
-    k_gather_ptpl<<<grid_for(h, n, 128), 128, 0, h->stream>>>(h->map, h->sb, n, h->d_ptpl);
+    IM_LAUNCH(k_prepare, grid_for(h, n, 128), 128, 0, h->stream, h->P, h->sb, n);
+    IM_LAUNCH(k_residual, grid_for(h, n, RES_THREADS, 4), RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, 0, n);
+    IM_LAUNCH(k_gather_ptpl, grid_for(h, n, 128), 128, 0, h->stream, h->map, h->sb, n, h->d_ptpl);
     IM_CUDA(cudaGetLastError());
     std::vector<int> node(n), layer(n);
     std::vector<double> vals((size_t)n * 31);
@@ -440,6 +436,13 @@ int immesh_lio_matches(immesh_lio_t* h, int* plane_layer, int n) {
     IM_CUDA(cudaMemcpyAsync(layer.data(), h->sb.match_layer, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     IM_CUDA(cudaStreamSynchronize(h->stream));
     for (int i = 0; i < n; ++i) plane_layer[i] = node[i] >= 0 ? layer[i] : -1;
+    return IMMESH_OK;
+}
+
+int immesh_lio_match_nodes(immesh_lio_t* h, int* node, int n) {
+    if (!h || !node || n > h->max_scan) return im_fail(IMMESH_E_INVALID, "bad argument");
+    IM_CUDA(cudaMemcpyAsync(node, h->sb.match_node, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
     return IMMESH_OK;
 }
 

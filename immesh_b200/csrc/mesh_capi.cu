@@ -10,7 +10,7 @@
 
 #include "../../include/immesh_b200.h"
 #include "common_host.hpp"
-#include "mesh_voxel.cuh"
+#include "handles.hpp"
 
 using namespace immesh;
 
@@ -20,7 +20,7 @@ __global__ void k_frame_begin(MeshDev M, FrameBuf F) {
     for (unsigned int i = tid; i <= F.cmask; i += nt) { F.ckeys[i] = IM_EMPTY_KEY; F.chead[i] = -1; }
     if (tid == 0) {
         for (int k = 5; k <= 10; ++k) M.cnt[k] = 0;
-        M.cnt[18] = 0;
+        for (int k = 18; k <= 24; ++k) M.cnt[k] = 0;
     }
 }
 __global__ void __launch_bounds__(128) k_cand_init(MeshDev M, MeshParams P, FrameBuf F) {
@@ -219,26 +219,6 @@ __global__ void __launch_bounds__(128) k_knn(MeshDev M, MeshParams P, const floa
 }
 
 // ------------------------------------------------------------------ host side
-struct immesh_mesh {
-    MeshParams P;
-    MeshDev M;
-    FrameBuf F;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    float* d_pts = nullptr;
-    float* h_pts = nullptr;  // pinned
-    int* h_cnt = nullptr;    // pinned
-    int* d_snap_tri = nullptr;
-    int* d_snap_flip = nullptr;
-    int* d_snap_n = nullptr;
-    int max_frame_points = 0;
-    int frame_counter = 0;
-    int n_sm = 148;
-    size_t ccap = 0;
-    double last_ms[4] = {0, 0, 0, 0};
-    int last_cnt[32];
-    std::vector<void*> allocs;
-};
 
 template <class T>
 static cudaError_t mdev_alloc(immesh_mesh* h, T** p, size_t count, int memset_byte = -1) {
@@ -368,8 +348,39 @@ static int mesh_grid(const immesh_mesh* h, int n, int threads, int waves = 8) {
     return g < 1 ? 1 : g;
 }
 
+// transformLidar of the full-resolution scan with the converged state (ImMesh_mesh_reconstruction.cpp:413 ->
+// voxel_mapping_common.cpp:709-726): p_w = (float)( R (R_ext p + t_ext) + t )
+__global__ void __launch_bounds__(128) k_transform_full(LioParams P, const LioCtrl* ctrl, const float* body, int n, float* world) {
+    __shared__ double s[12];
+    if (threadIdx.x < 12) s[threadIdx.x] = ctrl->state[threadIdx.x];
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double pb[3] = {(double)body[(size_t)i * 3 + 0], (double)body[(size_t)i * 3 + 1], (double)body[(size_t)i * 3 + 2]};
+        double pw[3];
+        body_to_world(P, s, s + 9, pb, pw);
+        world[(size_t)i * 3 + 0] = (float)pw[0]; world[(size_t)i * 3 + 1] = (float)pw[1]; world[(size_t)i * 3 + 2] = (float)pw[2];
+    }
+}
+
+static int mesh_push_impl(immesh_mesh_t* h, const float* world_xyz, int n, const double* pose_t, int src_mode, immesh_lio* lio);
+
 int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, const double* pose_t, int frame_idx) {
     (void)frame_idx;
+    return mesh_push_impl(h, world_xyz, n, pose_t, 0, nullptr);
+}
+int immesh_mesh_push_frame_dev(immesh_mesh_t* h, const float* d_world_xyz, int n, const double* pose_t, int frame_idx) {
+    (void)frame_idx;
+    return mesh_push_impl(h, d_world_xyz, n, pose_t, 1, nullptr);
+}
+int immesh_mesh_push_frame_from_lio(immesh_mesh_t* h, immesh_lio_t* lio, const float* body_xyz, int n, int on_device) {
+    if (!lio) return im_fail(IMMESH_E_INVALID, "null lio handle");
+    // pose_t = state.pos_end of the scan just localised (kept in pinned memory by immesh_lio_step / get_state)
+    double pose_t[3] = {lio->h_state[9], lio->h_state[10], lio->h_state[11]};
+    return mesh_push_impl(h, body_xyz, n, pose_t, on_device ? 3 : 2, lio);
+}
+
+// src_mode: 0 host world points, 1 device world points, 2 host body points + lio state, 3 device body points + lio state
+static int mesh_push_impl(immesh_mesh_t* h, const float* world_xyz, int n, const double* pose_t, int src_mode, immesh_lio* lio) {
     if (!h || (!world_xyz && n > 0) || !pose_t || n < 0) return im_fail(IMMESH_E_INVALID, "bad argument");
     if (n > h->max_frame_points) return im_fail(IMMESH_E_CAPACITY, "frame larger than max_frame_points");
     FrameBuf& F = h->F;
@@ -387,37 +398,52 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     F.cmask = (unsigned)(pow2_at_least((size_t)std::max(F.m, 1) * 2) - 1);
     cudaStream_t st = h->stream;
     IM_CUDA(cudaEventRecord(h->ev[0], st));
+    F.pts = h->d_pts;
     if (n > 0) {
-        std::memcpy(h->h_pts, world_xyz, (size_t)n * 3 * sizeof(float));
-        IM_CUDA(cudaMemcpyAsync(h->d_pts, h->h_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (src_mode == 0) {
+            std::memcpy(h->h_pts, world_xyz, (size_t)n * 3 * sizeof(float));
+            IM_CUDA(cudaMemcpyAsync(h->d_pts, h->h_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        } else if (src_mode == 1) {
+            F.pts = world_xyz;
+        } else {
+            const float* d_body = world_xyz;
+            if (src_mode == 2) {
+                if (!h->d_body) IM_CUDA(mdev_alloc(h, &h->d_body, (size_t)h->max_frame_points * 3));
+                std::memcpy(h->h_pts, world_xyz, (size_t)n * 3 * sizeof(float));
+                IM_CUDA(cudaMemcpyAsync(h->d_body, h->h_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+                d_body = h->d_body;
+            }
+            IM_LAUNCH(k_transform_full, mesh_grid(h, n, 128), 128, 0, st, lio->P, lio->d_ctrl, d_body, n, h->d_pts);
+        }
     }
-    k_frame_begin<<<mesh_grid(h, (int)F.cmask + 1, 256), 256, 0, st>>>(h->M, F);
+    IM_LAUNCH(k_frame_begin, mesh_grid(h, (int)F.cmask + 1, 256), 256, 0, st, h->M, F);
     IM_CUDA(cudaEventRecord(h->ev[1], st));
     if (F.m > 0) {
         const int g = mesh_grid(h, F.m, 128);
-        k_cand_init<<<g, 128, 0, st>>>(h->M, P, F);
-        k_cand_conflicts<<<g, 128, 0, st>>>(h->M, P, F);
-        k_cand_resolve<<<mesh_grid(h, F.m, 128, 16), 128, 0, st>>>(h->M, P, F);
-        k_cand_scan<<<1, 1024, 0, st>>>(h->M, F);
-        k_cand_commit<<<g, 128, 0, st>>>(h->M, P, F);
-        k_voxel_select<<<mesh_grid(h, F.m, 128), 128, 0, st>>>(h->M, F);
+        IM_LAUNCH(k_cand_init, g, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_cand_conflicts, g, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_cand_resolve, mesh_grid(h, F.m, 128, 16), 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_cand_scan, 1, 1024, 0, st, h->M, F);
+        IM_LAUNCH(k_cand_commit, g, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_voxel_select, mesh_grid(h, F.m, 128), 128, 0, st, h->M, F);
     }
     IM_CUDA(cudaEventRecord(h->ev[2], st));
     if (F.m > 0) {
-        k_voxel_dilate<<<h->n_sm * 4, 128, 0, st>>>(h->M, P, F);
-        k_voxel_mesh<256><<<h->n_sm * 6, 128, sizeof(MeshSmem<256>), st>>>(h->M, P, F, 0);
-        k_voxel_mesh<1024><<<h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st>>>(h->M, P, F, 256);
+        IM_LAUNCH(k_voxel_dilate, h->n_sm * 4, 128, 0, st, h->M, P, F);
+        IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * 6, 128, sizeof(MeshSmem<256>), st, h->M, P, F, 0);
+        IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st, h->M, P, F, 256);
     }
     IM_CUDA(cudaEventRecord(h->ev[3], st));
     if (F.m > 0) {
-        k_push_remove<<<h->n_sm * 2, 128, 0, st>>>(h->M, F);
-        k_push_add<<<h->n_sm * 2, 128, 0, st>>>(h->M, F);
+        IM_LAUNCH(k_push_remove, h->n_sm * 2, 128, 0, st, h->M, F);
+        IM_LAUNCH(k_push_add, h->n_sm * 2, 128, 0, st, h->M, F);
     }
-    k_frame_end<<<1, 1, 0, st>>>(h->M);
+    IM_LAUNCH(k_frame_end, 1, 1, 0, st, h->M);
     IM_CUDA(cudaGetLastError());
     IM_CUDA(cudaMemcpyAsync(h->h_cnt, h->M.cnt, 32 * sizeof(int), cudaMemcpyDeviceToHost, st));
     IM_CUDA(cudaEventRecord(h->ev[4], st));
     IM_CUDA(cudaStreamSynchronize(st));
+    if (profiler().enabled) profiler().collect();
     std::memcpy(h->last_cnt, h->h_cnt, 32 * sizeof(int));
     float a = 0, b = 0, c = 0, d = 0;
     cudaEventElapsedTime(&a, h->ev[0], h->ev[4]);
@@ -438,6 +464,13 @@ int immesh_mesh_counts(immesh_mesh_t* h, int64_t* out) {
     return IMMESH_OK;
 }
 
+int immesh_mesh_work_stats(immesh_mesh_t* h, int64_t* out) {
+    if (!h || !out) return im_fail(IMMESH_E_INVALID, "null argument");
+    const int* c = h->last_cnt;
+    out[0] = h->F.m; out[1] = c[20]; out[2] = c[21]; out[3] = c[22]; out[4] = c[23]; out[5] = c[6]; out[6] = c[7]; out[7] = c[8];
+    return IMMESH_OK;
+}
+
 int immesh_mesh_snapshot(immesh_mesh_t* h, float* vertices, int32_t* triangles, int32_t* flips) {
     if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
     int cnt[32];
@@ -454,7 +487,7 @@ int immesh_mesh_snapshot(immesh_mesh_t* h, float* vertices, int32_t* triangles, 
         IM_CUDA(cudaMalloc(&d_flip, (size_t)nlive * sizeof(int)));
         IM_CUDA(cudaMalloc(&d_n, sizeof(int)));
         IM_CUDA(cudaMemset(d_n, 0, sizeof(int)));
-        k_snapshot<<<mesh_grid(h, nalloc, 128), 128, 0, h->stream>>>(h->M, nalloc, d_tri, d_flip, d_n);
+        IM_LAUNCH(k_snapshot, mesh_grid(h, nalloc, 128), 128, 0, h->stream, h->M, nalloc, d_tri, d_flip, d_n);
         std::vector<int> t((size_t)nlive * 3), f(nlive);
         IM_CUDA(cudaMemcpyAsync(t.data(), d_tri, (size_t)nlive * 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         IM_CUDA(cudaMemcpyAsync(f.data(), d_flip, (size_t)nlive * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -486,7 +519,7 @@ int immesh_knn(immesh_mesh_t* h, const float* query_xyz, int nq, int k, double m
     IM_CUDA(cudaMalloc(&di, (size_t)nq * k * sizeof(int)));
     IM_CUDA(cudaMalloc(&dd, (size_t)nq * k * sizeof(float)));
     IM_CUDA(cudaMemcpyAsync(dq, query_xyz, (size_t)nq * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    k_knn<<<mesh_grid(h, nq * 32, 128), 128, 0, h->stream>>>(h->M, h->P, dq, nq, k, max_dist, di, dd);
+    IM_LAUNCH(k_knn, mesh_grid(h, nq * 32, 128), 128, 0, h->stream, h->M, h->P, dq, nq, k, max_dist, di, dd);
     IM_CUDA(cudaGetLastError());
     IM_CUDA(cudaMemcpyAsync(idx, di, (size_t)nq * k * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     IM_CUDA(cudaMemcpyAsync(d2, dd, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, h->stream));

@@ -181,6 +181,10 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
     if (tid == 0) {
         F.work_n_ids[w] = n;
         if (S->overflow) im_atomic_or(&M.cnt[3], IM_MERR_VOXEL_CAP);
+        // work accounting for the roofline: gathered candidates, queries, dilated vertices
+        im_atomic_add(&M.cnt[20], nc);
+        im_atomic_add(&M.cnt[21], nq);
+        im_atomic_add(&M.cnt[22], n);
     }
 }
 
@@ -278,6 +282,7 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
     }
     IM_SYNCBLOCK_M();
     const int nf = S->nface;
+    if (tid == 0) im_atomic_add(&M.cnt[23], nf);
     // flip priority of this voxel: its key relative to the frame origin (ascending (x,y,z) order, last one wins)
     int kx, ky, kz;
     unpack_ikey(M.vkeys[vs], &kx, &ky, &kz);

@@ -81,6 +81,10 @@ int immesh_voxelmap_update(immesh_lio_t* h);
 int immesh_lio_step(immesh_lio_t* h, const float* body_xyz, int n, double dt, double cov_gyr, double cov_acc,
                     double* state_out /*[348] or NULL*/, int* iters_run /*or NULL*/);
 
+/* same, with the scan already resident in device memory (d_body_xyz must stay valid until the next call on h) */
+int immesh_lio_step_dev(immesh_lio_t* h, const float* d_body_xyz, int n, double dt, double cov_gyr, double cov_acc,
+                        double* state_out, int* iters_run);
+
 /* BuildResidualListOMP (src/voxel_mapping.hpp:103-105, src/voxel_mapping.cpp:153-245) as a stand-alone call at
  * the current state: fills, for every accepted match in scan order, its scan index, octree layer and the ptpl
  * payload.  Returns the number of matches in *n_out (written entries are capped by cap). */
@@ -90,6 +94,7 @@ int immesh_residual_build(immesh_lio_t* h, const float* body_xyz, int n, int* in
 /* diagnostics used by the parity tests */
 int immesh_lio_iter_stats(immesh_lio_t* h, int iter, double* out /*[63]*/);
 int immesh_lio_matches(immesh_lio_t* h, int* plane_layer /*[n] layer or -1*/, int n);
+int immesh_lio_match_nodes(immesh_lio_t* h, int* plane_node /*[n] plane record index or -1*/, int n);
 /* canonical dump of the VoxelMap (roots by ascending key, nodes in pre-order), 45 doubles per node */
 int64_t immesh_voxelmap_dump(immesh_lio_t* h, double* rows, int64_t cap_rows);
 int immesh_voxelmap_counts(immesh_lio_t* h, int64_t* out /*[4]: roots, nodes, chunks_in_use, error_flags*/);
@@ -114,6 +119,13 @@ int immesh_mesh_destroy(immesh_mesh_t* h);
  * append vertices, find activated voxels, per voxel retrieve + dilate + project + 2-D Delaunay + pull/commit,
  * then push.  world_xyz is the full-resolution scan already in the world frame (float, as pcl::PointXYZI). */
 int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz /*[n][3]*/, int n, const double* pose_t /*[3]*/, int frame_idx);
+/* same, with the world-frame scan already resident in device memory */
+int immesh_mesh_push_frame_dev(immesh_mesh_t* h, const float* d_world_xyz, int n, const double* pose_t, int frame_idx);
+/* The hand-off at the end of Voxel_mapping::map_incremental_grow (src/ImMesh_mesh_reconstruction.cpp:413-417):
+ * transformLidar of the full-resolution body-frame scan with the state the localization handle just converged to
+ * (on the device, no host round trip of the world cloud), then incremental_mesh_reconstruction on it.
+ * on_device != 0: body_xyz is a device pointer. */
+int immesh_mesh_push_frame_from_lio(immesh_mesh_t* h, immesh_lio_t* lio, const float* body_xyz, int n, int on_device);
 /* counts: [n_vertices, n_live_triangles, frame_new_vertices, frame_voxels_meshed, frame_added, frame_removed, n_voxels, n_activated] */
 int immesh_mesh_counts(immesh_mesh_t* h, int64_t* out /*[8]*/);
 /* Triangle_manager::get_all_triangle_list (src/meshing/r3live/triangle.cpp:12-33) + the vertex array:
@@ -124,7 +136,16 @@ int immesh_mesh_snapshot(immesh_mesh_t* h, float* vertices /*[nv][3] or NULL*/, 
  * exact k nearest by float squared distance, ascending, ties by lower id; idx = -1 / d2 = inf when fewer exist. */
 int immesh_knn(immesh_mesh_t* h, const float* query_xyz /*[nq][3]*/, int nq, int k, double max_dist, int32_t* idx /*[nq][k]*/,
                float* d2 /*[nq][k]*/);
+/* per-frame work accounting used for the roofline arithmetic: [candidates, kNN candidates gathered, kNN queries,
+ * dilated vertices, facets produced, voxels meshed, add-list entries, remove-list entries] */
+int immesh_mesh_work_stats(immesh_mesh_t* h, int64_t* out /*[8]*/);
 int immesh_mesh_last_timing(immesh_mesh_t* h, double* ms /*[4]: whole frame incl. H2D, append, per-voxel, push*/);
+
+/* optional per-kernel CUDA-event profiler (off by default) and launch accounting, process-wide */
+int immesh_profile_enable(int on);
+int immesh_profile_reset(void);
+int immesh_profile_report(char* buf, int cap); /* "kernel ms launches\n" lines; returns bytes needed */
+long long immesh_launch_count(void);
 
 const char* immesh_last_error(void);
 const char* immesh_version(void);

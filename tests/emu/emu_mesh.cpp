@@ -81,6 +81,7 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     if (n > 0) std::memcpy(h->pts.data(), world_xyz, (size_t)n * 12);
     for (unsigned i = 0; i <= F.cmask; ++i) { F.ckeys[i] = IM_EMPTY_KEY; F.chead[i] = -1; }
     for (int k = 5; k <= 10; ++k) M.cnt[k] = 0;
+    for (int k = 18; k <= 24; ++k) M.cnt[k] = 0;
     for (int c = 0; c < F.m; ++c) cand_init(M, P, F, c);
     for (int c = 0; c < F.m; ++c) cand_conflicts(M, P, F, c);
     for (int c = 0; c < F.m; ++c)

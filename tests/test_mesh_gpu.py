@@ -40,7 +40,7 @@ def test_empty_frame_and_restart(cuda_lib):
     g = api.Mesh(cfg, lib=cuda_lib)
     g.push_frame(np.zeros((0, 3), np.float32), np.zeros(3), 0)
     assert g.counts()["n_vertices"] == 0
-    pts = np.array([[1.0, 0, 0], [1.0, 0.3, 0], [1.2, 0.1, 0.05]], np.float32)
+    pts = np.array([[1.0, 0, 0], [1.1, 0.1, 0], [1.0, 0.15, 0.05]], np.float32)   # one 0.4 m voxel, three xi-cells
     g.push_frame(pts, np.zeros(3), 1)
     c = g.counts()
     assert c["n_vertices"] == 3 and c["n_triangles"] == 1
