@@ -4,6 +4,7 @@
 // There is no CPU path: every entry point needs a CUDA device and fails loudly without one.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -113,6 +114,14 @@ __global__ void k_grow_finish(VoxelMapDev map, ScanBuf sb, int* work_counter) {
         *sb.n_touched = 0;
         *sb.seg_top = 0;
         *work_counter = 0;
+    }
+}
+// BuildResidualListOMP on caller-supplied Point_with_var data (world point + covariance per point)
+__global__ void __launch_bounds__(128) k_match_pv(VoxelMapDev map, LioParams P, ScanBuf sb, const double* pw, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const MatchResult mr = match_point(map, P, pw + (size_t)i * 3, sb.var + (size_t)i * 6);
+        sb.match_node[i] = mr.node;
+        sb.match_layer[i] = mr.layer;
     }
 }
 // ptpl payload of every matched point (diagnostic / drop-in immesh_residual_build)
@@ -409,6 +418,87 @@ int immesh_residual_build(immesh_lio_t* h, const float* body, int n, int* index_
         if (m < cap) {
             if (index_layer) { index_layer[2 * m] = i; index_layer[2 * m + 1] = layer[i]; }
             if (ptpl) std::memcpy(ptpl + (size_t)m * 31, vals.data() + (size_t)i * 31, 31 * 8);
+        }
+        ++m;
+    }
+    *n_out = m;
+    return check_flags(h);
+}
+
+static void var9_to_6(const double* v9, double* v6) {  // upper triangle of the caller's (symmetric) 3x3
+    v6[0] = v9[0]; v6[1] = v9[1]; v6[2] = v9[2]; v6[3] = v9[4]; v6[4] = v9[5]; v6[5] = v9[8];
+}
+static int upload_pv(immesh_lio* h, const double* pts_world, const double* var9, int n) {
+    if ((!pts_world || !var9) && n > 0) return im_fail(IMMESH_E_INVALID, "null argument");
+    if (n < 0 || n > h->max_scan) return im_fail(IMMESH_E_CAPACITY, "too many points");
+    std::vector<float> pw((size_t)n * 3);
+    std::vector<double> v6((size_t)n * 6);
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < 3; ++j) pw[(size_t)i * 3 + j] = (float)pts_world[(size_t)i * 3 + j];  // already float-valued in the reference
+        var9_to_6(var9 + (size_t)i * 9, v6.data() + (size_t)i * 6);
+    }
+    IM_CUDA(cudaMemcpyAsync(h->sb.pw, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    IM_CUDA(cudaMemcpyAsync(h->sb.var, v6.data(), v6.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    h->sb.n = n;
+    h->last_n = n;
+    return IMMESH_OK;
+}
+int immesh_voxelmap_build_pv(immesh_lio_t* h, const double* pts_world, const double* var9, int n) {
+    if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
+    int rc = upload_pv(h, pts_world, var9, n);
+    if (rc) return rc;
+    launch_grow(h, n, 3);
+    IM_CUDA(cudaGetLastError());
+    return check_flags(h);
+}
+int immesh_voxelmap_update_pv(immesh_lio_t* h, const double* pts_world, const double* var9, int n) {
+    if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
+    int rc = upload_pv(h, pts_world, var9, n);
+    if (rc) return rc;
+    launch_grow(h, n, 2);
+    IM_CUDA(cudaGetLastError());
+    return check_flags(h);
+}
+int immesh_residual_build_pv(immesh_lio_t* h, const double* pts_body, const double* pts_world, const double* var9, int n, int* index_layer,
+                             double* ptpl, int cap, int* n_out) {
+    if (!h || !n_out || ((!pts_body || !pts_world || !var9) && n > 0)) return im_fail(IMMESH_E_INVALID, "null argument");
+    if (n < 0 || n > h->max_scan) return im_fail(IMMESH_E_CAPACITY, "too many points");
+    *n_out = 0;
+    if (n == 0) return IMMESH_OK;
+    std::vector<double> v6((size_t)n * 6);
+    for (int i = 0; i < n; ++i) var9_to_6(var9 + (size_t)i * 9, v6.data() + (size_t)i * 6);
+    IM_CUDA(cudaMemcpyAsync(h->sb.var, v6.data(), v6.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    IM_CUDA(cudaMemcpyAsync(h->sb.p_imu, pts_world, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));  // p_imu doubles as scratch for the world points
+    IM_LAUNCH(k_match_pv, grid_for(h, n, 128), 128, 0, h->stream, h->map, h->P, h->sb, h->sb.p_imu, n);
+    IM_CUDA(cudaGetLastError());
+    std::vector<int> node(n), layer(n);
+    IM_CUDA(cudaMemcpyAsync(node.data(), h->sb.match_node, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaMemcpyAsync(layer.data(), h->sb.match_layer, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    int m = 0, nn = 0;
+    for (int i = 0; i < n; ++i) nn = node[i] > nn ? node[i] : nn;
+    std::vector<PlaneRec> planes;
+    // fetch only the matched plane records
+    std::vector<int> uniq;
+    for (int i = 0; i < n; ++i) if (node[i] >= 0) uniq.push_back(node[i]);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    planes.resize(uniq.size());
+    for (size_t u = 0; u < uniq.size(); ++u)
+        IM_CUDA(cudaMemcpyAsync(&planes[u], h->map.planes + uniq[u], sizeof(PlaneRec), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; ++i) {
+        if (node[i] < 0) continue;
+        if (m < cap) {
+            const PlaneRec& pl = planes[std::lower_bound(uniq.begin(), uniq.end(), node[i]) - uniq.begin()];
+            if (index_layer) { index_layer[2 * m] = i; index_layer[2 * m + 1] = layer[i]; }
+            if (ptpl) {
+                double* o = ptpl + (size_t)m * 31;
+                for (int j = 0; j < 3; ++j) { o[j] = pts_body[(size_t)i * 3 + j]; o[3 + j] = pl.normal[j]; o[6 + j] = pl.center[j]; }
+                o[9] = (double)pl.d;
+                for (int j = 0; j < 21; ++j) o[10 + j] = pl.pv[j];
+            }
         }
         ++m;
     }

@@ -366,16 +366,23 @@ IM_HDN inline void predict_const_vel(double* state, double dt, double cov_gyr, d
 // pass 1 (thread / point): world point + covariance with the converged state, sort key, root-voxel insert, count
 //   mode 0: map_incremental_grow (ImMesh_mesh_reconstruction.cpp:393-404)   cov uses (R R_ext) and [p_imu]x
 //   mode 1: voxel_map_init       (voxel_mapping.cpp:1249-1265)              cov uses R and [p_lidar]x, input order kept
+//   mode | 2: world points (sb.pw) and covariances (sb.var) were supplied by the caller (Point_with_var lists of
+//             updateVoxelMap / buildVoxelMap, voxel_mapping.hpp:80-92), caller's order is kept
 IM_HDN inline void grow_point(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, int mode) {
     const double* R = state;
     const double* t = state + 9;
     const double* cov = state + 24;
+    float wx, wy, wz;
+    double* v6 = sb.var + (size_t)i * 6;
+    if (mode & 2) {
+        wx = sb.pw[(size_t)i * 3 + 0]; wy = sb.pw[(size_t)i * 3 + 1]; wz = sb.pw[(size_t)i * 3 + 2];
+        sb.sortkey[i] = (double)i;
+    } else {
     const double pb[3] = {(double)sb.body[i * 3 + 0], (double)sb.body[i * 3 + 1], (double)sb.body[i * 3 + 2]};
     double pwd[3];
     body_to_world(P, R, t, pb, pwd);
-    const float wx = (float)pwd[0], wy = (float)pwd[1], wz = (float)pwd[2];
+    wx = (float)pwd[0]; wy = (float)pwd[1]; wz = (float)pwd[2];
     sb.pw[(size_t)i * 3 + 0] = wx; sb.pw[(size_t)i * 3 + 1] = wy; sb.pw[(size_t)i * 3 + 2] = wz;
-    double* v6 = sb.var + (size_t)i * 6;
     if (mode == 0) {
         double RRe[9];
         m3_mul(R, P.extR, RRe);
@@ -387,6 +394,7 @@ IM_HDN inline void grow_point(const VoxelMapDev& map, const LioParams& P, const 
         calc_body_var(pt, P.dept_err, P.dir_var, bv);
         world_cov(R, bv, pt, cov, v6);
         sb.sortkey[i] = (double)i;
+    }
     }
     const double pw[3] = {(double)wx, (double)wy, (double)wz};
     long long k[3];
@@ -439,7 +447,7 @@ IM_HDN inline void grow_voxel(const VoxelMapDev& map, const LioParams& P, const 
     IM_SYNCWARP();
     const int root = map.root_node[slot];
     if (root >= 0) {
-        if (mode == 0) {
+        if ((mode & 1) == 0) {
             for (int a = 0; a < cnt; ++a) {
                 const int i = sorted_scratch[off + a];
                 update_octo_tree(map, P, root, sb.pw[(size_t)i * 3 + 0], sb.pw[(size_t)i * 3 + 1], sb.pw[(size_t)i * 3 + 2], sb.var + (size_t)i * 6, lane, nlanes);

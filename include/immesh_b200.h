@@ -91,6 +91,15 @@ int immesh_lio_step_dev(immesh_lio_t* h, const float* d_body_xyz, int n, double 
 int immesh_residual_build(immesh_lio_t* h, const float* body_xyz, int n, int* index_layer /*[cap][2]*/,
                           double* ptpl /*[cap][31]*/, int cap, int* n_out);
 
+/* The three free functions of src/voxel_mapping.hpp:80-105 on caller-built Point_with_var lists (what the shim in
+ * immesh_b200/csrc/immesh_shim.hpp forwards to).  pts_world: m_point (insert path) / m_point_world (lookup path),
+ * var9: m_var row-major, pts_body: m_point of the lookup path.  The caller's order is kept (updateVoxelMap expects
+ * its input already sorted by var_contrast). */
+int immesh_voxelmap_build_pv(immesh_lio_t* h, const double* pts_world /*[n][3]*/, const double* var9 /*[n][9]*/, int n);
+int immesh_voxelmap_update_pv(immesh_lio_t* h, const double* pts_world /*[n][3]*/, const double* var9 /*[n][9]*/, int n);
+int immesh_residual_build_pv(immesh_lio_t* h, const double* pts_body, const double* pts_world, const double* var9, int n,
+                             int* index_layer /*[cap][2]*/, double* ptpl /*[cap][31]*/, int cap, int* n_out);
+
 /* diagnostics used by the parity tests */
 int immesh_lio_iter_stats(immesh_lio_t* h, int iter, double* out /*[63]*/);
 int immesh_lio_matches(immesh_lio_t* h, int* plane_layer /*[n] layer or -1*/, int n);
