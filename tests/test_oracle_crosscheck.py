@@ -1,0 +1,186 @@
+"""CPU tier: the oracle against independent implementations (numpy / scipy / brute force).  The reference ships no
+golden vectors (parity unpinned), so these checks are what keeps oracle bugs from being baked in."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy.spatial import Delaunay
+
+import oracle_api as oa
+from immesh_b200 import api, synth
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_deterministic_libm_subset():
+    L = oa.lib()
+    x = np.concatenate([np.linspace(-3.1, 3.1, 2001), np.linspace(-1e-3, 1e-3, 101), [0.0, 1.0, -1.0, 0.5, -0.5]])
+    s, c, e, ac = (np.zeros_like(x) for _ in range(4))
+    L.orc_math_probe(_p(x), C.c_int(x.size), _p(s), _p(c), _p(e), _p(ac))
+    assert np.max(np.abs(s - np.sin(x))) < 4e-16
+    assert np.max(np.abs(c - np.cos(x))) < 4e-16
+    assert np.max(np.abs(e / np.exp(-np.abs(x)) - 1)) < 1e-15
+    xc = np.clip(x, -1, 1)
+    assert np.max(np.abs(ac - np.arccos(xc))) < 1e-15 * np.pi + 5e-16
+
+
+def test_jacobi_matches_eigh():
+    L = oa.lib()
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        A = rng.normal(size=(3, 3)) * rng.uniform(1e-3, 10)
+        S = A @ A.T
+        if rng.random() < 0.3:
+            S = S * np.array([1.0, 1e-3, 1e-6])[:, None] * np.array([1.0, 1e-3, 1e-6])[None, :]
+        a6 = np.array([S[0, 0], S[0, 1], S[0, 2], S[1, 1], S[1, 2], S[2, 2]])
+        d, V = np.zeros(3), np.zeros(9)
+        L.orc_jacobi_eig3(_p(a6), _p(d), _p(V))
+        V = V.reshape(3, 3)
+        w = np.linalg.eigvalsh(S)
+        assert np.allclose(np.sort(d), w, rtol=1e-12, atol=1e-14 * abs(w).max())
+        assert np.allclose(V @ np.diag(d) @ V.T, S, rtol=1e-12, atol=1e-14 * abs(S).max())
+        assert np.allclose(V.T @ V, np.eye(3), atol=1e-14)
+
+
+def test_lu_inverse18_matches_numpy():
+    L = oa.lib()
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        B = rng.normal(size=(18, 18))
+        A = B @ B.T + np.diag(rng.uniform(1e-6, 1e3, 18))
+        out = np.zeros((18, 18))
+        L.orc_lu_inverse18(_p(np.ascontiguousarray(A)), _p(out))
+        assert np.allclose(out @ A, np.eye(18), atol=1e-8)
+        assert np.allclose(out, np.linalg.inv(A), rtol=1e-7, atol=1e-10)
+
+
+def test_voxel_key_rule():
+    L = oa.lib()
+    # truncation toward zero after the -1.0f shift; exact negative multiples land one cell lower than floor
+    cases = [((0.24, 0.26, 0.74), 0.5, (0, 0, 1)), ((-0.01, -0.5, -0.51), 0.5, (-1, -2, -2)), ((-1.0, 1.0, 0.0), 0.5, (-3, 2, 0)), ((3.9999, -3.0, 2.99), 3.0, (1, -2, 0))]
+    for p, vs, want in cases:
+        out = np.zeros(3, dtype=np.int64)
+        L.orc_voxel_key(_p(np.array(p, dtype=np.float64)), C.c_double(vs), _p(out))
+        assert tuple(out) == want, (p, vs, tuple(out))
+
+
+def test_calc_body_var_matches_formula():
+    L = oa.lib()
+    rng = np.random.default_rng(2)
+    for _ in range(100):
+        p = rng.normal(size=3) * rng.uniform(1, 50)
+        out = np.zeros(6)
+        L.orc_calc_body_var(_p(p), 0.02, 0.05, _p(out))
+        V = np.array([[out[0], out[1], out[2]], [out[1], out[3], out[4]], [out[2], out[4], out[5]]])
+        r = np.float32(np.linalg.norm(p))
+        d = p / np.linalg.norm(p)
+        hat = np.array([[0, -d[2], d[1]], [d[2], 0, -d[0]], [-d[1], d[0], 0]])
+        b1 = np.array([1, 1, -(d[0] + d[1]) / d[2]]); b1 /= np.linalg.norm(b1)
+        b2 = np.cross(b1, d); b2 /= np.linalg.norm(b2)
+        N = np.stack([b1, b2], 1)
+        A = float(r) * hat @ N
+        dv = np.sin(float(np.float32(0.05)) * 0.017453293) ** 2
+        ref = np.outer(d, d) * float(np.float32(0.02) ** 2) + A @ (np.eye(2) * dv) @ A.T
+        assert np.allclose(V, ref, rtol=1e-10, atol=1e-18)
+
+
+def test_delaunay_matches_qhull():
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        n = int(rng.integers(3, 300))
+        pts = rng.integers(-(1 << 22), 1 << 22, size=(n, 2))
+        if trial % 5 == 0:                       # clustered + collinear runs
+            pts[: n // 3, 1] = pts[0, 1]
+        pts = np.unique(pts, axis=0)
+        if len(pts) < 3:
+            continue
+        rng.shuffle(pts)
+        mine = oa.delaunay2d_int(pts)
+        try:
+            ref = Delaunay(pts.astype(np.float64)).simplices
+        except Exception:
+            continue
+        a = {tuple(sorted(t)) for t in mine.tolist()}
+        b = {tuple(sorted(t)) for t in ref.tolist()}
+        if a != b:
+            # differences can only be co-circular flips or zero-area hull slivers Qhull merges; check the empty-circle property
+            P = pts.astype(object)
+            for t in a ^ b:
+                x = [P[i] for i in t]
+                area2 = (x[1][0] - x[0][0]) * (x[2][1] - x[0][1]) - (x[1][1] - x[0][1]) * (x[2][0] - x[0][0])
+                assert area2 != 0 or t in b
+        for t in mine:                            # every face is counter-clockwise and has an empty circumcircle
+            A, B, Cc = (pts[i].astype(object) for i in t)
+            assert (B[0] - A[0]) * (Cc[1] - A[1]) - (B[1] - A[1]) * (Cc[0] - A[0]) > 0
+        idx = rng.integers(0, len(mine), size=min(30, len(mine)))
+        for f in idx:
+            A, B, Cc = (pts[i].astype(object) for i in mine[f])
+            for q in rng.integers(0, len(pts), size=20):
+                D = pts[q].astype(object)
+                adx, ady, bdx, bdy, cdx, cdy = A[0] - D[0], A[1] - D[1], B[0] - D[0], B[1] - D[1], Cc[0] - D[0], Cc[1] - D[1]
+                det = (adx * adx + ady * ady) * (bdx * cdy - bdy * cdx) + (bdx * bdx + bdy * bdy) * (cdx * ady - cdy * adx) + (cdx * cdx + cdy * cdy) * (adx * bdy - ady * bdx)
+                assert det <= 0
+
+
+def _greedy_append_bruteforce(frames, xi, res, target):
+    verts, grid = [], {}
+    for pts in frames:
+        step = max(1, round(len(pts) // target))
+        for i in range(0, len(pts), step):
+            p = pts[i]
+            g = tuple(int(np.round(np.float64(p[j]) / xi)) for j in range(3))
+            if g in grid:
+                continue
+            if verts:
+                V = np.asarray(verts, dtype=np.float32)
+                d = V - p
+                d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+                if np.sqrt(d2.min()) < xi:
+                    continue
+            grid[g] = len(verts)
+            verts.append(p.copy())
+    return np.asarray(verts, dtype=np.float32)
+
+
+def test_vertex_append_and_knn_match_bruteforce():
+    sensor, scans = synth.make_stream("avia", 3, seed=11, n_points=6000)
+    frames = [(s["body_full"].astype(np.float64) @ s["R_true"].T + s["t_true"]).astype(np.float32) for s in scans]
+    cfg = api.MeshConfig()
+    o = oa.OracleMesh(cfg)
+    for k, f in enumerate(frames):
+        o.push_frame(f, scans[k]["t_true"], k)
+    v, tris, flips = o.snapshot()
+    ref = _greedy_append_bruteforce(frames, cfg.points_minimum_scale, cfg.voxel_resolution, cfg.number_of_pts_append_to_map)
+    assert v.shape == ref.shape and np.array_equal(v, ref)
+    # exact kNN, float metric, ties by id
+    rng = np.random.default_rng(5)
+    q = (v[rng.integers(0, len(v), 64)] + rng.normal(0, 0.1, (64, 3))).astype(np.float32)
+    idx, d2 = o.knn(q, 20)
+    for i in range(len(q)):
+        d = v - q[i]
+        dd = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        order = np.lexsort((np.arange(len(v)), dd))[:20]
+        assert np.array_equal(idx[i], order)
+        assert np.array_equal(d2[i], dd[order])
+    # every live facet has its three vertices within the dilation reach and is stored sorted
+    assert np.all(tris[:, 0] < tris[:, 1]) and np.all(tris[:, 1] < tris[:, 2])
+    e = np.linalg.norm(v[tris[:, 0]] - v[tris[:, 1]], axis=1)
+    assert e.max() < 2 * (1.25 * cfg.voxel_resolution) + cfg.voxel_resolution * 3 ** 0.5 + 1e-3
+
+
+def test_fixed_point_sums_close_to_serial_double():
+    cfg = api.AVIA
+    sensor, scans = synth.make_stream("avia", 4, seed=9, ext_T=cfg.ext_T)
+    a, b = oa.OracleLio(cfg, sum_mode=0), oa.OracleLio(cfg, sum_mode=1)
+    for h in (a, b):
+        h.set_pose(scans[0]["R_true"], scans[0]["t_true"])
+        h.voxel_map_init(scans[0]["body_full"])
+    for k in (1, 2, 3):
+        for h in (a, b):
+            h.lio_state_estimation(scans[k]["body_ds"])
+            h.map_incremental_grow(scans[k]["body_ds"])
+        ia, ib = a.iter_stats(0), b.iter_stats(0)
+        assert np.allclose(ia["HTH"], ib["HTH"], rtol=1e-9, atol=1e-4)
+        assert np.allclose(a.get_state()[:12], b.get_state()[:12], rtol=1e-9, atol=1e-10)
