@@ -33,13 +33,161 @@ __global__ void k_reset_scan(ScanBuf sb, LioCtrl* ctrl, int copy_prop) {
         ctrl->stop = 0;
         ctrl->iters_run = 0;
         ctrl->rematch_num = 0;
+        for (int i = 0; i < IM_MAX_ITER; ++i) ctrl->blocks_done[i] = 0;
     }
+}
+
+// ---- IESKF solve on the device, executed by the LAST residual block of an iteration (no extra launch).
+// 18x18 partial-pivot LU inverse by one warp: lane i owns row i in registers, pivot row broadcast by shuffles.
+// Element update order is exactly that of the serial algorithm (lu_inverse18 / the oracle): bit-identical results.
+__device__ __noinline__ void warp_lu_inverse18(const double* a_in, double* lu, int* piv_s, double* inv_out, int lane) {
+    double r[18];
+    int piv = lane;
+#pragma unroll
+    for (int j = 0; j < 18; ++j) r[j] = (lane < 18) ? a_in[lane * 18 + j] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 18; ++k) {
+        // first maximum of |a[i][k]|, i >= k
+        double bv = (lane >= k && lane < 18) ? fabs(r[k]) : -1.0;
+        int bi = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        const int partner = (lane == k) ? bi : ((lane == bi) ? k : lane);
+        if (bi != k) {  // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 18; ++j) r[j] = __shfl_sync(0xffffffffu, r[j], partner);
+            piv = __shfl_sync(0xffffffffu, piv, partner);
+        }
+        const double pivv = __shfl_sync(0xffffffffu, r[k], k);
+        if (lane > k && lane < 18) r[k] = r[k] / pivv;
+#pragma unroll
+        for (int j = k + 1; j < 18; ++j) {
+            const double rkj = __shfl_sync(0xffffffffu, r[j], k);
+            if (lane > k && lane < 18) r[j] = r[j] - r[k] * rkj;
+        }
+    }
+    if (lane < 18) {
+#pragma unroll
+        for (int j = 0; j < 18; ++j) lu[lane * 18 + j] = r[j];
+        piv_s[lane] = piv;
+    }
+    __syncwarp();
+    if (lane < 18) {
+        const int c = lane;
+        double y[18];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) {
+            double s = (piv_s[i] == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int j = 0; j < i; ++j) s = s - lu[i * 18 + j] * y[j];
+            y[i] = s;
+        }
+#pragma unroll
+        for (int i = 17; i >= 0; --i) {
+            double s = y[i];
+#pragma unroll
+            for (int j = i + 1; j < 18; ++j) s = s - lu[i * 18 + j] * y[j];
+            y[i] = s / lu[i * 18 + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 18; ++i) inv_out[i * 18 + c] = y[i];
+    }
+    __syncwarp();
+}
+
+// same arithmetic as ieskf_solve (lio_core.cuh), block-cooperative with the two LU inverses done by warp 0
+__device__ __noinline__ void ieskf_solve_block(const LioParams& P, LioCtrl* ctrl, int iter, SolveScratch* S) {
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    double* state = ctrl->state;
+    double* cov = state + 24;
+    for (int e = tid; e < 29; e += nthreads) {
+        const long long hi = (long long)*(volatile unsigned long long*)&ctrl->acc[iter][2 * e];
+        const long long lo = (long long)*(volatile unsigned long long*)&ctrl->acc[iter][2 * e + 1];
+        const double v = fx_value(hi, lo);
+        if (e < 21) {
+            int ei = 0, base = 0;
+            while (e >= base + (6 - ei)) { base += 6 - ei; ++ei; }
+            const int ej = ei + (e - base);
+            S->HTH[ei * 6 + ej] = v;
+            S->HTH[ej * 6 + ei] = v;
+        } else if (e < 27) {
+            S->HTz[e - 21] = v;
+        } else if (e == 27) {
+            ctrl->stats[iter].total_residual = v;
+        } else {
+            ctrl->stats[iter].n_match = (double)((hi << 32) + lo);
+        }
+    }
+    for (int i = tid; i < 324; i += nthreads) S->a[i] = cov[i];
+    __syncthreads();
+    if (warp == 0) warp_lu_inverse18(S->a, S->ncov, S->piv, S->Pinv, lane);
+    __syncthreads();
+    for (int idx = tid; idx < 324; idx += nthreads) {
+        const int i = idx / 18, j = idx % 18;
+        const double hth = (i < 6 && j < 6) ? S->HTH[i * 6 + j] : 0.0;
+        S->a[idx] = hth + S->Pinv[idx];
+    }
+    __syncthreads();
+    if (warp == 0) warp_lu_inverse18(S->a, S->ncov, S->piv, S->K1, lane);
+    __syncthreads();
+    for (int idx = tid; idx < 18 * 6; idx += nthreads) {
+        const int i = idx / 6, j = idx % 6;
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) s = s + S->K1[i * 18 + k] * S->HTH[k * 6 + j];
+        ctrl->G[i * 18 + j] = s;
+    }
+    if (tid == 0) state_minus(ctrl->state_prop, state, S->vec);
+    __syncthreads();
+    for (int i = tid; i < 18; i += nthreads) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = 0; k < 6; ++k) s1 = s1 + S->K1[i * 18 + k] * S->HTz[k];
+        for (int k = 0; k < 6; ++k) s2 = s2 + ctrl->G[i * 18 + k] * S->vec[k];
+        S->sol[i] = (s1 + S->vec[i]) - s2;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        state_plus(state, S->sol);
+        const double* sol = S->sol;
+        const double rn = sqrt((sol[0] * sol[0] + sol[1] * sol[1]) + sol[2] * sol[2]);
+        const double tn = sqrt((sol[3] * sol[3] + sol[4] * sol[4]) + sol[5] * sol[5]);
+        const int converged = ((rn * 57.3 < 0.01) && (tn * 100 < 0.015)) ? 1 : 0;
+        IterStats& st = ctrl->stats[iter];
+        for (int i = 0; i < 36; ++i) st.HTH[i] = S->HTH[i];
+        for (int i = 0; i < 6; ++i) st.HTz[i] = S->HTz[i];
+        for (int i = 0; i < 18; ++i) st.solution[i] = sol[i];
+        st.converged = converged;
+        ctrl->iters_run = iter + 1;
+        int rematch = ctrl->rematch_num;
+        if (converged || ((rematch == 0) && (iter == P.max_iter - 2))) rematch++;
+        ctrl->rematch_num = rematch;
+        S->flags[0] = (rematch >= 2 || iter == P.max_iter - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (S->flags[0]) {
+        for (int idx = tid; idx < 324; idx += nthreads) {
+            const int i = idx / 18, j = idx % 18;
+            double s = 0.0;
+            for (int k = 0; k < 18; ++k) {
+                const double ig = ((i == k) ? 1.0 : 0.0) - ((k < 6) ? ctrl->G[i * 18 + k] : 0.0);
+                s = s + ig * cov[k * 18 + j];
+            }
+            S->ncov[idx] = s;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < 324; idx += nthreads) cov[idx] = S->ncov[idx];
+        if (tid == 0) ctrl->stop = 1;
+    }
+    __syncthreads();
 }
 
 // K2+K3: one thread per scan point; the block's 30 fixed-point sums are reduced with warp shuffles
 // (integer adds: exact, order-free) and folded into the iteration's global accumulators with 60 atomics.
 #define RES_THREADS 128
-__global__ void __launch_bounds__(RES_THREADS) k_residual(VoxelMapDev map, LioParams P, ScanBuf sb, LioCtrl* ctrl, int iter, int n) {
+__global__ void __launch_bounds__(RES_THREADS) k_residual(VoxelMapDev map, LioParams P, ScanBuf sb, LioCtrl* ctrl, int iter, int n, int fused_solve) {
     __shared__ double s_state[24 + 6 * 18];
     __shared__ long long s_part[RES_THREADS / 32][IM_NTERMS];
     if (ctrl->stop) return;
@@ -72,6 +220,18 @@ __global__ void __launch_bounds__(RES_THREADS) k_residual(VoxelMapDev map, LioPa
             atomicAdd(&ctrl->acc[iter][2 * threadIdx.x], (unsigned long long)(v >> 32));
             atomicAdd(&ctrl->acc[iter][2 * threadIdx.x + 1], (unsigned long long)(v & 0xffffffffLL));
         }
+    }
+    if (!fused_solve) return;
+    // the last block to publish its sums runs the 18x18 solve and the state update of this iteration
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl->blocks_done[iter], 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __shared__ SolveScratch S;
+        __threadfence();
+        ieskf_solve_block(P, ctrl, iter, &S);
     }
 }
 
@@ -220,6 +380,7 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     h->d_body_own = d_body;
     IM_CUDA(dev_alloc(h, &sb.body_cov, ms * 6));
     IM_CUDA(dev_alloc(h, &sb.p_imu, ms * 3));
+    IM_CUDA(dev_alloc(h, &sb.bv_imu, ms * 6));
     IM_CUDA(dev_alloc(h, &sb.match_node, ms, 0xFF));
     IM_CUDA(dev_alloc(h, &sb.match_layer, ms, 0));
     IM_CUDA(dev_alloc(h, &sb.pw, ms * 3));
@@ -314,8 +475,7 @@ static void launch_estimate(immesh_lio* h, int n) {
     IM_LAUNCH(k_prepare, grid_for(h, n, 128), 128, 0, h->stream, h->P, h->sb, n);
     const int g = grid_for(h, n, RES_THREADS, 4);
     for (int it = 0; it < h->P.max_iter; ++it) {
-        IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n);
-        IM_LAUNCH(k_solve, 1, SOLVE_THREADS, 0, h->stream, h->P, h->d_ctrl, it);
+        IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n, 1);
     }
 }
 
@@ -403,7 +563,7 @@ int immesh_residual_build(immesh_lio_t* h, const float* body, int n, int* index_
     *n_out = 0;
     if (n == 0) return IMMESH_OK;
     IM_LAUNCH(k_prepare, grid_for(h, n, 128), 128, 0, h->stream, h->P, h->sb, n);
-    IM_LAUNCH(k_residual, grid_for(h, n, RES_THREADS, 4), RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, 0, n);
+    IM_LAUNCH(k_residual, grid_for(h, n, RES_THREADS, 4), RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, 0, n, 0);
     IM_LAUNCH(k_gather_ptpl, grid_for(h, n, 128), 128, 0, h->stream, h->map, h->sb, n, h->d_ptpl);
     IM_CUDA(cudaGetLastError());
     std::vector<int> node(n), layer(n);

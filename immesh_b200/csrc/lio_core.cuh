@@ -40,6 +40,7 @@ struct LioCtrl {
     int iters_run;
     int rematch_num;
     int pad_;
+    int blocks_done[IM_MAX_ITER];  // residual blocks that have published their sums (the last one runs the solve)
 };
 
 struct ScanBuf {
@@ -47,6 +48,7 @@ struct ScanBuf {
     const float* body;   // [n][3] body-frame (LiDAR) points, float like pcl::PointXYZI
     double* body_cov;    // [n][6]
     double* p_imu;       // [n][3]  R_ext p + t_ext (z==0 -> 0.001 rule applied first, :1305-1312)
+    double* bv_imu;      // [n][6]  calcBodyVar at the IMU-frame point of the raw scan point (weights, :1498-1521); state independent
     int* match_node;     // [n] plane node of the accepted match, -1 otherwise (last residual pass)
     int* match_layer;    // [n]
     float* pw;           // [n][3] world points of the growth pass
@@ -74,6 +76,12 @@ IM_HDN inline void prepare_point(const LioParams& P, const ScanBuf& sb, int i) {
     sb.p_imu[(size_t)i * 3 + 0] = q[0] + P.extT[0];
     sb.p_imu[(size_t)i * 3 + 1] = q[1] + P.extT[1];
     sb.p_imu[(size_t)i * 3 + 2] = q[2] + P.extT[2];
+    // measurement covariance used by the IESKF weights: evaluated at R_ext p + t_ext of the RAW point (:1496-1521)
+    const double pr[3] = {(double)sb.body[i * 3 + 0], (double)sb.body[i * 3 + 1], (double)sb.body[i * 3 + 2]};
+    double qi[3];
+    m3_vec(P.extR, pr, qi);
+    qi[0] = qi[0] + P.extT[0]; qi[1] = qi[1] + P.extT[1]; qi[2] = qi[2] + P.extT[2];
+    calc_body_var(qi, P.dept_err, P.calib_laser ? P.dir_var_calib : P.dir_var, sb.bv_imu + (size_t)i * 6);
 }
 
 // world covariance for matching: R S_b R^T + (-[p]x) S_R (-[p]x)^T + S_t   (voxel_mapping.cpp:1356)
@@ -120,10 +128,8 @@ IM_HDN inline bool residual_point(const VoxelMapDev& map, const LioParams& P, co
     double pw2[3];
     m3_vec(R, p_imu, pw2);
     pw2[0] = pw2[0] + t[0]; pw2[1] = pw2[1] + t[1]; pw2[2] = pw2[2] + t[2];
-    double bv[6], Sb[9], RRe[9], wv[6];
-    double pv3[3] = {p_imu[0], p_imu[1], p_imu[2]};
-    calc_body_var(pv3, P.dept_err, P.calib_laser ? P.dir_var_calib : P.dir_var, bv);  // evaluated at the IMU-frame point (:1498-1521)
-    s6_full(bv, Sb);
+    double Sb[9], RRe[9], wv[6];
+    s6_full(sb.bv_imu + (size_t)i * 6, Sb);  // calcBodyVar at the IMU-frame point (:1498-1521), precomputed in prepare_point
     m3_mul(R, P.extR, RRe);
     congr6(RRe, Sb, wv);
     const double sigma_l = plane_sigma(pw2, pl.center, pl.normal, pl.pv);

@@ -244,17 +244,35 @@ IM_HDN inline void cand_init(const MeshDev& M, const MeshParams& P, const FrameB
     }
     // occupied xi-cell (:473-481)
     if (table_find(M.gkeys, M.gmask, gkey) >= 0) return;
-    // nearest existing vertex closer than xi (:507-517): any vertex with sqrtf(d2) < xi lies in the 27 surrounding cells
-    for (int dx = -1; dx <= 1; ++dx)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dz = -1; dz <= 1; ++dz) {
-                const int s = table_find(M.gkeys, M.gmask, pack_ikey(gx + dx, gy + dy, gz + dz));
-                if (s < 0) continue;
-                const int v = M.gval[s];
-                if (v < 0) continue;
-                const float4 q = M.vpos[v];
-                if ((double)sqrtf(dist2f(px, py, pz, q.x, q.y, q.z)) < P.xi) return;
-            }
+    // nearest existing vertex closer than xi (:507-517): any vertex with sqrtf(d2) < xi lies in the 27 surrounding cells.
+    // The 27 first-probe loads are issued together (independent addresses) before any of them is consumed.
+    {
+        unsigned long long want[27], got[27];
+        unsigned int slot[27];
+#pragma unroll
+        for (int q = 0; q < 27; ++q) {
+            want[q] = pack_ikey(gx + (q / 9 - 1), gy + ((q / 3) % 3 - 1), gz + (q % 3 - 1));
+            slot[q] = hash_key(want[q]) & M.gmask;
+        }
+#pragma unroll
+        for (int q = 0; q < 27; ++q) got[q] = M.gkeys[slot[q]];
+        int vid[27];
+#pragma unroll
+        for (int q = 0; q < 27; ++q) {
+            int s = -1;
+            if (got[q] == want[q]) s = (int)slot[q];
+            else if (got[q] != IM_EMPTY_KEY) s = table_find(M.gkeys, M.gmask, want[q]);  // collision chain: rare
+            vid[q] = s >= 0 ? M.gval[s] : -1;
+        }
+        bool close = false;
+#pragma unroll
+        for (int q = 0; q < 27; ++q) {
+            if (vid[q] < 0) continue;
+            const float4 v = M.vpos[vid[q]];
+            if ((double)sqrtf(dist2f(px, py, pz, v.x, v.y, v.z)) < P.xi) close = true;
+        }
+        if (close) return;
+    }
     // survives the old map: enters the per-frame candidate grid, decided in cand_resolve
     F.cand_status[c] = CAND_UNDECIDED;
     int cc = 0;

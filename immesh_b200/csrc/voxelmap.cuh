@@ -12,7 +12,7 @@
 //
 // Layout in HBM (struct-of-pools, index-linked, no pointers):
 //   keys[cap] u64 + root_node[cap] i32        open addressing, linear probing, 16 B / slot pair
-//   NodeRec[max_nodes]   96 B                 children, voxel centre, counters, chunk list head/tail
+//   NodeRec[max_nodes]  176 B                 children, voxel centre, counters, chunk list head/tail, running point sums
 //   PlaneRec[max_nodes]  256 B (2 x 128 B lines, first line = everything the residual range test reads)
 //   Chunk[max_chunks]    512 B                8 points SoA: xyz f32 + symmetric covariance 6 x f64
 // Work decomposition: residual selection = 1 thread / scan point (read-only map); update =
@@ -71,6 +71,9 @@ struct alignas(16) NodeRec {
     int update_enable;
     int octo_state;
     int root_slot;
+    double sum_p[3];   // running sum of the stored points, in append order (= the reference's loop order in init_plane)
+    double sum_pp[6];  // running sum of p p^T, upper triangle
+    double pad_;
 };
 struct alignas(16) Chunk {
     float x[8], y[8], z[8];
@@ -79,7 +82,7 @@ struct alignas(16) Chunk {
     double var[6][8];
 };
 static_assert(sizeof(PlaneRec) == 256, "PlaneRec must be 256 B");
-static_assert(sizeof(NodeRec) == 96, "NodeRec must be 96 B");
+static_assert(sizeof(NodeRec) == 176, "NodeRec must be 176 B");
 static_assert(sizeof(Chunk) == 512, "Chunk must be 512 B");
 
 enum : int {
@@ -226,6 +229,8 @@ IM_HD void init_node(const VoxelMapDev& m, int id, int layer, const double* vc, 
     n.update_enable = 1;
     n.octo_state = 0;
     n.root_slot = root_slot;
+    for (int i = 0; i < 3; ++i) n.sum_p[i] = 0.0;
+    for (int i = 0; i < 6; ++i) n.sum_pp[i] = 0.0;
     PlaneRec& p = m.planes[id];
     p.center[0] = p.center[1] = p.center[2] = 0.0;
     p.normal[0] = p.normal[1] = p.normal[2] = 0.0;
@@ -263,6 +268,10 @@ IM_HD void node_append(const VoxelMapDev& m, int nd, float x, float y, float z, 
     c.x[slot] = x; c.y[slot] = y; c.z[slot] = z;
     for (int k = 0; k < 6; ++k) c.var[k][slot] = var6[k];
     n.n_pts = pos + 1;
+    const double dx = (double)x, dy = (double)y, dz = (double)z;
+    n.sum_pp[0] += dx * dx; n.sum_pp[1] += dx * dy; n.sum_pp[2] += dx * dz;
+    n.sum_pp[3] += dy * dy; n.sum_pp[4] += dy * dz; n.sum_pp[5] += dz * dz;
+    n.sum_p[0] += dx; n.sum_p[1] += dy; n.sum_p[2] += dz;
 }
 // std::vector<Point_with_var>().swap(m_temp_points_): chunks go to the pending-free list (recycled between scans)
 IM_HD void node_free_points(const VoxelMapDev& m, int nd) {
@@ -277,6 +286,8 @@ IM_HD void node_free_points(const VoxelMapDev& m, int nd) {
     n.first_chunk = -1;
     n.last_chunk = -1;
     n.n_pts = 0;
+    for (int i = 0; i < 3; ++i) n.sum_p[i] = 0.0;
+    for (int i = 0; i < 6; ++i) n.sum_pp[i] = 0.0;
 }
 
 // ------------------------------------------------------------------ init_plane (voxel_loc.cpp:47-139)
@@ -292,19 +303,11 @@ IM_HDN inline void init_plane(const VoxelMapDev& m, const LioParams& P, int nd, 
     const NodeRec& n = m.nodes[nd];
     PlaneRec& pl = m.planes[nd];
     const int np = n.n_pts;
-    double cov[6] = {0, 0, 0, 0, 0, 0}, c[3] = {0, 0, 0};
-    {
-        int ch = n.first_chunk;
-        for (int i = 0; i < np; ++i) {
-            const int s = i & 7;
-            if (i && s == 0) ch = m.chunks[ch].next;
-            const Chunk& ck = m.chunks[ch];
-            const double x = (double)ck.x[s], y = (double)ck.y[s], z = (double)ck.z[s];
-            cov[0] += x * x; cov[1] += x * y; cov[2] += x * z;
-            cov[3] += y * y; cov[4] += y * z; cov[5] += z * z;
-            c[0] += x; c[1] += y; c[2] += z;
-        }
-    }
+    // centre / covariance sums are kept incrementally by node_append in append order: bit-identical to the
+    // reference's loop over m_temp_points_ (voxel_loc.cpp:55-59)
+    double cov[6], c[3];
+    for (int i = 0; i < 6; ++i) cov[i] = n.sum_pp[i];
+    for (int i = 0; i < 3; ++i) c[i] = n.sum_p[i];
     const double dn = (double)np;
     c[0] = c[0] / dn; c[1] = c[1] / dn; c[2] = c[2] / dn;
     cov[0] = cov[0] / dn - c[0] * c[0]; cov[1] = cov[1] / dn - c[0] * c[1]; cov[2] = cov[2] / dn - c[0] * c[2];
@@ -323,7 +326,8 @@ IM_HDN inline void init_plane(const VoxelMapDev& m, const LioParams& P, int nd, 
         const double invn = 1.0 / dn;
         const int m0 = (imin == 0) ? 1 : 0;            // the two rows of F that are not identically zero
         const int m1 = (imin == 2) ? 1 : 2;
-        const double s0 = dn * (ev[imin] - ev[m0]), s1 = dn * (ev[imin] - ev[m1]);
+        // (p - c) / (n (lambda_min - lambda_m)) as a multiplication by the reciprocal
+        const double s0 = 1.0 / (dn * (ev[imin] - ev[m0])), s1 = 1.0 / (dn * (ev[imin] - ev[m1]));
         double M0[9], M1[9];
         for (int j = 0; j < 3; ++j)
             for (int k = 0; k < 3; ++k) {
@@ -339,11 +343,11 @@ IM_HDN inline void init_plane(const VoxelMapDev& m, const LioParams& P, int nd, 
             double F[9];
             F[imin * 3 + 0] = 0.0; F[imin * 3 + 1] = 0.0; F[imin * 3 + 2] = 0.0;
             {
-                const double v0 = (px - c[0]) / s0, v1 = (py - c[1]) / s0, v2 = (pz - c[2]) / s0;
+                const double v0 = (px - c[0]) * s0, v1 = (py - c[1]) * s0, v2 = (pz - c[2]) * s0;
                 for (int k = 0; k < 3; ++k) F[m0 * 3 + k] = (v0 * M0[0 * 3 + k] + v1 * M0[1 * 3 + k]) + v2 * M0[2 * 3 + k];
             }
             {
-                const double v0 = (px - c[0]) / s1, v1 = (py - c[1]) / s1, v2 = (pz - c[2]) / s1;
+                const double v0 = (px - c[0]) * s1, v1 = (py - c[1]) * s1, v2 = (pz - c[2]) * s1;
                 for (int k = 0; k < 3; ++k) F[m1 * 3 + k] = (v0 * M1[0 * 3 + k] + v1 * M1[1 * 3 + k]) + v2 * M1[2 * 3 + k];
             }
             double A[9], S[9], T[9];

@@ -219,10 +219,12 @@ class LioOracle {
         (void)imid;
         if (ev[imin] < (double)planer_threshold) {
             const double invn = 1.0 / dn;
+            // F_m = (p - c)^T / (n (lambda_min - lambda_m)) * (...)  (voxel_loc.cpp:88-91).  The scalar division is applied as a
+            // multiplication by the reciprocal (one division per refit instead of three per point; <= 1 ulp per element).
             double Mm[3][9], sm[3];
             for (int m = 0; m < 3; ++m) {
                 if (m == imin) continue;
-                sm[m] = dn * (ev[imin] - ev[m]);
+                sm[m] = 1.0 / (dn * (ev[imin] - ev[m]));
                 for (int j = 0; j < 3; ++j)
                     for (int k = 0; k < 3; ++k)
                         Mm[m][j * 3 + k] = U[j * 3 + m] * U[k * 3 + imin] + U[j * 3 + imin] * U[k * 3 + m];
@@ -232,7 +234,7 @@ class LioOracle {
                 double F[9];
                 for (int m = 0; m < 3; ++m) {
                     if (m != imin) {
-                        const double v0 = (pv.pb[0] - c[0]) / sm[m], v1 = (pv.pb[1] - c[1]) / sm[m], v2 = (pv.pb[2] - c[2]) / sm[m];
+                        const double v0 = (pv.pb[0] - c[0]) * sm[m], v1 = (pv.pb[1] - c[1]) * sm[m], v2 = (pv.pb[2] - c[2]) * sm[m];
                         for (int k = 0; k < 3; ++k) F[m * 3 + k] = (v0 * Mm[m][0 * 3 + k] + v1 * Mm[m][1 * 3 + k]) + v2 * Mm[m][2 * 3 + k];
                     } else {
                         F[m * 3 + 0] = 0; F[m * 3 + 1] = 0; F[m * 3 + 2] = 0;

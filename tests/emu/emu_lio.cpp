@@ -24,7 +24,7 @@ struct immesh_lio {
     std::vector<PlaneRec> planes;
     std::vector<Chunk> chunks;
     std::vector<float> body, pw;
-    std::vector<double> body_cov, p_imu, var, sortkey;
+    std::vector<double> body_cov, p_imu, bv_imu, var, sortkey;
     std::vector<int> match_node, match_layer, slot, seg, seg2, slot_count, slot_offset, slot_cursor, touched;
     int counters[16];
     int max_scan;
@@ -75,11 +75,11 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     m.err = &h->counters[4]; m.n_roots = &h->counters[5];
     const int ms = h->max_scan;
     h->body.resize((size_t)ms * 3); h->pw.resize((size_t)ms * 3);
-    h->body_cov.resize((size_t)ms * 6); h->p_imu.resize((size_t)ms * 3); h->var.resize((size_t)ms * 6); h->sortkey.resize(ms);
+    h->body_cov.resize((size_t)ms * 6); h->p_imu.resize((size_t)ms * 3); h->bv_imu.resize((size_t)ms * 6); h->var.resize((size_t)ms * 6); h->sortkey.resize(ms);
     h->match_node.assign(ms, -1); h->match_layer.assign(ms, 0); h->slot.resize(ms); h->seg.resize(ms); h->seg2.resize(ms); h->touched.resize(ms);
     h->slot_count.assign(cap, 0); h->slot_offset.assign(cap, 0); h->slot_cursor.assign(cap, 0);
     ScanBuf& sb = h->sb;
-    sb.n = 0; sb.body = h->body.data(); sb.body_cov = h->body_cov.data(); sb.p_imu = h->p_imu.data();
+    sb.n = 0; sb.body = h->body.data(); sb.body_cov = h->body_cov.data(); sb.p_imu = h->p_imu.data(); sb.bv_imu = h->bv_imu.data();
     sb.match_node = h->match_node.data(); sb.match_layer = h->match_layer.data(); sb.pw = h->pw.data(); sb.var = h->var.data();
     sb.sortkey = h->sortkey.data(); sb.slot = h->slot.data(); sb.seg = h->seg.data();
     sb.slot_count = h->slot_count.data(); sb.slot_offset = h->slot_offset.data(); sb.slot_cursor = h->slot_cursor.data();
