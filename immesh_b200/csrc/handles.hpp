@@ -28,6 +28,7 @@ struct immesh_lio {
     int max_nodes = 0, max_chunks = 0, max_scan = 0;
     int n_sm = 148;
     int last_n = 0;
+    int fused_solve = 0;  // 1: the last residual block of an iteration runs the solve (no separate launch)
     double last_ms[3] = {0, 0, 0};
     std::vector<void*> allocs;
 };

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -40,15 +41,14 @@ __global__ void k_reset_scan(ScanBuf sb, LioCtrl* ctrl, int copy_prop) {
 // ---- IESKF solve on the device, executed by the LAST residual block of an iteration (no extra launch).
 // 18x18 partial-pivot LU inverse by one warp: lane i owns row i in registers, pivot row broadcast by shuffles.
 // Element update order is exactly that of the serial algorithm (lu_inverse18 / the oracle): bit-identical results.
-__device__ __noinline__ void warp_lu_inverse18(const double* a_in, double* lu, int* piv_s, double* inv_out, int lane) {
-    double r[18];
-    int piv = lane;
-#pragma unroll
-    for (int j = 0; j < 18; ++j) r[j] = (lane < 18) ? a_in[lane * 18 + j] : 0.0;
-#pragma unroll
+__device__ __noinline__ void warp_lu_inverse18(const double* a_in, double* lu /*[18][19] shared*/, int* piv_s, double* inv_out, int lane) {
+    // rows live in shared memory with a padded stride (19) so that a column access by 18 lanes is nearly conflict free
+    for (int idx = lane; idx < 324; idx += 32) lu[(idx / 18) * 19 + (idx % 18)] = a_in[idx];
+    if (lane < 18) piv_s[lane] = lane;
+    __syncwarp();
     for (int k = 0; k < 18; ++k) {
         // first maximum of |a[i][k]|, i >= k
-        double bv = (lane >= k && lane < 18) ? fabs(r[k]) : -1.0;
+        double bv = (lane >= k && lane < 18) ? fabs(lu[lane * 19 + k]) : -1.0;
         int bi = lane;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -56,52 +56,43 @@ __device__ __noinline__ void warp_lu_inverse18(const double* a_in, double* lu, i
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        const int partner = (lane == k) ? bi : ((lane == bi) ? k : lane);
-        if (bi != k) {  // warp-uniform
-#pragma unroll
-            for (int j = 0; j < 18; ++j) r[j] = __shfl_sync(0xffffffffu, r[j], partner);
-            piv = __shfl_sync(0xffffffffu, piv, partner);
+        if (bi != k) {
+            if (lane < 18) { const double t = lu[k * 19 + lane]; lu[k * 19 + lane] = lu[bi * 19 + lane]; lu[bi * 19 + lane] = t; }
+            if (lane == 0) { const int t = piv_s[k]; piv_s[k] = piv_s[bi]; piv_s[bi] = t; }
         }
-        const double pivv = __shfl_sync(0xffffffffu, r[k], k);
-        if (lane > k && lane < 18) r[k] = r[k] / pivv;
-#pragma unroll
-        for (int j = k + 1; j < 18; ++j) {
-            const double rkj = __shfl_sync(0xffffffffu, r[j], k);
-            if (lane > k && lane < 18) r[j] = r[j] - r[k] * rkj;
+        __syncwarp();
+        const double pivv = lu[k * 19 + k];
+        __syncwarp();
+        if (lane > k && lane < 18) lu[lane * 19 + k] = lu[lane * 19 + k] / pivv;
+        __syncwarp();
+        const int m = 17 - k;
+        for (int idx = lane; idx < m * m; idx += 32) {
+            const int i = k + 1 + idx / m, j = k + 1 + idx % m;
+            lu[i * 19 + j] = lu[i * 19 + j] - lu[i * 19 + k] * lu[k * 19 + j];
         }
+        __syncwarp();
     }
     if (lane < 18) {
-#pragma unroll
-        for (int j = 0; j < 18; ++j) lu[lane * 18 + j] = r[j];
-        piv_s[lane] = piv;
-    }
-    __syncwarp();
-    if (lane < 18) {
+        // column c of the inverse, substituted in place in inv_out (y[i] lives at inv_out[i][c])
         const int c = lane;
-        double y[18];
-#pragma unroll
         for (int i = 0; i < 18; ++i) {
             double s = (piv_s[i] == c) ? 1.0 : 0.0;
-#pragma unroll
-            for (int j = 0; j < i; ++j) s = s - lu[i * 18 + j] * y[j];
-            y[i] = s;
+            for (int j = 0; j < i; ++j) s = s - lu[i * 19 + j] * inv_out[j * 18 + c];
+            inv_out[i * 18 + c] = s;
         }
-#pragma unroll
         for (int i = 17; i >= 0; --i) {
-            double s = y[i];
-#pragma unroll
-            for (int j = i + 1; j < 18; ++j) s = s - lu[i * 18 + j] * y[j];
-            y[i] = s / lu[i * 18 + i];
+            double s = inv_out[i * 18 + c];
+            for (int j = i + 1; j < 18; ++j) s = s - lu[i * 19 + j] * inv_out[j * 18 + c];
+            inv_out[i * 18 + c] = s / lu[i * 19 + i];
         }
-#pragma unroll
-        for (int i = 0; i < 18; ++i) inv_out[i * 18 + c] = y[i];
     }
     __syncwarp();
 }
 
 // same arithmetic as ieskf_solve (lio_core.cuh), block-cooperative with the two LU inverses done by warp 0
 __device__ __noinline__ void ieskf_solve_block(const LioParams& P, LioCtrl* ctrl, int iter, SolveScratch* S) {
-    const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: no divergence handling around the LU shuffles
     double* state = ctrl->state;
     double* cov = state + 24;
     for (int e = tid; e < 29; e += nthreads) {
@@ -124,7 +115,7 @@ __device__ __noinline__ void ieskf_solve_block(const LioParams& P, LioCtrl* ctrl
     }
     for (int i = tid; i < 324; i += nthreads) S->a[i] = cov[i];
     __syncthreads();
-    if (warp == 0) warp_lu_inverse18(S->a, S->ncov, S->piv, S->Pinv, lane);
+    if (warp == 0) warp_lu_inverse18(S->a, S->lu, S->piv, S->Pinv, lane);
     __syncthreads();
     for (int idx = tid; idx < 324; idx += nthreads) {
         const int i = idx / 18, j = idx % 18;
@@ -132,7 +123,7 @@ __device__ __noinline__ void ieskf_solve_block(const LioParams& P, LioCtrl* ctrl
         S->a[idx] = hth + S->Pinv[idx];
     }
     __syncthreads();
-    if (warp == 0) warp_lu_inverse18(S->a, S->ncov, S->piv, S->K1, lane);
+    if (warp == 0) warp_lu_inverse18(S->a, S->lu, S->piv, S->K1, lane);
     __syncthreads();
     for (int idx = tid; idx < 18 * 6; idx += nthreads) {
         const int i = idx / 6, j = idx % 6;
@@ -239,6 +230,12 @@ __global__ void __launch_bounds__(RES_THREADS) k_residual(VoxelMapDev map, LioPa
 __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(LioParams P, LioCtrl* ctrl, int iter) {
     __shared__ SolveScratch S;
     ieskf_solve(P, ctrl, iter, &S, threadIdx.x, blockDim.x);
+}
+
+__global__ void __launch_bounds__(128) k_solve_warp(LioParams P, LioCtrl* ctrl, int iter) {
+    __shared__ SolveScratch S;
+    if (ctrl->stop) return;
+    ieskf_solve_block(P, ctrl, iter, &S);
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS) k_predict(LioCtrl* ctrl, double dt, double cov_gyr, double cov_acc) {
@@ -349,6 +346,7 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return im_fail(IMMESH_E_NO_DEVICE, "no CUDA device: immesh_b200 has no CPU path");
     immesh_lio* h = new immesh_lio();
     fill_params(cfg, h->P);
+    h->fused_solve = std::getenv("IMMESH_FUSED_SOLVE") ? std::atoi(std::getenv("IMMESH_FUSED_SOLVE")) : 0;
     const int caplog = cfg->hash_capacity_log2 ? cfg->hash_capacity_log2 : 22;
     h->cap = (size_t)1 << caplog;
     h->max_nodes = cfg->max_nodes ? cfg->max_nodes : (4 << 20);
@@ -475,7 +473,12 @@ static void launch_estimate(immesh_lio* h, int n) {
     IM_LAUNCH(k_prepare, grid_for(h, n, 128), 128, 0, h->stream, h->P, h->sb, n);
     const int g = grid_for(h, n, RES_THREADS, 4);
     for (int it = 0; it < h->P.max_iter; ++it) {
-        IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n, 1);
+        if (h->fused_solve) {
+            IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n, 1);
+        } else {
+            IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n, 0);
+            IM_LAUNCH(k_solve_warp, 1, 128, 0, h->stream, h->P, h->d_ctrl, it);
+        }
     }
 }
 

@@ -217,6 +217,7 @@ struct SolveScratch {
     double Pinv[324];
     double K1[324];
     double ncov[324];
+    double lu[18 * 19];
     double HTH[36];
     double HTz[6];
     double vec[18];

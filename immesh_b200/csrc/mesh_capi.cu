@@ -110,8 +110,24 @@ __global__ void __launch_bounds__(128) k_voxel_mesh(MeshDev M, MeshParams P, Fra
     const int nw = min(M.cnt[6], F.max_work);
     for (int w = blockIdx.x; w < nw; w += gridDim.x) {
         const int n = F.work_n_ids[w];
-        if (n > lo && n <= MAXD) voxel_mesh<MAXD>(M, P, F, w, S, threadIdx.x, blockDim.x);
+        if (n < 0 || (n > lo && n <= MAXD)) voxel_mesh<MAXD>(M, P, F, w, S, threadIdx.x, blockDim.x);
         __syncthreads();
+    }
+}
+// warp-level stage B: four independent voxels per block, voxels claimed dynamically
+__global__ void __launch_bounds__(128) k_voxel_mesh_warp(MeshDev M, MeshParams P, FrameBuf F) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    MeshWarpSmem<256>* S = reinterpret_cast<MeshWarpSmem<256>*>(smem_raw) + warp;
+    const int nw = min(M.cnt[6], F.max_work);
+    while (true) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&M.cnt[19], 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= nw) break;
+        voxel_mesh_warp<256>(M, P, F, w, S, lane, 32);
+        __syncwarp();
     }
 }
 __global__ void __launch_bounds__(128) k_push_remove(MeshDev M, FrameBuf F) {
@@ -323,7 +339,7 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(cudaMallocHost((void**)&h->h_pts, mc * 3 * sizeof(float)));
     IM_CUDA(cudaMallocHost((void**)&h->h_cnt, 32 * sizeof(int)));
     IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<1024>)));
-    IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<256>)));
+    IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(MeshWarpSmem<256>))));
     std::memset(h->last_cnt, 0, sizeof(h->last_cnt));
     IM_CUDA(cudaDeviceSynchronize());
     *out = h;
@@ -430,7 +446,7 @@ static int mesh_push_impl(immesh_mesh_t* h, const float* world_xyz, int n, const
     IM_CUDA(cudaEventRecord(h->ev[2], st));
     if (F.m > 0) {
         IM_LAUNCH(k_voxel_dilate, h->n_sm * 4, 128, 0, st, h->M, P, F);
-        IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * 6, 128, sizeof(MeshSmem<256>), st, h->M, P, F, 0);
+        IM_LAUNCH(k_voxel_mesh_warp, h->n_sm * 2, 128, 4 * sizeof(MeshWarpSmem<256>), st, h->M, P, F);
         IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st, h->M, P, F, 256);
     }
     IM_CUDA(cudaEventRecord(h->ev[3], st));

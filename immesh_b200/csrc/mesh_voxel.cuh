@@ -109,6 +109,61 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
         for (int qi = warp; qi < nq; qi += nwarps) {
             const int qv = S->q[qi];
             const float4 qp = M.vpos[qv];
+#if defined(__CUDA_ARCH__)
+            if (nc <= 512) {
+                // fast path: every lane keeps the distances of its <= 16 candidates in registers (computed once); 20 rounds
+                // of warp arg-min over the lanes' current minima, the winning lane retires its entry and rescans its 16.
+                float dreg[16];
+                int ireg[16];
+#pragma unroll
+                for (int sl = 0; sl < 16; ++sl) {
+                    const int i = lane + 32 * sl;
+                    float d2 = INFINITY;
+                    int id = 0x7fffffff;
+                    if (i < nc) {
+                        const float4 cp = S->cand[i];
+                        const float dd = dist2f(qp.x, qp.y, qp.z, cp.x, cp.y, cp.z);
+                        if ((double)dd <= max_d2) { d2 = dd; id = f2i(cp.w); }
+                    }
+                    dreg[sl] = d2; ireg[sl] = id;
+                }
+                double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
+                int cnt = 0, found = 0;
+                float last_d = 0.f;
+                for (int r = 0; r < 20; ++r) {
+                    float bd = INFINITY;
+                    int bid = 0x7fffffff, bsl = 0;
+#pragma unroll
+                    for (int sl = 0; sl < 16; ++sl)
+                        if (dreg[sl] < bd || (dreg[sl] == bd && ireg[sl] < bid)) { bd = dreg[sl]; bid = ireg[sl]; bsl = sl; }
+                    int aux = bsl * 32 + lane;  // candidate index of this lane's minimum
+                    warp_min_pair(&bd, &bid, &aux);
+                    if (bid == 0x7fffffff) break;
+                    if ((aux & 31) == lane) {
+#pragma unroll
+                        for (int sl = 0; sl < 16; ++sl)
+                            if (sl == (aux >> 5)) { dreg[sl] = INFINITY; ireg[sl] = 0x7fffffff; }
+                    }
+                    last_d = bd;
+                    ++found;
+                    const float sd = sqrtf(bd);
+                    if ((double)sd < P.accept && lane == 0) S->flag[aux] = 1;
+                    if ((double)sd < P.accept * 2) {
+                        ++cnt;
+                        const float4 cp = S->cand[aux];
+                        sv0 = sv0 + (double)cp.x; sv1 = sv1 + (double)cp.y; sv2 = sv2 + (double)cp.z;
+                    }
+                }
+                const bool complete = (lb > P.knn_max) || (found >= 20 && (double)last_d < lb * lb * 0.999999);
+                if (!complete && lane == 0) S->need_more = 1;
+                if (lane == 0) {
+                    M.vsmooth[(size_t)qv * 3 + 0] = (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f);
+                    M.vsmooth[(size_t)qv * 3 + 1] = (sv1 / (double)cnt) * (double)1.0f + (double)qp.y * (double)(1 - 1.0f);
+                    M.vsmooth[(size_t)qv * 3 + 2] = (sv2 / (double)cnt) * (double)1.0f + (double)qp.z * (double)(1 - 1.0f);
+                }
+                continue;
+            }
+#endif
             float prev_d = -1.0f;
             int prev_id = -1;
             double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
@@ -206,7 +261,8 @@ struct MeshSmem {
 
 template <int MAXD>
 IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, MeshSmem<MAXD>* S, int tid, int nthreads) {
-    const int n = F.work_n_ids[w];
+    const int nraw = F.work_n_ids[w];
+    const int n = nraw < 0 ? -nraw : nraw;   // negative: handed over by the warp-level stage after a cavity overflow
     if (n < 3 || n > MAXD) return;
     const int vs = F.work[w];
     for (int i = tid; i < n; i += nthreads) {
@@ -340,6 +396,273 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
                         const int k = S->fhash[hs];
                         if (k < 0) break;
                         if (S->faces[k][0] == r.x && S->faces[k][1] == r.y && S->faces[k][2] == r.z) { in_new = true; break; }
+                        hs = (hs + 1) & (4 * MAXD - 1);
+                    }
+                    if (!in_new) {
+                        const int e = im_atomic_add(&M.cnt[8], 1);
+                        if (e < F.max_list) F.rem_tri[e] = t; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+                    }
+                }
+            }
+            t = nx;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ stage B, warp-level variant (the common case)
+// One warp per voxel (n <= MAXD dilated vertices), __syncwarp only.  The Bowyer-Watson conflict search is pruned with a
+// cached float circumcircle per triangle (conservative margin; every survivor still goes through the exact predicate),
+// which removes ~90% of the exact in-circle evaluations.  Cavity / boundary capacity is 64 triangles; a voxel that
+// exceeds it is handed to the block-level stage (work_n_ids[w] negated).
+template <int MAXD>
+struct MeshWarpSmem {
+    int ids[MAXD];
+    double uv[MAXD][2];
+    int2 snap[MAXD];
+    DTri tris[3 * MAXD + 8];          // after face extraction: reused as the face hash (4*MAXD ints)
+    float circ[3 * MAXD + 8][3];      // before the triangulation: vertex positions; after it: faces (2*MAXD int3)
+    int scratch[8 + 64 + 136];
+    double axes[9];
+    double centre[3];
+    int ntri, nface;
+};
+
+IM_HD void circumcircle_f(const int2* P, int a, int b, int c, float* out) {
+    const double bx = (double)(P[b].x - P[a].x), by = (double)(P[b].y - P[a].y);
+    const double cx = (double)(P[c].x - P[a].x), cy = (double)(P[c].y - P[a].y);
+    const double d = 2.0 * (bx * cy - by * cx);
+    const double b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
+    const double ux = (cy * b2 - by * c2) / d, uy = (bx * c2 - cx * b2) / d;
+    const double r2 = ux * ux + uy * uy;
+    const double ccx = (double)P[a].x + ux, ccy = (double)P[a].y + uy;
+    if (!(fabs(ccx) < 1.0e9) || !(fabs(ccy) < 1.0e9) || !(r2 < 1.0e18)) { out[0] = 0.f; out[1] = 0.f; out[2] = INFINITY; return; }
+    out[0] = (float)ccx; out[1] = (float)ccy;
+    out[2] = (float)(r2 * 1.002) + 64.0f;   // conservative: float rounding of centre/radius is ~1e-6 relative
+}
+
+template <int MAXD>
+IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, MeshWarpSmem<MAXD>* S, int lane, int nlanes) {
+    const int n = F.work_n_ids[w];
+    if (n < 3 || n > MAXD) return;
+    const int vs = F.work[w];
+    float (*pos)[3] = S->circ;  // alias: positions are dead once projected
+    for (int i = lane; i < n; i += nlanes) {
+        const int id = F.work_ids[(size_t)w * IM_MAXD + i];
+        S->ids[i] = id;
+        const float4 p = M.vpos[id];
+        pos[i][0] = p.x; pos[i][1] = p.y; pos[i][2] = p.z;
+    }
+    if (lane == 0) S->nface = 0;
+    IM_SYNCWARP();
+    if (lane == 0) {
+        double c[3] = {0, 0, 0};
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < 3; ++j) c[j] = c[j] + (double)pos[i][j];
+        for (int j = 0; j < 3; ++j) c[j] = c[j] / (double)n;
+        double cov[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < n; ++i) {
+            const double d[3] = {(double)pos[i][0] - c[0], (double)pos[i][1] - c[1], (double)pos[i][2] - c[2]};
+            cov[0] += d[0] * d[0]; cov[1] += d[0] * d[1]; cov[2] += d[0] * d[2];
+            cov[3] += d[1] * d[1]; cov[4] += d[1] * d[2]; cov[5] += d[2] * d[2];
+        }
+        for (int k = 0; k < 6; ++k) cov[k] = cov[k] / (double)n;
+        double ev[3], U[9];
+        jacobi3(cov, ev, U);
+        int order[3] = {0, 1, 2};
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2 - a; ++b)
+                if (ev[order[b + 1]] < ev[order[b]]) { const int t = order[b]; order[b] = order[b + 1]; order[b + 1] = t; }
+        double sx[3], m[3];
+        for (int j = 0; j < 3; ++j) { sx[j] = U[j * 3 + order[0]]; m[j] = U[j * 3 + order[1]]; }
+        const double d0[3] = {(double)pos[0][0] - c[0], (double)pos[0][1] - c[1], (double)pos[0][2] - c[2]};
+        const double d1[3] = {(double)pos[1][0] - c[0], (double)pos[1][1] - c[1], (double)pos[1][2] - c[2]};
+        if (dot3(d0, sx) < 0) { sx[0] = -sx[0]; sx[1] = -sx[1]; sx[2] = -sx[2]; }
+        if (dot3(d1, m) < 0) { m[0] = -m[0]; m[1] = -m[1]; m[2] = -m[2]; }
+        S->axes[0] = sx[0]; S->axes[1] = sx[1]; S->axes[2] = sx[2];
+        S->axes[3] = m[0]; S->axes[4] = m[1]; S->axes[5] = m[2];
+        S->axes[6] = sx[1] * m[2] - sx[2] * m[1];
+        S->axes[7] = sx[2] * m[0] - sx[0] * m[2];
+        S->axes[8] = sx[0] * m[1] - sx[1] * m[0];
+        S->centre[0] = c[0]; S->centre[1] = c[1]; S->centre[2] = c[2];
+    }
+    IM_SYNCWARP();
+    for (int i = lane; i < n; i += nlanes) {
+        const double d[3] = {(double)pos[i][0] - S->centre[0], (double)pos[i][1] - S->centre[1], (double)pos[i][2] - S->centre[2]};
+        const double u = dot3(d, S->axes + 6), v = dot3(d, S->axes + 3);
+        S->uv[i][0] = u; S->uv[i][1] = v;
+        S->snap[i] = make_int2((int)im_llrint(u * P.inv_q), (int)im_llrint(v * P.inv_q));
+    }
+    IM_SYNCWARP();
+    // ---- Bowyer-Watson, warp-synchronous
+    const int2* Pt = S->snap;
+    DTri* tris = S->tris;
+    int* s_cav_n = S->scratch;
+    int* s_edge_n = S->scratch + 1;
+    int* s_seed = S->scratch + 2;   // i1, i2, ok
+    int* s_ovf = S->scratch + 6;
+    int* s_cav = S->scratch + 8;    // [64]
+    int* s_edges = S->scratch + 72; // [68*2]
+    const int max_tris = 3 * MAXD + 8;
+    if (lane == 0) {
+        *s_ovf = 0;
+        int i1 = -1, i2 = -1;
+        for (int i = 1; i < n; ++i)
+            if (Pt[i].x != Pt[0].x || Pt[i].y != Pt[0].y) { i1 = i; break; }
+        if (i1 >= 0)
+            for (int i = 1; i < n; ++i)
+                if (i != i1 && orient2d_i(Pt[0].x, Pt[0].y, Pt[i1].x, Pt[i1].y, Pt[i].x, Pt[i].y) != 0) { i2 = i; break; }
+        s_seed[0] = i1; s_seed[1] = i2; s_seed[2] = (i1 >= 0 && i2 >= 0) ? 1 : 0;
+        S->ntri = 0;
+        if (s_seed[2]) {
+            int a = 0, b = i1, c = i2;
+            if (orient2d_i(Pt[a].x, Pt[a].y, Pt[b].x, Pt[b].y, Pt[c].x, Pt[c].y) < 0) { const int t = b; b = c; c = t; }
+            const short tv[4][3] = {{(short)a, (short)b, (short)c}, {(short)c, (short)b, IM_GHOST}, {(short)a, (short)c, IM_GHOST}, {(short)b, (short)a, IM_GHOST}};
+            for (int k = 0; k < 4; ++k) { tris[k].v[0] = tv[k][0]; tris[k].v[1] = tv[k][1]; tris[k].v[2] = tv[k][2]; tris[k].alive = 1; }
+            circumcircle_f(Pt, a, b, c, S->circ[0]);
+            S->ntri = 4;
+        }
+    }
+    IM_SYNCWARP();
+    if (!s_seed[2]) return;
+    const int i1 = s_seed[0], i2 = s_seed[1];
+    for (int p = 1; p < n; ++p) {
+        if (p == i1 || p == i2) continue;
+        if (lane == 0) { *s_cav_n = 0; *s_edge_n = 0; }
+        IM_SYNCWARP();
+        const int nt = S->ntri;
+        const float pxf = (float)Pt[p].x, pyf = (float)Pt[p].y;
+        for (int t = lane; t < nt; t += nlanes) {
+            const DTri tr = tris[t];
+            if (!tr.alive) continue;
+            if (tr.v[0] != IM_GHOST && tr.v[1] != IM_GHOST && tr.v[2] != IM_GHOST) {
+                const float dx = pxf - S->circ[t][0], dy = pyf - S->circ[t][1];
+                if (dx * dx + dy * dy > S->circ[t][2]) continue;   // certainly outside the circumcircle
+            }
+            if (dt_conflict(tr, Pt, p)) {
+                const int k = im_atomic_add(s_cav_n, 1);
+                if (k < 64) s_cav[k] = t;
+            }
+        }
+        IM_SYNCWARP();
+        int nc = *s_cav_n;
+        if (nc > 64) { nc = 64; if (lane == 0) *s_ovf = 1; }
+        for (int e = lane; e < nc * 3; e += nlanes) {
+            const DTri& t = tris[s_cav[e / 3]];
+            const int a = t.v[(e % 3 + 1) % 3], b = t.v[(e % 3 + 2) % 3];
+            bool interior = false;
+            for (int f = 0; f < nc * 3 && !interior; ++f) {
+                const DTri& u = tris[s_cav[f / 3]];
+                if (u.v[(f % 3 + 1) % 3] == b && u.v[(f % 3 + 2) % 3] == a) interior = true;
+            }
+            if (!interior) {
+                const int k = im_atomic_add(s_edge_n, 1);
+                if (k < 68) { s_edges[2 * k] = a; s_edges[2 * k + 1] = b; }
+            }
+        }
+        IM_SYNCWARP();
+        int ne = *s_edge_n;
+        if (ne > 68) { ne = 68; if (lane == 0) *s_ovf = 1; }
+        for (int k = lane; k < nc; k += nlanes) tris[s_cav[k]].alive = 0;
+        IM_SYNCWARP();
+        for (int k = lane; k < ne; k += nlanes) {
+            const int slot = (k < nc) ? s_cav[k] : (nt + (k - nc));
+            if (slot < max_tris) {
+                const int a = s_edges[2 * k], b = s_edges[2 * k + 1];
+                tris[slot].v[0] = (short)a; tris[slot].v[1] = (short)b; tris[slot].v[2] = (short)p; tris[slot].alive = 1;
+                if (a != IM_GHOST && b != IM_GHOST) circumcircle_f(Pt, a, b, p, S->circ[slot]);
+            }
+        }
+        if (lane == 0 && ne > nc) {
+            if (nt + (ne - nc) <= max_tris) S->ntri = nt + (ne - nc);
+            else { S->ntri = max_tris; *s_ovf = 1; }
+        }
+        IM_SYNCWARP();
+        if (*s_ovf) break;
+    }
+    IM_SYNCWARP();
+    if (*s_ovf) {  // hand this voxel to the block-level stage
+        if (lane == 0) F.work_n_ids[w] = -n;
+        return;
+    }
+    // ---- faces passing the 150-degree filter, as sorted global id triples (stored over the dead circumcircle cache)
+    int (*faces)[3] = reinterpret_cast<int (*)[3]>(&S->circ[0][0]);
+    const int nt = S->ntri;
+    for (int t = lane; t < nt; t += nlanes) {
+        const DTri& tr = tris[t];
+        if (!tr.alive || tr.v[0] < 0 || tr.v[1] < 0 || tr.v[2] < 0) continue;
+        const int j0 = tr.v[0], j1 = tr.v[1], j2 = tr.v[2];
+        if (angle_bad(S->uv[j0][0], S->uv[j0][1], S->uv[j1][0], S->uv[j1][1], S->uv[j2][0], S->uv[j2][1])) continue;
+        if (angle_bad(S->uv[j1][0], S->uv[j1][1], S->uv[j2][0], S->uv[j2][1], S->uv[j0][0], S->uv[j0][1])) continue;
+        if (angle_bad(S->uv[j2][0], S->uv[j2][1], S->uv[j0][0], S->uv[j0][1], S->uv[j1][0], S->uv[j1][1])) continue;
+        int a = S->ids[j0], b = S->ids[j1], c = S->ids[j2];
+        if (a > b) { const int x = a; a = b; b = x; }
+        if (b > c) { const int x = b; b = c; c = x; }
+        if (a > b) { const int x = a; a = b; b = x; }
+        const int k = im_atomic_add(&S->nface, 1);
+        faces[k][0] = a; faces[k][1] = b; faces[k][2] = c;
+    }
+    IM_SYNCWARP();
+    const int nf = S->nface;
+    int* fhash = reinterpret_cast<int*>(S->tris);   // triangles are dead now
+    for (int i = lane; i < 4 * MAXD; i += nlanes) fhash[i] = -1;
+    IM_SYNCWARP();
+    for (int k = lane; k < nf; k += nlanes) {
+        unsigned int hs = tri_hash(faces[k][0], faces[k][1], faces[k][2]) & (4 * MAXD - 1);
+        while (im_atomic_cas32(&fhash[hs], -1, k) != -1) hs = (hs + 1) & (4 * MAXD - 1);
+    }
+    IM_SYNCWARP();
+    if (lane == 0) im_atomic_add(&M.cnt[23], nf);
+    int kx, ky, kz;
+    unpack_ikey(M.vkeys[vs], &kx, &ky, &kz);
+    const long long lx = kx - F.prio_origin[0], ly = ky - F.prio_origin[1], lz = kz - F.prio_origin[2];
+    if (lx < 0 || lx >= 2048 || ly < 0 || ly >= 2048 || lz < 0 || lz >= 2048) {
+        if (lane == 0) im_atomic_or(&M.cnt[3], IM_MERR_PRIO_RANGE);
+    }
+    const unsigned long long prio = ((unsigned long long)(lx & 2047) << 22) | ((unsigned long long)(ly & 2047) << 11) | (unsigned long long)(lz & 2047);
+    const unsigned long long word_base = ((unsigned long long)F.frame << 34) | (prio << 1);
+    for (int k = lane; k < nf; k += nlanes) {
+        const int a = faces[k][0], b = faces[k][1], c = faces[k][2];
+        const unsigned long long word = word_base | (unsigned long long)compute_flip(M, a, b, c, F.pose_t, S->axes);
+        const int t = tri_find(M, a, b, c);
+        if (t >= 0 && M.tri[t].w) {
+            im_atomic_max64(&M.tri_flip[t], word);
+        } else {
+            const int e = im_atomic_add(&M.cnt[7], 1);
+            if (e < F.max_list) {
+                F.add_tri[(size_t)e * 3 + 0] = a; F.add_tri[(size_t)e * 3 + 1] = b; F.add_tri[(size_t)e * 3 + 2] = c;
+                F.add_flip[e] = word;
+            } else {
+                im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+            }
+        }
+    }
+    for (int i = lane; i < n; i += nlanes) {
+        const int v = S->ids[i];
+        for (int t = M.v_tri_head[v]; t >= 0;) {
+            const int4 r = M.tri[t];
+            const int slot = (r.x == v) ? 0 : ((r.y == v) ? 1 : 2);
+            const int nx = M.tri_next[(size_t)t * 3 + slot];
+            if (r.w && r.x == v) {
+                bool in_set = true;
+                for (int pass = 0; pass < 2 && in_set; ++pass) {
+                    const int key = pass == 0 ? r.y : r.z;
+                    int lo = 0, hi = n - 1;
+                    bool hit = false;
+                    while (lo <= hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const int val = S->ids[mid];
+                        if (val == key) { hit = true; break; }
+                        if (val < key) lo = mid + 1; else hi = mid - 1;
+                    }
+                    in_set = hit;
+                }
+                if (in_set) {
+                    bool in_new = false;
+                    unsigned int hs = tri_hash(r.x, r.y, r.z) & (4 * MAXD - 1);
+                    for (int probe = 0; probe < 4 * MAXD; ++probe) {
+                        const int k = fhash[hs];
+                        if (k < 0) break;
+                        if (faces[k][0] == r.x && faces[k][1] == r.y && faces[k][2] == r.z) { in_new = true; break; }
                         hs = (hs + 1) & (4 * MAXD - 1);
                     }
                     if (!in_new) {

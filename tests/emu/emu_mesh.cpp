@@ -98,11 +98,13 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     delete DS;
     MeshSmem<256>* S1 = new MeshSmem<256>();
     MeshSmem<1024>* S2 = new MeshSmem<1024>();
+    MeshWarpSmem<256>* SW = new MeshWarpSmem<256>();
+    for (int w = 0; w < nw; ++w) voxel_mesh_warp<256>(M, P, F, w, SW, 0, 1);
     for (int w = 0; w < nw; ++w) {
         const int nd = F.work_n_ids[w];
-        if (nd <= 256) voxel_mesh<256>(M, P, F, w, S1, 0, 1); else voxel_mesh<1024>(M, P, F, w, S2, 0, 1);
+        if (nd < 0 || nd > 256) voxel_mesh<1024>(M, P, F, w, S2, 0, 1);
     }
-    delete S1; delete S2;
+    delete S1; delete S2; delete SW;
     const int nr = std::min(M.cnt[8], F.max_list), nadd = std::min(M.cnt[7], F.max_list);
     for (int e = 0; e < nr; ++e) tri_remove(M, F.rem_tri[e]);
     for (int e = 0; e < nadd; ++e) tri_add(M, F.add_tri[(size_t)e * 3], F.add_tri[(size_t)e * 3 + 1], F.add_tri[(size_t)e * 3 + 2], F.add_flip[e]);
