@@ -97,6 +97,13 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_mesh_push_frame_dev", [vp, vp, C.c_int, dp, C.c_int]),
         ("immesh_mesh_push_frame_from_lio", [vp, vp, vp, C.c_int, C.c_int]),
         ("immesh_lio_match_nodes", [vp, ip, C.c_int]),
+        ("immesh_lio_step_async", [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
+        ("immesh_lio_wait", [vp, dp, ip]),
+        ("immesh_lio_enqueue_memset", [vp, vp, C.c_size_t]),
+        ("immesh_mesh_push_frame_from_lio_async", [vp, vp, vp, C.c_int, C.c_int]),
+        ("immesh_mesh_wait", [vp]),
+        ("immesh_pipeline_mark_begin", [vp]),
+        ("immesh_pipeline_mark_end", [vp, vp, dp]),
         ("immesh_mesh_work_stats", [vp, C.POINTER(C.c_int64)]),
         ("immesh_profile_enable", [C.c_int]),
         ("immesh_profile_reset", []),
@@ -220,6 +227,26 @@ class Lio:
         self._last_n = n
         return s, it.value
 
+    def step_async(self, body, n=None, dt=0.0, cov_gyr=0.1, cov_acc=0.1, on_device=False):
+        """Queue one scan (predict + estimate + map update) without waiting; body: float32[n][3] host array or CUDA address."""
+        if on_device:
+            ptr = C.c_void_p(body)
+        else:
+            a, p = _f32(body)
+            n = a.shape[0]
+            ptr = C.cast(p, C.c_void_p)
+        _check(self.lib, self.lib.immesh_lio_step_async(self._h, ptr, n, 1 if on_device else 0, dt, cov_gyr, cov_acc), "lio_step_async")
+        self._last_n = n
+
+    def wait(self):
+        it = C.c_int(0)
+        s = np.zeros(STATE_DOUBLES)
+        _check(self.lib, self.lib.immesh_lio_wait(self._h, s.ctypes.data_as(C.POINTER(C.c_double)), C.byref(it)), "lio_wait")
+        return s, it.value
+
+    def enqueue_memset(self, dev_ptr, nbytes):
+        _check(self.lib, self.lib.immesh_lio_enqueue_memset(self._h, C.c_void_p(dev_ptr), nbytes), "enqueue_memset")
+
     def residual_build(self, body_ds):
         a, p = _f32(body_ds)
         n = a.shape[0]
@@ -307,6 +334,18 @@ class Mesh:
             ptr = C.cast(p, C.c_void_p)
         _check(self.lib, self.lib.immesh_mesh_push_frame_from_lio(self._h, lio._h, ptr, n, 1 if on_device else 0), "mesh_push_frame_from_lio")
 
+    def push_frame_from_lio_async(self, lio: "Lio", body_full, n=None, on_device=False):
+        if on_device:
+            ptr = C.c_void_p(body_full)
+        else:
+            a, p = _f32(body_full)
+            n = a.shape[0]
+            ptr = C.cast(p, C.c_void_p)
+        _check(self.lib, self.lib.immesh_mesh_push_frame_from_lio_async(self._h, lio._h, ptr, n, 1 if on_device else 0), "mesh_push_frame_from_lio_async")
+
+    def wait(self):
+        _check(self.lib, self.lib.immesh_mesh_wait(self._h), "mesh_wait")
+
     def counts(self):
         o = np.zeros(8, dtype=np.int64)
         _check(self.lib, self.lib.immesh_mesh_counts(self._h, o.ctypes.data_as(C.POINTER(C.c_int64))), "mesh_counts")
@@ -366,3 +405,13 @@ def profile_report(lib: Optional[C.CDLL] = None) -> dict:
 
 def launch_count(lib: Optional[C.CDLL] = None) -> int:
     return int((lib or load_library()).immesh_launch_count())
+
+
+def pipeline_mark_begin(lio: Lio):
+    _check(lio.lib, lio.lib.immesh_pipeline_mark_begin(lio._h), "pipeline_mark_begin")
+
+
+def pipeline_mark_end(lio: Lio, mesh: Mesh) -> float:
+    ms = C.c_double(0)
+    _check(lio.lib, lio.lib.immesh_pipeline_mark_end(lio._h, mesh._h, C.byref(ms)), "pipeline_mark_end")
+    return ms.value

@@ -8,7 +8,7 @@
 #include "mesh_voxel.cuh"
 
 using immesh::LioParams; using immesh::VoxelMapDev; using immesh::ScanBuf; using immesh::LioCtrl;
-using immesh::MeshParams; using immesh::MeshDev; using immesh::FrameBuf;
+using immesh::MeshParams; using immesh::MeshDev; using immesh::FrameBuf; using immesh::FramePose;
 
 struct immesh_lio {
     LioParams P;
@@ -19,8 +19,15 @@ struct immesh_lio {
     int* d_sorted = nullptr;
     double* d_ptpl = nullptr;
     float* d_body_own = nullptr;  // scan buffer owned by the handle (sb.body points here unless the caller passed a device pointer)
-    float* h_body = nullptr;   // pinned staging
-    double* h_state = nullptr; // pinned
+    float* h_body = nullptr;   // pinned staging, 2 slots
+    double* h_state = nullptr; // pinned, 2 slots of (IM_STATE_DOUBLES + 64)
+    cudaEvent_t ev_slot[2] = {nullptr, nullptr};  // completion of the step that used staging slot s
+    int slot_busy[2] = {0, 0};
+    int step_counter = 0;
+    int pending_rc = 0;
+    cudaStream_t stream2 = nullptr;   // side stream: P^-1 of the propagated covariance, concurrent with the first residual pass
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_mark = nullptr;   // pipeline timing mark (begin)
     int* h_ints = nullptr;     // pinned
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -39,10 +46,17 @@ struct immesh_mesh {
     FrameBuf F;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    float* d_pts = nullptr;
-    float* d_body = nullptr;  // staging for body-frame scans handed over by the localization handle
-    float* h_pts = nullptr;  // pinned
-    int* h_cnt = nullptr;    // pinned
+    float* d_pts = nullptr;   // 2 slots of max_frame_points*3
+    float* d_body = nullptr;  // 2 slots, staging for body-frame scans handed over by the localization handle
+    float* h_pts = nullptr;   // pinned, 2 slots
+    int* h_cnt = nullptr;     // pinned, 2 slots of 32
+    FramePose* d_fp = nullptr;  // 2 slots
+    FramePose* h_fp = nullptr;  // pinned, 2 slots
+    cudaEvent_t ev_in[2] = {nullptr, nullptr};    // inputs of slot s ready (recorded on the producer stream)
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};  // frame of slot s finished (mesh stream)
+    int inflight[2] = {0, 0};
+    cudaEvent_t ev_mark = nullptr, ev_sync = nullptr;  // pipeline timing mark (end) / cross-stream join
+    int pending_rc = 0;
     int* d_snap_tri = nullptr;
     int* d_snap_flip = nullptr;
     int* d_snap_n = nullptr;

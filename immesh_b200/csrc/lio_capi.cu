@@ -113,14 +113,13 @@ __device__ __noinline__ void ieskf_solve_block(const LioParams& P, LioCtrl* ctrl
             ctrl->stats[iter].n_match = (double)((hi << 32) + lo);
         }
     }
-    for (int i = tid; i < 324; i += nthreads) S->a[i] = cov[i];
     __syncthreads();
-    if (warp == 0) warp_lu_inverse18(S->a, S->lu, S->piv, S->Pinv, lane);
-    __syncthreads();
+    // state.cov.inverse() is the same matrix in every iteration of a scan (the covariance only changes at the end):
+    // it is computed once per scan by k_pinv and read here
     for (int idx = tid; idx < 324; idx += nthreads) {
         const int i = idx / 18, j = idx % 18;
         const double hth = (i < 6 && j < 6) ? S->HTH[i * 6 + j] : 0.0;
-        S->a[idx] = hth + S->Pinv[idx];
+        S->a[idx] = hth + ctrl->Pinv[idx];
     }
     __syncthreads();
     if (warp == 0) warp_lu_inverse18(S->a, S->lu, S->piv, S->K1, lane);
@@ -232,6 +231,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(LioParams P, LioCtrl* c
     ieskf_solve(P, ctrl, iter, &S, threadIdx.x, blockDim.x);
 }
 
+__global__ void __launch_bounds__(32) k_pinv(LioCtrl* ctrl) {
+    __shared__ double a[324], lu[18 * 19], inv[324];
+    __shared__ int piv[18];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 324; i += 32) a[i] = ctrl->state[24 + i];
+    __syncwarp();
+    warp_lu_inverse18(a, lu, piv, inv, lane);
+    for (int i = lane; i < 324; i += 32) ctrl->Pinv[i] = inv[i];
+}
 __global__ void __launch_bounds__(128) k_solve_warp(LioParams P, LioCtrl* ctrl, int iter) {
     __shared__ SolveScratch S;
     if (ctrl->stop) return;
@@ -357,6 +365,10 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
     IM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) IM_CUDA(cudaEventCreate(&e));
+    IM_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    IM_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    IM_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) IM_CUDA(cudaEventCreateWithFlags(&h->ev_slot[i], cudaEventDisableTiming));
     VoxelMapDev& m = h->map;
     IM_CUDA(dev_alloc(h, &m.keys, h->cap, 0xFF));
     IM_CUDA(dev_alloc(h, &m.root_node, h->cap, 0xFF));
@@ -394,8 +406,8 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     sb.n_touched = h->d_counters + 6; sb.seg_top = h->d_counters + 7;
     sb.n = 0;
     IM_CUDA(dev_alloc(h, &h->d_ctrl, 1, 0));
-    IM_CUDA(cudaMallocHost((void**)&h->h_body, ms * 3 * sizeof(float)));
-    IM_CUDA(cudaMallocHost((void**)&h->h_state, (IM_STATE_DOUBLES + 64) * sizeof(double)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_body, 2 * ms * 3 * sizeof(float)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_state, 2 * (IM_STATE_DOUBLES + 64) * sizeof(double)));
     IM_CUDA(cudaMallocHost((void**)&h->h_ints, 64 * sizeof(int)));
     // StatesGroup(): identity rotation, cov = INIT_COV * I  (include/common_lib.h:201-211)
     std::memset(h->h_state, 0, IM_STATE_DOUBLES * sizeof(double));
@@ -416,6 +428,10 @@ int immesh_lio_destroy(immesh_lio_t* h) {
     if (h->h_ints) cudaFreeHost(h->h_ints);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (int i = 0; i < 2; ++i) if (h->ev_slot[i]) cudaEventDestroy(h->ev_slot[i]);
     delete h;
     return IMMESH_OK;
 }
@@ -435,7 +451,7 @@ int immesh_lio_get_state(immesh_lio_t* h, double* s) {
     return IMMESH_OK;
 }
 
-static int upload_scan(immesh_lio* h, const float* body, int n, int on_device = 0) {
+static int upload_scan(immesh_lio* h, const float* body, int n, int on_device = 0, int slot = 0) {
     if ((!body && n > 0) || n < 0) return im_fail(IMMESH_E_INVALID, "bad scan");
     if (n > h->max_scan) return im_fail(IMMESH_E_CAPACITY, "scan larger than max_scan_points");
     if (on_device) {
@@ -443,8 +459,9 @@ static int upload_scan(immesh_lio* h, const float* body, int n, int on_device = 
     } else {
         h->sb.body = h->d_body_own;
         if (n > 0) {
-            std::memcpy(h->h_body, body, (size_t)n * 3 * sizeof(float));
-            IM_CUDA(cudaMemcpyAsync((void*)h->d_body_own, h->h_body, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            float* stage = h->h_body + (size_t)slot * h->max_scan * 3;
+            std::memcpy(stage, body, (size_t)n * 3 * sizeof(float));
+            IM_CUDA(cudaMemcpyAsync((void*)h->d_body_own, stage, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         }
     }
     h->sb.n = n;
@@ -468,15 +485,23 @@ static void launch_grow(immesh_lio* h, int n, int mode) {
     IM_LAUNCH(k_grow_finish, 1, 256, 0, h->stream, h->map, h->sb, h->d_counters + 8);
 }
 static void launch_estimate(immesh_lio* h, int n) {
+    if (n > 0) {  // P^-1 on the side stream, overlapped with the scan preparation and the first residual pass
+        cudaEventRecord(h->ev_fork, h->stream);
+        cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+        IM_LAUNCH(k_pinv, 1, 32, 0, h->stream2, h->d_ctrl);
+        cudaEventRecord(h->ev_join, h->stream2);
+    }
     IM_LAUNCH(k_reset_scan, 2, 256, 0, h->stream, h->sb, h->d_ctrl, 1);
     if (n <= 0) return;
     IM_LAUNCH(k_prepare, grid_for(h, n, 128), 128, 0, h->stream, h->P, h->sb, n);
     const int g = grid_for(h, n, RES_THREADS, 4);
     for (int it = 0; it < h->P.max_iter; ++it) {
+        if (it == 0 && h->fused_solve) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
         if (h->fused_solve) {
             IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n, 1);
         } else {
             IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n, 0);
+            if (it == 0) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
             IM_LAUNCH(k_solve_warp, 1, 128, 0, h->stream, h->P, h->d_ctrl, it);
         }
     }
@@ -518,10 +543,18 @@ int immesh_voxelmap_update(immesh_lio_t* h) {
     return check_flags(h);
 }
 
-static int lio_step_impl(immesh_lio_t* h, const float* body, int n, int on_device, double dt, double cov_gyr, double cov_acc, double* state_out, int* iters_run) {
+static int lio_flags_status(int err) {
+    if (err & (IM_ERR_NODE_POOL | IM_ERR_CHUNK_POOL | IM_ERR_HASH_FULL | IM_ERR_SEG_POOL)) return im_fail(IMMESH_E_CAPACITY, "device pool overflow (raise the capacities in immesh_lio_config)");
+    if (err & (IM_ERR_KEY_RANGE | IM_ERR_FX_RANGE)) return im_fail(IMMESH_E_RANGE, "coordinate / normal-equation term outside the representable range");
+    return IMMESH_OK;
+}
+// queue predict + estimate + update for one scan; no host synchronisation unless both staging slots are busy
+static int lio_enqueue(immesh_lio_t* h, const float* body, int n, int on_device, double dt, double cov_gyr, double cov_acc) {
     if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
+    const int s = (++h->step_counter) & 1;
+    if (h->slot_busy[s]) { IM_CUDA(cudaEventSynchronize(h->ev_slot[s])); h->slot_busy[s] = 0; }
     IM_CUDA(cudaEventRecord(h->ev[0], h->stream));
-    int rc = upload_scan(h, body, n, on_device);
+    int rc = upload_scan(h, body, n, on_device, s);
     if (rc) return rc;
     if (dt > 0) IM_LAUNCH(k_predict, 1, SOLVE_THREADS, 0, h->stream, h->d_ctrl, dt, cov_gyr, cov_acc);
     IM_CUDA(cudaEventRecord(h->ev[1], h->stream));
@@ -529,26 +562,51 @@ static int lio_step_impl(immesh_lio_t* h, const float* body, int n, int on_devic
     IM_CUDA(cudaEventRecord(h->ev[2], h->stream));
     launch_grow(h, n, 0);
     IM_CUDA(cudaGetLastError());
-    IM_CUDA(cudaMemcpyAsync(h->h_state, h->d_ctrl->state, IM_STATE_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    IM_CUDA(cudaMemcpyAsync(h->h_ints + 32, &h->d_ctrl->iters_run, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    double* hs = h->h_state + (size_t)s * (IM_STATE_DOUBLES + 64);
+    IM_CUDA(cudaMemcpyAsync(hs, h->d_ctrl->state, IM_STATE_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaMemcpyAsync(h->h_ints + 32 + s, &h->d_ctrl->iters_run, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaMemcpyAsync(h->h_ints + 16 * s, h->d_counters, 16 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     IM_CUDA(cudaEventRecord(h->ev[3], h->stream));
-    rc = check_flags(h);
-    if (profiler().enabled) profiler().collect();
-    if (state_out) std::memcpy(state_out, h->h_state, IM_STATE_DOUBLES * sizeof(double));
-    if (iters_run) *iters_run = h->h_ints[32];
-    float a = 0, b = 0, c = 0;
-    cudaEventElapsedTime(&a, h->ev[0], h->ev[3]);
-    cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
-    cudaEventElapsedTime(&c, h->ev[2], h->ev[3]);
-    h->last_ms[0] = a; h->last_ms[1] = b; h->last_ms[2] = c;
-    return rc;
+    IM_CUDA(cudaEventRecord(h->ev_slot[s], h->stream));
+    h->slot_busy[s] = 1;
+    return IMMESH_OK;
+}
+static int lio_wait_impl(immesh_lio_t* h, double* state_out, int* iters_run, bool timings) {
+    if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
+    const int s = h->step_counter & 1;
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    h->slot_busy[0] = h->slot_busy[1] = 0;
+    if (profiler().enabled) { cudaStreamSynchronize(h->stream2); profiler().collect(); }
+    const double* hs = h->h_state + (size_t)s * (IM_STATE_DOUBLES + 64);
+    if (state_out) std::memcpy(state_out, hs, IM_STATE_DOUBLES * sizeof(double));
+    if (iters_run) *iters_run = h->h_ints[32 + s];
+    if (timings) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, h->ev[0], h->ev[3]);
+        cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&c, h->ev[2], h->ev[3]);
+        h->last_ms[0] = a; h->last_ms[1] = b; h->last_ms[2] = c;
+    }
+    return lio_flags_status(h->h_ints[16 * s + 4]);
 }
 
 int immesh_lio_step(immesh_lio_t* h, const float* body, int n, double dt, double cov_gyr, double cov_acc, double* state_out, int* iters_run) {
-    return lio_step_impl(h, body, n, 0, dt, cov_gyr, cov_acc, state_out, iters_run);
+    int rc = lio_enqueue(h, body, n, 0, dt, cov_gyr, cov_acc);
+    return rc ? rc : lio_wait_impl(h, state_out, iters_run, true);
 }
 int immesh_lio_step_dev(immesh_lio_t* h, const float* d_body, int n, double dt, double cov_gyr, double cov_acc, double* state_out, int* iters_run) {
-    return lio_step_impl(h, d_body, n, 1, dt, cov_gyr, cov_acc, state_out, iters_run);
+    int rc = lio_enqueue(h, d_body, n, 1, dt, cov_gyr, cov_acc);
+    return rc ? rc : lio_wait_impl(h, state_out, iters_run, true);
+}
+int immesh_lio_step_async(immesh_lio_t* h, const float* body, int n, int on_device, double dt, double cov_gyr, double cov_acc) {
+    return lio_enqueue(h, body, n, on_device, dt, cov_gyr, cov_acc);
+}
+int immesh_lio_wait(immesh_lio_t* h, double* state_out, int* iters_run) { return lio_wait_impl(h, state_out, iters_run, false); }
+// queue a write of `bytes` bytes over a caller-provided device buffer on the localization stream (benchmark L2 flush)
+int immesh_lio_enqueue_memset(immesh_lio_t* h, void* d_buf, size_t bytes) {
+    if (!h || !d_buf) return im_fail(IMMESH_E_INVALID, "null argument");
+    IM_CUDA(cudaMemsetAsync(d_buf, 0, bytes, h->stream));
+    return IMMESH_OK;
 }
 
 int immesh_lio_last_timing(immesh_lio_t* h, double* ms) {

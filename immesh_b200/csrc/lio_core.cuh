@@ -34,6 +34,7 @@ struct LioCtrl {
     double state[IM_STATE_DOUBLES];
     double state_prop[IM_STATE_DOUBLES];
     double G[324];
+    double Pinv[324];  // inverse of the propagated covariance: constant over the iterations of one scan
     unsigned long long acc[IM_MAX_ITER][IM_NTERMS * 2];  // (hi, lo) pairs, two's complement sums
     IterStats stats[IM_MAX_ITER];
     int stop;

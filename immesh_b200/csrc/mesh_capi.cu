@@ -316,8 +316,10 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     F.max_work = max_vox < (1 << 16) ? max_vox : (1 << 16);
     F.max_act = (int)std::min<size_t>((size_t)max_vox, mc);
     F.max_list = 4 << 20;
-    IM_CUDA(mdev_alloc(h, &h->d_pts, mc * 3));
+    IM_CUDA(mdev_alloc(h, &h->d_pts, 2 * mc * 3));
     F.pts = h->d_pts;
+    IM_CUDA(mdev_alloc(h, &h->d_fp, 2));
+    for (int i = 0; i < 2; ++i) { IM_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming)); IM_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming)); }
     IM_CUDA(mdev_alloc(h, &F.cand_gkey, mc));
     IM_CUDA(mdev_alloc(h, &F.cand_vslot, mc));
     IM_CUDA(mdev_alloc(h, &F.cand_status, mc));
@@ -336,8 +338,9 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(mdev_alloc(h, &F.add_tri, (size_t)F.max_list * 3));
     IM_CUDA(mdev_alloc(h, &F.add_flip, (size_t)F.max_list));
     IM_CUDA(mdev_alloc(h, &F.rem_tri, (size_t)F.max_list));
-    IM_CUDA(cudaMallocHost((void**)&h->h_pts, mc * 3 * sizeof(float)));
-    IM_CUDA(cudaMallocHost((void**)&h->h_cnt, 32 * sizeof(int)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_pts, 2 * mc * 3 * sizeof(float)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_cnt, 2 * 32 * sizeof(int)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_fp, 2 * sizeof(FramePose)));
     IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<1024>)));
     IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(MeshWarpSmem<256>))));
     std::memset(h->last_cnt, 0, sizeof(h->last_cnt));
@@ -352,6 +355,8 @@ int immesh_mesh_destroy(immesh_mesh_t* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_pts) cudaFreeHost(h->h_pts);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
+    if (h->h_fp) cudaFreeHost(h->h_fp);
+    for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -378,26 +383,35 @@ __global__ void __launch_bounds__(128) k_transform_full(LioParams P, const LioCt
     }
 }
 
-static int mesh_push_impl(immesh_mesh_t* h, const float* world_xyz, int n, const double* pose_t, int src_mode, immesh_lio* lio);
-
-int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, const double* pose_t, int frame_idx) {
-    (void)frame_idx;
-    return mesh_push_impl(h, world_xyz, n, pose_t, 0, nullptr);
-}
-int immesh_mesh_push_frame_dev(immesh_mesh_t* h, const float* d_world_xyz, int n, const double* pose_t, int frame_idx) {
-    (void)frame_idx;
-    return mesh_push_impl(h, d_world_xyz, n, pose_t, 1, nullptr);
-}
-int immesh_mesh_push_frame_from_lio(immesh_mesh_t* h, immesh_lio_t* lio, const float* body_xyz, int n, int on_device) {
-    if (!lio) return im_fail(IMMESH_E_INVALID, "null lio handle");
-    // pose_t = state.pos_end of the scan just localised (kept in pinned memory by immesh_lio_step / get_state)
-    double pose_t[3] = {lio->h_state[9], lio->h_state[10], lio->h_state[11]};
-    return mesh_push_impl(h, body_xyz, n, pose_t, on_device ? 3 : 2, lio);
+// sensor position of the frame + origin of the flip-priority rank, taken from the state the localization converged to
+__global__ void k_pose_from_lio(const LioCtrl* ctrl, double res, FramePose* out) {
+    if (threadIdx.x < 3) {
+        const double t = ctrl->state[9 + threadIdx.x];
+        out->pose_t[threadIdx.x] = t;
+        out->prio_origin[threadIdx.x] = (long long)floor(t / res) - 1024;
+    }
 }
 
-// src_mode: 0 host world points, 1 device world points, 2 host body points + lio state, 3 device body points + lio state
-static int mesh_push_impl(immesh_mesh_t* h, const float* world_xyz, int n, const double* pose_t, int src_mode, immesh_lio* lio) {
-    if (!h || (!world_xyz && n > 0) || !pose_t || n < 0) return im_fail(IMMESH_E_INVALID, "bad argument");
+static int mesh_status(int err) {
+    if (err & (IM_MERR_VERT_POOL | IM_MERR_TRI_POOL | IM_MERR_HASH_FULL | IM_MERR_LIST_CAP | IM_MERR_VOXEL_CAP)) return im_fail(IMMESH_E_CAPACITY, "mesh pool / per-voxel working-set overflow");
+    if (err & (IM_MERR_KEY_RANGE | IM_MERR_PRIO_RANGE)) return im_fail(IMMESH_E_RANGE, "mesh key out of range");
+    return IMMESH_OK;
+}
+// wait for the frame queued in slot s and take over its counters
+static int mesh_harvest(immesh_mesh* h, int s) {
+    if (!h->inflight[s]) return IMMESH_OK;
+    IM_CUDA(cudaEventSynchronize(h->ev_done[s]));
+    h->inflight[s] = 0;
+    std::memcpy(h->last_cnt, h->h_cnt + 32 * s, 32 * sizeof(int));
+    const int rc = mesh_status(h->last_cnt[3]);
+    if (rc && !h->pending_rc) h->pending_rc = rc;
+    return rc;
+}
+
+// src_mode: 0 host world points, 1 device world points, 2 host body points + lio state, 3 device body points + lio state.
+// Queues one frame (no host synchronisation except when both staging slots are still busy).
+static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double* pose_t, int src_mode, immesh_lio* lio) {
+    if (!h || (!xyz && n > 0) || n < 0 || (src_mode < 2 && !pose_t)) return im_fail(IMMESH_E_INVALID, "bad argument");
     if (n > h->max_frame_points) return im_fail(IMMESH_E_CAPACITY, "frame larger than max_frame_points");
     FrameBuf& F = h->F;
     const MeshParams& P = h->P;
@@ -407,30 +421,44 @@ static int mesh_push_impl(immesh_mesh_t* h, const float* world_xyz, int n, const
     F.step = step;
     F.m = n > 0 ? (n + step - 1) / step : 0;
     F.frame = ++h->frame_counter;
-    for (int j = 0; j < 3; ++j) {
-        F.pose_t[j] = pose_t[j];
-        F.prio_origin[j] = (long long)std::floor(pose_t[j] / P.res) - 1024;
-    }
+    const int s = F.frame & 1;
+    int rc = mesh_harvest(h, s);  // the frame two calls ago used this slot
+    (void)rc;
+    const size_t slot_pts = (size_t)h->max_frame_points * 3;
+    float* d_pts = h->d_pts + s * slot_pts;
+    float* h_pts = h->h_pts + s * slot_pts;
+    FramePose* d_fp = h->d_fp + s;
+    F.fp = d_fp;
     F.cmask = (unsigned)(pow2_at_least((size_t)std::max(F.m, 1) * 2) - 1);
     cudaStream_t st = h->stream;
     IM_CUDA(cudaEventRecord(h->ev[0], st));
-    F.pts = h->d_pts;
-    if (n > 0) {
-        if (src_mode == 0) {
-            std::memcpy(h->h_pts, world_xyz, (size_t)n * 3 * sizeof(float));
-            IM_CUDA(cudaMemcpyAsync(h->d_pts, h->h_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-        } else if (src_mode == 1) {
-            F.pts = world_xyz;
-        } else {
-            const float* d_body = world_xyz;
-            if (src_mode == 2) {
-                if (!h->d_body) IM_CUDA(mdev_alloc(h, &h->d_body, (size_t)h->max_frame_points * 3));
-                std::memcpy(h->h_pts, world_xyz, (size_t)n * 3 * sizeof(float));
-                IM_CUDA(cudaMemcpyAsync(h->d_body, h->h_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-                d_body = h->d_body;
+    F.pts = d_pts;
+    if (src_mode < 2) {
+        FramePose* hp = h->h_fp + s;
+        for (int j = 0; j < 3; ++j) { hp->pose_t[j] = pose_t[j]; hp->prio_origin[j] = (long long)std::floor(pose_t[j] / P.res) - 1024; }
+        IM_CUDA(cudaMemcpyAsync(d_fp, hp, sizeof(FramePose), cudaMemcpyHostToDevice, st));
+        if (n > 0) {
+            if (src_mode == 0) {
+                std::memcpy(h_pts, xyz, (size_t)n * 3 * sizeof(float));
+                IM_CUDA(cudaMemcpyAsync(d_pts, h_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+            } else {
+                F.pts = xyz;
             }
-            IM_LAUNCH(k_transform_full, mesh_grid(h, n, 128), 128, 0, st, lio->P, lio->d_ctrl, d_body, n, h->d_pts);
         }
+    } else {
+        // producer side runs on the localization stream, right behind the step that produced the state
+        cudaStream_t ls = lio->stream;
+        const float* d_body = xyz;
+        if (src_mode == 2 && n > 0) {
+            if (!h->d_body) IM_CUDA(mdev_alloc(h, &h->d_body, 2 * slot_pts));
+            std::memcpy(h_pts, xyz, (size_t)n * 3 * sizeof(float));
+            IM_CUDA(cudaMemcpyAsync(h->d_body + s * slot_pts, h_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ls));
+            d_body = h->d_body + s * slot_pts;
+        }
+        if (n > 0) IM_LAUNCH(k_transform_full, mesh_grid(h, n, 128), 128, 0, ls, lio->P, lio->d_ctrl, d_body, n, d_pts);
+        IM_LAUNCH(k_pose_from_lio, 1, 32, 0, ls, lio->d_ctrl, P.res, d_fp);
+        IM_CUDA(cudaEventRecord(h->ev_in[s], ls));
+        IM_CUDA(cudaStreamWaitEvent(st, h->ev_in[s], 0));
     }
     IM_LAUNCH(k_frame_begin, mesh_grid(h, (int)F.cmask + 1, 256), 256, 0, st, h->M, F);
     IM_CUDA(cudaEventRecord(h->ev[1], st));
@@ -456,21 +484,75 @@ static int mesh_push_impl(immesh_mesh_t* h, const float* world_xyz, int n, const
     }
     IM_LAUNCH(k_frame_end, 1, 1, 0, st, h->M);
     IM_CUDA(cudaGetLastError());
-    IM_CUDA(cudaMemcpyAsync(h->h_cnt, h->M.cnt, 32 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    IM_CUDA(cudaMemcpyAsync(h->h_cnt + 32 * s, h->M.cnt, 32 * sizeof(int), cudaMemcpyDeviceToHost, st));
     IM_CUDA(cudaEventRecord(h->ev[4], st));
-    IM_CUDA(cudaStreamSynchronize(st));
-    if (profiler().enabled) profiler().collect();
-    std::memcpy(h->last_cnt, h->h_cnt, 32 * sizeof(int));
-    float a = 0, b = 0, c = 0, d = 0;
-    cudaEventElapsedTime(&a, h->ev[0], h->ev[4]);
-    cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
-    cudaEventElapsedTime(&c, h->ev[2], h->ev[3]);
-    cudaEventElapsedTime(&d, h->ev[3], h->ev[4]);
-    h->last_ms[0] = a; h->last_ms[1] = b; h->last_ms[2] = c; h->last_ms[3] = d;
-    const int err = h->last_cnt[3];
-    if (err & (IM_MERR_VERT_POOL | IM_MERR_TRI_POOL | IM_MERR_HASH_FULL | IM_MERR_LIST_CAP | IM_MERR_VOXEL_CAP)) return im_fail(IMMESH_E_CAPACITY, "mesh pool / per-voxel working-set overflow");
-    if (err & (IM_MERR_KEY_RANGE | IM_MERR_PRIO_RANGE)) return im_fail(IMMESH_E_RANGE, "mesh key out of range");
+    IM_CUDA(cudaEventRecord(h->ev_done[s], st));
+    h->inflight[s] = 1;
     return IMMESH_OK;
+}
+// drain the queue; returns the status of the frames harvested since the last call
+static int mesh_wait_impl(immesh_mesh_t* h, bool timings) {
+    const int cur = h->frame_counter & 1;
+    mesh_harvest(h, cur ^ 1);
+    mesh_harvest(h, cur);
+    if (profiler().enabled) {
+        cudaStreamSynchronize(h->stream);
+        profiler().collect();
+    }
+    if (timings) {
+        float a = 0, b = 0, c = 0, d = 0;
+        cudaEventElapsedTime(&a, h->ev[0], h->ev[4]);
+        cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&c, h->ev[2], h->ev[3]);
+        cudaEventElapsedTime(&d, h->ev[3], h->ev[4]);
+        h->last_ms[0] = a; h->last_ms[1] = b; h->last_ms[2] = c; h->last_ms[3] = d;
+    }
+    const int rc = h->pending_rc;
+    h->pending_rc = 0;
+    return rc;
+}
+
+int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, const double* pose_t, int frame_idx) {
+    (void)frame_idx;
+    int rc = mesh_enqueue(h, world_xyz, n, pose_t, 0, nullptr);
+    return rc ? rc : mesh_wait_impl(h, true);
+}
+int immesh_mesh_push_frame_dev(immesh_mesh_t* h, const float* d_world_xyz, int n, const double* pose_t, int frame_idx) {
+    (void)frame_idx;
+    int rc = mesh_enqueue(h, d_world_xyz, n, pose_t, 1, nullptr);
+    return rc ? rc : mesh_wait_impl(h, true);
+}
+int immesh_mesh_push_frame_from_lio(immesh_mesh_t* h, immesh_lio_t* lio, const float* body_xyz, int n, int on_device) {
+    if (!lio) return im_fail(IMMESH_E_INVALID, "null lio handle");
+    int rc = mesh_enqueue(h, body_xyz, n, nullptr, on_device ? 3 : 2, lio);
+    return rc ? rc : mesh_wait_impl(h, true);
+}
+int immesh_mesh_push_frame_from_lio_async(immesh_mesh_t* h, immesh_lio_t* lio, const float* body_xyz, int n, int on_device) {
+    if (!lio) return im_fail(IMMESH_E_INVALID, "null lio handle");
+    return mesh_enqueue(h, body_xyz, n, nullptr, on_device ? 3 : 2, lio);
+}
+// device-side timing of a pipelined batch: begin mark on the localization stream, end mark behind BOTH streams
+int immesh_pipeline_mark_begin(immesh_lio_t* lio) {
+    if (!lio) return im_fail(IMMESH_E_INVALID, "null handle");
+    if (!lio->ev_mark) IM_CUDA(cudaEventCreate(&lio->ev_mark));
+    IM_CUDA(cudaEventRecord(lio->ev_mark, lio->stream));
+    return IMMESH_OK;
+}
+int immesh_pipeline_mark_end(immesh_lio_t* lio, immesh_mesh_t* h, double* ms) {
+    if (!lio || !h || !ms || !lio->ev_mark) return im_fail(IMMESH_E_INVALID, "bad argument");
+    if (!h->ev_mark) { IM_CUDA(cudaEventCreate(&h->ev_mark)); IM_CUDA(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming)); }
+    IM_CUDA(cudaEventRecord(h->ev_sync, lio->stream));
+    IM_CUDA(cudaStreamWaitEvent(h->stream, h->ev_sync, 0));
+    IM_CUDA(cudaEventRecord(h->ev_mark, h->stream));
+    IM_CUDA(cudaEventSynchronize(h->ev_mark));
+    float t = 0.f;
+    IM_CUDA(cudaEventElapsedTime(&t, lio->ev_mark, h->ev_mark));
+    *ms = t;
+    return IMMESH_OK;
+}
+int immesh_mesh_wait(immesh_mesh_t* h) {
+    if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
+    return mesh_wait_impl(h, false);
 }
 
 int immesh_mesh_counts(immesh_mesh_t* h, int64_t* out) {

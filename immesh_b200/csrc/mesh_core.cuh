@@ -94,12 +94,15 @@ struct MeshDev {
     int* cnt;
 };
 
+struct FramePose {        // per-frame sensor position (device resident so that a frame can be queued behind the localization)
+    double pose_t[3];
+    long long prio_origin[3];  // floor(pose_t / res) - 1024: origin of the 11-bit-per-axis voxel rank used by the flip priority
+};
 struct FrameBuf {
     const float* pts;     // [n][3] world-frame scan
     int n, step, m;       // m = number of candidates = ceil(n / step)
     int frame;            // internal monotonically increasing frame counter
-    double pose_t[3];
-    long long prio_origin[3];
+    const FramePose* fp;
     // candidates
     unsigned long long* cand_gkey;
     int* cand_vslot;

@@ -78,7 +78,6 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
     IM_SYNCBLOCK_M();
     const int nq = S->n_q;
     const double max_d2 = P.knn_max * P.knn_max;
-    const int lane = tid % IM_NLANES, warp = tid / IM_NLANES, nwarps = (nthreads + IM_NLANES - 1) / IM_NLANES;
     for (int ring = 1; ring <= 3; ++ring) {
         // gather the shell of Chebyshev radius `ring`
         const int side = 2 * ring + 1;
@@ -106,103 +105,45 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
         IM_SYNCBLOCK_M();
         // after gathering rings 0..ring, every unseen vertex is at least ring*res away from any query of this voxel
         const double lb = (double)ring * P.res;
-        for (int qi = warp; qi < nq; qi += nwarps) {
+        // one THREAD per query: a sequential scan of the staged candidates (shared-memory broadcast reads) keeps the 20
+        // best (d2, id) in a sorted private list -- an insertion only happens when a candidate beats the current 20th.
+        for (int qi = tid; qi < nq; qi += nthreads) {
             const int qv = S->q[qi];
             const float4 qp = M.vpos[qv];
-#if defined(__CUDA_ARCH__)
-            if (nc <= 512) {
-                // fast path: every lane keeps the distances of its <= 16 candidates in registers (computed once); 20 rounds
-                // of warp arg-min over the lanes' current minima, the winning lane retires its entry and rescans its 16.
-                float dreg[16];
-                int ireg[16];
-#pragma unroll
-                for (int sl = 0; sl < 16; ++sl) {
-                    const int i = lane + 32 * sl;
-                    float d2 = INFINITY;
-                    int id = 0x7fffffff;
-                    if (i < nc) {
-                        const float4 cp = S->cand[i];
-                        const float dd = dist2f(qp.x, qp.y, qp.z, cp.x, cp.y, cp.z);
-                        if ((double)dd <= max_d2) { d2 = dd; id = f2i(cp.w); }
-                    }
-                    dreg[sl] = d2; ireg[sl] = id;
+            float kd[20];
+            int kid[20], kix[20];
+            int cntk = 0;
+            for (int i = 0; i < nc; ++i) {
+                const float4 cp = S->cand[i];
+                const float d2 = dist2f(qp.x, qp.y, qp.z, cp.x, cp.y, cp.z);
+                if (!((double)d2 <= max_d2)) continue;
+                const int id = f2i(cp.w);
+                if (cntk == 20 && !(d2 < kd[19] || (d2 == kd[19] && id < kid[19]))) continue;
+                int pos = cntk < 20 ? cntk : 19;
+                while (pos > 0 && (d2 < kd[pos - 1] || (d2 == kd[pos - 1] && id < kid[pos - 1]))) {
+                    kd[pos] = kd[pos - 1]; kid[pos] = kid[pos - 1]; kix[pos] = kix[pos - 1];
+                    --pos;
                 }
-                double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
-                int cnt = 0, found = 0;
-                float last_d = 0.f;
-                for (int r = 0; r < 20; ++r) {
-                    float bd = INFINITY;
-                    int bid = 0x7fffffff, bsl = 0;
-#pragma unroll
-                    for (int sl = 0; sl < 16; ++sl)
-                        if (dreg[sl] < bd || (dreg[sl] == bd && ireg[sl] < bid)) { bd = dreg[sl]; bid = ireg[sl]; bsl = sl; }
-                    int aux = bsl * 32 + lane;  // candidate index of this lane's minimum
-                    warp_min_pair(&bd, &bid, &aux);
-                    if (bid == 0x7fffffff) break;
-                    if ((aux & 31) == lane) {
-#pragma unroll
-                        for (int sl = 0; sl < 16; ++sl)
-                            if (sl == (aux >> 5)) { dreg[sl] = INFINITY; ireg[sl] = 0x7fffffff; }
-                    }
-                    last_d = bd;
-                    ++found;
-                    const float sd = sqrtf(bd);
-                    if ((double)sd < P.accept && lane == 0) S->flag[aux] = 1;
-                    if ((double)sd < P.accept * 2) {
-                        ++cnt;
-                        const float4 cp = S->cand[aux];
-                        sv0 = sv0 + (double)cp.x; sv1 = sv1 + (double)cp.y; sv2 = sv2 + (double)cp.z;
-                    }
-                }
-                const bool complete = (lb > P.knn_max) || (found >= 20 && (double)last_d < lb * lb * 0.999999);
-                if (!complete && lane == 0) S->need_more = 1;
-                if (lane == 0) {
-                    M.vsmooth[(size_t)qv * 3 + 0] = (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f);
-                    M.vsmooth[(size_t)qv * 3 + 1] = (sv1 / (double)cnt) * (double)1.0f + (double)qp.y * (double)(1 - 1.0f);
-                    M.vsmooth[(size_t)qv * 3 + 2] = (sv2 / (double)cnt) * (double)1.0f + (double)qp.z * (double)(1 - 1.0f);
-                }
-                continue;
+                kd[pos] = d2; kid[pos] = id; kix[pos] = i;
+                if (cntk < 20) ++cntk;
             }
-#endif
-            float prev_d = -1.0f;
-            int prev_id = -1;
             double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
-            int cnt = 0, found = 0;
-            float last_d = 0.f;
-            for (int r = 0; r < 20; ++r) {
-                float bd = INFINITY;
-                int bid = 0x7fffffff, bidx = -1;
-                for (int i = lane; i < nc; i += IM_NLANES) {
-                    const float4 cp = S->cand[i];
-                    const float d2 = dist2f(qp.x, qp.y, qp.z, cp.x, cp.y, cp.z);
-                    const int id = f2i(cp.w);
-                    if (!((double)d2 <= max_d2)) continue;
-                    if (d2 < prev_d || (d2 == prev_d && id <= prev_id)) continue;  // already reported
-                    if (d2 < bd || (d2 == bd && id < bid)) { bd = d2; bid = id; bidx = i; }
-                }
-                warp_min_pair(&bd, &bid, &bidx);
-                if (bidx < 0) break;
-                prev_d = bd; prev_id = bid;
-                last_d = bd;
-                ++found;
-                const float sd = sqrtf(bd);
-                if ((double)sd < P.accept && lane == 0) S->flag[bidx] = 1;
+            int cnt = 0;
+            for (int r = 0; r < cntk; ++r) {
+                const float sd = sqrtf(kd[r]);
+                if ((double)sd < P.accept) S->flag[kix[r]] = 1;
                 if ((double)sd < P.accept * 2) {
                     ++cnt;
-                    const float4 cp = S->cand[bidx];
+                    const float4 cp = S->cand[kix[r]];
                     sv0 = sv0 + (double)cp.x; sv1 = sv1 + (double)cp.y; sv2 = sv2 + (double)cp.z;
                 }
             }
-            const bool complete = (lb > P.knn_max) || (found >= 20 && (double)last_d < lb * lb * 0.999999);
-            if (!complete) {
-                if (lane == 0) S->need_more = 1;
-            }
-            if (lane == 0) {
-                // smooth_factor = 1.0f (mesh_rec_geometry.cpp:334,367-369)
-                M.vsmooth[(size_t)qv * 3 + 0] = (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f);
-                M.vsmooth[(size_t)qv * 3 + 1] = (sv1 / (double)cnt) * (double)1.0f + (double)qp.y * (double)(1 - 1.0f);
-                M.vsmooth[(size_t)qv * 3 + 2] = (sv2 / (double)cnt) * (double)1.0f + (double)qp.z * (double)(1 - 1.0f);
-            }
+            const bool complete = (lb > P.knn_max) || (cntk >= 20 && (double)kd[19] < lb * lb * 0.999999);
+            if (!complete) S->need_more = 1;
+            // smooth_factor = 1.0f (mesh_rec_geometry.cpp:334,367-369)
+            M.vsmooth[(size_t)qv * 3 + 0] = (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f);
+            M.vsmooth[(size_t)qv * 3 + 1] = (sv1 / (double)cnt) * (double)1.0f + (double)qp.y * (double)(1 - 1.0f);
+            M.vsmooth[(size_t)qv * 3 + 2] = (sv2 / (double)cnt) * (double)1.0f + (double)qp.z * (double)(1 - 1.0f);
         }
         IM_SYNCBLOCK_M();
         if (!S->need_more) break;
@@ -342,7 +283,7 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
     // flip priority of this voxel: its key relative to the frame origin (ascending (x,y,z) order, last one wins)
     int kx, ky, kz;
     unpack_ikey(M.vkeys[vs], &kx, &ky, &kz);
-    const long long lx = kx - F.prio_origin[0], ly = ky - F.prio_origin[1], lz = kz - F.prio_origin[2];
+    const long long lx = kx - F.fp->prio_origin[0], ly = ky - F.fp->prio_origin[1], lz = kz - F.fp->prio_origin[2];
     if (lx < 0 || lx >= 2048 || ly < 0 || ly >= 2048 || lz < 0 || lz >= 2048) {
         if (tid == 0) im_atomic_or(&M.cnt[3], IM_MERR_PRIO_RANGE);
     }
@@ -351,7 +292,7 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
     // commit, faces side (triangle_compare): a face already live in the store is "existing", otherwise "to add"
     for (int k = tid; k < nf; k += nthreads) {
         const int a = S->faces[k][0], b = S->faces[k][1], c = S->faces[k][2];
-        const unsigned long long word = word_base | (unsigned long long)compute_flip(M, a, b, c, F.pose_t, S->axes);
+        const unsigned long long word = word_base | (unsigned long long)compute_flip(M, a, b, c, F.fp->pose_t, S->axes);
         const int t = tri_find(M, a, b, c);
         if (t >= 0 && M.tri[t].w) {
             im_atomic_max64(&M.tri_flip[t], word);
@@ -614,7 +555,7 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
     if (lane == 0) im_atomic_add(&M.cnt[23], nf);
     int kx, ky, kz;
     unpack_ikey(M.vkeys[vs], &kx, &ky, &kz);
-    const long long lx = kx - F.prio_origin[0], ly = ky - F.prio_origin[1], lz = kz - F.prio_origin[2];
+    const long long lx = kx - F.fp->prio_origin[0], ly = ky - F.fp->prio_origin[1], lz = kz - F.fp->prio_origin[2];
     if (lx < 0 || lx >= 2048 || ly < 0 || ly >= 2048 || lz < 0 || lz >= 2048) {
         if (lane == 0) im_atomic_or(&M.cnt[3], IM_MERR_PRIO_RANGE);
     }
@@ -622,7 +563,7 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
     const unsigned long long word_base = ((unsigned long long)F.frame << 34) | (prio << 1);
     for (int k = lane; k < nf; k += nlanes) {
         const int a = faces[k][0], b = faces[k][1], c = faces[k][2];
-        const unsigned long long word = word_base | (unsigned long long)compute_flip(M, a, b, c, F.pose_t, S->axes);
+        const unsigned long long word = word_base | (unsigned long long)compute_flip(M, a, b, c, F.fp->pose_t, S->axes);
         const int t = tri_find(M, a, b, c);
         if (t >= 0 && M.tri[t].w) {
             im_atomic_max64(&M.tri_flip[t], word);

@@ -11,6 +11,7 @@
 #ifndef IMMESH_B200_H_
 #define IMMESH_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -85,6 +86,13 @@ int immesh_lio_step(immesh_lio_t* h, const float* body_xyz, int n, double dt, do
 int immesh_lio_step_dev(immesh_lio_t* h, const float* d_body_xyz, int n, double dt, double cov_gyr, double cov_acc,
                         double* state_out, int* iters_run);
 
+/* Pipelined form (the reference runs LIO and meshing concurrently: LIO thread || mesh thread pool):
+ * immesh_lio_step_async queues a scan on the localization stream and returns; immesh_lio_wait blocks until everything
+ * queued has finished and returns the latest state.  on_device != 0: body_xyz is a device pointer. */
+int immesh_lio_step_async(immesh_lio_t* h, const float* body_xyz, int n, int on_device, double dt, double cov_gyr, double cov_acc);
+int immesh_lio_wait(immesh_lio_t* h, double* state_out /*[348] or NULL*/, int* iters_run /*or NULL*/);
+int immesh_lio_enqueue_memset(immesh_lio_t* h, void* d_buf, size_t bytes); /* benchmark helper: in-stream L2 flush */
+
 /* BuildResidualListOMP (src/voxel_mapping.hpp:103-105, src/voxel_mapping.cpp:153-245) as a stand-alone call at
  * the current state: fills, for every accepted match in scan order, its scan index, octree layer and the ptpl
  * payload.  Returns the number of matches in *n_out (written entries are capped by cap). */
@@ -135,6 +143,13 @@ int immesh_mesh_push_frame_dev(immesh_mesh_t* h, const float* d_world_xyz, int n
  * (on the device, no host round trip of the world cloud), then incremental_mesh_reconstruction on it.
  * on_device != 0: body_xyz is a device pointer. */
 int immesh_mesh_push_frame_from_lio(immesh_mesh_t* h, immesh_lio_t* lio, const float* body_xyz, int n, int on_device);
+/* queued variant: the frame is transformed right behind the localization step that produced its pose (on the
+ * localization stream) and meshed on the mesh stream while the next scan is being localised; immesh_mesh_wait drains. */
+int immesh_mesh_push_frame_from_lio_async(immesh_mesh_t* h, immesh_lio_t* lio, const float* body_xyz, int n, int on_device);
+int immesh_mesh_wait(immesh_mesh_t* h);
+/* CUDA-event time (ms) of everything queued on both handles between the two marks */
+int immesh_pipeline_mark_begin(immesh_lio_t* lio);
+int immesh_pipeline_mark_end(immesh_lio_t* lio, immesh_mesh_t* h, double* ms);
 /* counts: [n_vertices, n_live_triangles, frame_new_vertices, frame_voxels_meshed, frame_added, frame_removed, n_voxels, n_activated] */
 int immesh_mesh_counts(immesh_mesh_t* h, int64_t* out /*[8]*/);
 /* Triangle_manager::get_all_triangle_list (src/meshing/r3live/triangle.cpp:12-33) + the vertex array:

@@ -76,7 +76,9 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     const MeshParams& P = h->P;
     const int step = std::max(1, (int)std::lround((double)(n / P.append_target)));
     F.n = n; F.step = step; F.m = n > 0 ? (n + step - 1) / step : 0; F.frame = ++h->frame_counter;
-    for (int j = 0; j < 3; ++j) { F.pose_t[j] = pose_t[j]; F.prio_origin[j] = (long long)std::floor(pose_t[j] / P.res) - 1024; }
+    static FramePose fp_storage;
+    for (int j = 0; j < 3; ++j) { fp_storage.pose_t[j] = pose_t[j]; fp_storage.prio_origin[j] = (long long)std::floor(pose_t[j] / P.res) - 1024; }
+    F.fp = &fp_storage;
     F.cmask = (unsigned)(p2((size_t)std::max(F.m, 1) * 2) - 1);
     if (n > 0) std::memcpy(h->pts.data(), world_xyz, (size_t)n * 12);
     for (unsigned i = 0; i <= F.cmask; ++i) { F.ckeys[i] = IM_EMPTY_KEY; F.chead[i] = -1; }

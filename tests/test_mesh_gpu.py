@@ -44,3 +44,33 @@ def test_empty_frame_and_restart(cuda_lib):
     g.push_frame(pts, np.zeros(3), 1)
     c = g.counts()
     assert c["n_vertices"] == 3 and c["n_triangles"] == 1
+
+
+def test_pipelined_equals_sequential(cuda_lib):
+    """LIO(k+1) overlapped with mesh(k) on two streams must give exactly the results of the blocking calls."""
+    from immesh_b200 import synth
+    from lio_common import init_velocity
+    cfg = api.AVIA
+    sensor, scans = synth.make_stream("avia", 7, seed=8, ext_T=cfg.ext_T)
+    res = []
+    for mode in ("sync", "async"):
+        lio, mesh = api.Lio(cfg, lib=cuda_lib), api.Mesh(api.MeshConfig(**SMALL), lib=cuda_lib)
+        lio.set_pose(scans[0]["R_true"], scans[0]["t_true"])
+        init_velocity(lio, sensor, scans)
+        lio.voxel_map_init(scans[0]["body_full"])
+        for k in range(1, 7):
+            if mode == "sync":
+                lio.step(scans[k]["body_ds"], scans[k]["dt"])
+                mesh.push_frame_from_lio(lio, scans[k]["body_full"])
+            else:
+                lio.step_async(scans[k]["body_ds"], dt=scans[k]["dt"])
+                mesh.push_frame_from_lio_async(lio, scans[k]["body_full"])
+        if mode == "async":
+            lio.wait()
+            mesh.wait()
+        res.append((lio.get_state(), lio.dump_map(), mesh.snapshot()))
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1])
+    for a, b in zip(res[0][2], res[1][2]):
+        assert np.array_equal(a, b)
+    assert len(res[0][2][1]) > 1000
