@@ -23,15 +23,27 @@ IM_HD void warp_min_pair(float* d, int* id, int* aux) {
         if (od < *d || (od == *d && oi < *id)) { *d = od; *id = oi; *aux = oa; }
     }
 }
+IM_HD unsigned im_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+IM_HD unsigned im_lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 #else
 #define IM_NLANES 1
 IM_HD void warp_min_pair(float*, int*, int*) {}
+IM_HD unsigned im_ballot(bool p) { return p ? 1u : 0u; }
+IM_HD unsigned im_lanemask_lt() { return 0u; }
 #endif
+IM_HD int im_popc(unsigned m) {
+#if defined(__CUDA_ARCH__)
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
+}
 
 struct DilateSmem {
     float4 cand[IM_MAXG];      // gathered neighbourhood vertices: xyz + id (bit-cast in w)
     int flag[IM_MAXG];         // member of the dilated set
     int q[IM_MAXIN];           // in-voxel vertex ids (the kNN queries)
+    int qdone[IM_MAXIN];       // query finished at an earlier ring (its 20-NN are provably complete)
     int ids[IM_MAXD];          // output, ascending
     int n_cand, n_q, n_out, need_more, overflow;
 };
@@ -77,7 +89,10 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
     }
     IM_SYNCBLOCK_M();
     const int nq = S->n_q;
+    for (int i = tid; i < nq; i += nthreads) { S->qdone[i] = 0; S->flag[i] = 0; }
+    int flag_init = nq;   // candidates [0, flag_init) have an initialised flag
     const double max_d2 = P.knn_max * P.knn_max;
+    const int lane = tid % IM_NLANES, warp = tid / IM_NLANES, nwarps = (nthreads + IM_NLANES - 1) / IM_NLANES;
     for (int ring = 1; ring <= 3; ++ring) {
         // gather the shell of Chebyshev radius `ring`
         const int side = 2 * ring + 1;
@@ -100,50 +115,122 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
         }
         IM_SYNCBLOCK_M();
         const int nc = S->n_cand < IM_MAXG ? S->n_cand : IM_MAXG;
-        for (int i = tid; i < nc; i += nthreads) S->flag[i] = 0;
+        for (int i = flag_init + tid; i < nc; i += nthreads) S->flag[i] = 0;
+        flag_init = nc;
         if (tid == 0) S->need_more = 0;
         IM_SYNCBLOCK_M();
         // after gathering rings 0..ring, every unseen vertex is at least ring*res away from any query of this voxel
         const double lb = (double)ring * P.res;
-        // one THREAD per query: a sequential scan of the staged candidates (shared-memory broadcast reads) keeps the 20
-        // best (d2, id) in a sorted private list -- an insertion only happens when a candidate beats the current 20th.
-        for (int qi = tid; qi < nq; qi += nthreads) {
+        for (int qi = warp; qi < nq; qi += nwarps) {
+            if (S->qdone[qi]) continue;   // complete at an earlier ring: more candidates cannot change its 20-NN
             const int qv = S->q[qi];
             const float4 qp = M.vpos[qv];
-            float kd[20];
-            int kid[20], kix[20];
-            int cntk = 0;
-            for (int i = 0; i < nc; ++i) {
-                const float4 cp = S->cand[i];
-                const float d2 = dist2f(qp.x, qp.y, qp.z, cp.x, cp.y, cp.z);
-                if (!((double)d2 <= max_d2)) continue;
-                const int id = f2i(cp.w);
-                if (cntk == 20 && !(d2 < kd[19] || (d2 == kd[19] && id < kid[19]))) continue;
-                int pos = cntk < 20 ? cntk : 19;
-                while (pos > 0 && (d2 < kd[pos - 1] || (d2 == kd[pos - 1] && id < kid[pos - 1]))) {
-                    kd[pos] = kd[pos - 1]; kid[pos] = kid[pos - 1]; kix[pos] = kix[pos - 1];
-                    --pos;
+#if defined(__CUDA_ARCH__)
+            if (nc <= 512) {
+                // fast path: every lane keeps the distances of its <= 16 candidates in registers (computed once); 20 rounds
+                // of warp arg-min over the lanes' current minima, the winning lane retires its entry and rescans its 16.
+                float dreg[16];
+                int ireg[16];
+                const int nsl = (nc + 31) >> 5;   // occupied register slots (warp-uniform)
+#pragma unroll
+                for (int sl = 0; sl < 16; ++sl) {
+                    const int i = lane + 32 * sl;
+                    float d2 = INFINITY;
+                    int id = 0x7fffffff;
+                    if (i < nc) {
+                        const float4 cp = S->cand[i];
+                        const float dd = dist2f(qp.x, qp.y, qp.z, cp.x, cp.y, cp.z);
+                        if ((double)dd <= max_d2) { d2 = dd; id = f2i(cp.w); }
+                    }
+                    dreg[sl] = d2; ireg[sl] = id;
                 }
-                kd[pos] = d2; kid[pos] = id; kix[pos] = i;
-                if (cntk < 20) ++cntk;
+                double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
+                int cnt = 0, found = 0;
+                float last_d = 0.f;
+                int widx = 0;      // lane r remembers the r-th nearest (candidate index, squared distance)
+                float wd = INFINITY;
+                for (int r = 0; r < 20; ++r) {
+                    float bd = INFINITY;
+                    int bid = 0x7fffffff, bsl = 0;
+#pragma unroll
+                    for (int sl = 0; sl < 16; ++sl)
+                        if (sl < nsl && (dreg[sl] < bd || (dreg[sl] == bd && ireg[sl] < bid))) { bd = dreg[sl]; bid = ireg[sl]; bsl = sl; }
+                    int aux = bsl * 32 + lane;  // candidate index of this lane's minimum
+                    warp_min_pair(&bd, &bid, &aux);
+                    if (bid == 0x7fffffff) break;
+                    if ((aux & 31) == lane) {
+#pragma unroll
+                        for (int sl = 0; sl < 16; ++sl)
+                            if (sl == (aux >> 5)) { dreg[sl] = INFINITY; ireg[sl] = 0x7fffffff; }
+                    }
+                    last_d = bd;
+                    if (lane == r) { widx = aux; wd = bd; }
+                    ++found;
+                    const float sd = sqrtf(bd);
+                    if ((double)sd < P.accept * 2) {
+                        ++cnt;
+                        const float4 cp = S->cand[aux];
+                        sv0 = sv0 + (double)cp.x; sv1 = sv1 + (double)cp.y; sv2 = sv2 + (double)cp.z;
+                    }
+                }
+                const bool complete = (lb > P.knn_max) || (found >= 20 && (double)last_d < lb * lb * 0.999999);
+                if (!complete) {
+                    if (lane == 0) S->need_more = 1;   // retried with the next ring; nothing is published yet
+                } else {
+                    if (lane < found && (double)sqrtf(wd) < P.accept) S->flag[widx] = 1;
+                    if (lane == 0) {
+                        S->qdone[qi] = 1;
+                        M.vsmooth[(size_t)qv * 3 + 0] = (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f);
+                        M.vsmooth[(size_t)qv * 3 + 1] = (sv1 / (double)cnt) * (double)1.0f + (double)qp.y * (double)(1 - 1.0f);
+                        M.vsmooth[(size_t)qv * 3 + 2] = (sv2 / (double)cnt) * (double)1.0f + (double)qp.z * (double)(1 - 1.0f);
+                    }
+                }
+                continue;
             }
+#endif
+            float prev_d = -1.0f;
+            int prev_id = -1;
             double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
-            int cnt = 0;
-            for (int r = 0; r < cntk; ++r) {
-                const float sd = sqrtf(kd[r]);
-                if ((double)sd < P.accept) S->flag[kix[r]] = 1;
+            int cnt = 0, found = 0;
+            float last_d = 0.f;
+            int widx_a[20];
+            float wd_a[20];
+            for (int r = 0; r < 20; ++r) {
+                float bd = INFINITY;
+                int bid = 0x7fffffff, bidx = -1;
+                for (int i = lane; i < nc; i += IM_NLANES) {
+                    const float4 cp = S->cand[i];
+                    const float d2 = dist2f(qp.x, qp.y, qp.z, cp.x, cp.y, cp.z);
+                    const int id = f2i(cp.w);
+                    if (!((double)d2 <= max_d2)) continue;
+                    if (d2 < prev_d || (d2 == prev_d && id <= prev_id)) continue;  // already reported
+                    if (d2 < bd || (d2 == bd && id < bid)) { bd = d2; bid = id; bidx = i; }
+                }
+                warp_min_pair(&bd, &bid, &bidx);
+                if (bidx < 0) break;
+                prev_d = bd; prev_id = bid;
+                last_d = bd;
+                widx_a[found] = bidx; wd_a[found] = bd;
+                ++found;
+                const float sd = sqrtf(bd);
                 if ((double)sd < P.accept * 2) {
                     ++cnt;
-                    const float4 cp = S->cand[kix[r]];
+                    const float4 cp = S->cand[bidx];
                     sv0 = sv0 + (double)cp.x; sv1 = sv1 + (double)cp.y; sv2 = sv2 + (double)cp.z;
                 }
             }
-            const bool complete = (lb > P.knn_max) || (cntk >= 20 && (double)kd[19] < lb * lb * 0.999999);
-            if (!complete) S->need_more = 1;
-            // smooth_factor = 1.0f (mesh_rec_geometry.cpp:334,367-369)
-            M.vsmooth[(size_t)qv * 3 + 0] = (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f);
-            M.vsmooth[(size_t)qv * 3 + 1] = (sv1 / (double)cnt) * (double)1.0f + (double)qp.y * (double)(1 - 1.0f);
-            M.vsmooth[(size_t)qv * 3 + 2] = (sv2 / (double)cnt) * (double)1.0f + (double)qp.z * (double)(1 - 1.0f);
+            const bool complete = (lb > P.knn_max) || (found >= 20 && (double)last_d < lb * lb * 0.999999);
+            if (!complete) {
+                if (lane == 0) S->need_more = 1;
+            } else if (lane == 0) {
+                for (int r = 0; r < found; ++r)
+                    if ((double)sqrtf(wd_a[r]) < P.accept) S->flag[widx_a[r]] = 1;
+                S->qdone[qi] = 1;
+                // smooth_factor = 1.0f (mesh_rec_geometry.cpp:334,367-369)
+                M.vsmooth[(size_t)qv * 3 + 0] = (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f);
+                M.vsmooth[(size_t)qv * 3 + 1] = (sv1 / (double)cnt) * (double)1.0f + (double)qp.y * (double)(1 - 1.0f);
+                M.vsmooth[(size_t)qv * 3 + 2] = (sv2 / (double)cnt) * (double)1.0f + (double)qp.z * (double)(1 - 1.0f);
+            }
         }
         IM_SYNCBLOCK_M();
         if (!S->need_more) break;
@@ -362,7 +449,7 @@ struct MeshWarpSmem {
     int2 snap[MAXD];
     DTri tris[3 * MAXD + 8];          // after face extraction: reused as the face hash (4*MAXD ints)
     float circ[3 * MAXD + 8][3];      // before the triangulation: vertex positions; after it: faces (2*MAXD int3)
-    int scratch[8 + 64 + 136];
+    int scratch[8 + 64 + 2 * 192];
     double axes[9];
     double centre[3];
     int ntri, nface;
@@ -466,60 +553,81 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
     IM_SYNCWARP();
     if (!s_seed[2]) return;
     const int i1 = s_seed[0], i2 = s_seed[1];
-    for (int p = 1; p < n; ++p) {
+    // per insertion: (1) conflict scan, compacted with ballots; (2) directed edge list of the cavity; (3) boundary edges
+    // (those whose reverse is not in the list) ranked with ballots, each writes its new triangle -- cavity slots first,
+    // then the pool tail.  Three warp barriers, no atomics.
+    int* s_ea = s_edges;            // [192] directed cavity edges: tails
+    int* s_eb = s_edges + 192;      // [192] heads
+    (void)s_cav_n; (void)s_edge_n;
+    const unsigned lt = im_lanemask_lt();
+    bool ovf = false;
+    for (int p = 1; p < n && !ovf; ++p) {
         if (p == i1 || p == i2) continue;
-        if (lane == 0) { *s_cav_n = 0; *s_edge_n = 0; }
-        IM_SYNCWARP();
         const int nt = S->ntri;
         const float pxf = (float)Pt[p].x, pyf = (float)Pt[p].y;
-        for (int t = lane; t < nt; t += nlanes) {
-            const DTri tr = tris[t];
-            if (!tr.alive) continue;
-            if (tr.v[0] != IM_GHOST && tr.v[1] != IM_GHOST && tr.v[2] != IM_GHOST) {
-                const float dx = pxf - S->circ[t][0], dy = pyf - S->circ[t][1];
-                if (dx * dx + dy * dy > S->circ[t][2]) continue;   // certainly outside the circumcircle
+        int nc = 0;
+        for (int t0 = 0; t0 < nt; t0 += nlanes) {
+            const int t = t0 + lane;
+            bool c = false;
+            if (t < nt) {
+                const DTri tr = tris[t];
+                if (tr.alive) {
+                    bool maybe = true;
+                    if (tr.v[0] != IM_GHOST && tr.v[1] != IM_GHOST && tr.v[2] != IM_GHOST) {
+                        const float dx = pxf - S->circ[t][0], dy = pyf - S->circ[t][1];
+                        if (dx * dx + dy * dy > S->circ[t][2]) maybe = false;   // certainly outside the circumcircle
+                    }
+                    if (maybe) c = dt_conflict(tr, Pt, p);
+                }
             }
-            if (dt_conflict(tr, Pt, p)) {
-                const int k = im_atomic_add(s_cav_n, 1);
+            const unsigned m = im_ballot(c);
+            if (c) {
+                const int k = nc + im_popc(m & lt);
                 if (k < 64) s_cav[k] = t;
             }
+            nc += im_popc(m);
         }
+        if (nc > 64) { ovf = true; break; }   // warp-uniform
         IM_SYNCWARP();
-        int nc = *s_cav_n;
-        if (nc > 64) { nc = 64; if (lane == 0) *s_ovf = 1; }
-        for (int e = lane; e < nc * 3; e += nlanes) {
+        if (nc == 0) continue;                // duplicate point: skipped (CGAL does the same)
+        const int ne3 = nc * 3;
+        for (int e = lane; e < ne3; e += nlanes) {
             const DTri& t = tris[s_cav[e / 3]];
-            const int a = t.v[(e % 3 + 1) % 3], b = t.v[(e % 3 + 2) % 3];
-            bool interior = false;
-            for (int f = 0; f < nc * 3 && !interior; ++f) {
-                const DTri& u = tris[s_cav[f / 3]];
-                if (u.v[(f % 3 + 1) % 3] == b && u.v[(f % 3 + 2) % 3] == a) interior = true;
-            }
-            if (!interior) {
-                const int k = im_atomic_add(s_edge_n, 1);
-                if (k < 68) { s_edges[2 * k] = a; s_edges[2 * k + 1] = b; }
-            }
+            s_ea[e] = t.v[(e % 3 + 1) % 3];
+            s_eb[e] = t.v[(e % 3 + 2) % 3];
         }
         IM_SYNCWARP();
-        int ne = *s_edge_n;
-        if (ne > 68) { ne = 68; if (lane == 0) *s_ovf = 1; }
-        for (int k = lane; k < nc; k += nlanes) tris[s_cav[k]].alive = 0;
-        IM_SYNCWARP();
-        for (int k = lane; k < ne; k += nlanes) {
-            const int slot = (k < nc) ? s_cav[k] : (nt + (k - nc));
-            if (slot < max_tris) {
-                const int a = s_edges[2 * k], b = s_edges[2 * k + 1];
-                tris[slot].v[0] = (short)a; tris[slot].v[1] = (short)b; tris[slot].v[2] = (short)p; tris[slot].alive = 1;
-                if (a != IM_GHOST && b != IM_GHOST) circumcircle_f(Pt, a, b, p, S->circ[slot]);
+        int nb = 0;
+        for (int e0 = 0; e0 < ne3; e0 += nlanes) {
+            const int e = e0 + lane;
+            bool isb = false;
+            int a = 0, b = 0;
+            if (e < ne3) {
+                a = s_ea[e]; b = s_eb[e];
+                isb = true;
+                for (int f = 0; f < ne3; ++f)
+                    if (s_ea[f] == b && s_eb[f] == a) { isb = false; break; }
             }
+            const unsigned m = im_ballot(isb);
+            if (isb) {
+                const int k = nb + im_popc(m & lt);
+                const int slot = (k < nc) ? s_cav[k] : (nt + (k - nc));
+                if (slot < max_tris) {
+                    tris[slot].v[0] = (short)a; tris[slot].v[1] = (short)b; tris[slot].v[2] = (short)p; tris[slot].alive = 1;
+                    if (a != IM_GHOST && b != IM_GHOST) circumcircle_f(Pt, a, b, p, S->circ[slot]);
+                }
+            }
+            nb += im_popc(m);
         }
-        if (lane == 0 && ne > nc) {
-            if (nt + (ne - nc) <= max_tris) S->ntri = nt + (ne - nc);
-            else { S->ntri = max_tris; *s_ovf = 1; }
+        // every cavity slot is reused (a valid cavity has nc + 2 boundary edges); kill leftovers defensively
+        for (int k = nb + lane; k < nc; k += nlanes) tris[s_cav[k]].alive = 0;
+        if (nb > nc) {
+            if (nt + (nb - nc) <= max_tris) { if (lane == 0) S->ntri = nt + (nb - nc); }
+            else ovf = true;
         }
         IM_SYNCWARP();
-        if (*s_ovf) break;
     }
+    if (lane == 0) *s_ovf = ovf ? 1 : 0;
     IM_SYNCWARP();
     if (*s_ovf) {  // hand this voxel to the block-level stage
         if (lane == 0) F.work_n_ids[w] = -n;
