@@ -20,7 +20,7 @@ __global__ void k_frame_begin(MeshDev M, FrameBuf F) {
     for (unsigned int i = tid; i <= F.cmask; i += nt) { F.ckeys[i] = IM_EMPTY_KEY; F.chead[i] = -1; }
     if (tid == 0) {
         for (int k = 5; k <= 10; ++k) M.cnt[k] = 0;
-        for (int k = 18; k <= 24; ++k) M.cnt[k] = 0;
+        for (int k = 17; k <= 24; ++k) M.cnt[k] = 0;
     }
 }
 __global__ void __launch_bounds__(128) k_cand_init(MeshDev M, MeshParams P, FrameBuf F) {
@@ -52,39 +52,36 @@ __global__ void __launch_bounds__(128) k_cand_resolve(MeshDev M, MeshParams P, F
         }
     }
 }
-// exclusive scan of the accept flags by one block (m is ~1e4 per frame)
+// exclusive scan of the accept flags by one block in ONE pass: thread t owns a contiguous chunk of ceil(m/1024) candidates
 __global__ void __launch_bounds__(1024) k_cand_scan(MeshDev M, FrameBuf F) {
     __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < F.m; base += 1024) {
-        const int c = base + threadIdx.x;
-        const int f = (c < F.m && F.cand_status[c] == CAND_ACCEPT) ? 1 : 0;
-        int v = f;
+    const int per = (F.m + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(lo + per, F.m);
+    int mine = 0;
+    for (int c = lo; c < hi; ++c) mine += (F.cand_status[c] == CAND_ACCEPT) ? 1 : 0;
+    int v = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        int wv = s_warp[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += u;
+            const int u = __shfl_up_sync(0xffffffffu, wv, o);
+            if (lane >= o) wv += u;
         }
-        if (lane == 31) s_warp[warp] = v;
-        __syncthreads();
-        if (warp == 0) {
-            int wv = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, wv, o);
-                if (lane >= o) wv += u;
-            }
-            s_warp[lane] = wv;
-        }
-        __syncthreads();
-        const int prefix = s_carry + (warp ? s_warp[warp - 1] : 0) + v - f;
-        if (c < F.m) F.cand_scan[c] = prefix;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = prefix + f;
-        __syncthreads();
+        s_warp[lane] = wv;
+    }
+    __syncthreads();
+    int run = (warp ? s_warp[warp - 1] : 0) + v - mine;
+    for (int c = lo; c < hi; ++c) {
+        F.cand_scan[c] = run;
+        run += (F.cand_status[c] == CAND_ACCEPT) ? 1 : 0;
     }
 }
 __global__ void __launch_bounds__(128) k_cand_commit(MeshDev M, MeshParams P, FrameBuf F) {
@@ -97,9 +94,15 @@ __global__ void __launch_bounds__(128) k_voxel_select(MeshDev M, FrameBuf F) {
 }
 __global__ void __launch_bounds__(128) k_voxel_dilate(MeshDev M, MeshParams P, FrameBuf F) {
     __shared__ DilateSmem S;
-    const int nw = min(M.cnt[6], F.max_work);
-    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
-        voxel_dilate(M, P, F, w, &S, threadIdx.x, blockDim.x);
+    __shared__ int s_item;
+    const int nw = work_total(M, F);
+    while (true) {   // dynamic claim in list order: the populous voxels go first
+        if (threadIdx.x == 0) s_item = atomicAdd(&M.cnt[24], 1);
+        __syncthreads();
+        const int i = s_item;
+        __syncthreads();
+        if (i >= nw) break;
+        voxel_dilate(M, P, F, work_slot(M, F, i), &S, threadIdx.x, blockDim.x);
         __syncthreads();
     }
 }
@@ -107,8 +110,9 @@ template <int MAXD>
 __global__ void __launch_bounds__(128) k_voxel_mesh(MeshDev M, MeshParams P, FrameBuf F, int lo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MeshSmem<MAXD>* S = reinterpret_cast<MeshSmem<MAXD>*>(smem_raw);
-    const int nw = min(M.cnt[6], F.max_work);
-    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+    const int nw = work_total(M, F);
+    for (int i = blockIdx.x; i < nw; i += gridDim.x) {
+        const int w = work_slot(M, F, i);
         const int n = F.work_n_ids[w];
         if (n < 0 || (n > lo && n <= MAXD)) voxel_mesh<MAXD>(M, P, F, w, S, threadIdx.x, blockDim.x);
         __syncthreads();
@@ -120,13 +124,13 @@ __global__ void __launch_bounds__(128) k_voxel_mesh_warp(MeshDev M, MeshParams P
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     MeshWarpSmem<256>* S = reinterpret_cast<MeshWarpSmem<256>*>(smem_raw) + warp;
-    const int nw = min(M.cnt[6], F.max_work);
+    const int nw = work_total(M, F);
     while (true) {
-        int w = 0;
-        if (lane == 0) w = atomicAdd(&M.cnt[19], 1);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= nw) break;
-        voxel_mesh_warp<256>(M, P, F, w, S, lane, 32);
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&M.cnt[19], 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= nw) break;
+        voxel_mesh_warp<256>(M, P, F, work_slot(M, F, i), S, lane, 32);
         __syncwarp();
     }
 }
@@ -558,14 +562,14 @@ int immesh_mesh_wait(immesh_mesh_t* h) {
 int immesh_mesh_counts(immesh_mesh_t* h, int64_t* out) {
     if (!h || !out) return im_fail(IMMESH_E_INVALID, "null argument");
     const int* c = h->last_cnt;
-    out[0] = c[0]; out[1] = c[2]; out[2] = c[10]; out[3] = c[6]; out[4] = c[7]; out[5] = c[8]; out[6] = c[4]; out[7] = c[5];
+    out[0] = c[0]; out[1] = c[2]; out[2] = c[10]; out[3] = c[6] + c[17]; out[4] = c[7]; out[5] = c[8]; out[6] = c[4]; out[7] = c[5];
     return IMMESH_OK;
 }
 
 int immesh_mesh_work_stats(immesh_mesh_t* h, int64_t* out) {
     if (!h || !out) return im_fail(IMMESH_E_INVALID, "null argument");
     const int* c = h->last_cnt;
-    out[0] = h->F.m; out[1] = c[20]; out[2] = c[21]; out[3] = c[22]; out[4] = c[23]; out[5] = c[6]; out[6] = c[7]; out[7] = c[8];
+    out[0] = h->F.m; out[1] = c[20]; out[2] = c[21]; out[3] = c[22]; out[4] = c[23]; out[5] = c[6] + c[17]; out[6] = c[7]; out[7] = c[8];
     return IMMESH_OK;
 }
 

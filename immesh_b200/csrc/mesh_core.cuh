@@ -404,8 +404,22 @@ IM_HDN inline void voxel_select(const MeshDev& M, const FrameBuf& F, int a) {
     M.vox_meshing_times[vs] += 1;
     M.vox_new_added[vs] = 0;
     if (M.vox_count[vs] < 3) return;
-    const int w = im_atomic_add(&M.cnt[6], 1);
-    if (w < F.max_work) F.work[w] = vs; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+    // two-ended work list: populous voxels (the expensive ones) from the front, the rest from the back, so that the
+    // per-voxel stages start the long jobs first (cnt[6] = front count, cnt[17] = back count)
+    int w;
+    if (M.vox_count[vs] >= 20) w = im_atomic_add(&M.cnt[6], 1);
+    else w = F.max_work - 1 - im_atomic_add(&M.cnt[17], 1);
+    if (w >= 0 && w < F.max_work && M.cnt[6] + M.cnt[17] <= F.max_work) F.work[w] = vs; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+}
+
+// i-th work item (0 <= i < cnt[6] + cnt[17]) -> slot in the two-ended work arrays
+IM_HD int work_slot(const MeshDev& M, const FrameBuf& F, int i) {
+    const int na = M.cnt[6];
+    return i < na ? i : F.max_work - 1 - (i - na);
+}
+IM_HD int work_total(const MeshDev& M, const FrameBuf& F) {
+    const int t = M.cnt[6] + M.cnt[17];
+    return t < F.max_work ? t : F.max_work;
 }
 
 // ------------------------------------------------------------------ exact integer predicates

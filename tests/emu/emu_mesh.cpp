@@ -83,7 +83,7 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     if (n > 0) std::memcpy(h->pts.data(), world_xyz, (size_t)n * 12);
     for (unsigned i = 0; i <= F.cmask; ++i) { F.ckeys[i] = IM_EMPTY_KEY; F.chead[i] = -1; }
     for (int k = 5; k <= 10; ++k) M.cnt[k] = 0;
-    for (int k = 18; k <= 24; ++k) M.cnt[k] = 0;
+    for (int k = 17; k <= 24; ++k) M.cnt[k] = 0;
     for (int c = 0; c < F.m; ++c) cand_init(M, P, F, c);
     for (int c = 0; c < F.m; ++c) cand_conflicts(M, P, F, c);
     for (int c = 0; c < F.m; ++c)
@@ -94,15 +94,16 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     for (int c = 0; c < F.m; ++c) cand_commit(M, P, F, c, base);
     const int na = std::min(M.cnt[5], F.max_act);
     for (int a = 0; a < na; ++a) voxel_select(M, F, a);
-    const int nw = std::min(M.cnt[6], F.max_work);
+    const int nw = work_total(M, F);
     DilateSmem* DS = new DilateSmem();
-    for (int w = 0; w < nw; ++w) voxel_dilate(M, P, F, w, DS, 0, 1);
+    for (int i = 0; i < nw; ++i) voxel_dilate(M, P, F, work_slot(M, F, i), DS, 0, 1);
     delete DS;
     MeshSmem<256>* S1 = new MeshSmem<256>();
     MeshSmem<1024>* S2 = new MeshSmem<1024>();
     MeshWarpSmem<256>* SW = new MeshWarpSmem<256>();
-    for (int w = 0; w < nw; ++w) voxel_mesh_warp<256>(M, P, F, w, SW, 0, 1);
-    for (int w = 0; w < nw; ++w) {
+    for (int i = 0; i < nw; ++i) voxel_mesh_warp<256>(M, P, F, work_slot(M, F, i), SW, 0, 1);
+    for (int i = 0; i < nw; ++i) {
+        const int w = work_slot(M, F, i);
         const int nd = F.work_n_ids[w];
         if (nd < 0 || nd > 256) voxel_mesh<1024>(M, P, F, w, S2, 0, 1);
     }
@@ -116,7 +117,7 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
 }
 int immesh_mesh_counts(immesh_mesh_t* h, int64_t* out) {
     const int* c = h->last_cnt;
-    out[0] = c[0]; out[1] = c[2]; out[2] = c[10]; out[3] = c[6]; out[4] = c[7]; out[5] = c[8]; out[6] = c[4]; out[7] = c[5];
+    out[0] = c[0]; out[1] = c[2]; out[2] = c[10]; out[3] = c[6] + c[17]; out[4] = c[7]; out[5] = c[8]; out[6] = c[4]; out[7] = c[5];
     return 0;
 }
 int immesh_mesh_snapshot(immesh_mesh_t* h, float* vertices, int32_t* triangles, int32_t* flips) {
