@@ -56,6 +56,8 @@ struct immesh_mesh {
     cudaEvent_t ev_done[2] = {nullptr, nullptr};  // frame of slot s finished (mesh stream)
     int inflight[2] = {0, 0};
     cudaEvent_t ev_mark = nullptr, ev_sync = nullptr;  // pipeline timing mark (end) / cross-stream join
+    cudaStream_t stream2 = nullptr;   // side stream: warp-level mesh stage, concurrent with the block-level one
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int pending_rc = 0;
     int* d_snap_tri = nullptr;
     int* d_snap_flip = nullptr;

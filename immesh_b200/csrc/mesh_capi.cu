@@ -114,23 +114,24 @@ __global__ void __launch_bounds__(128) k_voxel_mesh(MeshDev M, MeshParams P, Fra
     for (int i = blockIdx.x; i < nw; i += gridDim.x) {
         const int w = work_slot(M, F, i);
         const int n = F.work_n_ids[w];
-        if (n < 0 || (n > lo && n <= MAXD)) voxel_mesh<MAXD>(M, P, F, w, S, threadIdx.x, blockDim.x);
+        if ((n < 0 && MAXD > 256) || (n > lo && n <= MAXD)) voxel_mesh<MAXD>(M, P, F, w, S, threadIdx.x, blockDim.x);
         __syncthreads();
     }
 }
+#define IM_WARP_NMAX 96   // dilated sets up to this size go to the warp-level stage, larger ones to the block-level stages
 // warp-level stage B: four independent voxels per block, voxels claimed dynamically
 __global__ void __launch_bounds__(128) k_voxel_mesh_warp(MeshDev M, MeshParams P, FrameBuf F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    MeshWarpSmem<256>* S = reinterpret_cast<MeshWarpSmem<256>*>(smem_raw) + warp;
+    MeshWarpSmem<128>* S = reinterpret_cast<MeshWarpSmem<128>*>(smem_raw) + warp;
     const int nw = work_total(M, F);
     while (true) {
         int i = 0;
         if (lane == 0) i = atomicAdd(&M.cnt[19], 1);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= nw) break;
-        voxel_mesh_warp<256>(M, P, F, work_slot(M, F, i), S, lane, 32);
+        voxel_mesh_warp<128>(M, P, F, work_slot(M, F, i), S, lane, 32, IM_WARP_NMAX);
         __syncwarp();
     }
 }
@@ -346,7 +347,11 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(cudaMallocHost((void**)&h->h_cnt, 2 * 32 * sizeof(int)));
     IM_CUDA(cudaMallocHost((void**)&h->h_fp, 2 * sizeof(FramePose)));
     IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<1024>)));
-    IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(MeshWarpSmem<256>))));
+    IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(MeshWarpSmem<128>))));
+    IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<256>)));
+    IM_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    IM_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    IM_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     std::memset(h->last_cnt, 0, sizeof(h->last_cnt));
     IM_CUDA(cudaDeviceSynchronize());
     *out = h;
@@ -363,6 +368,9 @@ int immesh_mesh_destroy(immesh_mesh_t* h) {
     for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return IMMESH_OK;
 }
@@ -478,7 +486,14 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
     IM_CUDA(cudaEventRecord(h->ev[2], st));
     if (F.m > 0) {
         IM_LAUNCH(k_voxel_dilate, h->n_sm * 4, 128, 0, st, h->M, P, F);
-        IM_LAUNCH(k_voxel_mesh_warp, h->n_sm * 2, 128, 4 * sizeof(MeshWarpSmem<256>), st, h->M, P, F);
+        // small voxels (warp-level) on the side stream, mid-size voxels (block-level) on the main stream, concurrently;
+        // then the rare large / handed-over ones
+        IM_CUDA(cudaEventRecord(h->ev_fork, st));
+        IM_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+        IM_LAUNCH(k_voxel_mesh_warp, h->n_sm * 4, 128, 4 * sizeof(MeshWarpSmem<128>), h->stream2, h->M, P, F);
+        IM_CUDA(cudaEventRecord(h->ev_join, h->stream2));
+        IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * 4, 128, sizeof(MeshSmem<256>), st, h->M, P, F, IM_WARP_NMAX);
+        IM_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
         IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st, h->M, P, F, 256);
     }
     IM_CUDA(cudaEventRecord(h->ev[3], st));

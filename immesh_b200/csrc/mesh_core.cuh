@@ -464,11 +464,25 @@ IM_HDN inline bool dt_conflict(const DTri& t, const int2* P, int p) {
     return incircle_i(P[t.v[0]].x, P[t.v[0]].y, P[t.v[1]].x, P[t.v[1]].y, P[t.v[2]].x, P[t.v[2]].y, px, py) > 0;
 }
 
+// float circumcircle (centre, padded squared radius) used only to prune the exact in-circle tests
+IM_HD void circumcircle_f(const int2* P, int a, int b, int c, float* out) {
+    const double bx = (double)(P[b].x - P[a].x), by = (double)(P[b].y - P[a].y);
+    const double cx = (double)(P[c].x - P[a].x), cy = (double)(P[c].y - P[a].y);
+    const double d = 2.0 * (bx * cy - by * cx);
+    const double b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
+    const double ux = (cy * b2 - by * c2) / d, uy = (bx * c2 - cx * b2) / d;
+    const double r2 = ux * ux + uy * uy;
+    const double ccx = (double)P[a].x + ux, ccy = (double)P[a].y + uy;
+    if (!(fabs(ccx) < 1.0e9) || !(fabs(ccy) < 1.0e9) || !(r2 < 1.0e18)) { out[0] = 0.f; out[1] = 0.f; out[2] = INFINITY; return; }
+    out[0] = (float)ccx; out[1] = (float)ccy;
+    out[2] = (float)(r2 * 1.002) + 64.0f;   // conservative: float rounding of centre/radius is ~1e-6 relative
+}
+
 // Block-cooperative Delaunay triangulation of n snapped points (Bowyer-Watson, exact predicates, insertion in
 // index order after a non-degenerate seed).  tris/ntri: triangle pool in shared memory.  scratch: >= 784 ints
 // (scratch[4] = seed found, scratch[6] = capacity overflow).
 // Returns (via *ntri) the pool size; dead slots have alive == 0.  ok=false when all points are collinear.
-IM_HDN inline void delaunay_block(const int2* P, int n, DTri* tris, int max_tris, int* ntri, int* scratch, int tid, int nthreads) {
+IM_HDN inline void delaunay_block(const int2* P, int n, DTri* tris, int max_tris, int* ntri, int* scratch, int tid, int nthreads, float (*circ)[3] = nullptr) {
     int* s_cav_n = scratch;        // [0]
     int* s_edge_n = scratch + 1;   // [1]
     int* s_seed = scratch + 2;     // [2..4] i1, i2, ok
@@ -491,6 +505,7 @@ IM_HDN inline void delaunay_block(const int2* P, int n, DTri* tris, int max_tris
             if (orient2d_i(P[a].x, P[a].y, P[b].x, P[b].y, P[c].x, P[c].y) < 0) { const int t = b; b = c; c = t; }
             const short tv[4][3] = {{(short)a, (short)b, (short)c}, {(short)c, (short)b, IM_GHOST}, {(short)a, (short)c, IM_GHOST}, {(short)b, (short)a, IM_GHOST}};
             for (int k = 0; k < 4; ++k) { tris[k].v[0] = tv[k][0]; tris[k].v[1] = tv[k][1]; tris[k].v[2] = tv[k][2]; tris[k].alive = 1; }
+            if (circ) circumcircle_f(P, a, b, c, circ[0]);
             *ntri = 4;
         }
     }
@@ -502,11 +517,18 @@ IM_HDN inline void delaunay_block(const int2* P, int n, DTri* tris, int max_tris
         if (tid == 0) { *s_cav_n = 0; *s_edge_n = 0; *s_new_n = 0; }
         IM_SYNCBLOCK_M();
         const int nt = *ntri;
-        for (int t = tid; t < nt; t += nthreads)
-            if (tris[t].alive && dt_conflict(tris[t], P, p)) {
+        const float pxf = (float)P[p].x, pyf = (float)P[p].y;
+        for (int t = tid; t < nt; t += nthreads) {
+            if (!tris[t].alive) continue;
+            if (circ && tris[t].v[0] != IM_GHOST && tris[t].v[1] != IM_GHOST && tris[t].v[2] != IM_GHOST) {
+                const float dx = pxf - circ[t][0], dy = pyf - circ[t][1];
+                if (dx * dx + dy * dy > circ[t][2]) continue;   // certainly outside the circumcircle
+            }
+            if (dt_conflict(tris[t], P, p)) {
                 const int k = im_atomic_add(s_cav_n, 1);
                 if (k < 256) s_cav[k] = t;
             }
+        }
         IM_SYNCBLOCK_M();
         int nc = *s_cav_n;
         if (nc > 256) { nc = 256; *s_ovf = 1; }
@@ -537,6 +559,7 @@ IM_HDN inline void delaunay_block(const int2* P, int n, DTri* tris, int max_tris
                 tris[slot].v[1] = (short)s_edges[2 * k + 1];
                 tris[slot].v[2] = (short)p;
                 tris[slot].alive = 1;
+                if (circ && s_edges[2 * k] != IM_GHOST && s_edges[2 * k + 1] != IM_GHOST) circumcircle_f(P, s_edges[2 * k], s_edges[2 * k + 1], p, circ[slot]);
             }
         }
         if (tid == 0 && ne > nc) {

@@ -126,58 +126,74 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
             const int qv = S->q[qi];
             const float4 qp = M.vpos[qv];
 #if defined(__CUDA_ARCH__)
-            if (nc <= 512) {
-                // fast path: every lane keeps the distances of its <= 16 candidates in registers (computed once); 20 rounds
-                // of warp arg-min over the lanes' current minima, the winning lane retires its entry and rescans its 16.
-                float dreg[16];
-                int ireg[16];
-                const int nsl = (nc + 31) >> 5;   // occupied register slots (warp-uniform)
+            {
+                // Warp-cooperative exact 20-NN.  Candidates are consumed in chunks of 512: every lane holds the squared
+                // distances of its <= 16 chunk candidates in registers (computed once) plus, as a 17th slot, the entry of the
+                // running best-20 list it carries (lane r carries the r-th nearest so far).  Per chunk, 20 rounds of warp
+                // arg-min on (d2, id) over the lanes' current minima rebuild the best-20 list; the winning lane retires its
+                // entry and rescans its slots.
+                float cd = INFINITY;           // carried list entry of this lane
+                int cid = 0x7fffffff, cidx = 0, have = 0;
+                for (int base = 0; base < nc; base += 512) {
+                    float dreg[17];
+                    int ireg[17];
+                    const int nsl = (min(nc - base, 512) + 31) >> 5;   // occupied register slots (warp-uniform)
 #pragma unroll
-                for (int sl = 0; sl < 16; ++sl) {
-                    const int i = lane + 32 * sl;
-                    float d2 = INFINITY;
-                    int id = 0x7fffffff;
-                    if (i < nc) {
-                        const float4 cp = S->cand[i];
-                        const float dd = dist2f(qp.x, qp.y, qp.z, cp.x, cp.y, cp.z);
-                        if ((double)dd <= max_d2) { d2 = dd; id = f2i(cp.w); }
+                    for (int sl = 0; sl < 16; ++sl) {
+                        const int i = base + lane + 32 * sl;
+                        float d2 = INFINITY;
+                        int id = 0x7fffffff;
+                        if (sl < nsl && i < nc) {
+                            const float4 cp = S->cand[i];
+                            const float dd = dist2f(qp.x, qp.y, qp.z, cp.x, cp.y, cp.z);
+                            if ((double)dd <= max_d2) { d2 = dd; id = f2i(cp.w); }
+                        }
+                        dreg[sl] = d2; ireg[sl] = id;
                     }
-                    dreg[sl] = d2; ireg[sl] = id;
-                }
-                double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
-                int cnt = 0, found = 0;
-                float last_d = 0.f;
-                int widx = 0;      // lane r remembers the r-th nearest (candidate index, squared distance)
-                float wd = INFINITY;
-                for (int r = 0; r < 20; ++r) {
-                    float bd = INFINITY;
-                    int bid = 0x7fffffff, bsl = 0;
-#pragma unroll
-                    for (int sl = 0; sl < 16; ++sl)
-                        if (sl < nsl && (dreg[sl] < bd || (dreg[sl] == bd && ireg[sl] < bid))) { bd = dreg[sl]; bid = ireg[sl]; bsl = sl; }
-                    int aux = bsl * 32 + lane;  // candidate index of this lane's minimum
-                    warp_min_pair(&bd, &bid, &aux);
-                    if (bid == 0x7fffffff) break;
-                    if ((aux & 31) == lane) {
+                    dreg[16] = (lane < have) ? cd : INFINITY;
+                    ireg[16] = (lane < have) ? cid : 0x7fffffff;
+                    float nd = INFINITY;
+                    int nid = 0x7fffffff, nidx = 0, found = 0;
+                    for (int r = 0; r < 20; ++r) {
+                        float bd = dreg[16];
+                        int bid = ireg[16], bsl = 16;
 #pragma unroll
                         for (int sl = 0; sl < 16; ++sl)
-                            if (sl == (aux >> 5)) { dreg[sl] = INFINITY; ireg[sl] = 0x7fffffff; }
+                            if (sl < nsl && (dreg[sl] < bd || (dreg[sl] == bd && ireg[sl] < bid))) { bd = dreg[sl]; bid = ireg[sl]; bsl = sl; }
+                        // aux packs the winner's candidate index (11 bits), slot (5 bits) and lane (5 bits)
+                        int aux = ((bsl == 16) ? cidx : (base + bsl * 32 + lane)) | (bsl << 11) | (lane << 16);
+                        warp_min_pair(&bd, &bid, &aux);
+                        if (bid == 0x7fffffff) break;
+                        if ((aux >> 16) == lane) {
+                            const int wsl = (aux >> 11) & 31;
+#pragma unroll
+                            for (int sl = 0; sl < 17; ++sl)
+                                if (sl == wsl) { dreg[sl] = INFINITY; ireg[sl] = 0x7fffffff; }
+                        }
+                        if (lane == r) { nd = bd; nid = bid; nidx = aux & 2047; }
+                        ++found;
                     }
-                    last_d = bd;
-                    if (lane == r) { widx = aux; wd = bd; }
-                    ++found;
-                    const float sd = sqrtf(bd);
-                    if ((double)sd < P.accept * 2) {
+                    cd = nd; cid = nid; cidx = nidx; have = found;
+                }
+                // ordered pass over the final list: dilation membership and the smoothing mean (ascending distance)
+                double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
+                int cnt = 0;
+                float last_d = 0.f;
+                for (int r = 0; r < have; ++r) {
+                    const float rd = __shfl_sync(0xffffffffu, cd, r);
+                    const int ridx = __shfl_sync(0xffffffffu, cidx, r);
+                    last_d = rd;
+                    if ((double)sqrtf(rd) < P.accept * 2) {
                         ++cnt;
-                        const float4 cp = S->cand[aux];
+                        const float4 cp = S->cand[ridx];
                         sv0 = sv0 + (double)cp.x; sv1 = sv1 + (double)cp.y; sv2 = sv2 + (double)cp.z;
                     }
                 }
-                const bool complete = (lb > P.knn_max) || (found >= 20 && (double)last_d < lb * lb * 0.999999);
+                const bool complete = (lb > P.knn_max) || (have >= 20 && (double)last_d < lb * lb * 0.999999);
                 if (!complete) {
                     if (lane == 0) S->need_more = 1;   // retried with the next ring; nothing is published yet
                 } else {
-                    if (lane < found && (double)sqrtf(wd) < P.accept) S->flag[widx] = 1;
+                    if (lane < have && (double)sqrtf(cd) < P.accept) S->flag[cidx] = 1;
                     if (lane == 0) {
                         S->qdone[qi] = 1;
                         M.vsmooth[(size_t)qv * 3 + 0] = (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f);
@@ -282,6 +298,7 @@ struct MeshSmem {
     int faces[2 * MAXD][3];       // global ids, a<b<c
     int fhash[4 * MAXD];          // open-addressed set of face indices
     int scratch[8 + 256 + 520];
+    float circ[(MAXD <= 256) ? (3 * MAXD + 8) : 1][3];   // circumcircle cache (mid-size variant only)
     double axes[9];               // short, mid, long
     double centre[3];
     int ntri, nface;
@@ -342,7 +359,7 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
         S->snap[i] = make_int2((int)im_llrint(u * P.inv_q), (int)im_llrint(v * P.inv_q));
     }
     IM_SYNCBLOCK_M();
-    delaunay_block(S->snap, n, S->tris, 3 * MAXD + 8, &S->ntri, S->scratch, tid, nthreads);
+    delaunay_block(S->snap, n, S->tris, 3 * MAXD + 8, &S->ntri, S->scratch, tid, nthreads, (MAXD <= 256) ? S->circ : nullptr);
     IM_SYNCBLOCK_M();
     if (S->scratch[4] == 0) return;  // all points collinear: T.number_of_faces() == 0 (mesh_rec_geometry.cpp:257-260)
     if (S->scratch[6]) { if (tid == 0) im_atomic_or(&M.cnt[3], IM_MERR_VOXEL_CAP); return; }
@@ -455,23 +472,10 @@ struct MeshWarpSmem {
     int ntri, nface;
 };
 
-IM_HD void circumcircle_f(const int2* P, int a, int b, int c, float* out) {
-    const double bx = (double)(P[b].x - P[a].x), by = (double)(P[b].y - P[a].y);
-    const double cx = (double)(P[c].x - P[a].x), cy = (double)(P[c].y - P[a].y);
-    const double d = 2.0 * (bx * cy - by * cx);
-    const double b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
-    const double ux = (cy * b2 - by * c2) / d, uy = (bx * c2 - cx * b2) / d;
-    const double r2 = ux * ux + uy * uy;
-    const double ccx = (double)P[a].x + ux, ccy = (double)P[a].y + uy;
-    if (!(fabs(ccx) < 1.0e9) || !(fabs(ccy) < 1.0e9) || !(r2 < 1.0e18)) { out[0] = 0.f; out[1] = 0.f; out[2] = INFINITY; return; }
-    out[0] = (float)ccx; out[1] = (float)ccy;
-    out[2] = (float)(r2 * 1.002) + 64.0f;   // conservative: float rounding of centre/radius is ~1e-6 relative
-}
-
 template <int MAXD>
-IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, MeshWarpSmem<MAXD>* S, int lane, int nlanes) {
+IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, MeshWarpSmem<MAXD>* S, int lane, int nlanes, int n_max) {
     const int n = F.work_n_ids[w];
-    if (n < 3 || n > MAXD) return;
+    if (n < 3 || n > n_max || n > MAXD) return;
     const int vs = F.work[w];
     float (*pos)[3] = S->circ;  // alias: positions are dead once projected
     for (int i = lane; i < n; i += nlanes) {

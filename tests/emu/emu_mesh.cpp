@@ -100,8 +100,13 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     delete DS;
     MeshSmem<256>* S1 = new MeshSmem<256>();
     MeshSmem<1024>* S2 = new MeshSmem<1024>();
-    MeshWarpSmem<256>* SW = new MeshWarpSmem<256>();
-    for (int i = 0; i < nw; ++i) voxel_mesh_warp<256>(M, P, F, work_slot(M, F, i), SW, 0, 1);
+    MeshWarpSmem<128>* SW = new MeshWarpSmem<128>();
+    for (int i = 0; i < nw; ++i) voxel_mesh_warp<128>(M, P, F, work_slot(M, F, i), SW, 0, 1, 96);   // same split as the device
+    for (int i = 0; i < nw; ++i) {
+        const int w = work_slot(M, F, i);
+        const int nd = F.work_n_ids[w];
+        if (nd > 96 && nd <= 256) voxel_mesh<256>(M, P, F, w, S1, 0, 1);
+    }
     for (int i = 0; i < nw; ++i) {
         const int w = work_slot(M, F, i);
         const int nd = F.work_n_ids[w];
