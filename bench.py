@@ -85,12 +85,21 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
+def cpu_threads():
+    """Threads for the CPU arm: the residual loop is the only parallel part of localization (the reference pins it to 4
+    OpenMP threads, CMakeLists.txt:21-24); more than ~16 threads only adds fork/join cost on a 16k-point loop.  Meshing is
+    voxel-parallel over all cores like the reference's TBB loop (capped at 64: beyond that the serial push dominates)."""
+    n = os.cpu_count() or 1
+    return min(16, n), min(64, n)
+
+
 def run_cpu(cfg, scans, n_warm, n_timed, threads):
     """The reference algorithm on the host cores (oracle port): returns per-scan (t_loc, t_mesh) seconds."""
     from immesh_b200 import api
     from oracle_api import OracleLio, OracleMesh
-    lio = OracleLio(cfg, sum_mode=1, omp_threads=threads)
-    mesh = OracleMesh(api.MeshConfig(), threads=threads)
+    t_loc, t_mesh = cpu_threads()
+    lio = OracleLio(cfg, sum_mode=1, omp_threads=t_loc)
+    mesh = OracleMesh(api.MeshConfig(), threads=t_mesh)
     lio.set_state(init_state_vec(scans))
     lio.voxel_map_init(scans[0]["body_full"])
     times = []
@@ -148,6 +157,10 @@ def run_gpu(args, rank, world):
     lib = api.load_library()
     lio = api.Lio(cfg, lib=lib)
     mesh = api.Mesh(api.MeshConfig(), lib=lib)
+    if world > 1 and not args.independent_streams:
+        uid = [api.comm_unique_id(lib) if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        lio.shard(rank, world, uid[0])
     lio.set_state(init_state_vec(scans))
     lio.voxel_map_init(scans[0]["body_full"])
     dev = torch.device("cuda", local_rank)
@@ -285,7 +298,7 @@ def run_gpu(args, rank, world):
                    "l2_flush_ms_per_scan": round(flush_ms, 4),
                    "pipeline": "localization(k+1) overlaps meshing(k) on two CUDA streams (as the reference's LIO thread || mesh threads)",
                    "serial_ms_per_scan_blocking": round(float(np.mean(dev_ms)), 4),
-                   "parallelism": f"{world} x replica" if args.independent_streams else ("single GPU" if world == 1 else f"map sharded over {world} GPUs"),
+                   "parallelism": f"{world} independent streams (replicas)" if args.independent_streams else ("single GPU" if world == 1 else f"one stream, VoxelMap sharded by root-voxel key over {world} GPUs (2 NCCL all-reduces per IESKF iteration), mesher replicated"),
                    "map_warm_scans": MAP_WARM},
         "e2e": {"value": round(scans_done / e2e_s, 3), "unit": "scans/s", "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
                 "ms_per_step": round(e2e_s / K * 1e3, 4)},
@@ -305,7 +318,7 @@ def run_gpu(args, rank, world):
             n_s = 8
             tt = run_cpu(cfg, scans, MAP_WARM + 2, n_s, threads)
             per = tt.sum(axis=1)
-            out["cpu_baseline"] = {"value": round(1.0 / float(np.mean(per)), 3), "unit": "scans/s", "cores": threads, "kind": "port",
+            out["cpu_baseline"] = {"value": round(1.0 / float(np.mean(per)), 3), "unit": "scans/s", "cores": max(cpu_threads()), "threads_loc_mesh": list(cpu_threads()), "host_cores": threads, "kind": "port",
                                    "sample": f"{n_s} scans of the same stream after {MAP_WARM + 2} untimed scans; oracle (C++ restatement, -O3, OpenMP residual loop + voxel-parallel meshing)",
                                    "loc_ms": round(float(np.mean(tt[:, 0])) * 1e3, 3), "mesh_ms": round(float(np.mean(tt[:, 1])) * 1e3, 3),
                                    "reference_published": "Avia 24k-pt scans on i9-10900: localization 16.6 ms, meshing 25.3 ms (T-RO Table IV)"}
@@ -328,7 +341,7 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "scans/s", "n_gpus": world, "steps": K_eff, "warmup": W,
            "ms_per_step": round(float(np.mean(per)) * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": WORKLOAD, "map_warm_scans": MAP_WARM},
-           "cpu_baseline": {"value": round(v, 3), "unit": "scans/s", "cores": threads, "kind": "port",
+           "cpu_baseline": {"value": round(v, 3), "unit": "scans/s", "cores": max(cpu_threads()), "threads_loc_mesh": list(cpu_threads()), "host_cores": threads, "kind": "port",
                             "sample": f"{K_eff} scans (one per step); oracle port of the reference CPU path (the reference needs ROS/Eigen/PCL/CGAL and cannot be compiled here)",
                             "loc_ms": round(float(np.mean(tt[:, 0])) * 1e3, 3), "mesh_ms": round(float(np.mean(tt[:, 1])) * 1e3, 3)},
            "e2e": {"value": round(v, 3), "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -341,13 +354,16 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--independent-streams", action="store_true", default=None, help="N>1: every rank runs its own scan stream (replicas)")
+    ap.add_argument("--mode", default=None, choices=["sharded", "replicas"],
+                    help="N>1: 'sharded' = one scan stream, VoxelMap sharded by root-voxel key over the ranks (NCCL all-reduces inside the IESKF "
+                         "iterations), strong scaling; 'replicas' = every rank runs its own independent stream, weak scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
-    if args.independent_streams is None:
-        args.independent_streams = world > 1
+    if args.mode is None:
+        args.mode = "sharded"
+    args.independent_streams = (world > 1 and args.mode == "replicas")
     from immesh_b200 import build
     if rank == 0:
         build.build_oracle()

@@ -97,6 +97,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_mesh_push_frame_dev", [vp, vp, C.c_int, dp, C.c_int]),
         ("immesh_mesh_push_frame_from_lio", [vp, vp, vp, C.c_int, C.c_int]),
         ("immesh_lio_match_nodes", [vp, ip, C.c_int]),
+        ("immesh_comm_unique_id", [C.c_char_p]),
+        ("immesh_lio_shard", [vp, C.c_int, C.c_int, C.c_char_p]),
         ("immesh_lio_step_async", [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
         ("immesh_lio_wait", [vp, dp, ip]),
         ("immesh_lio_enqueue_memset", [vp, vp, C.c_size_t]),
@@ -246,6 +248,10 @@ class Lio:
 
     def enqueue_memset(self, dev_ptr, nbytes):
         _check(self.lib, self.lib.immesh_lio_enqueue_memset(self._h, C.c_void_p(dev_ptr), nbytes), "enqueue_memset")
+
+    def shard(self, rank: int, nranks: int, unique_id: bytes):
+        """Shard the VoxelMap over nranks processes (NCCL); unique_id: 128 bytes from comm_unique_id() of rank 0."""
+        _check(self.lib, self.lib.immesh_lio_shard(self._h, rank, nranks, unique_id), "lio_shard")
 
     def residual_build(self, body_ds):
         a, p = _f32(body_ds)
@@ -415,3 +421,10 @@ def pipeline_mark_end(lio: Lio, mesh: Mesh) -> float:
     ms = C.c_double(0)
     _check(lio.lib, lio.lib.immesh_pipeline_mark_end(lio._h, mesh._h, C.byref(ms)), "pipeline_mark_end")
     return ms.value
+
+
+def comm_unique_id(lib: Optional[C.CDLL] = None) -> bytes:
+    lib = lib or load_library()
+    buf = C.create_string_buffer(128)
+    _check(lib, lib.immesh_comm_unique_id(buf), "comm_unique_id")
+    return buf.raw

@@ -28,6 +28,8 @@ struct immesh_lio {
     cudaStream_t stream2 = nullptr;   // side stream: P^-1 of the propagated covariance, concurrent with the first residual pass
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_mark = nullptr;   // pipeline timing mark (begin)
+    void* nccl_comm = nullptr;       // ncclComm_t when the VoxelMap is sharded over several GPUs
+    unsigned int* d_bits = nullptr;  // [2][words] exists / matched-in-own-voxel bit words of the sharded residual pass
     int* h_ints = nullptr;     // pinned
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -225,6 +225,49 @@ __global__ void __launch_bounds__(RES_THREADS) k_residual(VoxelMapDev map, LioPa
     }
 }
 
+// sharded VoxelMap: pass 1 (match where this rank owns the voxel, publish bits) and pass 2 (terms + integer reduction)
+__global__ void __launch_bounds__(RES_THREADS) k_shard_pass1(VoxelMapDev map, LioParams P, ScanBuf sb, LioCtrl* ctrl, int n, unsigned int* bits, int words) {
+    __shared__ double s_state[24 + 6 * 18];
+    if (ctrl->stop) return;
+    for (int i = threadIdx.x; i < 24 + 6 * 18; i += blockDim.x) s_state[i] = ctrl->state[i];
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) shard_pass1_point(map, P, sb, s_state, i, bits, bits + words);
+}
+__global__ void __launch_bounds__(RES_THREADS) k_shard_pass2(VoxelMapDev map, LioParams P, ScanBuf sb, LioCtrl* ctrl, int iter, int n, const unsigned int* bits, int words) {
+    __shared__ double s_state[24 + 6 * 18];
+    __shared__ long long s_part[RES_THREADS / 32][IM_NTERMS];
+    if (ctrl->stop) return;
+    for (int i = threadIdx.x; i < 24 + 6 * 18; i += blockDim.x) s_state[i] = ctrl->state[i];
+    __syncthreads();
+    long long acc[IM_NTERMS];
+#pragma unroll
+    for (int k = 0; k < IM_NTERMS; ++k) acc[k] = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        long long t[IM_NTERMS];
+        if (shard_pass2_point(map, P, sb, s_state, i, bits, bits + words, t, map.err)) {
+#pragma unroll
+            for (int k = 0; k < IM_NTERMS; ++k) acc[k] += t[k];
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < IM_NTERMS - 1; ++k) {
+        long long v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < IM_NTERMS - 1) {
+        long long v = 0;
+        for (int w = 0; w < RES_THREADS / 32; ++w) v += s_part[w][threadIdx.x];
+        if (v != 0) {
+            atomicAdd(&ctrl->acc[iter][2 * threadIdx.x], (unsigned long long)(v >> 32));
+            atomicAdd(&ctrl->acc[iter][2 * threadIdx.x + 1], (unsigned long long)(v & 0xffffffffLL));
+        }
+    }
+}
+
 #define SOLVE_THREADS 352
 __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(LioParams P, LioCtrl* ctrl, int iter) {
     __shared__ SolveScratch S;
@@ -303,6 +346,34 @@ __global__ void k_gather_ptpl(VoxelMapDev map, ScanBuf sb, int n, double* out /*
 }
 
 // ------------------------------------------------------------------ host side
+
+// ---- NCCL, bound at run time (dlopen) so that the single-GPU library has no link-time dependency on it
+#include <dlfcn.h>
+namespace {
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void* nccl_comm_t;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        GetUniqueId = (int (*)(nccl_uid_t*))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (int (*)(nccl_comm_t*, int, nccl_uid_t, int))dlsym(lib, "ncclCommInitRank");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (int (*)(nccl_comm_t))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+    }
+};
+NcclApi& nccl() { static NcclApi a; return a; }
+const int kNcclUint32 = 3, kNcclUint64 = 5, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+}  // namespace
 
 static void fill_params(const immesh_lio_config* c, LioParams& P) {
     P.voxel_size = c->voxel_size;
@@ -422,6 +493,7 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
 int immesh_lio_destroy(immesh_lio_t* h) {
     if (!h) return IMMESH_OK;
     cudaStreamSynchronize(h->stream);
+    if (h->nccl_comm && nccl().CommDestroy) nccl().CommDestroy(h->nccl_comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_body) cudaFreeHost(h->h_body);
     if (h->h_state) cudaFreeHost(h->h_state);
@@ -433,6 +505,31 @@ int immesh_lio_destroy(immesh_lio_t* h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int i = 0; i < 2; ++i) if (h->ev_slot[i]) cudaEventDestroy(h->ev_slot[i]);
     delete h;
+    return IMMESH_OK;
+}
+
+// ---- multi-GPU: shard the VoxelMap of this handle over `nranks` processes (one GPU each, NCCL over NVLink)
+int immesh_comm_unique_id(char* out128) {
+    if (!out128) return im_fail(IMMESH_E_INVALID, "null argument");
+    if (!nccl().load()) return im_fail(IMMESH_E_CUDA, "libnccl.so.2 not found");
+    nccl_uid_t id;
+    if (nccl().GetUniqueId(&id)) return im_fail(IMMESH_E_CUDA, "ncclGetUniqueId failed");
+    std::memcpy(out128, id.internal, 128);
+    return IMMESH_OK;
+}
+int immesh_lio_shard(immesh_lio_t* h, int rank, int nranks, const char* unique_id128) {
+    if (!h || !unique_id128 || nranks < 1 || rank < 0 || rank >= nranks) return im_fail(IMMESH_E_INVALID, "bad argument");
+    if (nranks == 1) { h->P.shard_rank = 0; h->P.shard_n = 1; return IMMESH_OK; }
+    if (!nccl().load()) return im_fail(IMMESH_E_CUDA, "libnccl.so.2 not found");
+    nccl_uid_t id;
+    std::memcpy(id.internal, unique_id128, 128);
+    nccl_comm_t comm = nullptr;
+    const int rc = nccl().CommInitRank(&comm, nranks, id, rank);
+    if (rc) return im_fail(IMMESH_E_CUDA, nccl().GetErrorString ? nccl().GetErrorString(rc) : "ncclCommInitRank failed");
+    h->nccl_comm = comm;
+    h->P.shard_rank = rank;
+    h->P.shard_n = nranks;
+    if (!h->d_bits) IM_CUDA(dev_alloc(h, &h->d_bits, (size_t)2 * (h->max_scan / 32 + 2), 0));
     return IMMESH_OK;
 }
 
@@ -484,7 +581,29 @@ static void launch_grow(immesh_lio* h, int n, int mode) {
     IM_LAUNCH(k_grow_voxel, h->n_sm * 4, 128, 0, h->stream, h->map, h->P, h->sb, mode, h->d_sorted, h->d_counters + 8);
     IM_LAUNCH(k_grow_finish, 1, 256, 0, h->stream, h->map, h->sb, h->d_counters + 8);
 }
+// sharded VoxelMap: per iteration  pass1 -> all-reduce(bit words) -> pass2 -> all-reduce(58 int64 sums) -> solve (every rank)
+static int launch_estimate_sharded(immesh_lio* h, int n) {
+    const int words = (n + 31) / 32 + 1;
+    cudaEventRecord(h->ev_fork, h->stream);
+    cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+    IM_LAUNCH(k_pinv, 1, 32, 0, h->stream2, h->d_ctrl);
+    cudaEventRecord(h->ev_join, h->stream2);
+    IM_LAUNCH(k_reset_scan, 2, 256, 0, h->stream, h->sb, h->d_ctrl, 1);
+    if (n > 0) IM_LAUNCH(k_prepare, grid_for(h, n, 128), 128, 0, h->stream, h->P, h->sb, n);
+    const int g = grid_for(h, n > 0 ? n : 1, RES_THREADS, 4);
+    for (int it = 0; it < h->P.max_iter; ++it) {
+        IM_CUDA(cudaMemsetAsync(h->d_bits, 0, (size_t)2 * words * sizeof(unsigned int), h->stream));
+        if (n > 0) IM_LAUNCH(k_shard_pass1, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, n, h->d_bits, words);
+        if (nccl().AllReduce(h->d_bits, h->d_bits, (size_t)2 * words, kNcclUint32, kNcclSum, h->nccl_comm, h->stream)) return im_fail(IMMESH_E_CUDA, "ncclAllReduce(bits) failed");
+        if (n > 0) IM_LAUNCH(k_shard_pass2, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n, h->d_bits, words);
+        if (nccl().AllReduce(&h->d_ctrl->acc[it][0], &h->d_ctrl->acc[it][0], (size_t)IM_NTERMS * 2, kNcclUint64, kNcclSum, h->nccl_comm, h->stream)) return im_fail(IMMESH_E_CUDA, "ncclAllReduce(acc) failed");
+        if (it == 0) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+        IM_LAUNCH(k_solve_warp, 1, 128, 0, h->stream, h->P, h->d_ctrl, it);
+    }
+    return IMMESH_OK;
+}
 static void launch_estimate(immesh_lio* h, int n) {
+    if (h->P.shard_n > 1) { launch_estimate_sharded(h, n); return; }
     if (n > 0) {  // P^-1 on the side stream, overlapped with the scan preparation and the first residual pass
         cudaEventRecord(h->ev_fork, h->stream);
         cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);

@@ -102,20 +102,23 @@ IM_HDN inline void world_cov(const double* A, const double* body_cov6, const dou
 // ------------------------------------------------------------------ K2 + K3 (one scan point)
 // terms[0..20] = upper triangle of w h h^T, [21..26] = w h z, [27] = |r|, [28] = 1 (match count); as 2^-20 fixed point.
 // returns true when the point is matched.
-IM_HDN inline bool residual_point(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, long long* terms, int* err) {
+// world point (float-rounded, as transformLidar stores it) + its covariance for the matching step (:1344-1359)
+IM_HDN inline void residual_world(const LioParams& P, const ScanBuf& sb, const double* state, int i, double* pwd, double* pw, double* var6) {
     const double* R = state;
     const double* t = state + 9;
     const double* cov = state + 24;
     const double pb[3] = {(double)sb.body[i * 3 + 0], (double)sb.body[i * 3 + 1], (double)sb.body[i * 3 + 2]};
-    double pwd[3], pw[3], var6[6];
     body_to_world(P, R, t, pb, pwd);
     pw[0] = (double)(float)pwd[0]; pw[1] = (double)(float)pwd[1]; pw[2] = (double)(float)pwd[2];
     world_cov(R, sb.body_cov + (size_t)i * 6, sb.p_imu + (size_t)i * 3, cov, var6);
-    const MatchResult mr = match_point(map, P, pw, var6);
-    sb.match_node[i] = mr.node;
-    sb.match_layer[i] = mr.layer;
-    if (mr.node < 0) return false;
-    const PlaneRec& pl = map.planes[mr.node];
+}
+// residual, Jacobian row, weight and the 29 fixed-point normal-equation terms of point i matched to plane `node`
+// (voxel_mapping.cpp:1372-1392, :1487-1586)
+IM_HDN inline bool residual_terms(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, int node, const double* pwd, long long* terms, int* err) {
+    const double* R = state;
+    const double* t = state + 9;
+    const double pb[3] = {(double)sb.body[i * 3 + 0], (double)sb.body[i * 3 + 1], (double)sb.body[i * 3 + 2]};
+    const PlaneRec& pl = map.planes[node];
     // float-rounded normal / residual through the PCL point structs (voxel_mapping.cpp:1377-1389)
     const float nf[3] = {(float)pl.normal[0], (float)pl.normal[1], (float)pl.normal[2]};
     const float dis = (float)(((pwd[0] * (double)nf[0] + pwd[1] * (double)nf[1]) + pwd[2] * (double)nf[2]) + (double)pl.d);
@@ -164,6 +167,89 @@ IM_HDN inline bool residual_point(const VoxelMapDev& map, const LioParams& P, co
         return false;
     }
     return true;
+}
+IM_HDN inline bool residual_point(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, long long* terms, int* err) {
+    double pwd[3], pw[3], var6[6];
+    residual_world(P, sb, state, i, pwd, pw, var6);
+    const MatchResult mr = match_point(map, P, pw, var6);
+    sb.match_node[i] = mr.node;
+    sb.match_layer[i] = mr.layer;
+    if (mr.node < 0) return false;
+    return residual_terms(map, P, sb, state, i, mr.node, pwd, terms, err);
+}
+
+// ------------------------------------------------------------------ sharded VoxelMap (multi-GPU): split residual pass
+// The scan is replicated, root voxels are owned by voxel_owner(key).  Pass 1: the owner of a point's root voxel matches it
+// there and publishes two bits (root voxel exists / matched there); the owner of the point's retry neighbour voxel
+// evaluates that match speculatively.  The bit words of all ranks are summed (bits are disjoint: one owner per point), then
+// pass 2 lets exactly one rank contribute the point's normal-equation terms.  Integer sums => the all-reduced
+// accumulators, hence the state, are bit-identical to the single-GPU run for any number of ranks.
+//   sb.slot[i] : speculative neighbour match node (-1 none)      sb.seg[i] : its layer
+IM_HDN inline void shard_pass1_point(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, unsigned int* bits_exists, unsigned int* bits_ok) {
+    double pwd[3], pw[3], var6[6];
+    residual_world(P, sb, state, i, pwd, pw, var6);
+    sb.match_node[i] = -1;
+    sb.match_layer[i] = 0;
+    sb.slot[i] = -1;
+    sb.seg[i] = 0;
+    long long k[3];
+    float loc[3];
+    if (!voxel_key3_loc(pw, P.voxel_size, k, loc)) return;
+    const unsigned long long key = pack_key(k[0], k[1], k[2]);
+    long long nk[3];
+    neighbour_key(P, k, loc, nk);
+    const bool nk_ok = nk[0] > -1048000 && nk[0] < 1048000 && nk[1] > -1048000 && nk[1] < 1048000 && nk[2] > -1048000 && nk[2] < 1048000;
+    const unsigned long long nkey = nk_ok ? pack_key(nk[0], nk[1], nk[2]) : 0ull;
+    const int o1 = voxel_owner(key, P.shard_n);
+    const int o2 = nk_ok ? voxel_owner(nkey, P.shard_n) : -1;
+    if (o1 == P.shard_rank) {
+        const int slot = hash_find(map, key);
+        const int root = slot >= 0 ? map.root_node[slot] : -1;
+        if (root >= 0) {
+#if defined(__CUDA_ARCH__)
+            atomicOr(&bits_exists[i >> 5], 1u << (i & 31));
+#else
+            bits_exists[i >> 5] |= 1u << (i & 31);
+#endif
+            MatchResult best; best.node = -1; best.layer = 0; best.prob = 0.0;
+            bool ok = false;
+            match_in_voxel(map, P, root, pw, var6, &ok, &best);
+            if (ok) {
+#if defined(__CUDA_ARCH__)
+                atomicOr(&bits_ok[i >> 5], 1u << (i & 31));
+#else
+                bits_ok[i >> 5] |= 1u << (i & 31);
+#endif
+                sb.match_node[i] = best.node;
+                sb.match_layer[i] = best.layer;
+            } else if (o2 == P.shard_rank) {
+                const int s2 = hash_find(map, nkey);
+                if (s2 >= 0 && map.root_node[s2] >= 0) match_in_voxel(map, P, map.root_node[s2], pw, var6, &ok, &best);
+                if (ok) { sb.match_node[i] = best.node; sb.match_layer[i] = best.layer; }
+            }
+        }
+    } else if (o2 == P.shard_rank) {
+        const int s2 = hash_find(map, nkey);
+        if (s2 >= 0 && map.root_node[s2] >= 0) {
+            MatchResult best; best.node = -1; best.layer = 0; best.prob = 0.0;
+            bool ok = false;
+            match_in_voxel(map, P, map.root_node[s2], pw, var6, &ok, &best);
+            if (ok) { sb.slot[i] = best.node; sb.seg[i] = best.layer; }
+        }
+    }
+}
+// pass 2: after the bit words have been summed over the ranks
+IM_HDN inline bool shard_pass2_point(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, const unsigned int* bits_exists, const unsigned int* bits_ok, long long* terms, int* err) {
+    int node = sb.match_node[i];
+    if (node < 0 && sb.slot[i] >= 0) {
+        const bool ex = (bits_exists[i >> 5] >> (i & 31)) & 1u, ok1 = (bits_ok[i >> 5] >> (i & 31)) & 1u;
+        if (ex && !ok1) { node = sb.slot[i]; sb.match_node[i] = node; sb.match_layer[i] = sb.seg[i]; }
+    }
+    if (node < 0) return false;
+    double pwd[3];
+    const double pb[3] = {(double)sb.body[i * 3 + 0], (double)sb.body[i * 3 + 1], (double)sb.body[i * 3 + 2]};
+    body_to_world(P, state, state + 9, pb, pwd);
+    return residual_terms(map, P, sb, state, i, node, pwd, terms, err);
 }
 
 // ------------------------------------------------------------------ K4: 18x18 LU inverse, cooperative
@@ -410,6 +496,7 @@ IM_HDN inline void grow_point(const VoxelMapDev& map, const LioParams& P, const 
     if (!voxel_key3(pw, P.voxel_size_ins, k)) { im_atomic_or(map.err, IM_ERR_KEY_RANGE); return; }
     int created = 0;
     const unsigned long long key = pack_key(k[0], k[1], k[2]);
+    if (P.shard_n > 1 && voxel_owner(key, P.shard_n) != P.shard_rank) return;   // another rank owns this root voxel
     const int slot = hash_insert(map, key, &created);
     if (slot < 0) return;
     if (created) {

@@ -44,6 +44,7 @@ struct LioParams {
     int calib_laser;
     int max_iter;
     double extR[9], extT[3];
+    int shard_rank, shard_n;   // multi-GPU: this rank owns the root voxels with voxel_owner(key) == shard_rank (1 rank: owns all)
 };
 
 struct alignas(16) PlaneRec {
@@ -173,6 +174,10 @@ IM_HD void unpack_key(unsigned long long k, long long* x, long long* y, long lon
 IM_HD unsigned int hash_key(unsigned long long k) {
     k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
     return (unsigned int)k;
+}
+// owner rank of a root voxel when the VoxelMap is sharded over n ranks (bits independent of the table hash)
+IM_HD int voxel_owner(unsigned long long key, int n) {
+    return (int)((unsigned int)((key * 0x9E3779B97F4A7C15ull) >> 40) % (unsigned int)n);
 }
 IM_HD int hash_find(const VoxelMapDev& m, unsigned long long key) {
     unsigned int s = hash_key(key) & m.cap_mask;
@@ -642,6 +647,19 @@ IM_HDN inline void match_in_voxel(const VoxelMapDev& m, const LioParams& P, int 
     }
 }
 
+// neighbour voxel of the one-shot retry (voxel_mapping.cpp:192-216).  The root voxel's centre and quarter length are
+// functions of its key alone (:138-141), so the neighbour key does not need the map; the voxel-unit coordinate is
+// compared with metric bounds exactly as the reference does.
+IM_HD void neighbour_key(const LioParams& P, const long long* k, const float* loc, long long* nk) {
+    const double ql = (double)(P.voxel_size_f / 4);
+    for (int j = 0; j < 3; ++j) {
+        const double vc = (0.5 + (double)k[j]) * (double)P.voxel_size_f;
+        nk[j] = k[j];
+        if ((double)loc[j] > vc + ql) nk[j] = k[j] + 1;
+        else if ((double)loc[j] < vc - ql) nk[j] = k[j] - 1;
+    }
+}
+
 // BuildResidualListOMP body for one point (voxel_mapping.cpp:169-236): root voxel, then one neighbour retry
 IM_HDN inline MatchResult match_point(const VoxelMapDev& m, const LioParams& P, const double* pw, const double* var6) {
     MatchResult best;
@@ -656,14 +674,8 @@ IM_HDN inline MatchResult match_point(const VoxelMapDev& m, const LioParams& P, 
     bool ok = false;
     match_in_voxel(m, P, root, pw, var6, &ok, &best);
     if (!ok) {
-        const NodeRec& rn = m.nodes[root];
-        const double ql = (double)rn.quater;
-        long long nk[3] = {k[0], k[1], k[2]};
-        // voxel-unit coordinate compared with metric bounds, replicated from the reference (:193-216)
-        for (int j = 0; j < 3; ++j) {
-            if ((double)loc[j] > rn.vc[j] + ql) nk[j] = nk[j] + 1;
-            else if ((double)loc[j] < rn.vc[j] - ql) nk[j] = nk[j] - 1;
-        }
+        long long nk[3];
+        neighbour_key(P, k, loc, nk);
         if (nk[0] > -1048000 && nk[0] < 1048000 && nk[1] > -1048000 && nk[1] < 1048000 && nk[2] > -1048000 && nk[2] < 1048000) {
             const int s2 = hash_find(m, pack_key(nk[0], nk[1], nk[2]));
             if (s2 >= 0 && m.root_node[s2] >= 0) match_in_voxel(m, P, m.root_node[s2], pw, var6, &ok, &best);

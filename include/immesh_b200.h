@@ -93,6 +93,14 @@ int immesh_lio_step_async(immesh_lio_t* h, const float* body_xyz, int n, int on_
 int immesh_lio_wait(immesh_lio_t* h, double* state_out /*[348] or NULL*/, int* iters_run /*or NULL*/);
 int immesh_lio_enqueue_memset(immesh_lio_t* h, void* d_buf, size_t bytes); /* benchmark helper: in-stream L2 flush */
 
+/* Multi-GPU (one process per GPU): shard this handle's VoxelMap by root-voxel key over `nranks` ranks.  Every rank is
+ * given the same scans; a rank matches / updates only the root voxels it owns, and the IESKF iterations exchange two
+ * integer all-reduces over NCCL (per-point "own-voxel matched" bits, then the 58 fixed-point normal-equation sums), so
+ * every rank ends each scan with the bit-identical state of the single-GPU run.  unique_id128: bytes produced by
+ * immesh_comm_unique_id on rank 0 and distributed by the caller (e.g. torch.distributed broadcast). */
+int immesh_comm_unique_id(char* out128);
+int immesh_lio_shard(immesh_lio_t* h, int rank, int nranks, const char* unique_id128);
+
 /* BuildResidualListOMP (src/voxel_mapping.hpp:103-105, src/voxel_mapping.cpp:153-245) as a stand-alone call at
  * the current state: fills, for every accepted match in scan order, its scan index, octree layer and the ptpl
  * payload.  Returns the number of matches in *n_out (written entries are capped by cap). */

@@ -28,6 +28,7 @@ struct immesh_lio {
     std::vector<int> match_node, match_layer, slot, seg, seg2, slot_count, slot_offset, slot_cursor, touched;
     int counters[16];
     int max_scan;
+    std::vector<unsigned int> bits;   // sharded mode: [exists words | ok words]
 };
 
 static void fill_params(const immesh_lio_config* c, LioParams& P) {
@@ -172,5 +173,52 @@ int64_t immesh_voxelmap_dump(immesh_lio_t* h, double* rows, int64_t cap_rows) {
 int immesh_voxelmap_counts(immesh_lio_t* h, int64_t* out) {
     out[0] = h->counters[5]; out[1] = h->counters[0]; out[2] = h->counters[1]; out[3] = h->counters[4];
     return 0;
+}
+}
+
+// ------------------------------------------------------------------ sharded VoxelMap, split-phase (test-only entry points)
+// The CUDA library runs these phases back to back on one stream with ncclAllReduce in between; here the test does the two
+// all-reduces with torch.distributed (gloo) on the exposed host buffers.
+extern "C" {
+int emu_lio_set_shard(immesh_lio_t* h, int rank, int n) { h->P.shard_rank = rank; h->P.shard_n = n; return 0; }
+int emu_shard_begin(immesh_lio_t* h, const float* body, int n) {
+    load_scan(h, body, n);
+    LioCtrl& c = h->ctrl;
+    std::memcpy(c.state_prop, c.state, 348 * 8);
+    std::memset(c.acc, 0, sizeof(c.acc));
+    c.stop = 0; c.iters_run = 0; c.rematch_num = 0;
+    for (int i = 0; i < n; ++i) prepare_point(h->P, h->sb, i);
+    h->bits.assign(2 * ((size_t)(n + 31) / 32) + 2, 0u);
+    return 0;
+}
+unsigned int* emu_shard_bits(immesh_lio_t* h, int* nwords) { *nwords = (int)h->bits.size(); return h->bits.data(); }
+int emu_shard_pass1(immesh_lio_t* h) {
+    const int n = h->sb.n;
+    const size_t w = (size_t)(n + 31) / 32 + 1;
+    std::fill(h->bits.begin(), h->bits.end(), 0u);
+    for (int i = 0; i < n; ++i) shard_pass1_point(h->map, h->P, h->sb, h->ctrl.state, i, h->bits.data(), h->bits.data() + w);
+    return 0;
+}
+int emu_shard_pass2(immesh_lio_t* h, int it) {
+    const int n = h->sb.n;
+    const size_t w = (size_t)(n + 31) / 32 + 1;
+    long long sum[IM_NTERMS];
+    for (int k = 0; k < IM_NTERMS; ++k) sum[k] = 0;
+    for (int i = 0; i < n; ++i) {
+        long long t[IM_NTERMS];
+        if (shard_pass2_point(h->map, h->P, h->sb, h->ctrl.state, i, h->bits.data(), h->bits.data() + w, t, h->map.err))
+            for (int k = 0; k < IM_NTERMS; ++k) sum[k] += t[k];
+    }
+    for (int k = 0; k < IM_NTERMS; ++k) {
+        h->ctrl.acc[it][2 * k] = (unsigned long long)(sum[k] >> 32);
+        h->ctrl.acc[it][2 * k + 1] = (unsigned long long)(sum[k] & 0xffffffffLL);
+    }
+    return 0;
+}
+unsigned long long* emu_shard_acc(immesh_lio_t* h, int it) { return h->ctrl.acc[it]; }
+int emu_shard_solve(immesh_lio_t* h, int it) {
+    SolveScratch S;
+    ieskf_solve(h->P, &h->ctrl, it, &S, 0, 1);
+    return h->ctrl.stop;
 }
 }
