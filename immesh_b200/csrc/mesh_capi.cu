@@ -92,18 +92,45 @@ __global__ void __launch_bounds__(128) k_voxel_select(MeshDev M, FrameBuf F) {
     const int na = min(M.cnt[5], F.max_act);
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < na; a += gridDim.x * blockDim.x) voxel_select(M, F, a);
 }
-__global__ void __launch_bounds__(128) k_voxel_dilate(MeshDev M, MeshParams P, FrameBuf F) {
-    __shared__ DilateSmem S;
+// stage A+B fused per voxel: dilation (exact 20-NN of the in-voxel vertices, smoothing) immediately followed by the
+// projection + exact Delaunay + facet filter of the same voxel; facets go to global memory.  No grid-wide barrier between
+// the two: a block that has finished a voxel's dilation starts triangulating while other blocks are still dilating.
+// Voxels are claimed dynamically, populous ones first.
+union FusedSmem {
+    DilateSmem d;
+    MeshSmem<256> m;
+};
+__global__ void __launch_bounds__(128) k_voxel_fused(MeshDev M, MeshParams P, FrameBuf F) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
     __shared__ int s_item;
     const int nw = work_total(M, F);
-    while (true) {   // dynamic claim in list order: the populous voxels go first
+    while (true) {
         if (threadIdx.x == 0) s_item = atomicAdd(&M.cnt[24], 1);
         __syncthreads();
         const int i = s_item;
         __syncthreads();
         if (i >= nw) break;
-        voxel_dilate(M, P, F, work_slot(M, F, i), &S, threadIdx.x, blockDim.x);
+        const int w = work_slot(M, F, i);
+        voxel_dilate(M, P, F, w, &S->d, threadIdx.x, blockDim.x);
         __syncthreads();
+        voxel_mesh<256>(M, P, F, w, &S->m, threadIdx.x, blockDim.x, 1);
+        __syncthreads();
+    }
+}
+// stage C: commit / orientation / pull, one warp per voxel, after every voxel's smoothing is final
+__global__ void __launch_bounds__(128) k_voxel_commit(MeshDev M, MeshParams P, FrameBuf F) {
+    __shared__ CommitSmem S[4];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int nw = work_total(M, F);
+    while (true) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&M.cnt[19], 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= nw) break;
+        voxel_commit_warp(M, P, F, work_slot(M, F, i), &S[warp], lane, 32);
+        __syncwarp();
     }
 }
 template <int MAXD>
@@ -114,25 +141,9 @@ __global__ void __launch_bounds__(128) k_voxel_mesh(MeshDev M, MeshParams P, Fra
     for (int i = blockIdx.x; i < nw; i += gridDim.x) {
         const int w = work_slot(M, F, i);
         const int n = F.work_n_ids[w];
-        if ((n < 0 && MAXD > 256) || (n > lo && n <= MAXD)) voxel_mesh<MAXD>(M, P, F, w, S, threadIdx.x, blockDim.x);
+        const int na = n < 0 ? -n : n;
+        if (n < 0 || (na > lo && na <= MAXD)) voxel_mesh<MAXD>(M, P, F, w, S, threadIdx.x, blockDim.x);
         __syncthreads();
-    }
-}
-#define IM_WARP_NMAX 96   // dilated sets up to this size go to the warp-level stage, larger ones to the block-level stages
-// warp-level stage B: four independent voxels per block, voxels claimed dynamically
-__global__ void __launch_bounds__(128) k_voxel_mesh_warp(MeshDev M, MeshParams P, FrameBuf F) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    MeshWarpSmem<128>* S = reinterpret_cast<MeshWarpSmem<128>*>(smem_raw) + warp;
-    const int nw = work_total(M, F);
-    while (true) {
-        int i = 0;
-        if (lane == 0) i = atomicAdd(&M.cnt[19], 1);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= nw) break;
-        voxel_mesh_warp<128>(M, P, F, work_slot(M, F, i), S, lane, 32, IM_WARP_NMAX);
-        __syncwarp();
     }
 }
 __global__ void __launch_bounds__(128) k_push_remove(MeshDev M, FrameBuf F) {
@@ -340,6 +351,9 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(mdev_alloc(h, &F.work, (size_t)F.max_work));
     IM_CUDA(mdev_alloc(h, &F.work_n_ids, (size_t)F.max_work));
     IM_CUDA(mdev_alloc(h, &F.work_ids, (size_t)F.max_work * IM_MAXD));
+    IM_CUDA(mdev_alloc(h, &F.work_nfaces, (size_t)F.max_work));
+    IM_CUDA(mdev_alloc(h, &F.work_faces, (size_t)F.max_work * IM_MAXF * 3));
+    IM_CUDA(mdev_alloc(h, &F.work_axes, (size_t)F.max_work * 9));
     IM_CUDA(mdev_alloc(h, &F.add_tri, (size_t)F.max_list * 3));
     IM_CUDA(mdev_alloc(h, &F.add_flip, (size_t)F.max_list));
     IM_CUDA(mdev_alloc(h, &F.rem_tri, (size_t)F.max_list));
@@ -347,8 +361,7 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(cudaMallocHost((void**)&h->h_cnt, 2 * 32 * sizeof(int)));
     IM_CUDA(cudaMallocHost((void**)&h->h_fp, 2 * sizeof(FramePose)));
     IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<1024>)));
-    IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(MeshWarpSmem<128>))));
-    IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<256>)));
+    IM_CUDA(cudaFuncSetAttribute(k_voxel_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
     IM_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -485,16 +498,14 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
     }
     IM_CUDA(cudaEventRecord(h->ev[2], st));
     if (F.m > 0) {
-        IM_LAUNCH(k_voxel_dilate, h->n_sm * 4, 128, 0, st, h->M, P, F);
-        // small voxels (warp-level) on the side stream, mid-size voxels (block-level) on the main stream, concurrently;
-        // then the rare large / handed-over ones
+        IM_LAUNCH(k_voxel_fused, h->n_sm * 4, 128, sizeof(FusedSmem), st, h->M, P, F);
+        // commit of the regular voxels on the main stream; the rare large / handed-over voxels (monolithic variant) on the side stream
         IM_CUDA(cudaEventRecord(h->ev_fork, st));
         IM_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-        IM_LAUNCH(k_voxel_mesh_warp, h->n_sm * 4, 128, 4 * sizeof(MeshWarpSmem<128>), h->stream2, h->M, P, F);
+        IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), h->stream2, h->M, P, F, 256);
         IM_CUDA(cudaEventRecord(h->ev_join, h->stream2));
-        IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * 4, 128, sizeof(MeshSmem<256>), st, h->M, P, F, IM_WARP_NMAX);
+        IM_LAUNCH(k_voxel_commit, h->n_sm * 4, 128, 0, st, h->M, P, F);
         IM_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
-        IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st, h->M, P, F, 256);
     }
     IM_CUDA(cudaEventRecord(h->ev[3], st));
     if (F.m > 0) {

@@ -49,6 +49,7 @@ enum : int { CAND_UNDECIDED = 0, CAND_ACCEPT = 1, CAND_REJECT = 2 };
 #define IM_MAXG 2048        // max gathered kNN candidates per voxel neighbourhood
 #define IM_MAXT (3 * IM_MAXD + 8)
 #define IM_MAXPULL 4096
+#define IM_MAXF 512         // facets of a voxel with <= 256 dilated vertices (2n - 5 at most)
 #define IM_MAXIN 256        // max in-voxel vertices
 #define IM_CONF_K 24        // stored earlier-conflict candidates per candidate
 
@@ -120,6 +121,9 @@ struct FrameBuf {
     int* work;            // voxels to (re)mesh this frame
     int* work_n_ids;      // dilated set sizes
     int* work_ids;        // [max_work][IM_MAXD] ascending vertex ids
+    int* work_nfaces;     // facets produced by the fused dilate+triangulate stage (-1: left to the large variant)
+    int* work_faces;      // [max_work][IM_MAXF][3]
+    double* work_axes;    // [max_work][9] short / mid / long axis of the voxel's PCA frame
     // push lists
     int* add_tri;         // [max_list][3]
     unsigned long long* add_flip;

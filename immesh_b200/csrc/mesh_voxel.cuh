@@ -288,6 +288,80 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
 }
 
 // ------------------------------------------------------------------ stage B
+// commit (triangle_compare) + orientation (correct_triangle_index) + pull (find_relative_triangulation_combination) of one
+// voxel, given its ascending dilated id list, its new facets (sorted id triples) and a hash set over them.
+IM_HDN inline void voxel_commit_common(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int vs, int n, const int* ids, int nf,
+                                       const int (*faces)[3], const int* fhash, unsigned int hmask, const double* axes, int tid, int nthreads) {
+    // flip priority of this voxel: its key relative to the frame origin (ascending (x,y,z) order, last one wins)
+    int kx, ky, kz;
+    unpack_ikey(M.vkeys[vs], &kx, &ky, &kz);
+    const long long lx = kx - F.fp->prio_origin[0], ly = ky - F.fp->prio_origin[1], lz = kz - F.fp->prio_origin[2];
+    if (lx < 0 || lx >= 2048 || ly < 0 || ly >= 2048 || lz < 0 || lz >= 2048) {
+        if (tid == 0) im_atomic_or(&M.cnt[3], IM_MERR_PRIO_RANGE);
+    }
+    const unsigned long long prio = ((unsigned long long)(lx & 2047) << 22) | ((unsigned long long)(ly & 2047) << 11) | (unsigned long long)(lz & 2047);
+    const unsigned long long word_base = ((unsigned long long)F.frame << 34) | (prio << 1);
+    // commit, faces side (triangle_compare): a face already live in the store is "existing", otherwise "to add"
+    for (int k = tid; k < nf; k += nthreads) {
+        const int a = faces[k][0], b = faces[k][1], c = faces[k][2];
+        const unsigned long long word = word_base | (unsigned long long)compute_flip(M, a, b, c, F.fp->pose_t, axes);
+        const int t = tri_find(M, a, b, c);
+        if (t >= 0 && M.tri[t].w) {
+            im_atomic_max64(&M.tri_flip[t], word);
+        } else {
+            const int e = im_atomic_add(&M.cnt[7], 1);
+            if (e < F.max_list) {
+                F.add_tri[(size_t)e * 3 + 0] = a; F.add_tri[(size_t)e * 3 + 1] = b; F.add_tri[(size_t)e * 3 + 2] = c;
+                F.add_flip[e] = word;
+            } else {
+                im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+            }
+        }
+    }
+    // pull (find_relative_triangulation_combination) + commit, store side: live triangles with all three vertices in
+    // the dilated set that the new triangulation does not contain are removed.  Each triangle is visited from its
+    // smallest vertex only.
+    for (int i = tid; i < n; i += nthreads) {
+        const int v = ids[i];
+        for (int t = M.v_tri_head[v]; t >= 0;) {
+            const int4 r = M.tri[t];
+            const int slot = (r.x == v) ? 0 : ((r.y == v) ? 1 : 2);
+            const int nx = M.tri_next[(size_t)t * 3 + slot];
+            if (r.w && r.x == v) {
+                // binary search y and z in the ascending id list
+                bool in_set = true;
+                for (int pass = 0; pass < 2 && in_set; ++pass) {
+                    const int key = pass == 0 ? r.y : r.z;
+                    int lo = 0, hi = n - 1;
+                    bool hit = false;
+                    while (lo <= hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const int val = ids[mid];
+                        if (val == key) { hit = true; break; }
+                        if (val < key) lo = mid + 1; else hi = mid - 1;
+                    }
+                    in_set = hit;
+                }
+                if (in_set) {
+                    bool in_new = false;
+                    unsigned int hs = tri_hash(r.x, r.y, r.z) & hmask;
+                    for (int probe = 0; probe <= (int)hmask; ++probe) {
+                        const int k = fhash[hs];
+                        if (k < 0) break;
+                        if (faces[k][0] == r.x && faces[k][1] == r.y && faces[k][2] == r.z) { in_new = true; break; }
+                        hs = (hs + 1) & hmask;
+                    }
+                    if (!in_new) {
+                        const int e = im_atomic_add(&M.cnt[8], 1);
+                        if (e < F.max_list) F.rem_tri[e] = t; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+                    }
+                }
+            }
+            t = nx;
+        }
+    }
+}
+
 template <int MAXD>
 struct MeshSmem {
     int ids[MAXD];
@@ -305,9 +379,10 @@ struct MeshSmem {
 };
 
 template <int MAXD>
-IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, MeshSmem<MAXD>* S, int tid, int nthreads) {
+IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, MeshSmem<MAXD>* S, int tid, int nthreads, int store_only = 0) {
     const int nraw = F.work_n_ids[w];
-    const int n = nraw < 0 ? -nraw : nraw;   // negative: handed over by the warp-level stage after a cavity overflow
+    const int n = nraw < 0 ? -nraw : nraw;   // negative: handed over to the large variant after a capacity overflow
+    if (store_only && tid == 0) F.work_nfaces[w] = (n > MAXD) ? -1 : 0;   // -1: left to the large (monolithic) variant
     if (n < 3 || n > MAXD) return;
     const int vs = F.work[w];
     for (int i = tid; i < n; i += nthreads) {
@@ -362,7 +437,11 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
     delaunay_block(S->snap, n, S->tris, 3 * MAXD + 8, &S->ntri, S->scratch, tid, nthreads, (MAXD <= 256) ? S->circ : nullptr);
     IM_SYNCBLOCK_M();
     if (S->scratch[4] == 0) return;  // all points collinear: T.number_of_faces() == 0 (mesh_rec_geometry.cpp:257-260)
-    if (S->scratch[6]) { if (tid == 0) im_atomic_or(&M.cnt[3], IM_MERR_VOXEL_CAP); return; }
+    if (S->scratch[6]) {   // cavity capacity exceeded
+        if (store_only) { if (tid == 0) { F.work_nfaces[w] = -1; F.work_n_ids[w] = -n; } }
+        else if (tid == 0) im_atomic_or(&M.cnt[3], IM_MERR_VOXEL_CAP);
+        return;
+    }
     // finite faces passing the 150-degree filter (is_face_is_ok), as sorted global id triples
     const int nt = S->ntri;
     for (int t = tid; t < nt; t += nthreads) {
@@ -384,349 +463,45 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
     IM_SYNCBLOCK_M();
     const int nf = S->nface;
     if (tid == 0) im_atomic_add(&M.cnt[23], nf);
-    // flip priority of this voxel: its key relative to the frame origin (ascending (x,y,z) order, last one wins)
-    int kx, ky, kz;
-    unpack_ikey(M.vkeys[vs], &kx, &ky, &kz);
-    const long long lx = kx - F.fp->prio_origin[0], ly = ky - F.fp->prio_origin[1], lz = kz - F.fp->prio_origin[2];
-    if (lx < 0 || lx >= 2048 || ly < 0 || ly >= 2048 || lz < 0 || lz >= 2048) {
-        if (tid == 0) im_atomic_or(&M.cnt[3], IM_MERR_PRIO_RANGE);
-    }
-    const unsigned long long prio = ((unsigned long long)(lx & 2047) << 22) | ((unsigned long long)(ly & 2047) << 11) | (unsigned long long)(lz & 2047);
-    const unsigned long long word_base = ((unsigned long long)F.frame << 34) | (prio << 1);
-    // commit, faces side (triangle_compare): a face already live in the store is "existing", otherwise "to add"
-    for (int k = tid; k < nf; k += nthreads) {
-        const int a = S->faces[k][0], b = S->faces[k][1], c = S->faces[k][2];
-        const unsigned long long word = word_base | (unsigned long long)compute_flip(M, a, b, c, F.fp->pose_t, S->axes);
-        const int t = tri_find(M, a, b, c);
-        if (t >= 0 && M.tri[t].w) {
-            im_atomic_max64(&M.tri_flip[t], word);
-        } else {
-            const int e = im_atomic_add(&M.cnt[7], 1);
-            if (e < F.max_list) {
-                F.add_tri[(size_t)e * 3 + 0] = a; F.add_tri[(size_t)e * 3 + 1] = b; F.add_tri[(size_t)e * 3 + 2] = c;
-                F.add_flip[e] = word;
-            } else {
-                im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
-            }
+    if (store_only) {
+        // fused dilate+triangulate kernel: the facets and the voxel's principal axes go to global memory; commit / orientation
+        // run in a later kernel, once the smoothed positions of ALL voxels of the frame are final
+        for (int k = tid; k < nf; k += nthreads) {
+            int* o = F.work_faces + ((size_t)w * IM_MAXF + k) * 3;
+            o[0] = S->faces[k][0]; o[1] = S->faces[k][1]; o[2] = S->faces[k][2];
         }
-    }
-    // pull (find_relative_triangulation_combination) + commit, store side: live triangles with all three vertices in
-    // the dilated set that the new triangulation does not contain are removed.  Each triangle is visited from its
-    // smallest vertex only.
-    for (int i = tid; i < n; i += nthreads) {
-        const int v = S->ids[i];
-        for (int t = M.v_tri_head[v]; t >= 0;) {
-            const int4 r = M.tri[t];
-            const int slot = (r.x == v) ? 0 : ((r.y == v) ? 1 : 2);
-            const int nx = M.tri_next[(size_t)t * 3 + slot];
-            if (r.w && r.x == v) {
-                // binary search y and z in the ascending id list
-                bool in_set = true;
-                for (int pass = 0; pass < 2 && in_set; ++pass) {
-                    const int key = pass == 0 ? r.y : r.z;
-                    int lo = 0, hi = n - 1;
-                    bool hit = false;
-                    while (lo <= hi) {
-                        const int mid = (lo + hi) >> 1;
-                        const int val = S->ids[mid];
-                        if (val == key) { hit = true; break; }
-                        if (val < key) lo = mid + 1; else hi = mid - 1;
-                    }
-                    in_set = hit;
-                }
-                if (in_set) {
-                    bool in_new = false;
-                    unsigned int hs = tri_hash(r.x, r.y, r.z) & (4 * MAXD - 1);
-                    for (int probe = 0; probe < 4 * MAXD; ++probe) {
-                        const int k = S->fhash[hs];
-                        if (k < 0) break;
-                        if (S->faces[k][0] == r.x && S->faces[k][1] == r.y && S->faces[k][2] == r.z) { in_new = true; break; }
-                        hs = (hs + 1) & (4 * MAXD - 1);
-                    }
-                    if (!in_new) {
-                        const int e = im_atomic_add(&M.cnt[8], 1);
-                        if (e < F.max_list) F.rem_tri[e] = t; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
-                    }
-                }
-            }
-            t = nx;
-        }
-    }
-}
-
-// ------------------------------------------------------------------ stage B, warp-level variant (the common case)
-// One warp per voxel (n <= MAXD dilated vertices), __syncwarp only.  The Bowyer-Watson conflict search is pruned with a
-// cached float circumcircle per triangle (conservative margin; every survivor still goes through the exact predicate),
-// which removes ~90% of the exact in-circle evaluations.  Cavity / boundary capacity is 64 triangles; a voxel that
-// exceeds it is handed to the block-level stage (work_n_ids[w] negated).
-template <int MAXD>
-struct MeshWarpSmem {
-    int ids[MAXD];
-    double uv[MAXD][2];
-    int2 snap[MAXD];
-    DTri tris[3 * MAXD + 8];          // after face extraction: reused as the face hash (4*MAXD ints)
-    float circ[3 * MAXD + 8][3];      // before the triangulation: vertex positions; after it: faces (2*MAXD int3)
-    int scratch[8 + 64 + 2 * 192];
-    double axes[9];
-    double centre[3];
-    int ntri, nface;
-};
-
-template <int MAXD>
-IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, MeshWarpSmem<MAXD>* S, int lane, int nlanes, int n_max) {
-    const int n = F.work_n_ids[w];
-    if (n < 3 || n > n_max || n > MAXD) return;
-    const int vs = F.work[w];
-    float (*pos)[3] = S->circ;  // alias: positions are dead once projected
-    for (int i = lane; i < n; i += nlanes) {
-        const int id = F.work_ids[(size_t)w * IM_MAXD + i];
-        S->ids[i] = id;
-        const float4 p = M.vpos[id];
-        pos[i][0] = p.x; pos[i][1] = p.y; pos[i][2] = p.z;
-    }
-    if (lane == 0) S->nface = 0;
-    IM_SYNCWARP();
-    if (lane == 0) {
-        double c[3] = {0, 0, 0};
-        for (int i = 0; i < n; ++i)
-            for (int j = 0; j < 3; ++j) c[j] = c[j] + (double)pos[i][j];
-        for (int j = 0; j < 3; ++j) c[j] = c[j] / (double)n;
-        double cov[6] = {0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < n; ++i) {
-            const double d[3] = {(double)pos[i][0] - c[0], (double)pos[i][1] - c[1], (double)pos[i][2] - c[2]};
-            cov[0] += d[0] * d[0]; cov[1] += d[0] * d[1]; cov[2] += d[0] * d[2];
-            cov[3] += d[1] * d[1]; cov[4] += d[1] * d[2]; cov[5] += d[2] * d[2];
-        }
-        for (int k = 0; k < 6; ++k) cov[k] = cov[k] / (double)n;
-        double ev[3], U[9];
-        jacobi3(cov, ev, U);
-        int order[3] = {0, 1, 2};
-        for (int a = 0; a < 2; ++a)
-            for (int b = 0; b < 2 - a; ++b)
-                if (ev[order[b + 1]] < ev[order[b]]) { const int t = order[b]; order[b] = order[b + 1]; order[b + 1] = t; }
-        double sx[3], m[3];
-        for (int j = 0; j < 3; ++j) { sx[j] = U[j * 3 + order[0]]; m[j] = U[j * 3 + order[1]]; }
-        const double d0[3] = {(double)pos[0][0] - c[0], (double)pos[0][1] - c[1], (double)pos[0][2] - c[2]};
-        const double d1[3] = {(double)pos[1][0] - c[0], (double)pos[1][1] - c[1], (double)pos[1][2] - c[2]};
-        if (dot3(d0, sx) < 0) { sx[0] = -sx[0]; sx[1] = -sx[1]; sx[2] = -sx[2]; }
-        if (dot3(d1, m) < 0) { m[0] = -m[0]; m[1] = -m[1]; m[2] = -m[2]; }
-        S->axes[0] = sx[0]; S->axes[1] = sx[1]; S->axes[2] = sx[2];
-        S->axes[3] = m[0]; S->axes[4] = m[1]; S->axes[5] = m[2];
-        S->axes[6] = sx[1] * m[2] - sx[2] * m[1];
-        S->axes[7] = sx[2] * m[0] - sx[0] * m[2];
-        S->axes[8] = sx[0] * m[1] - sx[1] * m[0];
-        S->centre[0] = c[0]; S->centre[1] = c[1]; S->centre[2] = c[2];
-    }
-    IM_SYNCWARP();
-    for (int i = lane; i < n; i += nlanes) {
-        const double d[3] = {(double)pos[i][0] - S->centre[0], (double)pos[i][1] - S->centre[1], (double)pos[i][2] - S->centre[2]};
-        const double u = dot3(d, S->axes + 6), v = dot3(d, S->axes + 3);
-        S->uv[i][0] = u; S->uv[i][1] = v;
-        S->snap[i] = make_int2((int)im_llrint(u * P.inv_q), (int)im_llrint(v * P.inv_q));
-    }
-    IM_SYNCWARP();
-    // ---- Bowyer-Watson, warp-synchronous
-    const int2* Pt = S->snap;
-    DTri* tris = S->tris;
-    int* s_cav_n = S->scratch;
-    int* s_edge_n = S->scratch + 1;
-    int* s_seed = S->scratch + 2;   // i1, i2, ok
-    int* s_ovf = S->scratch + 6;
-    int* s_cav = S->scratch + 8;    // [64]
-    int* s_edges = S->scratch + 72; // [68*2]
-    const int max_tris = 3 * MAXD + 8;
-    if (lane == 0) {
-        *s_ovf = 0;
-        int i1 = -1, i2 = -1;
-        for (int i = 1; i < n; ++i)
-            if (Pt[i].x != Pt[0].x || Pt[i].y != Pt[0].y) { i1 = i; break; }
-        if (i1 >= 0)
-            for (int i = 1; i < n; ++i)
-                if (i != i1 && orient2d_i(Pt[0].x, Pt[0].y, Pt[i1].x, Pt[i1].y, Pt[i].x, Pt[i].y) != 0) { i2 = i; break; }
-        s_seed[0] = i1; s_seed[1] = i2; s_seed[2] = (i1 >= 0 && i2 >= 0) ? 1 : 0;
-        S->ntri = 0;
-        if (s_seed[2]) {
-            int a = 0, b = i1, c = i2;
-            if (orient2d_i(Pt[a].x, Pt[a].y, Pt[b].x, Pt[b].y, Pt[c].x, Pt[c].y) < 0) { const int t = b; b = c; c = t; }
-            const short tv[4][3] = {{(short)a, (short)b, (short)c}, {(short)c, (short)b, IM_GHOST}, {(short)a, (short)c, IM_GHOST}, {(short)b, (short)a, IM_GHOST}};
-            for (int k = 0; k < 4; ++k) { tris[k].v[0] = tv[k][0]; tris[k].v[1] = tv[k][1]; tris[k].v[2] = tv[k][2]; tris[k].alive = 1; }
-            circumcircle_f(Pt, a, b, c, S->circ[0]);
-            S->ntri = 4;
-        }
-    }
-    IM_SYNCWARP();
-    if (!s_seed[2]) return;
-    const int i1 = s_seed[0], i2 = s_seed[1];
-    // per insertion: (1) conflict scan, compacted with ballots; (2) directed edge list of the cavity; (3) boundary edges
-    // (those whose reverse is not in the list) ranked with ballots, each writes its new triangle -- cavity slots first,
-    // then the pool tail.  Three warp barriers, no atomics.
-    int* s_ea = s_edges;            // [192] directed cavity edges: tails
-    int* s_eb = s_edges + 192;      // [192] heads
-    (void)s_cav_n; (void)s_edge_n;
-    const unsigned lt = im_lanemask_lt();
-    bool ovf = false;
-    for (int p = 1; p < n && !ovf; ++p) {
-        if (p == i1 || p == i2) continue;
-        const int nt = S->ntri;
-        const float pxf = (float)Pt[p].x, pyf = (float)Pt[p].y;
-        int nc = 0;
-        for (int t0 = 0; t0 < nt; t0 += nlanes) {
-            const int t = t0 + lane;
-            bool c = false;
-            if (t < nt) {
-                const DTri tr = tris[t];
-                if (tr.alive) {
-                    bool maybe = true;
-                    if (tr.v[0] != IM_GHOST && tr.v[1] != IM_GHOST && tr.v[2] != IM_GHOST) {
-                        const float dx = pxf - S->circ[t][0], dy = pyf - S->circ[t][1];
-                        if (dx * dx + dy * dy > S->circ[t][2]) maybe = false;   // certainly outside the circumcircle
-                    }
-                    if (maybe) c = dt_conflict(tr, Pt, p);
-                }
-            }
-            const unsigned m = im_ballot(c);
-            if (c) {
-                const int k = nc + im_popc(m & lt);
-                if (k < 64) s_cav[k] = t;
-            }
-            nc += im_popc(m);
-        }
-        if (nc > 64) { ovf = true; break; }   // warp-uniform
-        IM_SYNCWARP();
-        if (nc == 0) continue;                // duplicate point: skipped (CGAL does the same)
-        const int ne3 = nc * 3;
-        for (int e = lane; e < ne3; e += nlanes) {
-            const DTri& t = tris[s_cav[e / 3]];
-            s_ea[e] = t.v[(e % 3 + 1) % 3];
-            s_eb[e] = t.v[(e % 3 + 2) % 3];
-        }
-        IM_SYNCWARP();
-        int nb = 0;
-        for (int e0 = 0; e0 < ne3; e0 += nlanes) {
-            const int e = e0 + lane;
-            bool isb = false;
-            int a = 0, b = 0;
-            if (e < ne3) {
-                a = s_ea[e]; b = s_eb[e];
-                isb = true;
-                for (int f = 0; f < ne3; ++f)
-                    if (s_ea[f] == b && s_eb[f] == a) { isb = false; break; }
-            }
-            const unsigned m = im_ballot(isb);
-            if (isb) {
-                const int k = nb + im_popc(m & lt);
-                const int slot = (k < nc) ? s_cav[k] : (nt + (k - nc));
-                if (slot < max_tris) {
-                    tris[slot].v[0] = (short)a; tris[slot].v[1] = (short)b; tris[slot].v[2] = (short)p; tris[slot].alive = 1;
-                    if (a != IM_GHOST && b != IM_GHOST) circumcircle_f(Pt, a, b, p, S->circ[slot]);
-                }
-            }
-            nb += im_popc(m);
-        }
-        // every cavity slot is reused (a valid cavity has nc + 2 boundary edges); kill leftovers defensively
-        for (int k = nb + lane; k < nc; k += nlanes) tris[s_cav[k]].alive = 0;
-        if (nb > nc) {
-            if (nt + (nb - nc) <= max_tris) { if (lane == 0) S->ntri = nt + (nb - nc); }
-            else ovf = true;
-        }
-        IM_SYNCWARP();
-    }
-    if (lane == 0) *s_ovf = ovf ? 1 : 0;
-    IM_SYNCWARP();
-    if (*s_ovf) {  // hand this voxel to the block-level stage
-        if (lane == 0) F.work_n_ids[w] = -n;
+        for (int k = tid; k < 9; k += nthreads) F.work_axes[(size_t)w * 9 + k] = S->axes[k];
+        if (tid == 0) F.work_nfaces[w] = nf;
         return;
     }
-    // ---- faces passing the 150-degree filter, as sorted global id triples (stored over the dead circumcircle cache)
-    int (*faces)[3] = reinterpret_cast<int (*)[3]>(&S->circ[0][0]);
-    const int nt = S->ntri;
-    for (int t = lane; t < nt; t += nlanes) {
-        const DTri& tr = tris[t];
-        if (!tr.alive || tr.v[0] < 0 || tr.v[1] < 0 || tr.v[2] < 0) continue;
-        const int j0 = tr.v[0], j1 = tr.v[1], j2 = tr.v[2];
-        if (angle_bad(S->uv[j0][0], S->uv[j0][1], S->uv[j1][0], S->uv[j1][1], S->uv[j2][0], S->uv[j2][1])) continue;
-        if (angle_bad(S->uv[j1][0], S->uv[j1][1], S->uv[j2][0], S->uv[j2][1], S->uv[j0][0], S->uv[j0][1])) continue;
-        if (angle_bad(S->uv[j2][0], S->uv[j2][1], S->uv[j0][0], S->uv[j0][1], S->uv[j1][0], S->uv[j1][1])) continue;
-        int a = S->ids[j0], b = S->ids[j1], c = S->ids[j2];
-        if (a > b) { const int x = a; a = b; b = x; }
-        if (b > c) { const int x = b; b = c; c = x; }
-        if (a > b) { const int x = a; a = b; b = x; }
-        const int k = im_atomic_add(&S->nface, 1);
-        faces[k][0] = a; faces[k][1] = b; faces[k][2] = c;
+    voxel_commit_common(M, P, F, vs, n, S->ids, nf, S->faces, S->fhash, 4 * MAXD - 1, S->axes, tid, nthreads);
+}
+
+struct CommitSmem {
+    int ids[256];
+    int faces[IM_MAXF][3];
+    int fhash[1024];
+    double axes[9];
+};
+// stage C for the fused path: one warp per voxel, facets read back from global memory
+IM_HDN inline void voxel_commit_warp(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, CommitSmem* S, int lane, int nlanes) {
+    const int n = F.work_n_ids[w];
+    const int nf = F.work_nfaces[w];
+    if (n < 3 || n > 256 || nf < 0) return;
+    for (int i = lane; i < n; i += nlanes) S->ids[i] = F.work_ids[(size_t)w * IM_MAXD + i];
+    for (int k = lane; k < nf; k += nlanes) {
+        const int* o = F.work_faces + ((size_t)w * IM_MAXF + k) * 3;
+        S->faces[k][0] = o[0]; S->faces[k][1] = o[1]; S->faces[k][2] = o[2];
     }
-    IM_SYNCWARP();
-    const int nf = S->nface;
-    int* fhash = reinterpret_cast<int*>(S->tris);   // triangles are dead now
-    for (int i = lane; i < 4 * MAXD; i += nlanes) fhash[i] = -1;
+    for (int i = lane; i < 1024; i += nlanes) S->fhash[i] = -1;
+    for (int i = lane; i < 9; i += nlanes) S->axes[i] = F.work_axes[(size_t)w * 9 + i];
     IM_SYNCWARP();
     for (int k = lane; k < nf; k += nlanes) {
-        unsigned int hs = tri_hash(faces[k][0], faces[k][1], faces[k][2]) & (4 * MAXD - 1);
-        while (im_atomic_cas32(&fhash[hs], -1, k) != -1) hs = (hs + 1) & (4 * MAXD - 1);
+        unsigned int hs = tri_hash(S->faces[k][0], S->faces[k][1], S->faces[k][2]) & 1023u;
+        while (im_atomic_cas32(&S->fhash[hs], -1, k) != -1) hs = (hs + 1) & 1023u;
     }
     IM_SYNCWARP();
-    if (lane == 0) im_atomic_add(&M.cnt[23], nf);
-    int kx, ky, kz;
-    unpack_ikey(M.vkeys[vs], &kx, &ky, &kz);
-    const long long lx = kx - F.fp->prio_origin[0], ly = ky - F.fp->prio_origin[1], lz = kz - F.fp->prio_origin[2];
-    if (lx < 0 || lx >= 2048 || ly < 0 || ly >= 2048 || lz < 0 || lz >= 2048) {
-        if (lane == 0) im_atomic_or(&M.cnt[3], IM_MERR_PRIO_RANGE);
-    }
-    const unsigned long long prio = ((unsigned long long)(lx & 2047) << 22) | ((unsigned long long)(ly & 2047) << 11) | (unsigned long long)(lz & 2047);
-    const unsigned long long word_base = ((unsigned long long)F.frame << 34) | (prio << 1);
-    for (int k = lane; k < nf; k += nlanes) {
-        const int a = faces[k][0], b = faces[k][1], c = faces[k][2];
-        const unsigned long long word = word_base | (unsigned long long)compute_flip(M, a, b, c, F.fp->pose_t, S->axes);
-        const int t = tri_find(M, a, b, c);
-        if (t >= 0 && M.tri[t].w) {
-            im_atomic_max64(&M.tri_flip[t], word);
-        } else {
-            const int e = im_atomic_add(&M.cnt[7], 1);
-            if (e < F.max_list) {
-                F.add_tri[(size_t)e * 3 + 0] = a; F.add_tri[(size_t)e * 3 + 1] = b; F.add_tri[(size_t)e * 3 + 2] = c;
-                F.add_flip[e] = word;
-            } else {
-                im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
-            }
-        }
-    }
-    for (int i = lane; i < n; i += nlanes) {
-        const int v = S->ids[i];
-        for (int t = M.v_tri_head[v]; t >= 0;) {
-            const int4 r = M.tri[t];
-            const int slot = (r.x == v) ? 0 : ((r.y == v) ? 1 : 2);
-            const int nx = M.tri_next[(size_t)t * 3 + slot];
-            if (r.w && r.x == v) {
-                bool in_set = true;
-                for (int pass = 0; pass < 2 && in_set; ++pass) {
-                    const int key = pass == 0 ? r.y : r.z;
-                    int lo = 0, hi = n - 1;
-                    bool hit = false;
-                    while (lo <= hi) {
-                        const int mid = (lo + hi) >> 1;
-                        const int val = S->ids[mid];
-                        if (val == key) { hit = true; break; }
-                        if (val < key) lo = mid + 1; else hi = mid - 1;
-                    }
-                    in_set = hit;
-                }
-                if (in_set) {
-                    bool in_new = false;
-                    unsigned int hs = tri_hash(r.x, r.y, r.z) & (4 * MAXD - 1);
-                    for (int probe = 0; probe < 4 * MAXD; ++probe) {
-                        const int k = fhash[hs];
-                        if (k < 0) break;
-                        if (faces[k][0] == r.x && faces[k][1] == r.y && faces[k][2] == r.z) { in_new = true; break; }
-                        hs = (hs + 1) & (4 * MAXD - 1);
-                    }
-                    if (!in_new) {
-                        const int e = im_atomic_add(&M.cnt[8], 1);
-                        if (e < F.max_list) F.rem_tri[e] = t; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
-                    }
-                }
-            }
-            t = nx;
-        }
-    }
+    voxel_commit_common(M, P, F, F.work[w], n, S->ids, nf, S->faces, S->fhash, 1023u, S->axes, lane, nlanes);
 }
 
 }  // namespace immesh

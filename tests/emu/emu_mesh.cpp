@@ -22,7 +22,8 @@ struct immesh_mesh {
     std::vector<unsigned long long> gkeys, vkeys, tri_flip, ckeys, cand_gkey, add_flip;
     std::vector<int4> tri;
     std::vector<float> pts;
-    std::vector<int> cand_vslot, cand_status, cand_scan, cand_conf, cand_nconf, cand_next, chead, act, work, work_n, work_ids, add_tri, rem_tri;
+    std::vector<int> cand_vslot, cand_status, cand_scan, cand_conf, cand_nconf, cand_next, chead, act, work, work_n, work_ids, add_tri, rem_tri, work_nf, work_faces;
+    std::vector<double> work_axes;
     int frame_counter = 0;
     int last_cnt[32];
 };
@@ -59,11 +60,12 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     const size_t ccap = p2(mc * 2);
     h->ckeys.resize(ccap); h->chead.resize(ccap);
     h->act.resize(F.max_act); h->work.resize(F.max_work); h->work_n.resize(F.max_work); h->work_ids.resize((size_t)F.max_work * IM_MAXD);
+    h->work_nf.resize(F.max_work); h->work_faces.resize((size_t)F.max_work * IM_MAXF * 3); h->work_axes.resize((size_t)F.max_work * 9);
     h->add_tri.resize((size_t)F.max_list * 3); h->add_flip.resize(F.max_list); h->rem_tri.resize(F.max_list);
     F.pts = h->pts.data(); F.cand_gkey = h->cand_gkey.data(); F.cand_vslot = h->cand_vslot.data(); F.cand_status = h->cand_status.data();
     F.cand_scan = h->cand_scan.data(); F.cand_conf = h->cand_conf.data(); F.cand_nconf = h->cand_nconf.data(); F.cand_next = h->cand_next.data();
     F.ckeys = h->ckeys.data(); F.chead = h->chead.data(); F.scan_block = nullptr;
-    F.act = h->act.data(); F.work = h->work.data(); F.work_n_ids = h->work_n.data(); F.work_ids = h->work_ids.data();
+    F.act = h->act.data(); F.work = h->work.data(); F.work_n_ids = h->work_n.data(); F.work_ids = h->work_ids.data(); F.work_nfaces = h->work_nf.data(); F.work_faces = h->work_faces.data(); F.work_axes = h->work_axes.data();
     F.add_tri = h->add_tri.data(); F.add_flip = h->add_flip.data(); F.rem_tri = h->rem_tri.data();
     std::memset(h->last_cnt, 0, sizeof(h->last_cnt));
     *out = h;
@@ -96,23 +98,21 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     for (int a = 0; a < na; ++a) voxel_select(M, F, a);
     const int nw = work_total(M, F);
     DilateSmem* DS = new DilateSmem();
-    for (int i = 0; i < nw; ++i) voxel_dilate(M, P, F, work_slot(M, F, i), DS, 0, 1);
-    delete DS;
     MeshSmem<256>* S1 = new MeshSmem<256>();
     MeshSmem<1024>* S2 = new MeshSmem<1024>();
-    MeshWarpSmem<128>* SW = new MeshWarpSmem<128>();
-    for (int i = 0; i < nw; ++i) voxel_mesh_warp<128>(M, P, F, work_slot(M, F, i), SW, 0, 1, 96);   // same split as the device
-    for (int i = 0; i < nw; ++i) {
+    CommitSmem* SC = new CommitSmem();
+    for (int i = 0; i < nw; ++i) {   // fused stage: dilation then triangulation of the same voxel
         const int w = work_slot(M, F, i);
-        const int nd = F.work_n_ids[w];
-        if (nd > 96 && nd <= 256) voxel_mesh<256>(M, P, F, w, S1, 0, 1);
+        voxel_dilate(M, P, F, w, DS, 0, 1);
+        voxel_mesh<256>(M, P, F, w, S1, 0, 1, 1);
     }
+    for (int i = 0; i < nw; ++i) voxel_commit_warp(M, P, F, work_slot(M, F, i), SC, 0, 1);
     for (int i = 0; i < nw; ++i) {
         const int w = work_slot(M, F, i);
         const int nd = F.work_n_ids[w];
         if (nd < 0 || nd > 256) voxel_mesh<1024>(M, P, F, w, S2, 0, 1);
     }
-    delete S1; delete S2; delete SW;
+    delete DS; delete S1; delete S2; delete SC;
     const int nr = std::min(M.cnt[8], F.max_list), nadd = std::min(M.cnt[7], F.max_list);
     for (int e = 0; e < nr; ++e) tri_remove(M, F.rem_tri[e]);
     for (int e = 0; e < nadd; ++e) tri_add(M, F.add_tri[(size_t)e * 3], F.add_tri[(size_t)e * 3 + 1], F.add_tri[(size_t)e * 3 + 2], F.add_flip[e]);
