@@ -18,9 +18,10 @@ using namespace immesh;
 __global__ void k_frame_begin(MeshDev M, FrameBuf F) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     for (unsigned int i = tid; i <= F.cmask; i += nt) { F.ckeys[i] = IM_EMPTY_KEY; F.chead[i] = -1; }
+    for (unsigned int i = tid; i <= F.fset_mask; i += nt) F.fset[i] = -1;
     if (tid == 0) {
         for (int k = 5; k <= 10; ++k) M.cnt[k] = 0;
-        for (int k = 17; k <= 24; ++k) M.cnt[k] = 0;
+        for (int k = 17; k <= 26; ++k) M.cnt[k] = 0;
     }
 }
 __global__ void __launch_bounds__(128) k_cand_init(MeshDev M, MeshParams P, FrameBuf F) {
@@ -88,6 +89,10 @@ __global__ void __launch_bounds__(128) k_cand_commit(MeshDev M, MeshParams P, Fr
     const int base = M.cnt[0];
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F.m; c += gridDim.x * blockDim.x) cand_commit(M, P, F, c, base);
 }
+__global__ void __launch_bounds__(128) k_cand_place(MeshDev M, FrameBuf F) {
+    const int base = M.cnt[0];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F.m; c += gridDim.x * blockDim.x) cand_place(M, F, c, base);
+}
 __global__ void __launch_bounds__(128) k_voxel_select(MeshDev M, FrameBuf F) {
     const int na = min(M.cnt[5], F.max_act);
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < na; a += gridDim.x * blockDim.x) voxel_select(M, F, a);
@@ -118,20 +123,14 @@ __global__ void __launch_bounds__(128) k_voxel_fused(MeshDev M, MeshParams P, Fr
         __syncthreads();
     }
 }
-// stage C: commit / orientation / pull, one warp per voxel, after every voxel's smoothing is final
-__global__ void __launch_bounds__(128) k_voxel_commit(MeshDev M, MeshParams P, FrameBuf F) {
-    __shared__ CommitSmem S[4];
-    const int lane = threadIdx.x & 31;
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const int nw = work_total(M, F);
-    while (true) {
-        int i = 0;
-        if (lane == 0) i = atomicAdd(&M.cnt[19], 1);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= nw) break;
-        voxel_commit_warp(M, P, F, work_slot(M, F, i), &S[warp], lane, 32);
-        __syncwarp();
-    }
+// stage C (flat): after every voxel's smoothing is final
+__global__ void __launch_bounds__(128) k_commit_faces(MeshDev M, MeshParams P, FrameBuf F) {
+    const int nf = min(M.cnt[25], F.max_list);
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) commit_face(M, P, F, f);
+}
+__global__ void __launch_bounds__(128) k_commit_vertices(MeshDev M, MeshParams P, FrameBuf F) {
+    const int nr = min(M.cnt[26], F.max_vref);
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nr; r += gridDim.x * blockDim.x) commit_vertex(M, P, F, r);
 }
 template <int MAXD>
 __global__ void __launch_bounds__(128) k_voxel_mesh(MeshDev M, MeshParams P, FrameBuf F, int lo) {
@@ -205,8 +204,11 @@ __global__ void __launch_bounds__(128) k_knn(MeshDev M, MeshParams P, const floa
                 if (!ikey_ok(cx + dx, cy + dy, cz + dz)) continue;
                 const int s = table_find(M.vkeys, M.vmask, pack_ikey(cx + dx, cy + dy, cz + dz));
                 if (s < 0) continue;
-                for (int v = M.vox_head[s]; v >= 0; v = M.v_next[v]) {
-                    const float4 p = M.vpos[v];
+                int cntv = M.vox_count[s];
+                if (cntv > IM_VCHUNKS * 16) cntv = IM_VCHUNKS * 16;
+                for (int kk = 0; kk < cntv; ++kk) {
+                    const float4 p = M.vchunk_pts[(size_t)M.vox_chunk[(size_t)s * IM_VCHUNKS + (kk >> 4)] * 16 + (kk & 15)];
+                    const int v = __float_as_int(p.w);
                     const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
                     if (!((double)d2 <= max_d2)) continue;
                     // insert (d2, v) into this lane's ascending list, keeping at most k
@@ -297,7 +299,6 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     M.max_t = max_t;
     IM_CUDA(mdev_alloc(h, &M.vpos, (size_t)max_v));
     IM_CUDA(mdev_alloc(h, &M.vsmooth, (size_t)max_v * 3));
-    IM_CUDA(mdev_alloc(h, &M.v_next, (size_t)max_v, 0xFF));
     IM_CUDA(mdev_alloc(h, &M.v_tri_head, (size_t)max_v, 0xFF));
     const size_t gcap = pow2_at_least((size_t)max_v * 2);
     IM_CUDA(mdev_alloc(h, &M.gkeys, gcap, 0xFF));
@@ -306,7 +307,9 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     const size_t vcap = pow2_at_least((size_t)max_vox * 2);
     IM_CUDA(mdev_alloc(h, &M.vkeys, vcap, 0xFF));
     M.vmask = (unsigned)(vcap - 1);
-    IM_CUDA(mdev_alloc(h, &M.vox_head, vcap, 0xFF));
+    IM_CUDA(mdev_alloc(h, &M.vox_chunk, vcap * IM_VCHUNKS, 0xFF));
+    M.max_vchunks = max_v / 4 + 1024;
+    IM_CUDA(mdev_alloc(h, &M.vchunk_pts, (size_t)M.max_vchunks * 16));
     IM_CUDA(mdev_alloc(h, &M.vox_count, vcap, 0));
     IM_CUDA(mdev_alloc(h, &M.vox_meshing_times, vcap, 0));
     IM_CUDA(mdev_alloc(h, &M.vox_new_added, vcap, 0));
@@ -343,6 +346,7 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(mdev_alloc(h, &F.cand_conf, mc * IM_CONF_K));
     IM_CUDA(mdev_alloc(h, &F.cand_nconf, mc));
     IM_CUDA(mdev_alloc(h, &F.cand_next, mc));
+    IM_CUDA(mdev_alloc(h, &F.cand_pos, mc));
     h->ccap = pow2_at_least(mc * 2);
     IM_CUDA(mdev_alloc(h, &F.ckeys, h->ccap));
     IM_CUDA(mdev_alloc(h, &F.chead, h->ccap));
@@ -352,7 +356,11 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(mdev_alloc(h, &F.work_n_ids, (size_t)F.max_work));
     IM_CUDA(mdev_alloc(h, &F.work_ids, (size_t)F.max_work * IM_MAXD));
     IM_CUDA(mdev_alloc(h, &F.work_nfaces, (size_t)F.max_work));
-    IM_CUDA(mdev_alloc(h, &F.work_faces, (size_t)F.max_work * IM_MAXF * 3));
+    F.max_vref = 8 << 20;
+    IM_CUDA(mdev_alloc(h, &F.all_faces, (size_t)F.max_list));
+    IM_CUDA(mdev_alloc(h, &F.all_vref, (size_t)F.max_vref));
+    F.fset_mask = (1u << 21) - 1;
+    IM_CUDA(mdev_alloc(h, &F.fset, (size_t)F.fset_mask + 1, 0xFF));
     IM_CUDA(mdev_alloc(h, &F.work_axes, (size_t)F.max_work * 9));
     IM_CUDA(mdev_alloc(h, &F.add_tri, (size_t)F.max_list * 3));
     IM_CUDA(mdev_alloc(h, &F.add_flip, (size_t)F.max_list));
@@ -485,7 +493,7 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         IM_CUDA(cudaEventRecord(h->ev_in[s], ls));
         IM_CUDA(cudaStreamWaitEvent(st, h->ev_in[s], 0));
     }
-    IM_LAUNCH(k_frame_begin, mesh_grid(h, (int)F.cmask + 1, 256), 256, 0, st, h->M, F);
+    IM_LAUNCH(k_frame_begin, mesh_grid(h, (int)std::max(F.cmask, F.fset_mask) + 1, 256), 256, 0, st, h->M, F);
     IM_CUDA(cudaEventRecord(h->ev[1], st));
     if (F.m > 0) {
         const int g = mesh_grid(h, F.m, 128);
@@ -494,6 +502,7 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         IM_LAUNCH(k_cand_resolve, mesh_grid(h, F.m, 128, 16), 128, 0, st, h->M, P, F);
         IM_LAUNCH(k_cand_scan, 1, 1024, 0, st, h->M, F);
         IM_LAUNCH(k_cand_commit, g, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_cand_place, g, 128, 0, st, h->M, F);
         IM_LAUNCH(k_voxel_select, mesh_grid(h, F.m, 128), 128, 0, st, h->M, F);
     }
     IM_CUDA(cudaEventRecord(h->ev[2], st));
@@ -504,7 +513,8 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         IM_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
         IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), h->stream2, h->M, P, F, 256);
         IM_CUDA(cudaEventRecord(h->ev_join, h->stream2));
-        IM_LAUNCH(k_voxel_commit, h->n_sm * 4, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_commit_faces, h->n_sm * 8, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_commit_vertices, h->n_sm * 8, 128, 0, st, h->M, P, F);
         IM_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
     }
     IM_CUDA(cudaEventRecord(h->ev[3], st));

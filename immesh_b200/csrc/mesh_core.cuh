@@ -52,6 +52,7 @@ enum : int { CAND_UNDECIDED = 0, CAND_ACCEPT = 1, CAND_REJECT = 2 };
 #define IM_MAXF 512         // facets of a voxel with <= 256 dilated vertices (2n - 5 at most)
 #define IM_MAXIN 256        // max in-voxel vertices
 #define IM_CONF_K 24        // stored earlier-conflict candidates per candidate
+#define IM_VCHUNKS 16        // 16 chunks x 16 vertices = IM_MAXIN vertices per mesh voxel
 
 enum : int {
     IM_MERR_VERT_POOL = 1,
@@ -67,7 +68,6 @@ struct MeshDev {
     // vertices
     float4* vpos;        // xyz, w unused
     double* vsmooth;     // [max_v][3]
-    int* v_next;         // next vertex in the same mesh voxel
     int* v_tri_head;     // head of the incidence list
     int max_v;
     // xi-grid hash: cell -> vertex id
@@ -77,7 +77,10 @@ struct MeshDev {
     // mesh-voxel hash (slot = voxel id)
     unsigned long long* vkeys;
     unsigned int vmask;
-    int* vox_head;
+    int* vox_chunk;      // [cap][IM_VCHUNKS] ids of the voxel's vertex chunks (-1 = none); vertex k of a voxel lives in
+                         // vchunk_pts[vox_chunk[k / 16] * 16 + k % 16] -> a voxel's vertices are fetched with a few wide, independent loads
+    float4* vchunk_pts;  // [max_vchunks][16] xyz + vertex id (bit-cast in w)
+    int max_vchunks;
     int* vox_count;
     int* vox_meshing_times;
     int* vox_new_added;
@@ -112,6 +115,7 @@ struct FrameBuf {
     int* cand_conf;       // [m][IM_CONF_K]
     int* cand_nconf;      // count, or -1 when the list overflowed
     int* cand_next;       // next candidate in the same xi-cell (per-frame candidate grid)
+    int* cand_pos;        // position of an accepted candidate inside its mesh voxel
     unsigned long long* ckeys;  // per-frame candidate grid
     int* chead;
     unsigned int cmask;
@@ -122,7 +126,11 @@ struct FrameBuf {
     int* work_n_ids;      // dilated set sizes
     int* work_ids;        // [max_work][IM_MAXD] ascending vertex ids
     int* work_nfaces;     // facets produced by the fused dilate+triangulate stage (-1: left to the large variant)
-    int* work_faces;      // [max_work][IM_MAXF][3]
+    int4* all_faces;      // compact list of this frame's new facets: (a, b, c, work slot)   [max_list]
+    int* all_vref;        // compact list of (work slot << 10 | index into its dilated id list) [max_vref]
+    int* fset;            // open-addressed set over all_faces (value = facet index), cleared per frame
+    unsigned int fset_mask;
+    int max_vref;
     double* work_axes;    // [max_work][9] short / mid / long axis of the voxel's PCA frame
     // push lists
     int* add_tri;         // [max_list][3]
@@ -382,23 +390,32 @@ IM_HDN inline void cand_commit(const MeshDev& M, const MeshParams& P, const Fram
     if (gs < 0) { im_atomic_or(&M.cnt[3], IM_MERR_HASH_FULL); return; }
     M.gval[gs] = id;
     const int vs = F.cand_vslot[c];
-#if defined(__CUDA_ARCH__)
-    int old = M.vox_head[vs];
-    while (true) {
-        M.v_next[id] = old;
-        __threadfence();
-        const int prev = atomicCAS(&M.vox_head[vs], old, id);
-        if (prev == old) break;
-        old = prev;
+    const int pos = im_atomic_add(&M.vox_count[vs], 1);
+    F.cand_pos[c] = pos;
+    if (pos >= IM_VCHUNKS * 16) { im_atomic_or(&M.cnt[3], IM_MERR_VOXEL_CAP); F.cand_pos[c] = -1; }
+    else if ((pos & 15) == 0) {   // first vertex of a chunk: allocate it (published for the placement kernel that follows)
+        const int ch = im_atomic_add(&M.cnt[27], 1);
+        if (ch >= M.max_vchunks) { im_atomic_or(&M.cnt[3], IM_MERR_VERT_POOL); F.cand_pos[c] = -1; }
+        else M.vox_chunk[(size_t)vs * IM_VCHUNKS + (pos >> 4)] = ch;
     }
-#else
-    M.v_next[id] = M.vox_head[vs];
-    M.vox_head[vs] = id;
-#endif
-    im_atomic_add(&M.vox_count[vs], 1);
     im_atomic_add(&M.vox_new_added[vs], 1);
     M.vox_meshing_times[vs] = 0;
     im_atomic_add(&M.cnt[10], 1);
+}
+
+// second half of the append: the vertex goes into its voxel's chunk (the chunk table is complete after cand_commit)
+IM_HDN inline void cand_place(const MeshDev& M, const FrameBuf& F, int c, int base) {
+    if (F.cand_status[c] != CAND_ACCEPT || F.cand_pos[c] < 0) return;
+    const int id = base + F.cand_scan[c];
+    if (id >= M.max_v) return;
+    const int vs = F.cand_vslot[c], pos = F.cand_pos[c];
+    const int ch = M.vox_chunk[(size_t)vs * IM_VCHUNKS + (pos >> 4)];
+    const float* p = F.pts + (size_t)c * F.step * 3;
+    float4 v;
+    v.x = p[0]; v.y = p[1]; v.z = p[2];
+    int idb = id;
+    memcpy(&v.w, &idb, 4);
+    M.vchunk_pts[(size_t)ch * 16 + (pos & 15)] = v;
 }
 
 // activation test of ImMesh_mesh_reconstruction.cpp:132-151 (thread per activated voxel)

@@ -71,21 +71,16 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
     if (tid == 0) { S->n_cand = 0; S->n_q = 0; S->n_out = 0; S->overflow = 0; }
     IM_SYNCBLOCK_M();
     // queries = the voxel's own vertices (retrieve_pts_in_voxels); they are also ring-0 candidates
-    if (tid == 0) {
-        int n = 0;
-        for (int v = M.vox_head[vs]; v >= 0; v = M.v_next[v]) {
-            if (n < IM_MAXIN && n < IM_MAXG) {
-                S->q[n] = v;
-                const float4 p = M.vpos[v];
-                S->cand[n] = make_float4(p.x, p.y, p.z, i2f(v));
-            } else {
-                S->overflow = 1;
-            }
-            ++n;
+    {
+        int n = M.vox_count[vs];
+        if (n > IM_VCHUNKS * 16) n = IM_VCHUNKS * 16;
+        if (n > IM_MAXIN) { n = IM_MAXIN; if (tid == 0) S->overflow = 1; }
+        for (int k = tid; k < n; k += nthreads) {
+            const float4 p = M.vchunk_pts[(size_t)M.vox_chunk[(size_t)vs * IM_VCHUNKS + (k >> 4)] * 16 + (k & 15)];
+            S->q[k] = f2i(p.w);
+            S->cand[k] = p;
         }
-        if (n > IM_MAXIN) n = IM_MAXIN;
-        S->n_q = n;
-        S->n_cand = n;
+        if (tid == 0) { S->n_q = n; S->n_cand = n; }
     }
     IM_SYNCBLOCK_M();
     const int nq = S->n_q;
@@ -103,14 +98,13 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
             if (!ikey_ok(kx + dx, ky + dy, kz + dz)) continue;
             const int s = table_find(M.vkeys, M.vmask, pack_ikey(kx + dx, ky + dy, kz + dz));
             if (s < 0) continue;
-            for (int v = M.vox_head[s]; v >= 0; v = M.v_next[v]) {
-                const int k = im_atomic_add(&S->n_cand, 1);
-                if (k < IM_MAXG) {
-                    const float4 p = M.vpos[v];
-                    S->cand[k] = make_float4(p.x, p.y, p.z, i2f(v));
-                } else {
-                    S->overflow = 1;
-                }
+            int cntv = M.vox_count[s];
+            if (cntv > IM_VCHUNKS * 16) cntv = IM_VCHUNKS * 16;
+            if (cntv <= 0) continue;
+            const int base_k = im_atomic_add(&S->n_cand, cntv);
+            for (int k = 0; k < cntv; ++k) {
+                if (base_k + k < IM_MAXG) S->cand[base_k + k] = M.vchunk_pts[(size_t)M.vox_chunk[(size_t)s * IM_VCHUNKS + (k >> 4)] * 16 + (k & 15)];
+                else S->overflow = 1;
             }
         }
         IM_SYNCBLOCK_M();
@@ -466,9 +460,18 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
     if (store_only) {
         // fused dilate+triangulate kernel: the facets and the voxel's principal axes go to global memory; commit / orientation
         // run in a later kernel, once the smoothed positions of ALL voxels of the frame are final
-        for (int k = tid; k < nf; k += nthreads) {
-            int* o = F.work_faces + ((size_t)w * IM_MAXF + k) * 3;
-            o[0] = S->faces[k][0]; o[1] = S->faces[k][1]; o[2] = S->faces[k][2];
+        // compact frame-wide lists (arbitrary order): facets (a,b,c,w) and vertex references (w,i)
+        if (tid == 0) {
+            S->scratch[0] = im_atomic_add(&M.cnt[25], nf);
+            S->scratch[1] = im_atomic_add(&M.cnt[26], n);
+        }
+        IM_SYNCBLOCK_M();
+        const int foff = S->scratch[0], voff = S->scratch[1];
+        if (foff + nf > F.max_list || voff + n > F.max_vref) {
+            if (tid == 0) im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+        } else {
+            for (int k = tid; k < nf; k += nthreads) F.all_faces[foff + k] = make_int4(S->faces[k][0], S->faces[k][1], S->faces[k][2], w);
+            for (int i = tid; i < n; i += nthreads) F.all_vref[voff + i] = (w << 10) | i;
         }
         for (int k = tid; k < 9; k += nthreads) F.work_axes[(size_t)w * 9 + k] = S->axes[k];
         if (tid == 0) F.work_nfaces[w] = nf;
@@ -477,31 +480,80 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
     voxel_commit_common(M, P, F, vs, n, S->ids, nf, S->faces, S->fhash, 4 * MAXD - 1, S->axes, tid, nthreads);
 }
 
-struct CommitSmem {
-    int ids[256];
-    int faces[IM_MAXF][3];
-    int fhash[1024];
-    double axes[9];
-};
-// stage C for the fused path: one warp per voxel, facets read back from global memory
-IM_HDN inline void voxel_commit_warp(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, CommitSmem* S, int lane, int nlanes) {
+// ------------------------------------------------------------------ stage C, flat: one thread per new facet / per dilated vertex
+// The per-voxel commit is a chain of dependent, DRAM-latency-bound accesses (triple-hash probes, smoothed positions,
+// incidence lists); spreading it over one thread per facet and one thread per (voxel, vertex) pair exposes the
+// memory-level parallelism instead.
+IM_HD bool face_is(const int4& f, int a, int b, int c, int w) { return f.x == a && f.y == b && f.z == c && f.w == w; }
+// C1: orientation + "existing / to add" decision of facet f, and registration in the frame's facet set
+IM_HDN inline void commit_face(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int f) {
+    const int4 fc = F.all_faces[f];
+    const int w = fc.w, vs = F.work[w];
+    int kx, ky, kz;
+    unpack_ikey(M.vkeys[vs], &kx, &ky, &kz);
+    const long long lx = kx - F.fp->prio_origin[0], ly = ky - F.fp->prio_origin[1], lz = kz - F.fp->prio_origin[2];
+    if (lx < 0 || lx >= 2048 || ly < 0 || ly >= 2048 || lz < 0 || lz >= 2048) im_atomic_or(&M.cnt[3], IM_MERR_PRIO_RANGE);
+    const unsigned long long prio = ((unsigned long long)(lx & 2047) << 22) | ((unsigned long long)(ly & 2047) << 11) | (unsigned long long)(lz & 2047);
+    const unsigned long long word = ((unsigned long long)F.frame << 34) | (prio << 1) |
+                                    (unsigned long long)compute_flip(M, fc.x, fc.y, fc.z, F.fp->pose_t, F.work_axes + (size_t)w * 9);
+    const int t = tri_find(M, fc.x, fc.y, fc.z);
+    if (t >= 0 && M.tri[t].w) {
+        im_atomic_max64(&M.tri_flip[t], word);
+    } else {
+        const int e = im_atomic_add(&M.cnt[7], 1);
+        if (e < F.max_list) {
+            F.add_tri[(size_t)e * 3 + 0] = fc.x; F.add_tri[(size_t)e * 3 + 1] = fc.y; F.add_tri[(size_t)e * 3 + 2] = fc.z;
+            F.add_flip[e] = word;
+        } else {
+            im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+        }
+    }
+    unsigned int hs = (tri_hash(fc.x, fc.y, fc.z) + (unsigned int)w * 0x9E3779B1u) & F.fset_mask;
+    while (im_atomic_cas32(&F.fset[hs], -1, f) != -1) hs = (hs + 1) & F.fset_mask;
+}
+// C2: pull + commit, store side, for vertex reference r = (w, i): every live triangle whose smallest vertex is this one and
+// whose other two vertices are in the voxel's dilated set is removed unless the voxel's new triangulation contains it
+IM_HDN inline void commit_vertex(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int r) {
+    const int ref = F.all_vref[r];
+    const int w = ref >> 10, i = ref & 1023;
     const int n = F.work_n_ids[w];
-    const int nf = F.work_nfaces[w];
-    if (n < 3 || n > 256 || nf < 0) return;
-    for (int i = lane; i < n; i += nlanes) S->ids[i] = F.work_ids[(size_t)w * IM_MAXD + i];
-    for (int k = lane; k < nf; k += nlanes) {
-        const int* o = F.work_faces + ((size_t)w * IM_MAXF + k) * 3;
-        S->faces[k][0] = o[0]; S->faces[k][1] = o[1]; S->faces[k][2] = o[2];
+    const int* ids = F.work_ids + (size_t)w * IM_MAXD;
+    const int v = ids[i];
+    for (int t = M.v_tri_head[v]; t >= 0;) {
+        const int4 tr = M.tri[t];
+        const int slot = (tr.x == v) ? 0 : ((tr.y == v) ? 1 : 2);
+        const int nx = M.tri_next[(size_t)t * 3 + slot];
+        if (tr.w && tr.x == v) {
+            bool in_set = true;
+            for (int pass = 0; pass < 2 && in_set; ++pass) {
+                const int key = pass == 0 ? tr.y : tr.z;
+                int lo = 0, hi = n - 1;
+                bool hit = false;
+                while (lo <= hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int val = ids[mid];
+                    if (val == key) { hit = true; break; }
+                    if (val < key) lo = mid + 1; else hi = mid - 1;
+                }
+                in_set = hit;
+            }
+            if (in_set) {
+                bool in_new = false;
+                unsigned int hs = (tri_hash(tr.x, tr.y, tr.z) + (unsigned int)w * 0x9E3779B1u) & F.fset_mask;
+                for (unsigned int probe = 0; probe <= F.fset_mask; ++probe) {
+                    const int k = F.fset[hs];
+                    if (k < 0) break;
+                    if (face_is(F.all_faces[k], tr.x, tr.y, tr.z, w)) { in_new = true; break; }
+                    hs = (hs + 1) & F.fset_mask;
+                }
+                if (!in_new) {
+                    const int e = im_atomic_add(&M.cnt[8], 1);
+                    if (e < F.max_list) F.rem_tri[e] = t; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+                }
+            }
+        }
+        t = nx;
     }
-    for (int i = lane; i < 1024; i += nlanes) S->fhash[i] = -1;
-    for (int i = lane; i < 9; i += nlanes) S->axes[i] = F.work_axes[(size_t)w * 9 + i];
-    IM_SYNCWARP();
-    for (int k = lane; k < nf; k += nlanes) {
-        unsigned int hs = tri_hash(S->faces[k][0], S->faces[k][1], S->faces[k][2]) & 1023u;
-        while (im_atomic_cas32(&S->fhash[hs], -1, k) != -1) hs = (hs + 1) & 1023u;
-    }
-    IM_SYNCWARP();
-    voxel_commit_common(M, P, F, F.work[w], n, S->ids, nf, S->faces, S->fhash, 1023u, S->axes, lane, nlanes);
 }
 
 }  // namespace immesh

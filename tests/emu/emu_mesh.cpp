@@ -16,13 +16,14 @@ struct immesh_mesh {
     MeshParams P;
     MeshDev M;
     FrameBuf F;
-    std::vector<float4> vpos;
+    std::vector<float4> vpos, vchunk_pts;
     std::vector<double> vsmooth;
-    std::vector<int> v_next, v_tri_head, gval, vox_head, vox_count, vox_mt, vox_na, vox_frame, tri_next, thash, cnt;
+    std::vector<int> v_tri_head, gval, vox_chunk, cand_pos, vox_count, vox_mt, vox_na, vox_frame, tri_next, thash, cnt;
     std::vector<unsigned long long> gkeys, vkeys, tri_flip, ckeys, cand_gkey, add_flip;
     std::vector<int4> tri;
     std::vector<float> pts;
-    std::vector<int> cand_vslot, cand_status, cand_scan, cand_conf, cand_nconf, cand_next, chead, act, work, work_n, work_ids, add_tri, rem_tri, work_nf, work_faces;
+    std::vector<int> cand_vslot, cand_status, cand_scan, cand_conf, cand_nconf, cand_next, chead, act, work, work_n, work_ids, add_tri, rem_tri, work_nf, all_vref, fset;
+    std::vector<int4> all_faces;
     std::vector<double> work_axes;
     int frame_counter = 0;
     int last_cnt[32];
@@ -39,16 +40,16 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     const int max_vox = cfg->max_voxels ? cfg->max_voxels : (1 << 18), mfp = cfg->max_frame_points ? cfg->max_frame_points : (1 << 20);
     MeshDev& M = h->M;
     M.max_v = max_v; M.max_t = max_t;
-    h->vpos.resize(max_v); h->vsmooth.resize((size_t)max_v * 3); h->v_next.assign(max_v, -1); h->v_tri_head.assign(max_v, -1);
+    h->vpos.resize(max_v); h->vsmooth.resize((size_t)max_v * 3); h->v_tri_head.assign(max_v, -1);
     const size_t gcap = p2((size_t)max_v * 2), vcap = p2((size_t)max_vox * 2), tcap = p2((size_t)max_t * 2);
     h->gkeys.assign(gcap, IM_EMPTY_KEY); h->gval.assign(gcap, -1);
-    h->vkeys.assign(vcap, IM_EMPTY_KEY); h->vox_head.assign(vcap, -1); h->vox_count.assign(vcap, 0); h->vox_mt.assign(vcap, 0); h->vox_na.assign(vcap, 0); h->vox_frame.assign(vcap, -1);
+    h->vkeys.assign(vcap, IM_EMPTY_KEY); h->vox_chunk.assign(vcap * IM_VCHUNKS, -1); h->vox_count.assign(vcap, 0); h->vox_mt.assign(vcap, 0); h->vox_na.assign(vcap, 0); h->vox_frame.assign(vcap, -1);
     h->tri.resize(max_t); h->tri_next.resize((size_t)max_t * 3); h->tri_flip.resize(max_t); h->thash.assign(tcap, -1);
     h->cnt.assign(32, 0);
     h->cnt[11] = h->cnt[12] = h->cnt[13] = 0x7fffffff; h->cnt[14] = h->cnt[15] = h->cnt[16] = -0x7fffffff;
-    M.vpos = h->vpos.data(); M.vsmooth = h->vsmooth.data(); M.v_next = h->v_next.data(); M.v_tri_head = h->v_tri_head.data();
+    M.vpos = h->vpos.data(); M.vsmooth = h->vsmooth.data(); M.v_tri_head = h->v_tri_head.data();
     M.gkeys = h->gkeys.data(); M.gval = h->gval.data(); M.gmask = (unsigned)(gcap - 1);
-    M.vkeys = h->vkeys.data(); M.vmask = (unsigned)(vcap - 1); M.vox_head = h->vox_head.data(); M.vox_count = h->vox_count.data();
+    M.vkeys = h->vkeys.data(); M.vmask = (unsigned)(vcap - 1); M.vox_chunk = h->vox_chunk.data(); M.vox_count = h->vox_count.data(); M.max_vchunks = max_v / 4 + 1024; h->vchunk_pts.resize((size_t)M.max_vchunks * 16); M.vchunk_pts = h->vchunk_pts.data();
     M.vox_meshing_times = h->vox_mt.data(); M.vox_new_added = h->vox_na.data(); M.vox_frame = h->vox_frame.data(); M.vox_short_axis = nullptr;
     M.tri = h->tri.data(); M.tri_next = h->tri_next.data(); M.tri_flip = h->tri_flip.data(); M.thash = h->thash.data(); M.tmask = (unsigned)(tcap - 1);
     M.cnt = h->cnt.data();
@@ -56,16 +57,16 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     const size_t mc = mfp;
     F.max_cand = mfp; F.max_work = std::min(max_vox, 1 << 14); F.max_act = std::min<size_t>(max_vox, mc); F.max_list = 1 << 20;
     h->pts.resize(mc * 3); h->cand_gkey.resize(mc); h->cand_vslot.resize(mc); h->cand_status.resize(mc); h->cand_scan.resize(mc);
-    h->cand_conf.resize(mc * IM_CONF_K); h->cand_nconf.resize(mc); h->cand_next.resize(mc);
+    h->cand_conf.resize(mc * IM_CONF_K); h->cand_nconf.resize(mc); h->cand_next.resize(mc); h->cand_pos.resize(mc);
     const size_t ccap = p2(mc * 2);
     h->ckeys.resize(ccap); h->chead.resize(ccap);
     h->act.resize(F.max_act); h->work.resize(F.max_work); h->work_n.resize(F.max_work); h->work_ids.resize((size_t)F.max_work * IM_MAXD);
-    h->work_nf.resize(F.max_work); h->work_faces.resize((size_t)F.max_work * IM_MAXF * 3); h->work_axes.resize((size_t)F.max_work * 9);
+    h->work_nf.resize(F.max_work); F.max_vref = 1 << 21; h->all_faces.resize(F.max_list); h->all_vref.resize(F.max_vref); F.fset_mask = (1u << 19) - 1; h->fset.assign((size_t)F.fset_mask + 1, -1); h->work_axes.resize((size_t)F.max_work * 9);
     h->add_tri.resize((size_t)F.max_list * 3); h->add_flip.resize(F.max_list); h->rem_tri.resize(F.max_list);
     F.pts = h->pts.data(); F.cand_gkey = h->cand_gkey.data(); F.cand_vslot = h->cand_vslot.data(); F.cand_status = h->cand_status.data();
-    F.cand_scan = h->cand_scan.data(); F.cand_conf = h->cand_conf.data(); F.cand_nconf = h->cand_nconf.data(); F.cand_next = h->cand_next.data();
+    F.cand_scan = h->cand_scan.data(); F.cand_conf = h->cand_conf.data(); F.cand_nconf = h->cand_nconf.data(); F.cand_next = h->cand_next.data(); F.cand_pos = h->cand_pos.data();
     F.ckeys = h->ckeys.data(); F.chead = h->chead.data(); F.scan_block = nullptr;
-    F.act = h->act.data(); F.work = h->work.data(); F.work_n_ids = h->work_n.data(); F.work_ids = h->work_ids.data(); F.work_nfaces = h->work_nf.data(); F.work_faces = h->work_faces.data(); F.work_axes = h->work_axes.data();
+    F.act = h->act.data(); F.work = h->work.data(); F.work_n_ids = h->work_n.data(); F.work_ids = h->work_ids.data(); F.work_nfaces = h->work_nf.data(); F.all_faces = h->all_faces.data(); F.all_vref = h->all_vref.data(); F.fset = h->fset.data(); F.work_axes = h->work_axes.data();
     F.add_tri = h->add_tri.data(); F.add_flip = h->add_flip.data(); F.rem_tri = h->rem_tri.data();
     std::memset(h->last_cnt, 0, sizeof(h->last_cnt));
     *out = h;
@@ -85,7 +86,8 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     if (n > 0) std::memcpy(h->pts.data(), world_xyz, (size_t)n * 12);
     for (unsigned i = 0; i <= F.cmask; ++i) { F.ckeys[i] = IM_EMPTY_KEY; F.chead[i] = -1; }
     for (int k = 5; k <= 10; ++k) M.cnt[k] = 0;
-    for (int k = 17; k <= 24; ++k) M.cnt[k] = 0;
+    for (int k = 17; k <= 26; ++k) M.cnt[k] = 0;
+    for (unsigned i = 0; i <= F.fset_mask; ++i) F.fset[i] = -1;
     for (int c = 0; c < F.m; ++c) cand_init(M, P, F, c);
     for (int c = 0; c < F.m; ++c) cand_conflicts(M, P, F, c);
     for (int c = 0; c < F.m; ++c)
@@ -94,25 +96,26 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     for (int c = 0; c < F.m; ++c) { F.cand_scan[c] = run; run += F.cand_status[c] == CAND_ACCEPT; }
     const int base = M.cnt[0];
     for (int c = 0; c < F.m; ++c) cand_commit(M, P, F, c, base);
+    for (int c = 0; c < F.m; ++c) cand_place(M, F, c, base);
     const int na = std::min(M.cnt[5], F.max_act);
     for (int a = 0; a < na; ++a) voxel_select(M, F, a);
     const int nw = work_total(M, F);
     DilateSmem* DS = new DilateSmem();
     MeshSmem<256>* S1 = new MeshSmem<256>();
     MeshSmem<1024>* S2 = new MeshSmem<1024>();
-    CommitSmem* SC = new CommitSmem();
     for (int i = 0; i < nw; ++i) {   // fused stage: dilation then triangulation of the same voxel
         const int w = work_slot(M, F, i);
         voxel_dilate(M, P, F, w, DS, 0, 1);
         voxel_mesh<256>(M, P, F, w, S1, 0, 1, 1);
     }
-    for (int i = 0; i < nw; ++i) voxel_commit_warp(M, P, F, work_slot(M, F, i), SC, 0, 1);
+    for (int f = 0; f < std::min(M.cnt[25], F.max_list); ++f) commit_face(M, P, F, f);
+    for (int r = 0; r < std::min(M.cnt[26], F.max_vref); ++r) commit_vertex(M, P, F, r);
     for (int i = 0; i < nw; ++i) {
         const int w = work_slot(M, F, i);
         const int nd = F.work_n_ids[w];
         if (nd < 0 || nd > 256) voxel_mesh<1024>(M, P, F, w, S2, 0, 1);
     }
-    delete DS; delete S1; delete S2; delete SC;
+    delete DS; delete S1; delete S2;
     const int nr = std::min(M.cnt[8], F.max_list), nadd = std::min(M.cnt[7], F.max_list);
     for (int e = 0; e < nr; ++e) tri_remove(M, F.rem_tri[e]);
     for (int e = 0; e < nadd; ++e) tri_add(M, F.add_tri[(size_t)e * 3], F.add_tri[(size_t)e * 3 + 1], F.add_tri[(size_t)e * 3 + 2], F.add_flip[e]);
