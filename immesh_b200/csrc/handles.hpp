@@ -65,6 +65,7 @@ struct immesh_mesh {
     int* d_snap_flip = nullptr;
     int* d_snap_n = nullptr;
     int max_frame_points = 0;
+    int fused_threads = 256;   // block size of the per-voxel fused kernel
     int frame_counter = 0;
     int n_sm = 148;
     size_t ccap = 0;

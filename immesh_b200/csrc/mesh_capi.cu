@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -105,7 +106,7 @@ union FusedSmem {
     DilateSmem d;
     MeshSmem<256> m;
 };
-__global__ void __launch_bounds__(128) k_voxel_fused(MeshDev M, MeshParams P, FrameBuf F) {
+__global__ void __launch_bounds__(256) k_voxel_fused(MeshDev M, MeshParams P, FrameBuf F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
     __shared__ int s_item;
@@ -278,6 +279,8 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return im_fail(IMMESH_E_NO_DEVICE, "no CUDA device: immesh_b200 has no CPU path");
     immesh_mesh* h = new immesh_mesh();
+    h->fused_threads = std::getenv("IMMESH_FUSED_THREADS") ? std::atoi(std::getenv("IMMESH_FUSED_THREADS")) : 256;
+    if (h->fused_threads != 128 && h->fused_threads != 256) h->fused_threads = 256;
     MeshParams& P = h->P;
     P.xi = cfg->points_minimum_scale;
     P.res = cfg->voxel_resolution;
@@ -507,7 +510,7 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
     }
     IM_CUDA(cudaEventRecord(h->ev[2], st));
     if (F.m > 0) {
-        IM_LAUNCH(k_voxel_fused, h->n_sm * 4, 128, sizeof(FusedSmem), st, h->M, P, F);
+        IM_LAUNCH(k_voxel_fused, h->n_sm * 4, h->fused_threads, sizeof(FusedSmem), st, h->M, P, F);
         // commit of the regular voxels on the main stream; the rare large / handed-over voxels (monolithic variant) on the side stream
         IM_CUDA(cudaEventRecord(h->ev_fork, st));
         IM_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));

@@ -385,7 +385,7 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
         const float4 p = M.vpos[id];
         S->pos[i][0] = p.x; S->pos[i][1] = p.y; S->pos[i][2] = p.z;
     }
-    for (int i = tid; i < 4 * MAXD; i += nthreads) S->fhash[i] = -1;
+    if (!store_only) for (int i = tid; i < 4 * MAXD; i += nthreads) S->fhash[i] = -1;
     if (tid == 0) S->nface = 0;
     IM_SYNCBLOCK_M();
     if (tid == 0) {
@@ -451,8 +451,10 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
         if (a > b) { const int x = a; a = b; b = x; }
         const int k = im_atomic_add(&S->nface, 1);
         S->faces[k][0] = a; S->faces[k][1] = b; S->faces[k][2] = c;
-        unsigned int hs = tri_hash(a, b, c) & (4 * MAXD - 1);
-        while (im_atomic_cas32(&S->fhash[hs], -1, k) != -1) hs = (hs + 1) & (4 * MAXD - 1);
+        if (!store_only) {   // the monolithic variant looks new facets up in shared memory; the fused path uses the frame-wide set
+            unsigned int hs = tri_hash(a, b, c) & (4 * MAXD - 1);
+            while (im_atomic_cas32(&S->fhash[hs], -1, k) != -1) hs = (hs + 1) & (4 * MAXD - 1);
+        }
     }
     IM_SYNCBLOCK_M();
     const int nf = S->nface;
