@@ -58,8 +58,9 @@ struct immesh_mesh {
     cudaEvent_t ev_done[2] = {nullptr, nullptr};  // frame of slot s finished (mesh stream)
     int inflight[2] = {0, 0};
     cudaEvent_t ev_mark = nullptr, ev_sync = nullptr;  // pipeline timing mark (end) / cross-stream join
-    cudaStream_t stream2 = nullptr;   // side stream: warp-level mesh stage, concurrent with the block-level one
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream2 = nullptr;   // side stream: warp-level triangulation, concurrent with the block-level one
+    cudaStream_t stream3 = nullptr;   // side stream: pull (incidence-list walk), concurrent with the triangulation
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
     int pending_rc = 0;
     int* d_snap_tri = nullptr;
     int* d_snap_flip = nullptr;

@@ -23,6 +23,7 @@ __global__ void k_frame_begin(MeshDev M, FrameBuf F) {
     if (tid == 0) {
         for (int k = 5; k <= 10; ++k) M.cnt[k] = 0;
         for (int k = 17; k <= 26; ++k) M.cnt[k] = 0;
+        M.cnt[28] = 0;
     }
 }
 __global__ void __launch_bounds__(128) k_cand_init(MeshDev M, MeshParams P, FrameBuf F) {
@@ -98,17 +99,9 @@ __global__ void __launch_bounds__(128) k_voxel_select(MeshDev M, FrameBuf F) {
     const int na = min(M.cnt[5], F.max_act);
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < na; a += gridDim.x * blockDim.x) voxel_select(M, F, a);
 }
-// stage A+B fused per voxel: dilation (exact 20-NN of the in-voxel vertices, smoothing) immediately followed by the
-// projection + exact Delaunay + facet filter of the same voxel; facets go to global memory.  No grid-wide barrier between
-// the two: a block that has finished a voxel's dilation starts triangulating while other blocks are still dilating.
-// Voxels are claimed dynamically, populous ones first.
-union FusedSmem {
-    DilateSmem d;
-    MeshSmem<256> m;
-};
-__global__ void __launch_bounds__(256) k_voxel_fused(MeshDev M, MeshParams P, FrameBuf F) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
+// stage A: dilation (exact 20-NN of the in-voxel vertices + smoothing), one block per voxel, populous voxels first
+__global__ void __launch_bounds__(128) k_voxel_dilate(MeshDev M, MeshParams P, FrameBuf F) {
+    __shared__ DilateSmem S;
     __shared__ int s_item;
     const int nw = work_total(M, F);
     while (true) {
@@ -117,11 +110,25 @@ __global__ void __launch_bounds__(256) k_voxel_fused(MeshDev M, MeshParams P, Fr
         const int i = s_item;
         __syncthreads();
         if (i >= nw) break;
-        const int w = work_slot(M, F, i);
-        voxel_dilate(M, P, F, w, &S->d, threadIdx.x, blockDim.x);
+        voxel_dilate(M, P, F, work_slot(M, F, i), &S, threadIdx.x, blockDim.x);
         __syncthreads();
-        voxel_mesh<256>(M, P, F, w, &S->m, threadIdx.x, blockDim.x, 1);
-        __syncthreads();
+    }
+}
+// stage B, small dilated sets: one warp per voxel (four independent voxels per block), voxels claimed dynamically
+#define IM_WARP_NMAX 96
+__global__ void __launch_bounds__(128) k_voxel_tri_warp(MeshDev M, MeshParams P, FrameBuf F) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    MeshWarpSmem<128>* S = reinterpret_cast<MeshWarpSmem<128>*>(smem_raw) + warp;
+    const int nw = work_total(M, F);
+    while (true) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&M.cnt[19], 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= nw) break;
+        voxel_mesh_warp<128>(M, P, F, work_slot(M, F, i), S, lane, 32, IM_WARP_NMAX);
+        __syncwarp();
     }
 }
 // stage C (flat): after every voxel's smoothing is final
@@ -129,12 +136,16 @@ __global__ void __launch_bounds__(128) k_commit_faces(MeshDev M, MeshParams P, F
     const int nf = min(M.cnt[25], F.max_list);
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) commit_face(M, P, F, f);
 }
-__global__ void __launch_bounds__(128) k_commit_vertices(MeshDev M, MeshParams P, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_pull_vertices(MeshDev M, MeshParams P, FrameBuf F) {
     const int nr = min(M.cnt[26], F.max_vref);
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nr; r += gridDim.x * blockDim.x) commit_vertex(M, P, F, r);
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nr; r += gridDim.x * blockDim.x) pull_vertex(M, P, F, r);
+}
+__global__ void __launch_bounds__(128) k_pull_check(MeshDev M, FrameBuf F) {
+    const int ne = min(M.cnt[28], F.max_list);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) pull_check(M, F, e);
 }
 template <int MAXD>
-__global__ void __launch_bounds__(128) k_voxel_mesh(MeshDev M, MeshParams P, FrameBuf F, int lo) {
+__global__ void __launch_bounds__(128) k_voxel_mesh(MeshDev M, MeshParams P, FrameBuf F, int lo, int store_only) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MeshSmem<MAXD>* S = reinterpret_cast<MeshSmem<MAXD>*>(smem_raw);
     const int nw = work_total(M, F);
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(128) k_voxel_mesh(MeshDev M, MeshParams P, Fra
         const int w = work_slot(M, F, i);
         const int n = F.work_n_ids[w];
         const int na = n < 0 ? -n : n;
-        if (n < 0 || (na > lo && na <= MAXD)) voxel_mesh<MAXD>(M, P, F, w, S, threadIdx.x, blockDim.x);
+        if ((n < 0 && !store_only) || (n > 0 && na > lo && na <= MAXD)) voxel_mesh<MAXD>(M, P, F, w, S, threadIdx.x, blockDim.x, store_only);
         __syncthreads();
     }
 }
@@ -362,6 +373,7 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     F.max_vref = 8 << 20;
     IM_CUDA(mdev_alloc(h, &F.all_faces, (size_t)F.max_list));
     IM_CUDA(mdev_alloc(h, &F.all_vref, (size_t)F.max_vref));
+    IM_CUDA(mdev_alloc(h, &F.pulled, (size_t)F.max_list * 2));
     F.fset_mask = (1u << 21) - 1;
     IM_CUDA(mdev_alloc(h, &F.fset, (size_t)F.fset_mask + 1, 0xFF));
     IM_CUDA(mdev_alloc(h, &F.work_axes, (size_t)F.max_work * 9));
@@ -372,10 +384,13 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(cudaMallocHost((void**)&h->h_cnt, 2 * 32 * sizeof(int)));
     IM_CUDA(cudaMallocHost((void**)&h->h_fp, 2 * sizeof(FramePose)));
     IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<1024>)));
-    IM_CUDA(cudaFuncSetAttribute(k_voxel_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+    IM_CUDA(cudaFuncSetAttribute(k_voxel_tri_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(MeshWarpSmem<128>))));
+    IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<256>)));
     IM_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    IM_CUDA(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    IM_CUDA(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
     std::memset(h->last_cnt, 0, sizeof(h->last_cnt));
     IM_CUDA(cudaDeviceSynchronize());
     *out = h;
@@ -393,8 +408,10 @@ int immesh_mesh_destroy(immesh_mesh_t* h) {
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_join3) cudaEventDestroy(h->ev_join3);
     delete h;
     return IMMESH_OK;
 }
@@ -510,15 +527,22 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
     }
     IM_CUDA(cudaEventRecord(h->ev[2], st));
     if (F.m > 0) {
-        IM_LAUNCH(k_voxel_fused, h->n_sm * 4, h->fused_threads, sizeof(FusedSmem), st, h->M, P, F);
-        // commit of the regular voxels on the main stream; the rare large / handed-over voxels (monolithic variant) on the side stream
+        IM_LAUNCH(k_voxel_dilate, h->n_sm * 4, 128, 0, st, h->M, P, F);
+        // triangulation: small dilated sets warp-level on the side stream, mid-size ones block-level on the main stream,
+        // concurrently; then the rare large / handed-over ones (monolithic: triangulate + commit in shared memory)
         IM_CUDA(cudaEventRecord(h->ev_fork, st));
         IM_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-        IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), h->stream2, h->M, P, F, 256);
+        IM_CUDA(cudaStreamWaitEvent(h->stream3, h->ev_fork, 0));
+        IM_LAUNCH(k_voxel_tri_warp, h->n_sm * 4, 128, 4 * sizeof(MeshWarpSmem<128>), h->stream2, h->M, P, F);
         IM_CUDA(cudaEventRecord(h->ev_join, h->stream2));
-        IM_LAUNCH(k_commit_faces, h->n_sm * 8, 128, 0, st, h->M, P, F);
-        IM_LAUNCH(k_commit_vertices, h->n_sm * 8, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_pull_vertices, h->n_sm * 8, 128, 0, h->stream3, h->M, P, F);   // incidence-list walk: only needs the dilation
+        IM_CUDA(cudaEventRecord(h->ev_join3, h->stream3));
+        IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * 4, 128, sizeof(MeshSmem<256>), st, h->M, P, F, IM_WARP_NMAX, 1);
         IM_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+        IM_CUDA(cudaStreamWaitEvent(st, h->ev_join3, 0));
+        IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st, h->M, P, F, 256, 0);
+        IM_LAUNCH(k_commit_faces, h->n_sm * 8, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_pull_check, h->n_sm * 8, 128, 0, st, h->M, F);
     }
     IM_CUDA(cudaEventRecord(h->ev[3], st));
     if (F.m > 0) {

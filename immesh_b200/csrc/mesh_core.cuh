@@ -128,6 +128,7 @@ struct FrameBuf {
     int* work_nfaces;     // facets produced by the fused dilate+triangulate stage (-1: left to the large variant)
     int4* all_faces;      // compact list of this frame's new facets: (a, b, c, work slot)   [max_list]
     int* all_vref;        // compact list of (work slot << 10 | index into its dilated id list) [max_vref]
+    int* pulled;          // [max_list][2] (work slot, triangle) pairs found by the pull stage
     int* fset;            // open-addressed set over all_faces (value = facet index), cleared per frame
     unsigned int fset_mask;
     int max_vref;

@@ -271,7 +271,18 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
             IM_SYNCBLOCK_M();
         }
     for (int i = tid; i < n; i += nthreads) F.work_ids[(size_t)w * IM_MAXD + i] = S->ids[i];
+    // frame-wide list of (voxel, dilated vertex) references for the flat pull stage
+    if (tid == 0) S->need_more = (n >= 3) ? im_atomic_add(&M.cnt[26], n) : -1;
+    IM_SYNCBLOCK_M();
+    {
+        const int voff = S->need_more;
+        if (voff >= 0) {
+            if (voff + n > F.max_vref) { if (tid == 0) im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP); }
+            else for (int i = tid; i < n; i += nthreads) F.all_vref[voff + i] = (w << 10) | i;
+        }
+    }
     if (tid == 0) {
+        F.work_nfaces[w] = 0;
         F.work_n_ids[w] = n;
         if (S->overflow) im_atomic_or(&M.cnt[3], IM_MERR_VOXEL_CAP);
         // work accounting for the roofline: gathered candidates, queries, dilated vertices
@@ -463,23 +474,238 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
         // fused dilate+triangulate kernel: the facets and the voxel's principal axes go to global memory; commit / orientation
         // run in a later kernel, once the smoothed positions of ALL voxels of the frame are final
         // compact frame-wide lists (arbitrary order): facets (a,b,c,w) and vertex references (w,i)
-        if (tid == 0) {
-            S->scratch[0] = im_atomic_add(&M.cnt[25], nf);
-            S->scratch[1] = im_atomic_add(&M.cnt[26], n);
-        }
+        if (tid == 0) S->scratch[0] = im_atomic_add(&M.cnt[25], nf);
         IM_SYNCBLOCK_M();
-        const int foff = S->scratch[0], voff = S->scratch[1];
-        if (foff + nf > F.max_list || voff + n > F.max_vref) {
+        const int foff = S->scratch[0];
+        if (foff + nf > F.max_list) {
             if (tid == 0) im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
         } else {
             for (int k = tid; k < nf; k += nthreads) F.all_faces[foff + k] = make_int4(S->faces[k][0], S->faces[k][1], S->faces[k][2], w);
-            for (int i = tid; i < n; i += nthreads) F.all_vref[voff + i] = (w << 10) | i;
         }
         for (int k = tid; k < 9; k += nthreads) F.work_axes[(size_t)w * 9 + k] = S->axes[k];
         if (tid == 0) F.work_nfaces[w] = nf;
         return;
     }
     voxel_commit_common(M, P, F, vs, n, S->ids, nf, S->faces, S->fhash, 4 * MAXD - 1, S->axes, tid, nthreads);
+}
+
+// ------------------------------------------------------------------ stage B, warp-level variant (small dilated sets)
+// One warp per voxel (n <= MAXD dilated vertices), __syncwarp only.  The Bowyer-Watson conflict search is pruned with a
+// cached float circumcircle per triangle (conservative margin; every survivor still goes through the exact predicate),
+// which removes ~90% of the exact in-circle evaluations.  Cavity / boundary capacity is 64 triangles; a voxel that
+// exceeds it is handed to the large block-level variant (work_n_ids[w] negated).  Triangulation only: the facets go to
+// the frame-wide lists, commit / orientation / pull are done by the flat stage-C kernels.
+template <int MAXD>
+struct MeshWarpSmem {
+    int ids[MAXD];
+    double uv[MAXD][2];
+    int2 snap[MAXD];
+    DTri tris[3 * MAXD + 8];          // after face extraction: reused as the face hash (4*MAXD ints)
+    float circ[3 * MAXD + 8][3];      // before the triangulation: vertex positions; after it: faces (2*MAXD int3)
+    int scratch[8 + 64 + 2 * 192];
+    double axes[9];
+    double centre[3];
+    int ntri, nface;
+};
+
+template <int MAXD>
+IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, MeshWarpSmem<MAXD>* S, int lane, int nlanes, int n_max) {
+    const int n = F.work_n_ids[w];
+    if (n < 3 || n > n_max || n > MAXD) return;
+    const int vs = F.work[w];
+    float (*pos)[3] = S->circ;  // alias: positions are dead once projected
+    for (int i = lane; i < n; i += nlanes) {
+        const int id = F.work_ids[(size_t)w * IM_MAXD + i];
+        S->ids[i] = id;
+        const float4 p = M.vpos[id];
+        pos[i][0] = p.x; pos[i][1] = p.y; pos[i][2] = p.z;
+    }
+    if (lane == 0) S->nface = 0;
+    IM_SYNCWARP();
+    if (lane == 0) {
+        double c[3] = {0, 0, 0};
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < 3; ++j) c[j] = c[j] + (double)pos[i][j];
+        for (int j = 0; j < 3; ++j) c[j] = c[j] / (double)n;
+        double cov[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < n; ++i) {
+            const double d[3] = {(double)pos[i][0] - c[0], (double)pos[i][1] - c[1], (double)pos[i][2] - c[2]};
+            cov[0] += d[0] * d[0]; cov[1] += d[0] * d[1]; cov[2] += d[0] * d[2];
+            cov[3] += d[1] * d[1]; cov[4] += d[1] * d[2]; cov[5] += d[2] * d[2];
+        }
+        for (int k = 0; k < 6; ++k) cov[k] = cov[k] / (double)n;
+        double ev[3], U[9];
+        jacobi3(cov, ev, U);
+        int order[3] = {0, 1, 2};
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2 - a; ++b)
+                if (ev[order[b + 1]] < ev[order[b]]) { const int t = order[b]; order[b] = order[b + 1]; order[b + 1] = t; }
+        double sx[3], m[3];
+        for (int j = 0; j < 3; ++j) { sx[j] = U[j * 3 + order[0]]; m[j] = U[j * 3 + order[1]]; }
+        const double d0[3] = {(double)pos[0][0] - c[0], (double)pos[0][1] - c[1], (double)pos[0][2] - c[2]};
+        const double d1[3] = {(double)pos[1][0] - c[0], (double)pos[1][1] - c[1], (double)pos[1][2] - c[2]};
+        if (dot3(d0, sx) < 0) { sx[0] = -sx[0]; sx[1] = -sx[1]; sx[2] = -sx[2]; }
+        if (dot3(d1, m) < 0) { m[0] = -m[0]; m[1] = -m[1]; m[2] = -m[2]; }
+        S->axes[0] = sx[0]; S->axes[1] = sx[1]; S->axes[2] = sx[2];
+        S->axes[3] = m[0]; S->axes[4] = m[1]; S->axes[5] = m[2];
+        S->axes[6] = sx[1] * m[2] - sx[2] * m[1];
+        S->axes[7] = sx[2] * m[0] - sx[0] * m[2];
+        S->axes[8] = sx[0] * m[1] - sx[1] * m[0];
+        S->centre[0] = c[0]; S->centre[1] = c[1]; S->centre[2] = c[2];
+    }
+    IM_SYNCWARP();
+    for (int i = lane; i < n; i += nlanes) {
+        const double d[3] = {(double)pos[i][0] - S->centre[0], (double)pos[i][1] - S->centre[1], (double)pos[i][2] - S->centre[2]};
+        const double u = dot3(d, S->axes + 6), v = dot3(d, S->axes + 3);
+        S->uv[i][0] = u; S->uv[i][1] = v;
+        S->snap[i] = make_int2((int)im_llrint(u * P.inv_q), (int)im_llrint(v * P.inv_q));
+    }
+    IM_SYNCWARP();
+    // ---- Bowyer-Watson, warp-synchronous
+    const int2* Pt = S->snap;
+    DTri* tris = S->tris;
+    int* s_cav_n = S->scratch;
+    int* s_edge_n = S->scratch + 1;
+    int* s_seed = S->scratch + 2;   // i1, i2, ok
+    int* s_ovf = S->scratch + 6;
+    int* s_cav = S->scratch + 8;    // [64]
+    int* s_edges = S->scratch + 72; // [68*2]
+    const int max_tris = 3 * MAXD + 8;
+    if (lane == 0) {
+        *s_ovf = 0;
+        int i1 = -1, i2 = -1;
+        for (int i = 1; i < n; ++i)
+            if (Pt[i].x != Pt[0].x || Pt[i].y != Pt[0].y) { i1 = i; break; }
+        if (i1 >= 0)
+            for (int i = 1; i < n; ++i)
+                if (i != i1 && orient2d_i(Pt[0].x, Pt[0].y, Pt[i1].x, Pt[i1].y, Pt[i].x, Pt[i].y) != 0) { i2 = i; break; }
+        s_seed[0] = i1; s_seed[1] = i2; s_seed[2] = (i1 >= 0 && i2 >= 0) ? 1 : 0;
+        S->ntri = 0;
+        if (s_seed[2]) {
+            int a = 0, b = i1, c = i2;
+            if (orient2d_i(Pt[a].x, Pt[a].y, Pt[b].x, Pt[b].y, Pt[c].x, Pt[c].y) < 0) { const int t = b; b = c; c = t; }
+            const short tv[4][3] = {{(short)a, (short)b, (short)c}, {(short)c, (short)b, IM_GHOST}, {(short)a, (short)c, IM_GHOST}, {(short)b, (short)a, IM_GHOST}};
+            for (int k = 0; k < 4; ++k) { tris[k].v[0] = tv[k][0]; tris[k].v[1] = tv[k][1]; tris[k].v[2] = tv[k][2]; tris[k].alive = 1; }
+            circumcircle_f(Pt, a, b, c, S->circ[0]);
+            S->ntri = 4;
+        }
+    }
+    IM_SYNCWARP();
+    if (!s_seed[2]) return;
+    const int i1 = s_seed[0], i2 = s_seed[1];
+    // per insertion: (1) conflict scan, compacted with ballots; (2) directed edge list of the cavity; (3) boundary edges
+    // (those whose reverse is not in the list) ranked with ballots, each writes its new triangle -- cavity slots first,
+    // then the pool tail.  Three warp barriers, no atomics.
+    int* s_ea = s_edges;            // [192] directed cavity edges: tails
+    int* s_eb = s_edges + 192;      // [192] heads
+    (void)s_cav_n; (void)s_edge_n;
+    const unsigned lt = im_lanemask_lt();
+    bool ovf = false;
+    for (int p = 1; p < n && !ovf; ++p) {
+        if (p == i1 || p == i2) continue;
+        const int nt = S->ntri;
+        const float pxf = (float)Pt[p].x, pyf = (float)Pt[p].y;
+        int nc = 0;
+        for (int t0 = 0; t0 < nt; t0 += nlanes) {
+            const int t = t0 + lane;
+            bool c = false;
+            if (t < nt) {
+                const DTri tr = tris[t];
+                if (tr.alive) {
+                    bool maybe = true;
+                    if (tr.v[0] != IM_GHOST && tr.v[1] != IM_GHOST && tr.v[2] != IM_GHOST) {
+                        const float dx = pxf - S->circ[t][0], dy = pyf - S->circ[t][1];
+                        if (dx * dx + dy * dy > S->circ[t][2]) maybe = false;   // certainly outside the circumcircle
+                    }
+                    if (maybe) c = dt_conflict(tr, Pt, p);
+                }
+            }
+            const unsigned m = im_ballot(c);
+            if (c) {
+                const int k = nc + im_popc(m & lt);
+                if (k < 64) s_cav[k] = t;
+            }
+            nc += im_popc(m);
+        }
+        if (nc > 64) { ovf = true; break; }   // warp-uniform
+        IM_SYNCWARP();
+        if (nc == 0) continue;                // duplicate point: skipped (CGAL does the same)
+        const int ne3 = nc * 3;
+        for (int e = lane; e < ne3; e += nlanes) {
+            const DTri& t = tris[s_cav[e / 3]];
+            s_ea[e] = t.v[(e % 3 + 1) % 3];
+            s_eb[e] = t.v[(e % 3 + 2) % 3];
+        }
+        IM_SYNCWARP();
+        int nb = 0;
+        for (int e0 = 0; e0 < ne3; e0 += nlanes) {
+            const int e = e0 + lane;
+            bool isb = false;
+            int a = 0, b = 0;
+            if (e < ne3) {
+                a = s_ea[e]; b = s_eb[e];
+                isb = true;
+                for (int f = 0; f < ne3; ++f)
+                    if (s_ea[f] == b && s_eb[f] == a) { isb = false; break; }
+            }
+            const unsigned m = im_ballot(isb);
+            if (isb) {
+                const int k = nb + im_popc(m & lt);
+                const int slot = (k < nc) ? s_cav[k] : (nt + (k - nc));
+                if (slot < max_tris) {
+                    tris[slot].v[0] = (short)a; tris[slot].v[1] = (short)b; tris[slot].v[2] = (short)p; tris[slot].alive = 1;
+                    if (a != IM_GHOST && b != IM_GHOST) circumcircle_f(Pt, a, b, p, S->circ[slot]);
+                }
+            }
+            nb += im_popc(m);
+        }
+        // every cavity slot is reused (a valid cavity has nc + 2 boundary edges); kill leftovers defensively
+        for (int k = nb + lane; k < nc; k += nlanes) tris[s_cav[k]].alive = 0;
+        if (nb > nc) {
+            if (nt + (nb - nc) <= max_tris) { if (lane == 0) S->ntri = nt + (nb - nc); }
+            else ovf = true;
+        }
+        IM_SYNCWARP();
+    }
+    if (lane == 0) *s_ovf = ovf ? 1 : 0;
+    IM_SYNCWARP();
+    if (*s_ovf) {  // hand this voxel to the block-level stage
+        if (lane == 0) F.work_n_ids[w] = -n;
+        return;
+    }
+    // ---- faces passing the 150-degree filter, as sorted global id triples (stored over the dead circumcircle cache)
+    int (*faces)[3] = reinterpret_cast<int (*)[3]>(&S->circ[0][0]);
+    const int nt = S->ntri;
+    for (int t = lane; t < nt; t += nlanes) {
+        const DTri& tr = tris[t];
+        if (!tr.alive || tr.v[0] < 0 || tr.v[1] < 0 || tr.v[2] < 0) continue;
+        const int j0 = tr.v[0], j1 = tr.v[1], j2 = tr.v[2];
+        if (angle_bad(S->uv[j0][0], S->uv[j0][1], S->uv[j1][0], S->uv[j1][1], S->uv[j2][0], S->uv[j2][1])) continue;
+        if (angle_bad(S->uv[j1][0], S->uv[j1][1], S->uv[j2][0], S->uv[j2][1], S->uv[j0][0], S->uv[j0][1])) continue;
+        if (angle_bad(S->uv[j2][0], S->uv[j2][1], S->uv[j0][0], S->uv[j0][1], S->uv[j1][0], S->uv[j1][1])) continue;
+        int a = S->ids[j0], b = S->ids[j1], c = S->ids[j2];
+        if (a > b) { const int x = a; a = b; b = x; }
+        if (b > c) { const int x = b; b = c; c = x; }
+        if (a > b) { const int x = a; a = b; b = x; }
+        const int k = im_atomic_add(&S->nface, 1);
+        faces[k][0] = a; faces[k][1] = b; faces[k][2] = c;
+    }
+    IM_SYNCWARP();
+    const int nf = S->nface;
+    // facets + principal axes to the frame-wide lists; commit / orientation / pull run in the flat stage-C kernels
+    if (lane == 0) {
+        im_atomic_add(&M.cnt[23], nf);
+        S->scratch[0] = im_atomic_add(&M.cnt[25], nf);
+    }
+    IM_SYNCWARP();
+    const int foff = S->scratch[0];
+    if (foff + nf > F.max_list) {
+        if (lane == 0) im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+    } else {
+        for (int k = lane; k < nf; k += nlanes) F.all_faces[foff + k] = make_int4(faces[k][0], faces[k][1], faces[k][2], w);
+    }
+    for (int k = lane; k < 9; k += nlanes) F.work_axes[(size_t)w * 9 + k] = S->axes[k];
+    if (lane == 0) F.work_nfaces[w] = nf;
 }
 
 // ------------------------------------------------------------------ stage C, flat: one thread per new facet / per dilated vertex
@@ -513,12 +739,14 @@ IM_HDN inline void commit_face(const MeshDev& M, const MeshParams& P, const Fram
     unsigned int hs = (tri_hash(fc.x, fc.y, fc.z) + (unsigned int)w * 0x9E3779B1u) & F.fset_mask;
     while (im_atomic_cas32(&F.fset[hs], -1, f) != -1) hs = (hs + 1) & F.fset_mask;
 }
-// C2: pull + commit, store side, for vertex reference r = (w, i): every live triangle whose smallest vertex is this one and
-// whose other two vertices are in the voxel's dilated set is removed unless the voxel's new triangulation contains it
-IM_HDN inline void commit_vertex(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int r) {
+// C2a: pull (find_relative_triangulation_combination) for vertex reference r = (w, i): every live triangle whose smallest
+// vertex is this one and whose other two vertices are in the voxel's dilated set.  Needs only the dilation result, so it
+// runs concurrently with the triangulation kernels.
+IM_HDN inline void pull_vertex(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int r) {
     const int ref = F.all_vref[r];
     const int w = ref >> 10, i = ref & 1023;
     const int n = F.work_n_ids[w];
+    if (n > 256) return;   // large voxels pull inside the monolithic variant
     const int* ids = F.work_ids + (size_t)w * IM_MAXD;
     const int v = ids[i];
     for (int t = M.v_tri_head[v]; t >= 0;) {
@@ -540,22 +768,28 @@ IM_HDN inline void commit_vertex(const MeshDev& M, const MeshParams& P, const Fr
                 in_set = hit;
             }
             if (in_set) {
-                bool in_new = false;
-                unsigned int hs = (tri_hash(tr.x, tr.y, tr.z) + (unsigned int)w * 0x9E3779B1u) & F.fset_mask;
-                for (unsigned int probe = 0; probe <= F.fset_mask; ++probe) {
-                    const int k = F.fset[hs];
-                    if (k < 0) break;
-                    if (face_is(F.all_faces[k], tr.x, tr.y, tr.z, w)) { in_new = true; break; }
-                    hs = (hs + 1) & F.fset_mask;
-                }
-                if (!in_new) {
-                    const int e = im_atomic_add(&M.cnt[8], 1);
-                    if (e < F.max_list) F.rem_tri[e] = t; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
-                }
+                const int e = im_atomic_add(&M.cnt[28], 1);
+                if (e < F.max_list) { F.pulled[2 * (size_t)e] = w; F.pulled[2 * (size_t)e + 1] = t; }
+                else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
             }
         }
         t = nx;
     }
+}
+// C2b: commit, store side (triangle_compare): a pulled triangle that the voxel's new triangulation does not contain is removed
+IM_HDN inline void pull_check(const MeshDev& M, const FrameBuf& F, int e) {
+    const int w = F.pulled[2 * (size_t)e], t = F.pulled[2 * (size_t)e + 1];
+    if (F.work_n_ids[w] < 0) return;   // handed over to the monolithic variant after a capacity overflow
+    const int4 tr = M.tri[t];
+    unsigned int hs = (tri_hash(tr.x, tr.y, tr.z) + (unsigned int)w * 0x9E3779B1u) & F.fset_mask;
+    for (unsigned int probe = 0; probe <= F.fset_mask; ++probe) {
+        const int k = F.fset[hs];
+        if (k < 0) break;
+        if (face_is(F.all_faces[k], tr.x, tr.y, tr.z, w)) return;
+        hs = (hs + 1) & F.fset_mask;
+    }
+    const int o = im_atomic_add(&M.cnt[8], 1);
+    if (o < F.max_list) F.rem_tri[o] = t; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
 }
 
 }  // namespace immesh
