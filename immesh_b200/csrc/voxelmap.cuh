@@ -339,6 +339,80 @@ IM_HDN inline void init_plane(const VoxelMapDev& m, const LioParams& P, int nd, 
                 M0[j * 3 + k] = U[j * 3 + m0] * U[k * 3 + imin] + U[j * 3 + imin] * U[k * 3 + m0];
                 M1[j * 3 + k] = U[j * 3 + m1] * U[k * 3 + imin] + U[j * 3 + imin] * U[k * 3 + m1];
             }
+#if defined(__CUDA_ARCH__)
+        {
+            // Warp-cooperative evaluation of J Sigma J^T: per point, lanes 0-5 produce the six non-zero entries of F, lanes
+            // 0-8 the entries of A = U F and of T = A Sigma, every lane e < 21 its own covariance entry; operands travel by
+            // warp shuffles.  Every value is produced by the same expression as in the generic path below (which the host
+            // emulation runs): bit-identical results, ~2.5x fewer instructions per point than recomputing A and T per lane.
+            const int b3 = lane % 3, a3 = (lane / 3) % 3;
+            // lane constants, selected without dynamic register indexing
+            const bool fl1 = lane >= 3;                                   // F row: m0 (lanes 0-2) or m1 (lanes 3-5)
+            const double fs = fl1 ? s1 : s0;
+            double fm0, fm1, fm2;                                         // column b3 of M0 / M1
+            {
+                const double* Mx = fl1 ? M1 : M0;
+                fm0 = b3 == 0 ? Mx[0] : (b3 == 1 ? Mx[1] : Mx[2]);
+                fm1 = b3 == 0 ? Mx[3] : (b3 == 1 ? Mx[4] : Mx[5]);
+                fm2 = b3 == 0 ? Mx[6] : (b3 == 1 ? Mx[7] : Mx[8]);
+            }
+            const double ua0 = a3 == 0 ? U[0] : (a3 == 1 ? U[3] : U[6]);  // row a3 of U
+            const double ua1 = a3 == 0 ? U[1] : (a3 == 1 ? U[4] : U[7]);
+            const double ua2 = a3 == 0 ? U[2] : (a3 == 1 ? U[5] : U[8]);
+            // which F row feeds rows 0,1,2 of the product: 0 -> zero row (imin), 1 -> m0 (lanes b), 2 -> m1 (lanes 3+b)
+            const int r0 = (imin == 0) ? 0 : ((m0 == 0) ? 1 : 2);
+            const int r1 = (imin == 1) ? 0 : ((m0 == 1) ? 1 : 2);
+            const int r2 = (imin == 2) ? 0 : ((m0 == 2) ? 1 : 2);
+            // covariance entry of this lane
+            int ei = 0, ej = 0;
+            {
+                const int e = lane < 21 ? lane : 0;
+                int base = 0;
+                while (e >= base + (6 - ei)) { base += 6 - ei; ++ei; }
+                ej = ei + (e - base);
+            }
+            const int ti = ei < 3 ? ei : 0;            // T row needed (TL / TR entries)
+            const int aj = ej < 3 ? ej : 0;            // A row needed (TL entries)
+            const int trk = (ej >= 3 && ei < 3) ? (ej - 3) : 0;
+            int ch = n.first_chunk;
+            double accv = 0.0;
+            for (int i = 0; i < np; ++i) {
+                const int s = i & 7;
+                if (i && s == 0) ch = m.chunks[ch].next;
+                const Chunk& ck = m.chunks[ch];
+                const double px = (double)ck.x[s], py = (double)ck.y[s], pz = (double)ck.z[s];
+                const double S0 = ck.var[0][s], S1 = ck.var[1][s], S2 = ck.var[2][s], S4 = ck.var[3][s], S5 = ck.var[4][s], S8 = ck.var[5][s];
+                // F entry (lanes 0-5)
+                const double v0 = (px - c[0]) * fs, v1 = (py - c[1]) * fs, v2 = (pz - c[2]) * fs;
+                const double Fv = (v0 * fm0 + v1 * fm1) + v2 * fm2;
+                const double f_m0b = __shfl_sync(0xffffffffu, Fv, b3), f_m1b = __shfl_sync(0xffffffffu, Fv, 3 + b3);
+                const double F0b = r0 == 0 ? 0.0 : (r0 == 1 ? f_m0b : f_m1b);
+                const double F1b = r1 == 0 ? 0.0 : (r1 == 1 ? f_m0b : f_m1b);
+                const double F2b = r2 == 0 ? 0.0 : (r2 == 1 ? f_m0b : f_m1b);
+                // A entry (a3, b3) (lanes 0-8)
+                const double Av = (ua0 * F0b + ua1 * F1b) + ua2 * F2b;
+                // T entry (a3, b3) = row a3 of A times column b3 of Sigma
+                const double Aa0 = __shfl_sync(0xffffffffu, Av, a3 * 3 + 0), Aa1 = __shfl_sync(0xffffffffu, Av, a3 * 3 + 1), Aa2 = __shfl_sync(0xffffffffu, Av, a3 * 3 + 2);
+                const double Sc0 = b3 == 0 ? S0 : (b3 == 1 ? S1 : S2);   // Sigma[0][b3]
+                const double Sc1 = b3 == 0 ? S1 : (b3 == 1 ? S4 : S5);   // Sigma[1][b3]
+                const double Sc2 = b3 == 0 ? S2 : (b3 == 1 ? S5 : S8);   // Sigma[2][b3]
+                const double Tv = (Aa0 * Sc0 + Aa1 * Sc1) + Aa2 * Sc2;
+                // this lane's covariance entry
+                const double Ti0 = __shfl_sync(0xffffffffu, Tv, ti * 3 + 0), Ti1 = __shfl_sync(0xffffffffu, Tv, ti * 3 + 1), Ti2 = __shfl_sync(0xffffffffu, Tv, ti * 3 + 2);
+                const double Aj0 = __shfl_sync(0xffffffffu, Av, aj * 3 + 0), Aj1 = __shfl_sync(0xffffffffu, Av, aj * 3 + 1), Aj2 = __shfl_sync(0xffffffffu, Av, aj * 3 + 2);
+                double term;
+                if (ej < 3) term = (Ti0 * Aj0 + Ti1 * Aj1) + Ti2 * Aj2;
+                else if (ei < 3) term = (trk == 0 ? Ti0 : (trk == 1 ? Ti1 : Ti2)) * invn;
+                else {
+                    const int k3 = ei - 3, l3 = ej - 3;   // Sigma[k3][l3], k3 <= l3
+                    const double Skl = k3 == 0 ? (l3 == 0 ? S0 : (l3 == 1 ? S1 : S2)) : (k3 == 1 ? (l3 == 1 ? S4 : S5) : S8);
+                    term = (invn * Skl) * invn;
+                }
+                accv += term;
+            }
+            acc[0] = accv;
+        }
+#else
         int ch = n.first_chunk;
         for (int i = 0; i < np; ++i) {
             const int s = i & 7;
@@ -375,6 +449,7 @@ IM_HDN inline void init_plane(const VoxelMapDev& m, const LioParams& P, int nd, 
                 acc[k] += term;
             }
         }
+#endif
     }
     IM_SYNCWARP();  // all lanes have finished reading the old record
     for (int k = 0; k < IM_ENT_PER_LANE; ++k) {
