@@ -24,6 +24,7 @@ __global__ void k_frame_begin(MeshDev M, FrameBuf F) {
         for (int k = 5; k <= 10; ++k) M.cnt[k] = 0;
         for (int k = 17; k <= 26; ++k) M.cnt[k] = 0;
         M.cnt[28] = 0;
+        M.cnt[29] = 0;
     }
 }
 __global__ void __launch_bounds__(128) k_cand_init(MeshDev M, MeshParams P, FrameBuf F) {
@@ -99,18 +100,18 @@ __global__ void __launch_bounds__(128) k_voxel_select(MeshDev M, FrameBuf F) {
     const int na = min(M.cnt[5], F.max_act);
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < na; a += gridDim.x * blockDim.x) voxel_select(M, F, a);
 }
-// stage A: dilation (exact 20-NN of the in-voxel vertices + smoothing), one block per voxel, populous voxels first
+// stage A: dilation (exact 20-NN of the in-voxel vertices + smoothing); one block per (voxel, group of <= 8 queries)
 __global__ void __launch_bounds__(128) k_voxel_dilate(MeshDev M, MeshParams P, FrameBuf F) {
     __shared__ DilateSmem S;
     __shared__ int s_item;
-    const int nw = work_total(M, F);
+    const int ni = min(M.cnt[29], F.max_ditem);
     while (true) {
         if (threadIdx.x == 0) s_item = atomicAdd(&M.cnt[24], 1);
         __syncthreads();
         const int i = s_item;
         __syncthreads();
-        if (i >= nw) break;
-        voxel_dilate(M, P, F, work_slot(M, F, i), &S, threadIdx.x, blockDim.x);
+        if (i >= ni) break;
+        voxel_dilate(M, P, F, F.ditem[i], &S, threadIdx.x, blockDim.x);
         __syncthreads();
     }
 }
@@ -370,6 +371,11 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(mdev_alloc(h, &F.work_n_ids, (size_t)F.max_work));
     IM_CUDA(mdev_alloc(h, &F.work_ids, (size_t)F.max_work * IM_MAXD));
     IM_CUDA(mdev_alloc(h, &F.work_nfaces, (size_t)F.max_work));
+    IM_CUDA(mdev_alloc(h, &F.work_bits, (size_t)F.max_work * (IM_MAXG / 32), 0));
+    IM_CUDA(mdev_alloc(h, &F.work_ring, (size_t)F.max_work, 0));
+    IM_CUDA(mdev_alloc(h, &F.work_done, (size_t)F.max_work, 0));
+    F.max_ditem = F.max_work * 4;
+    IM_CUDA(mdev_alloc(h, &F.ditem, (size_t)F.max_ditem));
     F.max_vref = 8 << 20;
     IM_CUDA(mdev_alloc(h, &F.all_faces, (size_t)F.max_list));
     IM_CUDA(mdev_alloc(h, &F.all_vref, (size_t)F.max_vref));

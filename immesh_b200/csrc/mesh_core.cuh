@@ -125,6 +125,11 @@ struct FrameBuf {
     int* work;            // voxels to (re)mesh this frame
     int* work_n_ids;      // dilated set sizes
     int* work_ids;        // [max_work][IM_MAXD] ascending vertex ids
+    unsigned int* work_bits;  // [max_work][IM_MAXG/32] dilation-member bitmap shared by the groups of a voxel
+    int* work_ring;       // largest ring any group of the voxel gathered
+    int* work_done;       // groups of the voxel that have finished
+    int* ditem;           // dilation items: work slot << 5 | query group
+    int max_ditem;
     int* work_nfaces;     // facets produced by the fused dilate+triangulate stage (-1: left to the large variant)
     int4* all_faces;      // compact list of this frame's new facets: (a, b, c, work slot)   [max_list]
     int* all_vref;        // compact list of (work slot << 10 | index into its dilated id list) [max_vref]
@@ -431,7 +436,15 @@ IM_HDN inline void voxel_select(const MeshDev& M, const FrameBuf& F, int a) {
     int w;
     if (M.vox_count[vs] >= 20) w = im_atomic_add(&M.cnt[6], 1);
     else w = F.max_work - 1 - im_atomic_add(&M.cnt[17], 1);
-    if (w >= 0 && w < F.max_work && M.cnt[6] + M.cnt[17] <= F.max_work) F.work[w] = vs; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+    if (w >= 0 && w < F.max_work && M.cnt[6] + M.cnt[17] <= F.max_work) F.work[w] = vs; else { im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP); return; }
+    // dilation items: groups of up to 8 of the voxel's vertices (the kNN queries), so that a populous voxel is spread over
+    // several thread blocks instead of serialising on one
+    int nq = M.vox_count[vs];
+    if (nq > IM_MAXIN) nq = IM_MAXIN;
+    const int ng = (nq + 7) >> 3;
+    const int base = im_atomic_add(&M.cnt[29], ng);
+    if (base + ng > F.max_ditem) { im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP); return; }
+    for (int g = 0; g < ng; ++g) F.ditem[base + g] = (w << 5) | g;
 }
 
 // i-th work item (0 <= i < cnt[6] + cnt[17]) -> slot in the two-ended work arrays

@@ -41,7 +41,9 @@ IM_HD int im_popc(unsigned m) {
 
 struct DilateSmem {
     float4 cand[IM_MAXG];      // gathered neighbourhood vertices: xyz + id (bit-cast in w)
-    int flag[IM_MAXG];         // member of the dilated set
+    unsigned char flag[IM_MAXG];  // member of the dilated set (byte stores of 1 only, so concurrent warps do not race)
+    int cell_slot[344];        // per shell cell: voxel slot (-1 none) / running candidate offset
+    int cell_off[344];
     int q[IM_MAXIN];           // in-voxel vertex ids (the kNN queries)
     int qdone[IM_MAXIN];       // query finished at an earlier ring (its 20-NN are provably complete)
     int ids[IM_MAXD];          // output, ascending
@@ -63,51 +65,75 @@ IM_HD float i2f(int i) {
 #endif
 }
 
-// stage A for work item w (one thread block; warps take queries round-robin)
-IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, DilateSmem* S, int tid, int nthreads) {
+// deterministic gather of the shell of Chebyshev radius `ring` around voxel (kx,ky,kz) behind the candidates already staged:
+// cells in lexicographic order, a cell's vertices in chunk order -> every block working on the same voxel in this frame builds
+// the identical candidate array (indices are shared through a per-voxel bitmap)
+IM_HDN inline void dilate_gather_ring(const MeshDev& M, DilateSmem* S, int kx, int ky, int kz, int ring, int tid, int nthreads) {
+    const int side = 2 * ring + 1, ncell = side * side * side;
+    for (int c = tid; c < ncell; c += nthreads) {
+        const int dx = c / (side * side) - ring, dy = (c / side) % side - ring, dz = c % side - ring;
+        const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, az = dz < 0 ? -dz : dz;
+        int slot = -1, cntv = 0;
+        if ((ax > ay ? (ax > az ? ax : az) : (ay > az ? ay : az)) == ring && ikey_ok(kx + dx, ky + dy, kz + dz)) {
+            slot = table_find(M.vkeys, M.vmask, pack_ikey(kx + dx, ky + dy, kz + dz));
+            if (slot >= 0) {
+                cntv = M.vox_count[slot];
+                if (cntv > IM_VCHUNKS * 16) cntv = IM_VCHUNKS * 16;
+            }
+        }
+        S->cell_slot[c] = slot;
+        S->cell_off[c] = cntv;
+    }
+    IM_SYNCBLOCK_M();
+    if (tid == 0) {
+        int run = S->n_cand;
+        for (int c = 0; c < ncell; ++c) { const int k = S->cell_off[c]; S->cell_off[c] = run; run += k; }
+        S->cell_off[ncell] = run;
+        if (run > IM_MAXG) S->overflow = 1;
+        S->n_cand = run < IM_MAXG ? run : IM_MAXG;
+    }
+    IM_SYNCBLOCK_M();
+    for (int c = tid; c < ncell; c += nthreads) {
+        const int slot = S->cell_slot[c];
+        if (slot < 0) continue;
+        const int o = S->cell_off[c], cntv = S->cell_off[c + 1] - o;
+        for (int k = 0; k < cntv; ++k)
+            if (o + k < IM_MAXG) S->cand[o + k] = M.vchunk_pts[(size_t)M.vox_chunk[(size_t)slot * IM_VCHUNKS + (k >> 4)] * 16 + (k & 15)];
+    }
+    IM_SYNCBLOCK_M();
+}
+
+// stage A for one dilation item = (work slot w, group g of up to 8 queries).  All groups of a voxel stage the same
+// candidate array; each runs the exact 20-NN of its own queries and ORs the indices of the dilation members into the
+// voxel's global bitmap; the last group to finish turns the bitmap into the ascending id list of the dilated set.
+IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int item, DilateSmem* S, int tid, int nthreads) {
+    const int w = item >> 5, grp = item & 31;
     const int vs = F.work[w];
     int kx, ky, kz;
     unpack_ikey(M.vkeys[vs], &kx, &ky, &kz);
     if (tid == 0) { S->n_cand = 0; S->n_q = 0; S->n_out = 0; S->overflow = 0; }
     IM_SYNCBLOCK_M();
-    // queries = the voxel's own vertices (retrieve_pts_in_voxels); they are also ring-0 candidates
-    {
-        int n = M.vox_count[vs];
-        if (n > IM_VCHUNKS * 16) n = IM_VCHUNKS * 16;
-        if (n > IM_MAXIN) { n = IM_MAXIN; if (tid == 0) S->overflow = 1; }
-        for (int k = tid; k < n; k += nthreads) {
-            const float4 p = M.vchunk_pts[(size_t)M.vox_chunk[(size_t)vs * IM_VCHUNKS + (k >> 4)] * 16 + (k & 15)];
-            S->q[k] = f2i(p.w);
-            S->cand[k] = p;
-        }
-        if (tid == 0) { S->n_q = n; S->n_cand = n; }
+    // ring 0 = the voxel's own vertices (retrieve_pts_in_voxels): candidates for everybody, queries for their group
+    int nqt = M.vox_count[vs];
+    if (nqt > IM_VCHUNKS * 16) nqt = IM_VCHUNKS * 16;
+    if (nqt > IM_MAXIN) { nqt = IM_MAXIN; if (tid == 0) S->overflow = 1; }
+    for (int k = tid; k < nqt; k += nthreads) {
+        const float4 p = M.vchunk_pts[(size_t)M.vox_chunk[(size_t)vs * IM_VCHUNKS + (k >> 4)] * 16 + (k & 15)];
+        S->q[k] = f2i(p.w);
+        S->cand[k] = p;
     }
+    if (tid == 0) { S->n_q = nqt; S->n_cand = nqt; }
     IM_SYNCBLOCK_M();
-    const int nq = S->n_q;
-    for (int i = tid; i < nq; i += nthreads) { S->qdone[i] = 0; S->flag[i] = 0; }
-    int flag_init = nq;   // candidates [0, flag_init) have an initialised flag
+    const int ngroups = (nqt + 7) >> 3;
+    const int q_lo = grp * 8, q_hi = (q_lo + 8 < nqt) ? q_lo + 8 : nqt;
+    for (int i = tid; i < nqt; i += nthreads) { S->qdone[i] = 0; S->flag[i] = 0; }
+    int flag_init = nqt;   // candidates [0, flag_init) have an initialised flag
     const double max_d2 = P.knn_max * P.knn_max;
     const int lane = tid % IM_NLANES, warp = tid / IM_NLANES, nwarps = (nthreads + IM_NLANES - 1) / IM_NLANES;
+    int ring_used = 0;
     for (int ring = 1; ring <= 3; ++ring) {
-        // gather the shell of Chebyshev radius `ring`
-        const int side = 2 * ring + 1;
-        for (int c = tid; c < side * side * side; c += nthreads) {
-            const int dx = c / (side * side) - ring, dy = (c / side) % side - ring, dz = c % side - ring;
-            const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, az = dz < 0 ? -dz : dz;
-            if ((ax > ay ? (ax > az ? ax : az) : (ay > az ? ay : az)) != ring) continue;
-            if (!ikey_ok(kx + dx, ky + dy, kz + dz)) continue;
-            const int s = table_find(M.vkeys, M.vmask, pack_ikey(kx + dx, ky + dy, kz + dz));
-            if (s < 0) continue;
-            int cntv = M.vox_count[s];
-            if (cntv > IM_VCHUNKS * 16) cntv = IM_VCHUNKS * 16;
-            if (cntv <= 0) continue;
-            const int base_k = im_atomic_add(&S->n_cand, cntv);
-            for (int k = 0; k < cntv; ++k) {
-                if (base_k + k < IM_MAXG) S->cand[base_k + k] = M.vchunk_pts[(size_t)M.vox_chunk[(size_t)s * IM_VCHUNKS + (k >> 4)] * 16 + (k & 15)];
-                else S->overflow = 1;
-            }
-        }
-        IM_SYNCBLOCK_M();
+        dilate_gather_ring(M, S, kx, ky, kz, ring, tid, nthreads);
+        ring_used = ring;
         const int nc = S->n_cand < IM_MAXG ? S->n_cand : IM_MAXG;
         for (int i = flag_init + tid; i < nc; i += nthreads) S->flag[i] = 0;
         flag_init = nc;
@@ -115,7 +141,7 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
         IM_SYNCBLOCK_M();
         // after gathering rings 0..ring, every unseen vertex is at least ring*res away from any query of this voxel
         const double lb = (double)ring * P.res;
-        for (int qi = warp; qi < nq; qi += nwarps) {
+        for (int qi = q_lo + warp; qi < q_hi; qi += nwarps) {
             if (S->qdone[qi]) continue;   // complete at an earlier ring: more candidates cannot change its 20-NN
             const int qv = S->q[qi];
             const float4 qp = M.vpos[qv];
@@ -245,13 +271,47 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
         IM_SYNCBLOCK_M();
         if (!S->need_more) break;
     }
-    // dilated set = flagged candidates, ascending by id (std::set<long>, ImMesh_mesh_reconstruction.cpp:157-170)
-    const int nc = S->n_cand < IM_MAXG ? S->n_cand : IM_MAXG;
-    for (int i = tid; i < nc; i += nthreads)
-        if (S->flag[i]) {
-            const int k = im_atomic_add(&S->n_out, 1);
-            if (k < IM_MAXD) S->ids[k] = f2i(S->cand[i].w); else S->overflow = 1;
+    // publish this group's dilation members in the voxel's bitmap
+    {
+        const int nc = S->n_cand < IM_MAXG ? S->n_cand : IM_MAXG;
+        unsigned int* bits = F.work_bits + (size_t)w * (IM_MAXG / 32);
+        for (int i = tid; i < nc; i += nthreads)
+            if (S->flag[i]) {
+#if defined(__CUDA_ARCH__)
+                atomicOr(&bits[i >> 5], 1u << (i & 31));
+#else
+                bits[i >> 5] |= 1u << (i & 31);
+#endif
+            }
+        if (tid == 0) {
+            im_atomic_max(&F.work_ring[w], ring_used);
+            if (S->overflow) im_atomic_or(&M.cnt[3], IM_MERR_VOXEL_CAP);
         }
+    }
+    im_fence();
+    IM_SYNCBLOCK_M();
+    if (tid == 0) S->need_more = (im_atomic_add(&F.work_done[w], 1) == ngroups - 1) ? 1 : 0;
+    IM_SYNCBLOCK_M();
+    if (!S->need_more) return;
+    // ---- last group of the voxel: dilated set = union of all groups' members, ascending by id (std::set<long>,
+    // ImMesh_mesh_reconstruction.cpp:157-170)
+    im_fence();
+    const int ring_all = im_vload(&F.work_ring[w]);
+    for (int ring = ring_used + 1; ring <= ring_all; ++ring) dilate_gather_ring(M, S, kx, ky, kz, ring, tid, nthreads);
+    {
+        const int nc = S->n_cand < IM_MAXG ? S->n_cand : IM_MAXG;
+        unsigned int* bits = F.work_bits + (size_t)w * (IM_MAXG / 32);
+        for (int i = tid; i < nc; i += nthreads) {
+            const unsigned int word = (unsigned int)im_vload((const int*)&bits[i >> 5]);
+            if ((word >> (i & 31)) & 1u) {
+                const int k = im_atomic_add(&S->n_out, 1);
+                if (k < IM_MAXD) S->ids[k] = f2i(S->cand[i].w); else S->overflow = 1;
+            }
+        }
+        IM_SYNCBLOCK_M();
+        for (int i = tid; i < IM_MAXG / 32; i += nthreads) bits[i] = 0u;   // clean for the next frame
+        if (tid == 0) { F.work_ring[w] = 0; F.work_done[w] = 0; }
+    }
     IM_SYNCBLOCK_M();
     int n = S->n_out < IM_MAXD ? S->n_out : IM_MAXD;
     int np2 = 1;
@@ -286,8 +346,8 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
         F.work_n_ids[w] = n;
         if (S->overflow) im_atomic_or(&M.cnt[3], IM_MERR_VOXEL_CAP);
         // work accounting for the roofline: gathered candidates, queries, dilated vertices
-        im_atomic_add(&M.cnt[20], nc);
-        im_atomic_add(&M.cnt[21], nq);
+        im_atomic_add(&M.cnt[20], S->n_cand);
+        im_atomic_add(&M.cnt[21], nqt);
         im_atomic_add(&M.cnt[22], n);
     }
 }

@@ -22,7 +22,8 @@ struct immesh_mesh {
     std::vector<unsigned long long> gkeys, vkeys, tri_flip, ckeys, cand_gkey, add_flip;
     std::vector<int4> tri;
     std::vector<float> pts;
-    std::vector<int> cand_vslot, cand_status, cand_scan, cand_conf, cand_nconf, cand_next, chead, act, work, work_n, work_ids, add_tri, rem_tri, work_nf, all_vref, fset, pulled;
+    std::vector<int> cand_vslot, cand_status, cand_scan, cand_conf, cand_nconf, cand_next, chead, act, work, work_n, work_ids, add_tri, rem_tri, work_nf, all_vref, fset, pulled, work_ring, work_done, ditem;
+    std::vector<unsigned int> work_bits;
     std::vector<int4> all_faces;
     std::vector<double> work_axes;
     int frame_counter = 0;
@@ -61,12 +62,12 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     const size_t ccap = p2(mc * 2);
     h->ckeys.resize(ccap); h->chead.resize(ccap);
     h->act.resize(F.max_act); h->work.resize(F.max_work); h->work_n.resize(F.max_work); h->work_ids.resize((size_t)F.max_work * IM_MAXD);
-    h->work_nf.resize(F.max_work); F.max_vref = 1 << 21; h->all_faces.resize(F.max_list); h->all_vref.resize(F.max_vref); h->pulled.resize((size_t)F.max_list * 2); F.fset_mask = (1u << 19) - 1; h->fset.assign((size_t)F.fset_mask + 1, -1); h->work_axes.resize((size_t)F.max_work * 9);
+    h->work_nf.resize(F.max_work); h->work_bits.assign((size_t)F.max_work * (IM_MAXG / 32), 0u); h->work_ring.assign(F.max_work, 0); h->work_done.assign(F.max_work, 0); F.max_ditem = F.max_work * 4; h->ditem.resize(F.max_ditem); F.max_vref = 1 << 21; h->all_faces.resize(F.max_list); h->all_vref.resize(F.max_vref); h->pulled.resize((size_t)F.max_list * 2); F.fset_mask = (1u << 19) - 1; h->fset.assign((size_t)F.fset_mask + 1, -1); h->work_axes.resize((size_t)F.max_work * 9);
     h->add_tri.resize((size_t)F.max_list * 3); h->add_flip.resize(F.max_list); h->rem_tri.resize(F.max_list);
     F.pts = h->pts.data(); F.cand_gkey = h->cand_gkey.data(); F.cand_vslot = h->cand_vslot.data(); F.cand_status = h->cand_status.data();
     F.cand_scan = h->cand_scan.data(); F.cand_conf = h->cand_conf.data(); F.cand_nconf = h->cand_nconf.data(); F.cand_next = h->cand_next.data(); F.cand_pos = h->cand_pos.data();
     F.ckeys = h->ckeys.data(); F.chead = h->chead.data(); F.scan_block = nullptr;
-    F.act = h->act.data(); F.work = h->work.data(); F.work_n_ids = h->work_n.data(); F.work_ids = h->work_ids.data(); F.work_nfaces = h->work_nf.data(); F.all_faces = h->all_faces.data(); F.all_vref = h->all_vref.data(); F.pulled = h->pulled.data(); F.fset = h->fset.data(); F.work_axes = h->work_axes.data();
+    F.act = h->act.data(); F.work = h->work.data(); F.work_n_ids = h->work_n.data(); F.work_ids = h->work_ids.data(); F.work_nfaces = h->work_nf.data(); F.work_bits = h->work_bits.data(); F.work_ring = h->work_ring.data(); F.work_done = h->work_done.data(); F.ditem = h->ditem.data(); F.all_faces = h->all_faces.data(); F.all_vref = h->all_vref.data(); F.pulled = h->pulled.data(); F.fset = h->fset.data(); F.work_axes = h->work_axes.data();
     F.add_tri = h->add_tri.data(); F.add_flip = h->add_flip.data(); F.rem_tri = h->rem_tri.data();
     std::memset(h->last_cnt, 0, sizeof(h->last_cnt));
     *out = h;
@@ -88,6 +89,7 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     for (int k = 5; k <= 10; ++k) M.cnt[k] = 0;
     for (int k = 17; k <= 26; ++k) M.cnt[k] = 0;
     M.cnt[28] = 0;
+    M.cnt[29] = 0;
     for (unsigned i = 0; i <= F.fset_mask; ++i) F.fset[i] = -1;
     for (int c = 0; c < F.m; ++c) cand_init(M, P, F, c);
     for (int c = 0; c < F.m; ++c) cand_conflicts(M, P, F, c);
@@ -104,7 +106,7 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     DilateSmem* DS = new DilateSmem();
     MeshSmem<256>* S1 = new MeshSmem<256>();
     MeshSmem<1024>* S2 = new MeshSmem<1024>();
-    for (int i = 0; i < nw; ++i) voxel_dilate(M, P, F, work_slot(M, F, i), DS, 0, 1);
+    for (int i = 0; i < std::min(M.cnt[29], F.max_ditem); ++i) voxel_dilate(M, P, F, F.ditem[i], DS, 0, 1);
     MeshWarpSmem<128>* SW = new MeshWarpSmem<128>();
     for (int i = 0; i < nw; ++i) voxel_mesh_warp<128>(M, P, F, work_slot(M, F, i), SW, 0, 1, 96);   // same split as the device
     delete SW;
