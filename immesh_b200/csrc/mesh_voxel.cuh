@@ -48,6 +48,11 @@ struct DilateSmem {
     int qdone[IM_MAXIN];       // query finished at an earlier ring (its 20-NN are provably complete)
     int ids[IM_MAXD];          // output, ascending
     int n_cand, n_q, n_out, need_more, overflow;
+    // per-warp scratch of the kNN fast path: compacted (d2 bits << 32 | id) keys + candidate indices, ranked output
+    unsigned long long wl_key[4][64];
+    unsigned short wl_idx[4][64];
+    float wl_outd[4][20];
+    unsigned short wl_outi[4][20];
 };
 
 IM_HD int f2i(float f) {
@@ -154,7 +159,74 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
                 // entry and rescans its slots.
                 float cd = INFINITY;           // carried list entry of this lane
                 int cid = 0x7fffffff, cidx = 0, have = 0;
-                for (int base = 0; base < nc; base += 512) {
+                // Fast path.  The 20 nearest are the 20 smallest (d2, id) keys of ANY candidate subset {d2 <= T} that holds
+                // at least 20 of them, so: count the candidates under a ladder of radii (one pass), compact those under the
+                // first radius with >= 20 members (normally 20..40 of ~400) into a per-warp list, and rank the list by
+                // all-pairs comparison of its 64-bit keys -- no serial selection rounds.  Lists longer than 64 fall through
+                // to the general chunked selection below.
+                bool fast_done = false;
+                {
+                    const float r2 = (float)(P.res * P.res);
+                    float mf = (float)max_d2;                    // dd <= mf  <=>  (double)dd <= max_d2
+                    if ((double)mf > max_d2) mf = __uint_as_float(__float_as_uint(mf) - 1u);
+                    const float T0 = 0.30f * r2, T1 = 0.49f * r2, T2 = 0.72f * r2, T3 = 1.0f * r2, T4 = 2.25f * r2;
+                    int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+                    for (int i = lane; i < nc; i += 32) {
+                        const float4 cp = S->cand[i];
+                        const float dd = dist2f(qp.x, qp.y, qp.z, cp.x, cp.y, cp.z);
+                        c0 += (dd <= T0); c1 += (dd <= T1); c2 += (dd <= T2); c3 += (dd <= T3); c4 += (dd <= T4); c5 += (dd <= mf);
+                    }
+                    c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
+                    c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
+                    c4 = __reduce_add_sync(0xffffffffu, c4); c5 = __reduce_add_sync(0xffffffffu, c5);
+                    float T = mf; int C = c5;
+                    if (c4 >= 20) { T = T4; C = c4; }
+                    if (c3 >= 20) { T = T3; C = c3; }
+                    if (c2 >= 20) { T = T2; C = c2; }
+                    if (c1 >= 20) { T = T1; C = c1; }
+                    if (c0 >= 20) { T = T0; C = c0; }
+                    if (T > mf) { T = mf; C = c5; }
+                    if (C <= 64) {
+                        unsigned long long* wkey = S->wl_key[warp];
+                        unsigned short* widx = S->wl_idx[warp];
+                        const unsigned lt = im_lanemask_lt();
+                        int pos = 0;
+                        for (int i0 = 0; i0 < nc; i0 += 32) {
+                            const int i = i0 + lane;
+                            bool in = false;
+                            float dd = 0.f;
+                            int id = 0;
+                            if (i < nc) {
+                                const float4 cp = S->cand[i];
+                                dd = dist2f(qp.x, qp.y, qp.z, cp.x, cp.y, cp.z);
+                                id = f2i(cp.w);
+                                in = dd <= T;
+                            }
+                            const unsigned m = __ballot_sync(0xffffffffu, in);
+                            if (in) {
+                                const int k = pos + __popc(m & lt);
+                                wkey[k] = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned int)id;
+                                widx[k] = (unsigned short)i;
+                            }
+                            pos += __popc(m);
+                        }
+                        __syncwarp();
+                        const unsigned long long k0 = (lane < C) ? wkey[lane] : ~0ull, k1 = (lane + 32 < C) ? wkey[lane + 32] : ~0ull;
+                        int rk0 = 0, rk1 = 0;
+                        for (int j = 0; j < C; ++j) {
+                            const unsigned long long kj = wkey[j];
+                            rk0 += (kj < k0); rk1 += (kj < k1);
+                        }
+                        if (lane < C && rk0 < 20) { S->wl_outd[warp][rk0] = __uint_as_float((unsigned int)(k0 >> 32)); S->wl_outi[warp][rk0] = widx[lane]; }
+                        if (lane + 32 < C && rk1 < 20) { S->wl_outd[warp][rk1] = __uint_as_float((unsigned int)(k1 >> 32)); S->wl_outi[warp][rk1] = widx[lane + 32]; }
+                        __syncwarp();
+                        have = C < 20 ? C : 20;
+                        if (lane < have) { cd = S->wl_outd[warp][lane]; cidx = S->wl_outi[warp][lane]; }
+                        __syncwarp();
+                        fast_done = true;
+                    }
+                }
+                for (int base = 0; base < nc && !fast_done; base += 512) {
                     float dreg[17];
                     int ireg[17];
                     const int nsl = (min(nc - base, 512) + 31) >> 5;   // occupied register slots (warp-uniform)
@@ -199,14 +271,15 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
                 double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
                 int cnt = 0;
                 float last_d = 0.f;
-                for (int r = 0; r < have; ++r) {
-                    const float rd = __shfl_sync(0xffffffffu, cd, r);
-                    const int ridx = __shfl_sync(0xffffffffu, cidx, r);
-                    last_d = rd;
-                    if ((double)sqrtf(rd) < P.accept * 2) {
-                        ++cnt;
-                        const float4 cp = S->cand[ridx];
-                        sv0 = sv0 + (double)cp.x; sv1 = sv1 + (double)cp.y; sv2 = sv2 + (double)cp.z;
+                if (have > 0) last_d = __shfl_sync(0xffffffffu, cd, have - 1);
+                {
+                    const unsigned m2 = __ballot_sync(0xffffffffu, lane < have && (double)sqrtf(cd) < P.accept * 2);
+                    cnt = __popc(m2);
+                    const float4 mine = S->cand[cidx];
+                    for (unsigned mm = m2; mm; mm &= mm - 1) {
+                        const int r = __ffs(mm) - 1;
+                        const float x = __shfl_sync(0xffffffffu, mine.x, r), y = __shfl_sync(0xffffffffu, mine.y, r), z = __shfl_sync(0xffffffffu, mine.z, r);
+                        sv0 = sv0 + (double)x; sv1 = sv1 + (double)y; sv2 = sv2 + (double)z;
                     }
                 }
                 const bool complete = (lb > P.knn_max) || (have >= 20 && (double)last_d < lb * lb * 0.999999);
@@ -691,17 +764,40 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
         IM_SYNCWARP();
         if (nc == 0) continue;                // duplicate point: skipped (CGAL does the same)
         const int ne3 = nc * 3;
-        for (int e = lane; e < ne3; e += nlanes) {
-            const DTri& t = tris[s_cav[e / 3]];
-            s_ea[e] = t.v[(e % 3 + 1) % 3];
-            s_eb[e] = t.v[(e % 3 + 2) % 3];
+#if defined(__CUDA_ARCH__)
+        const bool one_pass = ne3 <= 32;   // every cavity edge in one lane: interior edges pair up through match.any
+#else
+        const bool one_pass = false;
+#endif
+        if (!one_pass) {
+            for (int e = lane; e < ne3; e += nlanes) {
+                const DTri& t = tris[s_cav[e / 3]];
+                s_ea[e] = t.v[(e % 3 + 1) % 3];
+                s_eb[e] = t.v[(e % 3 + 2) % 3];
+            }
+            IM_SYNCWARP();
         }
-        IM_SYNCWARP();
         int nb = 0;
         for (int e0 = 0; e0 < ne3; e0 += nlanes) {
             const int e = e0 + lane;
             bool isb = false;
             int a = 0, b = 0;
+#if defined(__CUDA_ARCH__)
+            if (one_pass) {
+                unsigned key = 0xfffe0000u | (unsigned)lane;
+                if (e < ne3) {
+                    const DTri t = tris[s_cav[e / 3]];
+                    const int k3 = e % 3;
+                    a = (k3 == 0) ? t.v[1] : (k3 == 1) ? t.v[2] : t.v[0];
+                    b = (k3 == 0) ? t.v[2] : (k3 == 1) ? t.v[0] : t.v[1];
+                    const unsigned ua = (unsigned)a & 0xffffu, ub = (unsigned)b & 0xffffu;
+                    key = ua < ub ? (ua << 16 | ub) : (ub << 16 | ua);
+                }
+                const unsigned peers = __match_any_sync(0xffffffffu, key);
+                isb = (e < ne3) && __popc(peers) == 1;
+                __syncwarp();   // all edge reads done before any cavity slot is overwritten
+            } else
+#endif
             if (e < ne3) {
                 a = s_ea[e]; b = s_eb[e];
                 isb = true;
