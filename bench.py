@@ -201,11 +201,13 @@ def run_gpu(args, rank, world):
     launches0 = api.launch_count(lib)
     barrier()
     api.pipeline_mark_begin(lio)
+    t_enq = time.perf_counter()
     for _ in range(K):
         lio.enqueue_memset(flush.data_ptr(), flush_bytes)
         lio.step_async(d_ds[k].data_ptr(), d_ds[k].shape[0], scans[k]["dt"], on_device=True)
         mesh.push_frame_from_lio_async(lio, d_full[k].data_ptr(), d_full[k].shape[0], on_device=True)
         k += 1
+    host_enqueue_ms = (time.perf_counter() - t_enq) * 1e3 / K   # host time to queue one scan (launch-bound check)
     total_ms = api.pipeline_mark_end(lio, mesh)
     lio.wait()
     mesh.wait()
@@ -298,6 +300,7 @@ def run_gpu(args, rank, world):
                    "l2_flush_ms_per_scan": round(flush_ms, 4),
                    "pipeline": "localization(k+1) overlaps meshing(k) on two CUDA streams (as the reference's LIO thread || mesh threads)",
                    "serial_ms_per_scan_blocking": round(float(np.mean(dev_ms)), 4),
+                   "host_enqueue_ms_per_scan": round(host_enqueue_ms, 4),
                    "parallelism": f"{world} independent streams (replicas)" if args.independent_streams else ("single GPU" if world == 1 else f"one stream, VoxelMap sharded by root-voxel key over {world} GPUs (2 NCCL all-reduces per IESKF iteration), mesher replicated"),
                    "map_warm_scans": MAP_WARM},
         "e2e": {"value": round(scans_done / e2e_s, 3), "unit": "scans/s", "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),

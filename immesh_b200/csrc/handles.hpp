@@ -4,6 +4,7 @@
 
 #include <vector>
 
+#include "common_host.hpp"
 #include "lio_core.cuh"
 #include "mesh_voxel.cuh"
 
@@ -37,6 +38,8 @@ struct immesh_lio {
     int max_nodes = 0, max_chunks = 0, max_scan = 0;
     int n_sm = 148;
     int last_n = 0;
+    immesh::GraphCtx graph;   // replay of the per-scan launch sequence (pipelined API)
+    int use_graph = 1;
     int fused_solve = 0;  // 1: the last residual block of an iteration runs the solve (no separate launch)
     double last_ms[3] = {0, 0, 0};
     std::vector<void*> allocs;
@@ -66,7 +69,8 @@ struct immesh_mesh {
     int* d_snap_flip = nullptr;
     int* d_snap_n = nullptr;
     int max_frame_points = 0;
-    int fused_threads = 256;   // block size of the per-voxel fused kernel
+    immesh::GraphCtx graph;   // replay of the per-frame launch sequence (pipelined API)
+    int use_graph = 1;
     int frame_counter = 0;
     int n_sm = 148;
     size_t ccap = 0;

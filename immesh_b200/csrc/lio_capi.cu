@@ -425,6 +425,7 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return im_fail(IMMESH_E_NO_DEVICE, "no CUDA device: immesh_b200 has no CPU path");
     immesh_lio* h = new immesh_lio();
     fill_params(cfg, h->P);
+    h->use_graph = std::getenv("IMMESH_GRAPH") ? std::atoi(std::getenv("IMMESH_GRAPH")) : 1;
     h->fused_solve = std::getenv("IMMESH_FUSED_SOLVE") ? std::atoi(std::getenv("IMMESH_FUSED_SOLVE")) : 0;
     const int caplog = cfg->hash_capacity_log2 ? cfg->hash_capacity_log2 : 22;
     h->cap = (size_t)1 << caplog;
@@ -434,9 +435,9 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
-    IM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    IM_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, im_stream_priority("IMMESH_LIO_PRIO")));
     for (auto& e : h->ev) IM_CUDA(cudaEventCreate(&e));
-    IM_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    IM_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, im_stream_priority("IMMESH_LIO_PRIO")));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) IM_CUDA(cudaEventCreateWithFlags(&h->ev_slot[i], cudaEventDisableTiming));
@@ -493,6 +494,7 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
 int immesh_lio_destroy(immesh_lio_t* h) {
     if (!h) return IMMESH_OK;
     cudaStreamSynchronize(h->stream);
+    h->graph.destroy();
     if (h->nccl_comm && nccl().CommDestroy) nccl().CommDestroy(h->nccl_comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_body) cudaFreeHost(h->h_body);
@@ -604,23 +606,23 @@ static int launch_estimate_sharded(immesh_lio* h, int n) {
 }
 static void launch_estimate(immesh_lio* h, int n) {
     if (h->P.shard_n > 1) { launch_estimate_sharded(h, n); return; }
+    const bool replay = immesh::im_replaying();   // graph replay: the fork/join edges are already part of the graph
     if (n > 0) {  // P^-1 on the side stream, overlapped with the scan preparation and the first residual pass
-        cudaEventRecord(h->ev_fork, h->stream);
-        cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+        if (!replay) { cudaEventRecord(h->ev_fork, h->stream); cudaStreamWaitEvent(h->stream2, h->ev_fork, 0); }
         IM_LAUNCH(k_pinv, 1, 32, 0, h->stream2, h->d_ctrl);
-        cudaEventRecord(h->ev_join, h->stream2);
+        if (!replay) cudaEventRecord(h->ev_join, h->stream2);
     }
     IM_LAUNCH(k_reset_scan, 2, 256, 0, h->stream, h->sb, h->d_ctrl, 1);
     if (n <= 0) return;
     IM_LAUNCH(k_prepare, grid_for(h, n, 128), 128, 0, h->stream, h->P, h->sb, n);
     const int g = grid_for(h, n, RES_THREADS, 4);
     for (int it = 0; it < h->P.max_iter; ++it) {
-        if (it == 0 && h->fused_solve) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+        if (it == 0 && h->fused_solve && !replay) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
         if (h->fused_solve) {
             IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n, 1);
         } else {
             IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n, 0);
-            if (it == 0) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+            if (it == 0 && !replay) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
             IM_LAUNCH(k_solve_warp, 1, 128, 0, h->stream, h->P, h->d_ctrl, it);
         }
     }
@@ -668,18 +670,32 @@ static int lio_flags_status(int err) {
     return IMMESH_OK;
 }
 // queue predict + estimate + update for one scan; no host synchronisation unless both staging slots are busy
-static int lio_enqueue(immesh_lio_t* h, const float* body, int n, int on_device, double dt, double cov_gyr, double cov_acc) {
+static int lio_enqueue(immesh_lio_t* h, const float* body, int n, int on_device, double dt, double cov_gyr, double cov_acc, bool allow_graph) {
     if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
     const int s = (++h->step_counter) & 1;
     if (h->slot_busy[s]) { IM_CUDA(cudaEventSynchronize(h->ev_slot[s])); h->slot_busy[s] = 0; }
-    IM_CUDA(cudaEventRecord(h->ev[0], h->stream));
     int rc = upload_scan(h, body, n, on_device, s);
     if (rc) return rc;
-    if (dt > 0) IM_LAUNCH(k_predict, 1, SOLVE_THREADS, 0, h->stream, h->d_ctrl, dt, cov_gyr, cov_acc);
-    IM_CUDA(cudaEventRecord(h->ev[1], h->stream));
-    launch_estimate(h, n);
-    IM_CUDA(cudaEventRecord(h->ev[2], h->stream));
-    launch_grow(h, n, 0);
+    // The pipelined entry points replay the scan's launch sequence as one CUDA graph (the sequence is host-launch-bound
+    // otherwise); the blocking ones launch directly, with stage timing events in between.
+    bool queued = false;
+    if (allow_graph && h->use_graph && !profiler().enabled && h->P.shard_n == 1 && n > 0) {
+        const unsigned sig = 1u | (dt > 0 ? 2u : 0u) | (h->fused_solve ? 4u : 0u) | ((unsigned)h->P.max_iter << 8);
+        queued = immesh::run_graphed(h->graph, sig, h->stream, [&] {
+            if (dt > 0) IM_LAUNCH(k_predict, 1, SOLVE_THREADS, 0, h->stream, h->d_ctrl, dt, cov_gyr, cov_acc);
+            launch_estimate(h, n);
+            launch_grow(h, n, 0);
+        }) == cudaSuccess;
+        if (!queued) h->use_graph = 0;   // not expected; keep working through direct launches
+    }
+    if (!queued) {
+        IM_CUDA(cudaEventRecord(h->ev[0], h->stream));
+        if (dt > 0) IM_LAUNCH(k_predict, 1, SOLVE_THREADS, 0, h->stream, h->d_ctrl, dt, cov_gyr, cov_acc);
+        IM_CUDA(cudaEventRecord(h->ev[1], h->stream));
+        launch_estimate(h, n);
+        IM_CUDA(cudaEventRecord(h->ev[2], h->stream));
+        launch_grow(h, n, 0);
+    }
     IM_CUDA(cudaGetLastError());
     double* hs = h->h_state + (size_t)s * (IM_STATE_DOUBLES + 64);
     IM_CUDA(cudaMemcpyAsync(hs, h->d_ctrl->state, IM_STATE_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -710,15 +726,15 @@ static int lio_wait_impl(immesh_lio_t* h, double* state_out, int* iters_run, boo
 }
 
 int immesh_lio_step(immesh_lio_t* h, const float* body, int n, double dt, double cov_gyr, double cov_acc, double* state_out, int* iters_run) {
-    int rc = lio_enqueue(h, body, n, 0, dt, cov_gyr, cov_acc);
+    int rc = lio_enqueue(h, body, n, 0, dt, cov_gyr, cov_acc, false);
     return rc ? rc : lio_wait_impl(h, state_out, iters_run, true);
 }
 int immesh_lio_step_dev(immesh_lio_t* h, const float* d_body, int n, double dt, double cov_gyr, double cov_acc, double* state_out, int* iters_run) {
-    int rc = lio_enqueue(h, d_body, n, 1, dt, cov_gyr, cov_acc);
+    int rc = lio_enqueue(h, d_body, n, 1, dt, cov_gyr, cov_acc, false);
     return rc ? rc : lio_wait_impl(h, state_out, iters_run, true);
 }
 int immesh_lio_step_async(immesh_lio_t* h, const float* body, int n, int on_device, double dt, double cov_gyr, double cov_acc) {
-    return lio_enqueue(h, body, n, on_device, dt, cov_gyr, cov_acc);
+    return lio_enqueue(h, body, n, on_device, dt, cov_gyr, cov_acc, true);
 }
 int immesh_lio_wait(immesh_lio_t* h, double* state_out, int* iters_run) { return lio_wait_impl(h, state_out, iters_run, false); }
 // queue a write of `bytes` bytes over a caller-provided device buffer on the localization stream (benchmark L2 flush)

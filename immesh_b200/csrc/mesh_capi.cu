@@ -291,8 +291,7 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return im_fail(IMMESH_E_NO_DEVICE, "no CUDA device: immesh_b200 has no CPU path");
     immesh_mesh* h = new immesh_mesh();
-    h->fused_threads = std::getenv("IMMESH_FUSED_THREADS") ? std::atoi(std::getenv("IMMESH_FUSED_THREADS")) : 256;
-    if (h->fused_threads != 128 && h->fused_threads != 256) h->fused_threads = 256;
+    h->use_graph = std::getenv("IMMESH_GRAPH") ? std::atoi(std::getenv("IMMESH_GRAPH")) : 1;
     MeshParams& P = h->P;
     P.xi = cfg->points_minimum_scale;
     P.res = cfg->voxel_resolution;
@@ -307,7 +306,7 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
-    IM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    IM_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
     for (auto& e : h->ev) IM_CUDA(cudaEventCreate(&e));
     MeshDev& M = h->M;
     M.max_v = max_v;
@@ -392,8 +391,8 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<1024>)));
     IM_CUDA(cudaFuncSetAttribute(k_voxel_tri_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(MeshWarpSmem<128>))));
     IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<256>)));
-    IM_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-    IM_CUDA(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+    IM_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
+    IM_CUDA(cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
@@ -406,6 +405,7 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
 int immesh_mesh_destroy(immesh_mesh_t* h) {
     if (!h) return IMMESH_OK;
     cudaStreamSynchronize(h->stream);
+    h->graph.destroy();
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_pts) cudaFreeHost(h->h_pts);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
@@ -469,7 +469,7 @@ static int mesh_harvest(immesh_mesh* h, int s) {
 
 // src_mode: 0 host world points, 1 device world points, 2 host body points + lio state, 3 device body points + lio state.
 // Queues one frame (no host synchronisation except when both staging slots are still busy).
-static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double* pose_t, int src_mode, immesh_lio* lio) {
+static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double* pose_t, int src_mode, immesh_lio* lio, bool allow_graph = false) {
     if (!h || (!xyz && n > 0) || n < 0 || (src_mode < 2 && !pose_t)) return im_fail(IMMESH_E_INVALID, "bad argument");
     if (n > h->max_frame_points) return im_fail(IMMESH_E_CAPACITY, "frame larger than max_frame_points");
     FrameBuf& F = h->F;
@@ -519,43 +519,57 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         IM_CUDA(cudaEventRecord(h->ev_in[s], ls));
         IM_CUDA(cudaStreamWaitEvent(st, h->ev_in[s], 0));
     }
-    IM_LAUNCH(k_frame_begin, mesh_grid(h, (int)std::max(F.cmask, F.fset_mask) + 1, 256), 256, 0, st, h->M, F);
-    IM_CUDA(cudaEventRecord(h->ev[1], st));
-    if (F.m > 0) {
-        const int g = mesh_grid(h, F.m, 128);
-        IM_LAUNCH(k_cand_init, g, 128, 0, st, h->M, P, F);
-        IM_LAUNCH(k_cand_conflicts, g, 128, 0, st, h->M, P, F);
-        IM_LAUNCH(k_cand_resolve, mesh_grid(h, F.m, 128, 16), 128, 0, st, h->M, P, F);
-        IM_LAUNCH(k_cand_scan, 1, 1024, 0, st, h->M, F);
-        IM_LAUNCH(k_cand_commit, g, 128, 0, st, h->M, P, F);
-        IM_LAUNCH(k_cand_place, g, 128, 0, st, h->M, F);
-        IM_LAUNCH(k_voxel_select, mesh_grid(h, F.m, 128), 128, 0, st, h->M, F);
+    // the frame's launch sequence; replayed as one CUDA graph by the pipelined entry points (host-launch-bound otherwise)
+    auto launch_frame = [&](bool timing) {
+        const bool replay = immesh::im_replaying();
+        IM_LAUNCH(k_frame_begin, mesh_grid(h, (int)std::max(F.cmask, F.fset_mask) + 1, 256), 256, 0, st, h->M, F);
+        if (timing) cudaEventRecord(h->ev[1], st);
+        if (F.m > 0) {
+            const int g = mesh_grid(h, F.m, 128);
+            IM_LAUNCH(k_cand_init, g, 128, 0, st, h->M, P, F);
+            IM_LAUNCH(k_cand_conflicts, g, 128, 0, st, h->M, P, F);
+            IM_LAUNCH(k_cand_resolve, mesh_grid(h, F.m, 128, 16), 128, 0, st, h->M, P, F);
+            IM_LAUNCH(k_cand_scan, 1, 1024, 0, st, h->M, F);
+            IM_LAUNCH(k_cand_commit, g, 128, 0, st, h->M, P, F);
+            IM_LAUNCH(k_cand_place, g, 128, 0, st, h->M, F);
+            IM_LAUNCH(k_voxel_select, mesh_grid(h, F.m, 128), 128, 0, st, h->M, F);
+        }
+        if (timing) cudaEventRecord(h->ev[2], st);
+        if (F.m > 0) {
+            IM_LAUNCH(k_voxel_dilate, h->n_sm * 4, 128, 0, st, h->M, P, F);
+            // triangulation: small dilated sets warp-level on the side stream, mid-size ones block-level on the main stream,
+            // concurrently; then the rare large / handed-over ones (monolithic: triangulate + commit in shared memory)
+            if (!replay) {
+                cudaEventRecord(h->ev_fork, st);
+                cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+                cudaStreamWaitEvent(h->stream3, h->ev_fork, 0);
+            }
+            IM_LAUNCH(k_voxel_tri_warp, h->n_sm * 4, 128, 4 * sizeof(MeshWarpSmem<128>), h->stream2, h->M, P, F);
+            if (!replay) cudaEventRecord(h->ev_join, h->stream2);
+            IM_LAUNCH(k_pull_vertices, h->n_sm * 8, 128, 0, h->stream3, h->M, P, F);   // incidence-list walk: only needs the dilation
+            if (!replay) cudaEventRecord(h->ev_join3, h->stream3);
+            IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * 4, 128, sizeof(MeshSmem<256>), st, h->M, P, F, IM_WARP_NMAX, 1);
+            if (!replay) {
+                cudaStreamWaitEvent(st, h->ev_join, 0);
+                cudaStreamWaitEvent(st, h->ev_join3, 0);
+            }
+            IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st, h->M, P, F, 256, 0);
+            IM_LAUNCH(k_commit_faces, h->n_sm * 8, 128, 0, st, h->M, P, F);
+            IM_LAUNCH(k_pull_check, h->n_sm * 8, 128, 0, st, h->M, F);
+        }
+        if (timing) cudaEventRecord(h->ev[3], st);
+        if (F.m > 0) {
+            IM_LAUNCH(k_push_remove, h->n_sm * 2, 128, 0, st, h->M, F);
+            IM_LAUNCH(k_push_add, h->n_sm * 2, 128, 0, st, h->M, F);
+        }
+        IM_LAUNCH(k_frame_end, 1, 1, 0, st, h->M);
+    };
+    bool queued = false;
+    if (allow_graph && h->use_graph && !profiler().enabled && F.m > 0) {
+        queued = immesh::run_graphed(h->graph, 1u, st, [&] { launch_frame(false); }) == cudaSuccess;
+        if (!queued) h->use_graph = 0;
     }
-    IM_CUDA(cudaEventRecord(h->ev[2], st));
-    if (F.m > 0) {
-        IM_LAUNCH(k_voxel_dilate, h->n_sm * 4, 128, 0, st, h->M, P, F);
-        // triangulation: small dilated sets warp-level on the side stream, mid-size ones block-level on the main stream,
-        // concurrently; then the rare large / handed-over ones (monolithic: triangulate + commit in shared memory)
-        IM_CUDA(cudaEventRecord(h->ev_fork, st));
-        IM_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
-        IM_CUDA(cudaStreamWaitEvent(h->stream3, h->ev_fork, 0));
-        IM_LAUNCH(k_voxel_tri_warp, h->n_sm * 4, 128, 4 * sizeof(MeshWarpSmem<128>), h->stream2, h->M, P, F);
-        IM_CUDA(cudaEventRecord(h->ev_join, h->stream2));
-        IM_LAUNCH(k_pull_vertices, h->n_sm * 8, 128, 0, h->stream3, h->M, P, F);   // incidence-list walk: only needs the dilation
-        IM_CUDA(cudaEventRecord(h->ev_join3, h->stream3));
-        IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * 4, 128, sizeof(MeshSmem<256>), st, h->M, P, F, IM_WARP_NMAX, 1);
-        IM_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
-        IM_CUDA(cudaStreamWaitEvent(st, h->ev_join3, 0));
-        IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st, h->M, P, F, 256, 0);
-        IM_LAUNCH(k_commit_faces, h->n_sm * 8, 128, 0, st, h->M, P, F);
-        IM_LAUNCH(k_pull_check, h->n_sm * 8, 128, 0, st, h->M, F);
-    }
-    IM_CUDA(cudaEventRecord(h->ev[3], st));
-    if (F.m > 0) {
-        IM_LAUNCH(k_push_remove, h->n_sm * 2, 128, 0, st, h->M, F);
-        IM_LAUNCH(k_push_add, h->n_sm * 2, 128, 0, st, h->M, F);
-    }
-    IM_LAUNCH(k_frame_end, 1, 1, 0, st, h->M);
+    if (!queued) launch_frame(true);
     IM_CUDA(cudaGetLastError());
     IM_CUDA(cudaMemcpyAsync(h->h_cnt + 32 * s, h->M.cnt, 32 * sizeof(int), cudaMemcpyDeviceToHost, st));
     IM_CUDA(cudaEventRecord(h->ev[4], st));
@@ -602,7 +616,7 @@ int immesh_mesh_push_frame_from_lio(immesh_mesh_t* h, immesh_lio_t* lio, const f
 }
 int immesh_mesh_push_frame_from_lio_async(immesh_mesh_t* h, immesh_lio_t* lio, const float* body_xyz, int n, int on_device) {
     if (!lio) return im_fail(IMMESH_E_INVALID, "null lio handle");
-    return mesh_enqueue(h, body_xyz, n, nullptr, on_device ? 3 : 2, lio);
+    return mesh_enqueue(h, body_xyz, n, nullptr, on_device ? 3 : 2, lio, true);
 }
 // device-side timing of a pipelined batch: begin mark on the localization stream, end mark behind BOTH streams
 int immesh_pipeline_mark_begin(immesh_lio_t* lio) {
