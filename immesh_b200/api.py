@@ -110,7 +110,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_profile_enable", [C.c_int]),
         ("immesh_profile_reset", []),
         ("immesh_profile_report", [C.c_char_p, C.c_int]),
+        ("immesh_profile_timeline", [C.c_char_p, C.c_int]),
         ("immesh_launch_count", []),
+        ("immesh_graph_stats", [vp, vp, C.POINTER(C.c_int64)]),
         ("immesh_lio_last_timing", [vp, dp]),
         ("immesh_mesh_create", [C.POINTER(_MeshCfg), C.POINTER(vp)]),
         ("immesh_mesh_destroy", [vp]),
@@ -389,7 +391,7 @@ class Mesh:
 
 def profile_enable(on: bool, lib: Optional[C.CDLL] = None):
     lib = lib or load_library()
-    lib.immesh_profile_enable(1 if on else 0)
+    lib.immesh_profile_enable(int(on))   # 0 off, 1 per-kernel totals, 2 totals + launch timeline
 
 
 def profile_reset(lib: Optional[C.CDLL] = None):
@@ -409,8 +411,30 @@ def profile_report(lib: Optional[C.CDLL] = None) -> dict:
     return out
 
 
+def profile_timeline(lib: Optional[C.CDLL] = None):
+    """[(kernel, t0_ms, t1_ms)] of every launch since profile_enable(2)."""
+    lib = lib or load_library()
+    need = lib.immesh_profile_timeline(None, 0)
+    buf = C.create_string_buffer(need + 16)
+    lib.immesh_profile_timeline(buf, need + 16)
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, t0, t1 = line.rsplit(" ", 2)
+        out.append((name.strip("()"), float(t0), float(t1)))
+    return out
+
+
 def launch_count(lib: Optional[C.CDLL] = None) -> int:
     return int((lib or load_library()).immesh_launch_count())
+
+
+def graph_stats(lio: Optional["Lio"], mesh: Optional["Mesh"]) -> dict:
+    """CUDA-graph replay accounting of the pipelined entry points."""
+    lib = (lio or mesh).lib
+    out = (C.c_int64 * 6)()
+    _check(lib, lib.immesh_graph_stats(lio._h if lio else None, mesh._h if mesh else None, out), "graph_stats")
+    keys = ("lio_captures", "lio_replays", "lio_failures", "mesh_captures", "mesh_replays", "mesh_failures")
+    return dict(zip(keys, [int(v) for v in out]))
 
 
 def pipeline_mark_begin(lio: Lio):

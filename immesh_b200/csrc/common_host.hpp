@@ -48,18 +48,40 @@ struct Profiler {
         pending.push_back(r);
     }
     void end(cudaStream_t st) { cudaEventRecord(pending.back().b, st); }
-    void collect() {  // call after the stream has been synchronised
+    // optional timeline: start/end of every launch relative to a base event (diagnosis of the two-stream pipeline)
+    bool timeline_on = false;
+    cudaEvent_t base = nullptr;
+    struct Span { const char* name; float t0, t1; };
+    std::vector<Span> timeline;
+    void start_timeline() {
+        if (!base) cudaEventCreate(&base);
+        cudaDeviceSynchronize();
+        cudaEventRecord(base, 0);
+        cudaEventSynchronize(base);
+        timeline.clear();
+        timeline_on = true;
+    }
+    void collect() {  // harvests every launch whose end event has completed; the others stay pending
+        std::vector<Rec> keep;
         for (Rec& r : pending) {
+            if (cudaEventQuery(r.b) == cudaErrorNotReady) { keep.push_back(r); continue; }
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
                 auto& t = totals[r.name];
                 t.first += ms;
                 t.second += 1;
+                if (timeline_on) {
+                    Span sp{r.name, 0.f, 0.f};
+                    cudaEventElapsedTime(&sp.t0, base, r.a);
+                    cudaEventElapsedTime(&sp.t1, base, r.b);
+                    timeline.push_back(sp);
+                }
             }
             pool.push_back(r.a);
             pool.push_back(r.b);
         }
-        pending.clear();
+        pending.swap(keep);
+        cudaGetLastError();
     }
 };
 Profiler& profiler();  // defined in misc_capi.cu
@@ -84,6 +106,7 @@ struct GraphCtx {
     size_t cursor = 0;
     unsigned sig = 0;                  // control-flow signature the graph was captured with
     cudaError_t err = cudaSuccess;
+    long long captures = 0, replays = 0, failures = 0;
     void destroy() {
         if (exec) cudaGraphExecDestroy(exec);
         if (graph) cudaGraphDestroy(graph);
@@ -147,15 +170,17 @@ inline cudaError_t run_graphed(GraphCtx& g, unsigned sig, cudaStream_t st, Body&
             e = cudaStreamEndCapture(st, &g.graph);
             if (e == cudaSuccess && g.err != cudaSuccess) e = g.err;
             if (e == cudaSuccess) e = cudaGraphInstantiate(&g.exec, g.graph, 0);
-            if (e != cudaSuccess) { g.destroy(); cudaGetLastError(); return e; }
+            if (e != cudaSuccess) { g.destroy(); cudaGetLastError(); g.failures++; return e; }
             g.sig = sig;
+            g.captures++;
         } else {
             g.mode = 2;
             g.cursor = 0;
             body();
             g.mode = 0;
             graph_ctx() = nullptr;
-            if (g.err != cudaSuccess || g.cursor != g.nodes.size()) { g.destroy(); cudaGetLastError(); continue; }  // re-capture
+            if (g.err != cudaSuccess || g.cursor != g.nodes.size()) { g.destroy(); cudaGetLastError(); g.failures++; continue; }  // re-capture
+            g.replays++;
         }
         return cudaGraphLaunch(g.exec, st);
     }

@@ -40,6 +40,7 @@ struct immesh_lio {
     int last_n = 0;
     immesh::GraphCtx graph;   // replay of the per-scan launch sequence (pipelined API)
     int use_graph = 1;
+    int bps = 4;              // (mesh: 3 by default, see immesh_mesh_create) resident blocks per SM of the persistent per-voxel kernels (headroom for the other stream)
     int fused_solve = 0;  // 1: the last residual block of an iteration runs the solve (no separate launch)
     double last_ms[3] = {0, 0, 0};
     std::vector<void*> allocs;
@@ -71,6 +72,7 @@ struct immesh_mesh {
     int max_frame_points = 0;
     immesh::GraphCtx graph;   // replay of the per-frame launch sequence (pipelined API)
     int use_graph = 1;
+    int bps = 4;              // (mesh: 3 by default, see immesh_mesh_create) resident blocks per SM of the persistent per-voxel kernels (headroom for the other stream)
     int frame_counter = 0;
     int n_sm = 148;
     size_t ccap = 0;

@@ -425,6 +425,7 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return im_fail(IMMESH_E_NO_DEVICE, "no CUDA device: immesh_b200 has no CPU path");
     immesh_lio* h = new immesh_lio();
     fill_params(cfg, h->P);
+    h->bps = std::getenv("IMMESH_LIO_BPS") ? std::atoi(std::getenv("IMMESH_LIO_BPS")) : 4;
     h->use_graph = std::getenv("IMMESH_GRAPH") ? std::atoi(std::getenv("IMMESH_GRAPH")) : 1;
     h->fused_solve = std::getenv("IMMESH_FUSED_SOLVE") ? std::atoi(std::getenv("IMMESH_FUSED_SOLVE")) : 0;
     const int caplog = cfg->hash_capacity_log2 ? cfg->hash_capacity_log2 : 22;
@@ -580,7 +581,7 @@ static void launch_grow(immesh_lio* h, int n, int mode) {
     IM_LAUNCH(k_grow_point, grid_for(h, n, 128), 128, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, n, mode);
     IM_LAUNCH(k_grow_segment, grid_for(h, n, 128, 2), 128, 0, h->stream, h->sb);
     IM_LAUNCH(k_grow_scatter, grid_for(h, n, 128), 128, 0, h->stream, h->sb, n);
-    IM_LAUNCH(k_grow_voxel, h->n_sm * 4, 128, 0, h->stream, h->map, h->P, h->sb, mode, h->d_sorted, h->d_counters + 8);
+    IM_LAUNCH(k_grow_voxel, h->n_sm * h->bps, 128, 0, h->stream, h->map, h->P, h->sb, mode, h->d_sorted, h->d_counters + 8);
     IM_LAUNCH(k_grow_finish, 1, 256, 0, h->stream, h->map, h->sb, h->d_counters + 8);
 }
 // sharded VoxelMap: per iteration  pass1 -> all-reduce(bit words) -> pass2 -> all-reduce(58 int64 sums) -> solve (every rank)
@@ -679,7 +680,7 @@ static int lio_enqueue(immesh_lio_t* h, const float* body, int n, int on_device,
     // The pipelined entry points replay the scan's launch sequence as one CUDA graph (the sequence is host-launch-bound
     // otherwise); the blocking ones launch directly, with stage timing events in between.
     bool queued = false;
-    if (allow_graph && h->use_graph && !profiler().enabled && h->P.shard_n == 1 && n > 0) {
+    if (allow_graph && h->use_graph && !profiler().enabled && h->P.shard_n <= 1 && n > 0) {
         const unsigned sig = 1u | (dt > 0 ? 2u : 0u) | (h->fused_solve ? 4u : 0u) | ((unsigned)h->P.max_iter << 8);
         queued = immesh::run_graphed(h->graph, sig, h->stream, [&] {
             if (dt > 0) IM_LAUNCH(k_predict, 1, SOLVE_THREADS, 0, h->stream, h->d_ctrl, dt, cov_gyr, cov_acc);

@@ -291,6 +291,7 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return im_fail(IMMESH_E_NO_DEVICE, "no CUDA device: immesh_b200 has no CPU path");
     immesh_mesh* h = new immesh_mesh();
+    h->bps = std::getenv("IMMESH_MESH_BPS") ? std::atoi(std::getenv("IMMESH_MESH_BPS")) : 3;
     h->use_graph = std::getenv("IMMESH_GRAPH") ? std::atoi(std::getenv("IMMESH_GRAPH")) : 1;
     MeshParams& P = h->P;
     P.xi = cfg->points_minimum_scale;
@@ -536,7 +537,7 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         }
         if (timing) cudaEventRecord(h->ev[2], st);
         if (F.m > 0) {
-            IM_LAUNCH(k_voxel_dilate, h->n_sm * 4, 128, 0, st, h->M, P, F);
+            IM_LAUNCH(k_voxel_dilate, h->n_sm * h->bps, 128, 0, st, h->M, P, F);
             // triangulation: small dilated sets warp-level on the side stream, mid-size ones block-level on the main stream,
             // concurrently; then the rare large / handed-over ones (monolithic: triangulate + commit in shared memory)
             if (!replay) {
@@ -544,11 +545,11 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
                 cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
                 cudaStreamWaitEvent(h->stream3, h->ev_fork, 0);
             }
-            IM_LAUNCH(k_voxel_tri_warp, h->n_sm * 4, 128, 4 * sizeof(MeshWarpSmem<128>), h->stream2, h->M, P, F);
+            IM_LAUNCH(k_voxel_tri_warp, h->n_sm * h->bps, 128, 4 * sizeof(MeshWarpSmem<128>), h->stream2, h->M, P, F);
             if (!replay) cudaEventRecord(h->ev_join, h->stream2);
             IM_LAUNCH(k_pull_vertices, h->n_sm * 8, 128, 0, h->stream3, h->M, P, F);   // incidence-list walk: only needs the dilation
             if (!replay) cudaEventRecord(h->ev_join3, h->stream3);
-            IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * 4, 128, sizeof(MeshSmem<256>), st, h->M, P, F, IM_WARP_NMAX, 1);
+            IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * h->bps, 128, sizeof(MeshSmem<256>), st, h->M, P, F, IM_WARP_NMAX, 1);
             if (!replay) {
                 cudaStreamWaitEvent(st, h->ev_join, 0);
                 cudaStreamWaitEvent(st, h->ev_join3, 0);
@@ -635,6 +636,13 @@ int immesh_pipeline_mark_end(immesh_lio_t* lio, immesh_mesh_t* h, double* ms) {
     float t = 0.f;
     IM_CUDA(cudaEventElapsedTime(&t, lio->ev_mark, h->ev_mark));
     *ms = t;
+    return IMMESH_OK;
+}
+int immesh_graph_stats(immesh_lio_t* lio, immesh_mesh_t* mesh, int64_t* out) {
+    if (!out) return im_fail(IMMESH_E_INVALID, "null argument");
+    for (int i = 0; i < 6; ++i) out[i] = 0;
+    if (lio) { out[0] = lio->graph.captures; out[1] = lio->graph.replays; out[2] = lio->graph.failures; }
+    if (mesh) { out[3] = mesh->graph.captures; out[4] = mesh->graph.replays; out[5] = mesh->graph.failures; }
     return IMMESH_OK;
 }
 int immesh_mesh_wait(immesh_mesh_t* h) {

@@ -738,20 +738,40 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
         if (p == i1 || p == i2) continue;
         const int nt = S->ntri;
         const float pxf = (float)Pt[p].x, pyf = (float)Pt[p].y;
-        int nc = 0;
+        // (1a) cheap pass over the whole pool: live triangles whose cached circumcircle does not exclude p (ghosts always
+        // qualify) are compacted into a short list; (1b) the exact predicates then run on that list only, all lanes busy
+        int nm = 0;
+        int* s_may = s_ea;   // [<= 192] reused: the edge arrays are filled after the scan
         for (int t0 = 0; t0 < nt; t0 += nlanes) {
             const int t = t0 + lane;
-            bool c = false;
+            bool maybe = false;
             if (t < nt) {
                 const DTri tr = tris[t];
                 if (tr.alive) {
-                    bool maybe = true;
+                    maybe = true;
                     if (tr.v[0] != IM_GHOST && tr.v[1] != IM_GHOST && tr.v[2] != IM_GHOST) {
                         const float dx = pxf - S->circ[t][0], dy = pyf - S->circ[t][1];
                         if (dx * dx + dy * dy > S->circ[t][2]) maybe = false;   // certainly outside the circumcircle
                     }
-                    if (maybe) c = dt_conflict(tr, Pt, p);
                 }
+            }
+            const unsigned m = im_ballot(maybe);
+            if (maybe) {
+                const int k = nm + im_popc(m & lt);
+                if (k < 192) s_may[k] = t;
+            }
+            nm += im_popc(m);
+        }
+        if (nm > 192) { ovf = true; break; }   // warp-uniform
+        IM_SYNCWARP();
+        int nc = 0;
+        for (int j0 = 0; j0 < nm; j0 += nlanes) {
+            const int j = j0 + lane;
+            bool c = false;
+            int t = 0;
+            if (j < nm) {
+                t = s_may[j];
+                c = dt_conflict(tris[t], Pt, p);
             }
             const unsigned m = im_ballot(c);
             if (c) {

@@ -16,6 +16,8 @@ const char* immesh_version(void) { return "immesh_b200 0.1.0 (sm_100a)"; }
 
 int immesh_profile_enable(int on) {
     immesh::profiler().enabled = on != 0;
+    if (on == 2) immesh::profiler().start_timeline();   // also record every launch's start / end time
+    else immesh::profiler().timeline_on = false;
     return IMMESH_OK;
 }
 int immesh_profile_reset(void) {
@@ -24,6 +26,20 @@ int immesh_profile_reset(void) {
     return IMMESH_OK;
 }
 long long immesh_launch_count(void) { return immesh::profiler().launches; }
+// "name t0_ms t1_ms\n" per launch recorded since immesh_profile_enable(2); returns the number of bytes needed
+int immesh_profile_timeline(char* buf, int cap) {
+    std::string s;
+    for (auto& sp : immesh::profiler().timeline) {
+        char line[256];
+        std::snprintf(line, sizeof(line), "%s %.6f %.6f\n", sp.name, sp.t0, sp.t1);
+        s += line;
+    }
+    if (buf && cap > 0) {
+        std::strncpy(buf, s.c_str(), (size_t)cap - 1);
+        buf[cap - 1] = 0;
+    }
+    return (int)s.size() + 1;
+}
 // writes "name ms launches\n" lines into buf; returns the number of bytes needed
 int immesh_profile_report(char* buf, int cap) {
     std::string s;

@@ -174,10 +174,14 @@ int immesh_mesh_work_stats(immesh_mesh_t* h, int64_t* out /*[8]*/);
 int immesh_mesh_last_timing(immesh_mesh_t* h, double* ms /*[4]: whole frame incl. H2D, append, per-voxel, push*/);
 
 /* optional per-kernel CUDA-event profiler (off by default) and launch accounting, process-wide */
-int immesh_profile_enable(int on);
+int immesh_profile_enable(int on);   /* 0 off, 1 per-kernel totals, 2 totals + timeline */
+int immesh_profile_timeline(char* buf, int cap); /* "kernel t0_ms t1_ms\n" per launch; returns bytes needed */
 int immesh_profile_reset(void);
 int immesh_profile_report(char* buf, int cap); /* "kernel ms launches\n" lines; returns bytes needed */
 long long immesh_launch_count(void);
+/* CUDA-graph replay accounting of the pipelined entry points: [lio captures, lio replays, lio failures, mesh captures,
+ * mesh replays, mesh failures]; either handle may be NULL */
+int immesh_graph_stats(immesh_lio_t* lio, immesh_mesh_t* mesh, int64_t* out /*[6]*/);
 
 const char* immesh_last_error(void);
 const char* immesh_version(void);
