@@ -166,9 +166,10 @@ def run_gpu(args, rank, world):
     lio = api.Lio(cfg, lib=lib)
     mesh = api.Mesh(api.MeshConfig(), lib=lib)
     if world > 1 and not args.independent_streams:
-        uid = [api.comm_unique_id(lib) if rank == 0 else None]
+        uid = [api.comm_unique_id(lib) if rank == 0 else None, api.comm_unique_id(lib) if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         lio.shard(rank, world, uid[0])
+        mesh.shard(rank, world, uid[1])
     lio.set_state(init_state_vec(scans))
     lio.voxel_map_init(scans[0]["body_full"])
     dev = torch.device("cuda", local_rank)

@@ -99,6 +99,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_lio_match_nodes", [vp, ip, C.c_int]),
         ("immesh_comm_unique_id", [C.c_char_p]),
         ("immesh_lio_shard", [vp, C.c_int, C.c_int, C.c_char_p]),
+        ("immesh_mesh_shard", [vp, C.c_int, C.c_int, C.c_char_p]),
         ("immesh_lio_step_async", [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
         ("immesh_lio_wait", [vp, dp, ip]),
         ("immesh_lio_enqueue_memset", [vp, vp, C.c_size_t]),
@@ -359,6 +360,10 @@ class Mesh:
         _check(self.lib, self.lib.immesh_mesh_counts(self._h, o.ctypes.data_as(C.POINTER(C.c_int64))), "mesh_counts")
         keys = ["n_vertices", "n_triangles", "frame_new_vertices", "frame_voxels_meshed", "frame_added", "frame_removed", "n_voxels", "n_activated"]
         return dict(zip(keys, (int(v) for v in o)))
+
+    def shard(self, rank: int, nranks: int, unique_id: bytes):
+        """Shard the per-voxel meshing stage over nranks processes (NCCL, own communicator: pass a second unique id)."""
+        _check(self.lib, self.lib.immesh_mesh_shard(self._h, rank, nranks, unique_id), "mesh_shard")
 
     def work_stats(self):
         o = np.zeros(8, dtype=np.int64)

@@ -66,6 +66,9 @@ struct immesh_mesh {
     cudaStream_t stream3 = nullptr;   // side stream: pull (incidence-list walk), concurrent with the triangulation
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
     int pending_rc = 0;
+    void* nccl_comm = nullptr;        // ncclComm_t when the per-voxel stage is sharded over several GPUs
+    unsigned char *d_seg1 = nullptr, *d_seg2 = nullptr, *d_recv1 = nullptr, *d_recv2 = nullptr;   // exchange segments
+    size_t seg1_bytes = 0, seg2_bytes = 0;
     int* d_snap_tri = nullptr;
     int* d_snap_flip = nullptr;
     int* d_snap_n = nullptr;

@@ -12,6 +12,7 @@
 #include "../../include/immesh_b200.h"
 #include "common_host.hpp"
 #include "handles.hpp"
+#include "nccl_api.hpp"
 
 using namespace immesh;
 
@@ -25,6 +26,7 @@ __global__ void k_frame_begin(MeshDev M, FrameBuf F) {
         for (int k = 17; k <= 26; ++k) M.cnt[k] = 0;
         M.cnt[28] = 0;
         M.cnt[29] = 0;
+        M.cnt[30] = 0; M.cnt[31] = 0; M.cnt[32] = 0;
     }
 }
 __global__ void __launch_bounds__(128) k_cand_init(MeshDev M, MeshParams P, FrameBuf F) {
@@ -291,6 +293,7 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return im_fail(IMMESH_E_NO_DEVICE, "no CUDA device: immesh_b200 has no CPU path");
     immesh_mesh* h = new immesh_mesh();
+    h->F.shard_rank = 0; h->F.shard_n = 1; h->F.x_cap = 0;
     h->bps = std::getenv("IMMESH_MESH_BPS") ? std::atoi(std::getenv("IMMESH_MESH_BPS")) : 3;
     h->use_graph = std::getenv("IMMESH_GRAPH") ? std::atoi(std::getenv("IMMESH_GRAPH")) : 1;
     MeshParams& P = h->P;
@@ -336,7 +339,7 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     const size_t tcap = pow2_at_least((size_t)max_t * 2);
     IM_CUDA(mdev_alloc(h, &M.thash, tcap, 0xFF));
     M.tmask = (unsigned)(tcap - 1);
-    IM_CUDA(mdev_alloc(h, &M.cnt, 32, 0));
+    IM_CUDA(mdev_alloc(h, &M.cnt, 64, 0));
     {
         int init[32];
         std::memset(init, 0, sizeof(init));
@@ -407,6 +410,7 @@ int immesh_mesh_destroy(immesh_mesh_t* h) {
     if (!h) return IMMESH_OK;
     cudaStreamSynchronize(h->stream);
     h->graph.destroy();
+    if (h->nccl_comm && immesh::nccl().CommDestroy) immesh::nccl().CommDestroy(h->nccl_comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_pts) cudaFreeHost(h->h_pts);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
@@ -440,6 +444,45 @@ __global__ void __launch_bounds__(128) k_transform_full(LioParams P, const LioCt
         double pw[3];
         body_to_world(P, s, s + 9, pb, pw);
         world[(size_t)i * 3 + 0] = (float)pw[0]; world[(size_t)i * 3 + 1] = (float)pw[1]; world[(size_t)i * 3 + 2] = (float)pw[2];
+    }
+}
+
+// ---- multi-GPU exchange of the per-voxel stage (sharded mesher).  A segment = [16-B header: counts][entries, x_cap each].
+struct XHeader { int n_smooth, n_face, n_rem, pad; };
+__global__ void k_xhdr(MeshDev M, FrameBuf F, XHeader* hdr) {
+    if (threadIdx.x == 0) {
+        hdr->n_smooth = min(M.cnt[32], F.x_cap);
+        hdr->n_face = min(M.cnt[30], F.x_cap);
+        hdr->n_rem = min(M.cnt[31], F.x_cap);
+        hdr->pad = 0;
+    }
+}
+// smoothed positions written by the other ranks' dilations -> this rank's replica
+__global__ void __launch_bounds__(256) k_apply_smooth(MeshDev M, FrameBuf F, const unsigned char* recv, size_t seg_bytes) {
+    for (int r = 0; r < F.shard_n; ++r) {
+        if (r == F.shard_rank) continue;
+        const unsigned char* seg = recv + (size_t)r * seg_bytes;
+        const int n = ((const XHeader*)seg)->n_smooth;
+        const XSmooth* e = (const XSmooth*)(seg + 16);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const XSmooth v = e[i];
+            M.vsmooth[(size_t)v.id * 3 + 0] = v.x; M.vsmooth[(size_t)v.id * 3 + 1] = v.y; M.vsmooth[(size_t)v.id * 3 + 2] = v.z;
+        }
+    }
+}
+// facets / removals of ALL ranks (own segment included) -> add / remove lists of this rank's replica
+__global__ void __launch_bounds__(256) k_apply_lists(MeshDev M, FrameBuf F, const unsigned char* recv, size_t seg_bytes) {
+    for (int r = 0; r < F.shard_n; ++r) {
+        const unsigned char* seg = recv + (size_t)r * seg_bytes;
+        const XHeader* h = (const XHeader*)seg;
+        const int4* face = (const int4*)(seg + 16);
+        const unsigned long long* word = (const unsigned long long*)(seg + 16 + (size_t)F.x_cap * 16);
+        const int4* rem = (const int4*)(seg + 16 + (size_t)F.x_cap * 24);
+        const int nf = h->n_face, nr = h->n_rem;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf + nr; i += gridDim.x * blockDim.x) {
+            if (i < nf) { const int4 f = face[i]; apply_face(M, F, f.x, f.y, f.z, word[i]); }
+            else { const int4 t = rem[i - nf]; apply_remove(M, F, t.x, t.y, t.z); }
+        }
     }
 }
 
@@ -521,6 +564,7 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         IM_CUDA(cudaStreamWaitEvent(st, h->ev_in[s], 0));
     }
     // the frame's launch sequence; replayed as one CUDA graph by the pipelined entry points (host-launch-bound otherwise)
+    bool nccl_failed = false;
     auto launch_frame = [&](bool timing) {
         const bool replay = immesh::im_replaying();
         IM_LAUNCH(k_frame_begin, mesh_grid(h, (int)std::max(F.cmask, F.fset_mask) + 1, 256), 256, 0, st, h->M, F);
@@ -538,6 +582,11 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         if (timing) cudaEventRecord(h->ev[2], st);
         if (F.m > 0) {
             IM_LAUNCH(k_voxel_dilate, h->n_sm * h->bps, 128, 0, st, h->M, P, F);
+            if (F.shard_n > 1) {   // smoothed positions of the other ranks' voxels (the facet orientation reads them)
+                IM_LAUNCH(k_xhdr, 1, 32, 0, st, h->M, F, (XHeader*)h->d_seg1);
+                if (immesh::nccl().AllGather(h->d_seg1, h->d_recv1, h->seg1_bytes, immesh::kNcclUint8, h->nccl_comm, st)) nccl_failed = true;
+                IM_LAUNCH(k_apply_smooth, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv1, h->seg1_bytes);
+            }
             // triangulation: small dilated sets warp-level on the side stream, mid-size ones block-level on the main stream,
             // concurrently; then the rare large / handed-over ones (monolithic: triangulate + commit in shared memory)
             if (!replay) {
@@ -557,6 +606,11 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
             IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st, h->M, P, F, 256, 0);
             IM_LAUNCH(k_commit_faces, h->n_sm * 8, 128, 0, st, h->M, P, F);
             IM_LAUNCH(k_pull_check, h->n_sm * 8, 128, 0, st, h->M, F);
+            if (F.shard_n > 1) {   // every rank applies the facets / removals of all ranks to its replica of the store
+                IM_LAUNCH(k_xhdr, 1, 32, 0, st, h->M, F, (XHeader*)h->d_seg2);
+                if (immesh::nccl().AllGather(h->d_seg2, h->d_recv2, h->seg2_bytes, immesh::kNcclUint8, h->nccl_comm, st)) nccl_failed = true;
+                IM_LAUNCH(k_apply_lists, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv2, h->seg2_bytes);
+            }
         }
         if (timing) cudaEventRecord(h->ev[3], st);
         if (F.m > 0) {
@@ -566,11 +620,12 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         IM_LAUNCH(k_frame_end, 1, 1, 0, st, h->M);
     };
     bool queued = false;
-    if (allow_graph && h->use_graph && !profiler().enabled && F.m > 0) {
+    if (allow_graph && h->use_graph && !profiler().enabled && F.m > 0 && F.shard_n <= 1) {
         queued = immesh::run_graphed(h->graph, 1u, st, [&] { launch_frame(false); }) == cudaSuccess;
         if (!queued) h->use_graph = 0;
     }
     if (!queued) launch_frame(true);
+    if (nccl_failed) return im_fail(IMMESH_E_CUDA, "ncclAllGather failed");
     IM_CUDA(cudaGetLastError());
     IM_CUDA(cudaMemcpyAsync(h->h_cnt + 32 * s, h->M.cnt, 32 * sizeof(int), cudaMemcpyDeviceToHost, st));
     IM_CUDA(cudaEventRecord(h->ev[4], st));
@@ -636,6 +691,35 @@ int immesh_pipeline_mark_end(immesh_lio_t* lio, immesh_mesh_t* h, double* ms) {
     float t = 0.f;
     IM_CUDA(cudaEventElapsedTime(&t, lio->ev_mark, h->ev_mark));
     *ms = t;
+    return IMMESH_OK;
+}
+int immesh_mesh_shard(immesh_mesh_t* h, int rank, int nranks, const char* unique_id128) {
+    if (!h || !unique_id128 || nranks < 1 || rank < 0 || rank >= nranks) return im_fail(IMMESH_E_INVALID, "bad argument");
+    if (nranks == 1) { h->F.shard_rank = 0; h->F.shard_n = 1; return IMMESH_OK; }
+    if (!immesh::nccl().load()) return im_fail(IMMESH_E_CUDA, "libnccl.so.2 not found");
+    immesh::nccl_uid_t id;
+    std::memcpy(id.internal, unique_id128, 128);
+    immesh::nccl_comm_t comm = nullptr;
+    const int rc = immesh::nccl().CommInitRank(&comm, nranks, id, rank);
+    if (rc) return im_fail(IMMESH_E_CUDA, immesh::nccl().GetErrorString ? immesh::nccl().GetErrorString(rc) : "ncclCommInitRank failed");
+    h->nccl_comm = comm;
+    FrameBuf& F = h->F;
+    F.shard_rank = rank;
+    F.shard_n = nranks;
+    F.x_cap = 1 << 16;
+    // segment 1: header + smoothed positions; segment 2: header + facets + words + removals
+    h->seg1_bytes = 16 + (size_t)F.x_cap * sizeof(immesh::XSmooth);
+    h->seg2_bytes = 16 + (size_t)F.x_cap * (16 + 8 + 16);
+    unsigned char *s1 = nullptr, *s2 = nullptr;
+    IM_CUDA(mdev_alloc(h, &s1, h->seg1_bytes, 0));
+    IM_CUDA(mdev_alloc(h, &s2, h->seg2_bytes, 0));
+    IM_CUDA(mdev_alloc(h, &h->d_recv1, h->seg1_bytes * nranks, 0));
+    IM_CUDA(mdev_alloc(h, &h->d_recv2, h->seg2_bytes * nranks, 0));
+    h->d_seg1 = s1; h->d_seg2 = s2;
+    F.x_smooth = (immesh::XSmooth*)(s1 + 16);
+    F.x_face = (int4*)(s2 + 16);
+    F.x_word = (unsigned long long*)(s2 + 16 + (size_t)F.x_cap * 16);
+    F.x_rem = (int4*)(s2 + 16 + (size_t)F.x_cap * 24);
     return IMMESH_OK;
 }
 int immesh_graph_stats(immesh_lio_t* lio, immesh_mesh_t* mesh, int64_t* out) {

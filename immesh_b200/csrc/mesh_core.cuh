@@ -102,6 +102,7 @@ struct FramePose {        // per-frame sensor position (device resident so that 
     double pose_t[3];
     long long prio_origin[3];  // floor(pose_t / res) - 1024: origin of the 11-bit-per-axis voxel rank used by the flip priority
 };
+struct XSmooth { int id, pad; double x, y, z; };   // 32 B
 struct FrameBuf {
     const float* pts;     // [n][3] world-frame scan
     int n, step, m;       // m = number of candidates = ceil(n / step)
@@ -143,6 +144,14 @@ struct FrameBuf {
     unsigned long long* add_flip;
     int* rem_tri;         // [max_list] triangle indices
     int max_cand, max_act, max_work, max_list;
+    // multi-GPU: the per-voxel stage of a frame is sharded by mesh-voxel owner; what a rank produces is recorded in these
+    // exchange lists (all-gathered, then applied by every rank to its replica of the store) instead of being applied
+    int shard_rank, shard_n;
+    int x_cap;            // capacity of each exchange list (entries)
+    XSmooth* x_smooth;    // smoothed positions written by this rank's dilations      (count: cnt[32])
+    int4* x_face;         // new facets (a, b, c, -) of this rank's voxels             (count: cnt[30])
+    unsigned long long* x_word;   // their flip-priority words
+    int4* x_rem;          // triangles (a, b, c, -) this rank's voxels want removed    (count: cnt[31])
 };
 
 // ------------------------------------------------------------------ keys
@@ -431,6 +440,7 @@ IM_HDN inline void voxel_select(const MeshDev& M, const FrameBuf& F, int a) {
     M.vox_meshing_times[vs] += 1;
     M.vox_new_added[vs] = 0;
     if (M.vox_count[vs] < 3) return;
+    if (F.shard_n > 1 && voxel_owner(M.vkeys[vs], F.shard_n) != F.shard_rank) return;   // another rank meshes this voxel
     // two-ended work list: populous voxels (the expensive ones) from the front, the rest from the back, so that the
     // per-voxel stages start the long jobs first (cnt[6] = front count, cnt[17] = back count)
     int w;

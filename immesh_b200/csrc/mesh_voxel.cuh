@@ -39,6 +39,59 @@ IM_HD int im_popc(unsigned m) {
 #endif
 }
 
+// ------------------------------------------------------------------ results of the per-voxel stage
+// One GPU: applied directly.  Sharded (F.shard_n > 1): recorded in the exchange lists; every rank applies the
+// all-gathered lists of all ranks to its replica (apply_*), so the replicas stay set-identical.
+IM_HD void apply_face(const MeshDev& M, const FrameBuf& F, int a, int b, int c, unsigned long long word) {
+    // commit, faces side (triangle_compare): a face already live in the store is "existing" (its flip priority word is
+    // raised), otherwise it goes to the add list
+    const int t = tri_find(M, a, b, c);
+    if (t >= 0 && M.tri[t].w) {
+        im_atomic_max64(&M.tri_flip[t], word);
+    } else {
+        const int e = im_atomic_add(&M.cnt[7], 1);
+        if (e < F.max_list) {
+            F.add_tri[(size_t)e * 3 + 0] = a; F.add_tri[(size_t)e * 3 + 1] = b; F.add_tri[(size_t)e * 3 + 2] = c;
+            F.add_flip[e] = word;
+        } else {
+            im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+        }
+    }
+}
+IM_HD void emit_face(const MeshDev& M, const FrameBuf& F, int a, int b, int c, unsigned long long word) {
+    if (F.shard_n > 1) {
+        const int e = im_atomic_add(&M.cnt[30], 1);
+        if (e < F.x_cap) { F.x_face[e] = make_int4(a, b, c, 0); F.x_word[e] = word; }
+        else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+        return;
+    }
+    apply_face(M, F, a, b, c, word);
+}
+IM_HD void emit_remove(const MeshDev& M, const FrameBuf& F, int t) {
+    if (F.shard_n > 1) {
+        const int4 tr = M.tri[t];
+        const int e = im_atomic_add(&M.cnt[31], 1);
+        if (e < F.x_cap) F.x_rem[e] = make_int4(tr.x, tr.y, tr.z, 0); else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+        return;
+    }
+    const int e = im_atomic_add(&M.cnt[8], 1);
+    if (e < F.max_list) F.rem_tri[e] = t; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+}
+IM_HD void apply_remove(const MeshDev& M, const FrameBuf& F, int a, int b, int c) {
+    const int t = tri_find(M, a, b, c);
+    if (t < 0 || !M.tri[t].w) return;
+    const int e = im_atomic_add(&M.cnt[8], 1);
+    if (e < F.max_list) F.rem_tri[e] = t; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+}
+IM_HD void emit_smooth(const MeshDev& M, const FrameBuf& F, int v, double x, double y, double z) {
+    M.vsmooth[(size_t)v * 3 + 0] = x; M.vsmooth[(size_t)v * 3 + 1] = y; M.vsmooth[(size_t)v * 3 + 2] = z;
+    if (F.shard_n > 1) {
+        const int e = im_atomic_add(&M.cnt[32], 1);
+        if (e < F.x_cap) { XSmooth r; r.id = v; r.pad = 0; r.x = x; r.y = y; r.z = z; F.x_smooth[e] = r; }
+        else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+    }
+}
+
 struct DilateSmem {
     float4 cand[IM_MAXG];      // gathered neighbourhood vertices: xyz + id (bit-cast in w)
     unsigned char flag[IM_MAXG];  // member of the dilated set (byte stores of 1 only, so concurrent warps do not race)
@@ -289,9 +342,9 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
                     if (lane < have && (double)sqrtf(cd) < P.accept) S->flag[cidx] = 1;
                     if (lane == 0) {
                         S->qdone[qi] = 1;
-                        M.vsmooth[(size_t)qv * 3 + 0] = (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f);
-                        M.vsmooth[(size_t)qv * 3 + 1] = (sv1 / (double)cnt) * (double)1.0f + (double)qp.y * (double)(1 - 1.0f);
-                        M.vsmooth[(size_t)qv * 3 + 2] = (sv2 / (double)cnt) * (double)1.0f + (double)qp.z * (double)(1 - 1.0f);
+                        emit_smooth(M, F, qv, (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f),
+                                    (sv1 / (double)cnt) * (double)1.0f + (double)qp.y * (double)(1 - 1.0f),
+                                    (sv2 / (double)cnt) * (double)1.0f + (double)qp.z * (double)(1 - 1.0f));
                     }
                 }
                 continue;
@@ -336,9 +389,9 @@ IM_HDN inline void voxel_dilate(const MeshDev& M, const MeshParams& P, const Fra
                     if ((double)sqrtf(wd_a[r]) < P.accept) S->flag[widx_a[r]] = 1;
                 S->qdone[qi] = 1;
                 // smooth_factor = 1.0f (mesh_rec_geometry.cpp:334,367-369)
-                M.vsmooth[(size_t)qv * 3 + 0] = (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f);
-                M.vsmooth[(size_t)qv * 3 + 1] = (sv1 / (double)cnt) * (double)1.0f + (double)qp.y * (double)(1 - 1.0f);
-                M.vsmooth[(size_t)qv * 3 + 2] = (sv2 / (double)cnt) * (double)1.0f + (double)qp.z * (double)(1 - 1.0f);
+                emit_smooth(M, F, qv, (sv0 / (double)cnt) * (double)1.0f + (double)qp.x * (double)(1 - 1.0f),
+                            (sv1 / (double)cnt) * (double)1.0f + (double)qp.y * (double)(1 - 1.0f),
+                            (sv2 / (double)cnt) * (double)1.0f + (double)qp.z * (double)(1 - 1.0f));
             }
         }
         IM_SYNCBLOCK_M();
@@ -443,18 +496,7 @@ IM_HDN inline void voxel_commit_common(const MeshDev& M, const MeshParams& P, co
     for (int k = tid; k < nf; k += nthreads) {
         const int a = faces[k][0], b = faces[k][1], c = faces[k][2];
         const unsigned long long word = word_base | (unsigned long long)compute_flip(M, a, b, c, F.fp->pose_t, axes);
-        const int t = tri_find(M, a, b, c);
-        if (t >= 0 && M.tri[t].w) {
-            im_atomic_max64(&M.tri_flip[t], word);
-        } else {
-            const int e = im_atomic_add(&M.cnt[7], 1);
-            if (e < F.max_list) {
-                F.add_tri[(size_t)e * 3 + 0] = a; F.add_tri[(size_t)e * 3 + 1] = b; F.add_tri[(size_t)e * 3 + 2] = c;
-                F.add_flip[e] = word;
-            } else {
-                im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
-            }
-        }
+        emit_face(M, F, a, b, c, word);
     }
     // pull (find_relative_triangulation_combination) + commit, store side: live triangles with all three vertices in
     // the dilated set that the new triangulation does not contain are removed.  Each triangle is visited from its
@@ -489,10 +531,7 @@ IM_HDN inline void voxel_commit_common(const MeshDev& M, const MeshParams& P, co
                         if (faces[k][0] == r.x && faces[k][1] == r.y && faces[k][2] == r.z) { in_new = true; break; }
                         hs = (hs + 1) & hmask;
                     }
-                    if (!in_new) {
-                        const int e = im_atomic_add(&M.cnt[8], 1);
-                        if (e < F.max_list) F.rem_tri[e] = t; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
-                    }
+                    if (!in_new) emit_remove(M, F, t);
                 }
             }
             t = nx;
@@ -900,18 +939,7 @@ IM_HDN inline void commit_face(const MeshDev& M, const MeshParams& P, const Fram
     const unsigned long long prio = ((unsigned long long)(lx & 2047) << 22) | ((unsigned long long)(ly & 2047) << 11) | (unsigned long long)(lz & 2047);
     const unsigned long long word = ((unsigned long long)F.frame << 34) | (prio << 1) |
                                     (unsigned long long)compute_flip(M, fc.x, fc.y, fc.z, F.fp->pose_t, F.work_axes + (size_t)w * 9);
-    const int t = tri_find(M, fc.x, fc.y, fc.z);
-    if (t >= 0 && M.tri[t].w) {
-        im_atomic_max64(&M.tri_flip[t], word);
-    } else {
-        const int e = im_atomic_add(&M.cnt[7], 1);
-        if (e < F.max_list) {
-            F.add_tri[(size_t)e * 3 + 0] = fc.x; F.add_tri[(size_t)e * 3 + 1] = fc.y; F.add_tri[(size_t)e * 3 + 2] = fc.z;
-            F.add_flip[e] = word;
-        } else {
-            im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
-        }
-    }
+    emit_face(M, F, fc.x, fc.y, fc.z, word);
     unsigned int hs = (tri_hash(fc.x, fc.y, fc.z) + (unsigned int)w * 0x9E3779B1u) & F.fset_mask;
     while (im_atomic_cas32(&F.fset[hs], -1, f) != -1) hs = (hs + 1) & F.fset_mask;
 }
@@ -964,8 +992,7 @@ IM_HDN inline void pull_check(const MeshDev& M, const FrameBuf& F, int e) {
         if (face_is(F.all_faces[k], tr.x, tr.y, tr.z, w)) return;
         hs = (hs + 1) & F.fset_mask;
     }
-    const int o = im_atomic_add(&M.cnt[8], 1);
-    if (o < F.max_list) F.rem_tri[o] = t; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
+    emit_remove(M, F, t);
 }
 
 }  // namespace immesh

@@ -100,6 +100,13 @@ int immesh_lio_enqueue_memset(immesh_lio_t* h, void* d_buf, size_t bytes); /* be
  * immesh_comm_unique_id on rank 0 and distributed by the caller (e.g. torch.distributed broadcast). */
 int immesh_comm_unique_id(char* out128);
 int immesh_lio_shard(immesh_lio_t* h, int rank, int nranks, const char* unique_id128);
+/* Same for the mesher (its own communicator: use a second unique id).  Every rank is given the same frames and runs the
+ * vertex append itself (replicated: identical vertex ids everywhere); the per-voxel stage -- dilation, triangulation
+ * (mesh_rec_geometry.cpp:174-295), pull, commit -- runs only for the mesh voxels the rank owns.  Two all-gathers per frame
+ * exchange (i) the smoothed vertex positions written by the dilations and (ii) the new facets with their flip-priority
+ * words plus the removals, which every rank then applies to its replica of the triangle store, so that all replicas hold
+ * the single-GPU facet set after every frame. */
+int immesh_mesh_shard(immesh_mesh_t* h, int rank, int nranks, const char* unique_id128);
 
 /* BuildResidualListOMP (src/voxel_mapping.hpp:103-105, src/voxel_mapping.cpp:153-245) as a stand-alone call at
  * the current state: fills, for every accepted match in scan order, its scan index, octree layer and the ptpl

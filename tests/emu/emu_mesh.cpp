@@ -26,6 +26,11 @@ struct immesh_mesh {
     std::vector<unsigned int> work_bits;
     std::vector<int4> all_faces;
     std::vector<double> work_axes;
+    std::vector<XSmooth> x_smooth;
+    std::vector<int4> x_face, x_rem;
+    std::vector<unsigned long long> x_word;
+    FramePose fp_storage;
+    int nw = 0;
     int frame_counter = 0;
     int last_cnt[32];
 };
@@ -46,7 +51,7 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     h->gkeys.assign(gcap, IM_EMPTY_KEY); h->gval.assign(gcap, -1);
     h->vkeys.assign(vcap, IM_EMPTY_KEY); h->vox_chunk.assign(vcap * IM_VCHUNKS, -1); h->vox_count.assign(vcap, 0); h->vox_mt.assign(vcap, 0); h->vox_na.assign(vcap, 0); h->vox_frame.assign(vcap, -1);
     h->tri.resize(max_t); h->tri_next.resize((size_t)max_t * 3); h->tri_flip.resize(max_t); h->thash.assign(tcap, -1);
-    h->cnt.assign(32, 0);
+    h->cnt.assign(64, 0);
     h->cnt[11] = h->cnt[12] = h->cnt[13] = 0x7fffffff; h->cnt[14] = h->cnt[15] = h->cnt[16] = -0x7fffffff;
     M.vpos = h->vpos.data(); M.vsmooth = h->vsmooth.data(); M.v_tri_head = h->v_tri_head.data();
     M.gkeys = h->gkeys.data(); M.gval = h->gval.data(); M.gmask = (unsigned)(gcap - 1);
@@ -69,20 +74,22 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     F.ckeys = h->ckeys.data(); F.chead = h->chead.data(); F.scan_block = nullptr;
     F.act = h->act.data(); F.work = h->work.data(); F.work_n_ids = h->work_n.data(); F.work_ids = h->work_ids.data(); F.work_nfaces = h->work_nf.data(); F.work_bits = h->work_bits.data(); F.work_ring = h->work_ring.data(); F.work_done = h->work_done.data(); F.ditem = h->ditem.data(); F.all_faces = h->all_faces.data(); F.all_vref = h->all_vref.data(); F.pulled = h->pulled.data(); F.fset = h->fset.data(); F.work_axes = h->work_axes.data();
     F.add_tri = h->add_tri.data(); F.add_flip = h->add_flip.data(); F.rem_tri = h->rem_tri.data();
+    F.shard_rank = 0; F.shard_n = 1; F.x_cap = 0; F.x_smooth = nullptr; F.x_face = nullptr; F.x_word = nullptr; F.x_rem = nullptr;
     std::memset(h->last_cnt, 0, sizeof(h->last_cnt));
     *out = h;
     return 0;
 }
 int immesh_mesh_destroy(immesh_mesh_t* h) { delete h; return 0; }
-int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, const double* pose_t, int) {
+// ---- one frame in three phases (the sharded test exchanges the lists between them, like the device path does with NCCL)
+// A: append (replicated) + activation + dilation of the voxels this rank owns
+int emu_mesh_phase_a(immesh_mesh_t* h, const float* world_xyz, int n, const double* pose_t) {
     FrameBuf& F = h->F;
     MeshDev& M = h->M;
     const MeshParams& P = h->P;
     const int step = std::max(1, (int)std::lround((double)(n / P.append_target)));
     F.n = n; F.step = step; F.m = n > 0 ? (n + step - 1) / step : 0; F.frame = ++h->frame_counter;
-    static FramePose fp_storage;
-    for (int j = 0; j < 3; ++j) { fp_storage.pose_t[j] = pose_t[j]; fp_storage.prio_origin[j] = (long long)std::floor(pose_t[j] / P.res) - 1024; }
-    F.fp = &fp_storage;
+    for (int j = 0; j < 3; ++j) { h->fp_storage.pose_t[j] = pose_t[j]; h->fp_storage.prio_origin[j] = (long long)std::floor(pose_t[j] / P.res) - 1024; }
+    F.fp = &h->fp_storage;
     F.cmask = (unsigned)(p2((size_t)std::max(F.m, 1) * 2) - 1);
     if (n > 0) std::memcpy(h->pts.data(), world_xyz, (size_t)n * 12);
     for (unsigned i = 0; i <= F.cmask; ++i) { F.ckeys[i] = IM_EMPTY_KEY; F.chead[i] = -1; }
@@ -90,6 +97,7 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     for (int k = 17; k <= 26; ++k) M.cnt[k] = 0;
     M.cnt[28] = 0;
     M.cnt[29] = 0;
+    M.cnt[30] = 0; M.cnt[31] = 0; M.cnt[32] = 0;
     for (unsigned i = 0; i <= F.fset_mask; ++i) F.fset[i] = -1;
     for (int c = 0; c < F.m; ++c) cand_init(M, P, F, c);
     for (int c = 0; c < F.m; ++c) cand_conflicts(M, P, F, c);
@@ -102,11 +110,20 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
     for (int c = 0; c < F.m; ++c) cand_place(M, F, c, base);
     const int na = std::min(M.cnt[5], F.max_act);
     for (int a = 0; a < na; ++a) voxel_select(M, F, a);
-    const int nw = work_total(M, F);
+    h->nw = work_total(M, F);
     DilateSmem* DS = new DilateSmem();
+    for (int i = 0; i < std::min(M.cnt[29], F.max_ditem); ++i) voxel_dilate(M, P, F, F.ditem[i], DS, 0, 1);
+    delete DS;
+    return 0;
+}
+// B: triangulation + pull + commit decisions of the owned voxels
+int emu_mesh_phase_b(immesh_mesh_t* h) {
+    FrameBuf& F = h->F;
+    MeshDev& M = h->M;
+    const MeshParams& P = h->P;
+    const int nw = h->nw;
     MeshSmem<256>* S1 = new MeshSmem<256>();
     MeshSmem<1024>* S2 = new MeshSmem<1024>();
-    for (int i = 0; i < std::min(M.cnt[29], F.max_ditem); ++i) voxel_dilate(M, P, F, F.ditem[i], DS, 0, 1);
     MeshWarpSmem<128>* SW = new MeshWarpSmem<128>();
     for (int i = 0; i < nw; ++i) voxel_mesh_warp<128>(M, P, F, work_slot(M, F, i), SW, 0, 1, 96);   // same split as the device
     delete SW;
@@ -123,13 +140,56 @@ int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, cons
         const int nd = F.work_n_ids[w];
         if (nd < 0 || nd > 256) voxel_mesh<1024>(M, P, F, w, S2, 0, 1);
     }
-    delete DS; delete S1; delete S2;
+    delete S1; delete S2;
+    return 0;
+}
+// C: push (all removals, then all insertions)
+int emu_mesh_phase_c(immesh_mesh_t* h) {
+    FrameBuf& F = h->F;
+    MeshDev& M = h->M;
     const int nr = std::min(M.cnt[8], F.max_list), nadd = std::min(M.cnt[7], F.max_list);
     for (int e = 0; e < nr; ++e) tri_remove(M, F.rem_tri[e]);
     for (int e = 0; e < nadd; ++e) tri_add(M, F.add_tri[(size_t)e * 3], F.add_tri[(size_t)e * 3 + 1], F.add_tri[(size_t)e * 3 + 2], F.add_flip[e]);
     M.cnt[0] += M.cnt[10];
     std::memcpy(h->last_cnt, M.cnt, 32 * sizeof(int));
     return M.cnt[3] ? IMMESH_E_CAPACITY : 0;
+}
+int immesh_mesh_push_frame(immesh_mesh_t* h, const float* world_xyz, int n, const double* pose_t, int) {
+    int rc = emu_mesh_phase_a(h, world_xyz, n, pose_t);
+    if (rc) return rc;
+    emu_mesh_phase_b(h);
+    return emu_mesh_phase_c(h);
+}
+// ---- sharded per-voxel stage: exchange lists
+int emu_mesh_set_shard(immesh_mesh_t* h, int rank, int nranks) {
+    FrameBuf& F = h->F;
+    F.shard_rank = rank; F.shard_n = nranks; F.x_cap = 1 << 16;
+    h->x_smooth.resize(F.x_cap); h->x_face.resize(F.x_cap); h->x_word.resize(F.x_cap); h->x_rem.resize(F.x_cap);
+    F.x_smooth = h->x_smooth.data(); F.x_face = h->x_face.data(); F.x_word = h->x_word.data(); F.x_rem = h->x_rem.data();
+    return 0;
+}
+int emu_mesh_xcounts(immesh_mesh_t* h, int* out) {   // smooth, face, remove
+    out[0] = std::min(h->M.cnt[32], h->F.x_cap); out[1] = std::min(h->M.cnt[30], h->F.x_cap); out[2] = std::min(h->M.cnt[31], h->F.x_cap);
+    return 0;
+}
+int emu_mesh_xget(immesh_mesh_t* h, void* smooth32, int* face4, unsigned long long* word, int* rem4) {
+    int c[3];
+    emu_mesh_xcounts(h, c);
+    if (smooth32) std::memcpy(smooth32, h->x_smooth.data(), (size_t)c[0] * sizeof(XSmooth));
+    if (face4) std::memcpy(face4, h->x_face.data(), (size_t)c[1] * sizeof(int4));
+    if (word) std::memcpy(word, h->x_word.data(), (size_t)c[1] * 8);
+    if (rem4) std::memcpy(rem4, h->x_rem.data(), (size_t)c[2] * sizeof(int4));
+    return 0;
+}
+int emu_mesh_xapply_smooth(immesh_mesh_t* h, const void* smooth32, int n) {
+    const XSmooth* e = (const XSmooth*)smooth32;
+    for (int i = 0; i < n; ++i) { h->M.vsmooth[(size_t)e[i].id * 3] = e[i].x; h->M.vsmooth[(size_t)e[i].id * 3 + 1] = e[i].y; h->M.vsmooth[(size_t)e[i].id * 3 + 2] = e[i].z; }
+    return 0;
+}
+int emu_mesh_xapply_lists(immesh_mesh_t* h, const int* face4, const unsigned long long* word, int nf, const int* rem4, int nr) {
+    for (int i = 0; i < nf; ++i) apply_face(h->M, h->F, face4[i * 4], face4[i * 4 + 1], face4[i * 4 + 2], word[i]);
+    for (int i = 0; i < nr; ++i) apply_remove(h->M, h->F, rem4[i * 4], rem4[i * 4 + 1], rem4[i * 4 + 2]);
+    return 0;
 }
 int immesh_mesh_counts(immesh_mesh_t* h, int64_t* out) {
     const int* c = h->last_cnt;

@@ -2,7 +2,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_shard_check.py
 Every rank runs the same scan stream twice on its GPU: once with the VoxelMap sharded over all ranks (NCCL all-reduces
 inside the C library) and once unsharded.  The sharded state must equal the unsharded one bit for bit on every rank,
-and the union of the ranks' map shards must equal the unsharded map."""
+and the union of the ranks' map shards must equal the unsharded map.  The mesher runs sharded (per-voxel stage by voxel
+owner, two all-gathers per frame) next to an unsharded instance: vertices, facet set and flags must be identical."""
 import os
 import sys
 
@@ -23,7 +24,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = api.load_library()
-    uid = [api.comm_unique_id(lib) if rank == 0 else None]
+    uid = [api.comm_unique_id(lib) if rank == 0 else None, api.comm_unique_id(lib) if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     cfg = api.AVIA
     n_scans = 8
@@ -36,13 +37,27 @@ def main():
         s[12:15] = (scans[1]["t_true"] - scans[0]["t_true"]) / scans[0]["dt"]
         h.set_state(s)
         h.voxel_map_init(scans[0]["body_full"])
+    # the mesher: per-voxel stage sharded by voxel owner (own NCCL communicator) vs one GPU, fed by the same poses
+    from mesh_common import SMALL
+    meshes = {"sharded": api.Mesh(api.MeshConfig(**SMALL), lib=lib), "single": api.Mesh(api.MeshConfig(**SMALL), lib=lib)}
+    meshes["sharded"].shard(rank, world, uid[1])
     ok = True
+    mesh_ok = True
     for k in range(1, n_scans):
         ss, _ = handles["sharded"].step(scans[k]["body_ds"], scans[k]["dt"])
         s1, _ = handles["single"].step(scans[k]["body_ds"], scans[k]["dt"])
         if not np.array_equal(ss, s1):
             ok = False
             print(f"[rank {rank}] scan {k}: sharded state differs, max |d| = {np.abs(ss - s1).max()}", flush=True)
+        meshes["sharded"].push_frame_from_lio(handles["sharded"], scans[k]["body_full"])
+        meshes["single"].push_frame_from_lio(handles["single"], scans[k]["body_full"])
+        (va, ta, fa), (vb, tb, fb) = meshes["sharded"].snapshot(), meshes["single"].snapshot()
+        same = np.array_equal(va, vb) and ta.shape == tb.shape and np.array_equal(ta, tb) and np.array_equal(fa, fb)
+        if not same:
+            mesh_ok = False
+            print(f"[rank {rank}] frame {k}: sharded mesh differs: vertices {va.shape} vs {vb.shape}, facets {ta.shape} vs {tb.shape}", flush=True)
+    n_facets = len(meshes["single"].snapshot()[1])
+    owned = meshes["sharded"].work_stats()["voxels_meshed"]
     dumps = [None] * world
     dist.all_gather_object(dumps, handles["sharded"].dump_map())
     ref = handles["single"].dump_map()
@@ -61,8 +76,9 @@ def main():
     map_ok = merged.keys() == br.keys() and all(np.array_equal(merged[k], br[k]) for k in br)
     sizes = [len(d) for d in dumps]
     if rank == 0:
-        print(f"ranks={world} state_bit_exact={ok} map_union_bit_exact={map_ok} shard_rows={sizes} single_rows={len(ref)}", flush=True)
-    flag = torch.tensor([int(ok and map_ok)], device="cuda")
+        print(f"ranks={world} state_bit_exact={ok} map_union_bit_exact={map_ok} shard_rows={sizes} single_rows={len(ref)} "
+              f"mesh_replicas_bit_exact={mesh_ok} facets={n_facets} voxels_meshed_last_frame_rank0={owned}", flush=True)
+    flag = torch.tensor([int(ok and map_ok and mesh_ok)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)

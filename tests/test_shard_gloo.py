@@ -114,3 +114,79 @@ def test_sharded_lio_two_ranks_equals_oracle(tmp_path, built):
         assert np.array_equal(bm[key], br[key]), key
     n0 = len(np.load(tmp_path / "map_0.npy"))
     assert 0.3 < n0 / len(ref) < 0.7               # the shards are balanced
+
+
+def _gather_padded(arr, world):
+    """all_gather of variable-length uint8 buffers: lengths first, then buffers padded to the maximum."""
+    raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+    n = torch.tensor([raw.size], dtype=torch.int64)
+    lens = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(lens, n)
+    m = max(int(x) for x in lens)
+    buf = torch.zeros(max(m, 1), dtype=torch.uint8)
+    buf[:raw.size] = torch.from_numpy(raw.copy())
+    outs = [torch.zeros(max(m, 1), dtype=torch.uint8) for _ in range(world)]
+    dist.all_gather(outs, buf)
+    return [o.numpy()[:int(l)].copy() for o, l in zip(outs, lens)]
+
+
+def _mesh_worker(rank, world, port, n_frames, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from immesh_b200 import api, build
+    from mesh_common import SMALL, world_scans
+    lib = api.load_library(build.EMU)
+    u64p, i32p = C.POINTER(C.c_uint64), C.POINTER(C.c_int)
+    cfg = api.MeshConfig(**SMALL)
+    g = api.Mesh(cfg, lib=lib)
+    lib.emu_mesh_set_shard(g._h, rank, world)
+    owned = []
+    for k, (w, t) in enumerate(world_scans("avia", n_frames, 3, 20000)):
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        assert lib.emu_mesh_phase_a(g._h, w.ctypes.data_as(C.POINTER(C.c_float)), w.shape[0], t.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        c = (C.c_int * 3)()
+        lib.emu_mesh_xcounts(g._h, c)
+        sm = np.zeros(c[0] * 32, dtype=np.uint8)
+        lib.emu_mesh_xget(g._h, sm.ctypes.data_as(C.c_void_p), None, None, None)
+        for r, buf in enumerate(_gather_padded(sm, world)):          # exchange 1: smoothed positions
+            if r != rank and buf.size:
+                lib.emu_mesh_xapply_smooth(g._h, buf.ctypes.data_as(C.c_void_p), buf.size // 32)
+        lib.emu_mesh_phase_b(g._h)
+        lib.emu_mesh_xcounts(g._h, c)
+        face = np.zeros((c[1], 4), dtype=np.int32); word = np.zeros(c[1], dtype=np.uint64); rem = np.zeros((c[2], 4), dtype=np.int32)
+        lib.emu_mesh_xget(g._h, None, face.ctypes.data_as(i32p), word.ctypes.data_as(u64p), rem.ctypes.data_as(i32p))
+        owned.append(int(c[1]))
+        faces, words, rems = _gather_padded(face, world), _gather_padded(word, world), _gather_padded(rem, world)
+        for r in range(world):                                          # exchange 2: facets + removals of every rank
+            f = np.ascontiguousarray(faces[r].view(np.int32)); wd = np.ascontiguousarray(words[r].view(np.uint64)); rm = np.ascontiguousarray(rems[r].view(np.int32))
+            lib.emu_mesh_xapply_lists(g._h, f.ctypes.data_as(i32p), wd.ctypes.data_as(u64p), wd.size, rm.ctypes.data_as(i32p), rm.size // 4)
+        assert lib.emu_mesh_phase_c(g._h) == 0
+    v, tri, fl = g.snapshot()
+    np.savez(os.path.join(out_dir, f"mesh_{rank}.npz"), v=v, tri=tri, fl=fl, owned=np.array(owned))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_mesher_two_ranks_equals_oracle(tmp_path, built):
+    """Per-voxel meshing stage sharded by voxel owner over 2 ranks (replicated append, two list exchanges per frame):
+    both replicas must hold the oracle's vertex array, facet set and orientation flags."""
+    from immesh_b200 import api
+    from mesh_common import SMALL, world_scans
+    from oracle_api import OracleMesh
+    n_frames = 5
+    port = _free_port()
+    mp.spawn(_mesh_worker, args=(2, port, n_frames, str(tmp_path)), nprocs=2, join=True)
+    o = OracleMesh(api.MeshConfig(**SMALL))
+    for k, (w, t) in enumerate(world_scans("avia", n_frames, 3, 20000)):
+        o.push_frame(w, t, k)
+    vo, to, fo = o.snapshot()
+    r0, r1 = np.load(tmp_path / "mesh_0.npz"), np.load(tmp_path / "mesh_1.npz")
+    for r in (r0, r1):
+        assert np.array_equal(r["v"], vo)
+        assert r["tri"].shape == to.shape and np.array_equal(r["tri"], to)
+        assert np.array_equal(r["fl"], fo)
+    assert len(to) > 1000
+    share = r0["owned"].sum() / max(1, r0["owned"].sum() + r1["owned"].sum())
+    assert 0.3 < share < 0.7, share               # both ranks meshed a comparable number of voxels
