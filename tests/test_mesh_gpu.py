@@ -35,6 +35,42 @@ def test_knn_matches_oracle(cuda_lib):
         assert np.array_equal(dg, do), (k, md)
 
 
+def _golden(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+
+
+def test_golden_reference_ikdtree_append_and_knn(cuda_lib):
+    """CUDA vertex append + kNN against fixtures produced by the REFERENCE's own ikd-Tree (tools/make_golden.py)."""
+    import ref_ikd
+    ga, gk = _golden("ikd_append.npz"), _golden("ikd_knn.npz")
+    g = api.Mesh(api.MeshConfig(), lib=cuda_lib)
+    for k in range(3):
+        g.push_frame(ga[f"frame{k}"], ga["pose_t"][k], k)
+    v = g.snapshot()[0]
+    assert v.shape == ga["verts"].shape and np.array_equal(v, ga["verts"])
+    for c, (k, md) in enumerate(gk["cases"]):
+        idx, d2 = g.knn(gk["queries"], int(k), float(md))
+        assert ref_ikd.same_knn(idx.astype(np.int64), d2, gk[f"idx{c}"].astype(np.int64), gk[f"d2{c}"]), (k, md)
+
+
+def test_knn_matches_reference_ikdtree_live(cuda_lib):
+    """CUDA kNN against the reference ikd-Tree library itself (oracle/_ref travels with the snapshot)."""
+    import ref_ikd
+    if not ref_ikd.available():
+        pytest.skip("oracle/_ref/libref_ikd.so not present")
+    g, o, _ = run_mesh_parity(cuda_lib, "avia", 3, seed=9)
+    v = g.snapshot()[0]
+    t = ref_ikd.RefIkdTree()
+    t.add(v)
+    rng = np.random.default_rng(1)
+    q = (v[rng.integers(0, len(v), 4000)] + rng.normal(0, 0.2, (4000, 3))).astype(np.float32)
+    for k, md in ((20, np.inf), (1, 0.1), (20, 1.0)):
+        ig, dg = g.knn(q, k, md)
+        ir, dr, _ = t.knn(q, k, md)
+        assert ref_ikd.same_knn(ig.astype(np.int64), dg, ir, dr), (k, md)
+
+
 def test_empty_frame_and_restart(cuda_lib):
     cfg = api.MeshConfig(**SMALL)
     g = api.Mesh(cfg, lib=cuda_lib)
