@@ -100,6 +100,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_comm_unique_id", [C.c_char_p]),
         ("immesh_lio_shard", [vp, C.c_int, C.c_int, C.c_char_p]),
         ("immesh_mesh_shard", [vp, C.c_int, C.c_int, C.c_char_p]),
+        ("immesh_lio_shard_transport", [vp]),
+        ("immesh_mesh_shard_transport", [vp]),
         ("immesh_lio_step_async", [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
         ("immesh_lio_wait", [vp, dp, ip]),
         ("immesh_lio_enqueue_memset", [vp, vp, C.c_size_t]),
@@ -256,6 +258,9 @@ class Lio:
         """Shard the VoxelMap over nranks processes (NCCL); unique_id: 128 bytes from comm_unique_id() of rank 0."""
         _check(self.lib, self.lib.immesh_lio_shard(self._h, rank, nranks, unique_id), "lio_shard")
 
+    def shard_transport(self) -> str:
+        return ("none", "nccl", "peer-window")[self.lib.immesh_lio_shard_transport(self._h)]
+
     def residual_build(self, body_ds):
         a, p = _f32(body_ds)
         n = a.shape[0]
@@ -364,6 +369,9 @@ class Mesh:
     def shard(self, rank: int, nranks: int, unique_id: bytes):
         """Shard the per-voxel meshing stage over nranks processes (NCCL, own communicator: pass a second unique id)."""
         _check(self.lib, self.lib.immesh_mesh_shard(self._h, rank, nranks, unique_id), "mesh_shard")
+
+    def shard_transport(self) -> str:
+        return ("none", "nccl", "peer-window")[self.lib.immesh_mesh_shard_transport(self._h)]
 
     def work_stats(self):
         o = np.zeros(8, dtype=np.int64)

@@ -7,6 +7,7 @@
 #include "common_host.hpp"
 #include "lio_core.cuh"
 #include "mesh_voxel.cuh"
+#include "peer_win.cuh"
 
 using immesh::LioParams; using immesh::VoxelMapDev; using immesh::ScanBuf; using immesh::LioCtrl;
 using immesh::MeshParams; using immesh::MeshDev; using immesh::FrameBuf; using immesh::FramePose;
@@ -31,6 +32,8 @@ struct immesh_lio {
     cudaEvent_t ev_mark = nullptr;   // pipeline timing mark (begin)
     void* nccl_comm = nullptr;       // ncclComm_t when the VoxelMap is sharded over several GPUs
     unsigned int* d_bits = nullptr;  // [2][words] exists / matched-in-own-voxel bit words of the sharded residual pass
+    immesh::PeerWindow win;          // peer window of the sharded residual pass (NVLink peer memory, replaces the NCCL all-reduces)
+    int words_cap = 0;
     int* h_ints = nullptr;     // pinned
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -68,6 +71,8 @@ struct immesh_mesh {
     int pending_rc = 0;
     void* nccl_comm = nullptr;        // ncclComm_t when the per-voxel stage is sharded over several GPUs
     unsigned char *d_seg1 = nullptr, *d_seg2 = nullptr, *d_recv1 = nullptr, *d_recv2 = nullptr;   // exchange segments
+    immesh::PeerWindow win;           // peer window: [flags][recv1 x n][recv2 x n] when the segments are pushed over NVLink
+    int* d_xdone = nullptr;           // block-done counters of the two push kernels
     size_t seg1_bytes = 0, seg2_bytes = 0;
     int* d_snap_tri = nullptr;
     int* d_snap_flip = nullptr;

@@ -13,6 +13,7 @@
 
 #include "../../include/immesh_b200.h"
 #include "common_host.hpp"
+#include "peer_win.cuh"
 #include "handles.hpp"
 #include "map_dump.hpp"
 
@@ -89,8 +90,81 @@ __device__ __noinline__ void warp_lu_inverse18(const double* a_in, double* lu /*
     __syncwarp();
 }
 
+// ---- 18x18 inverse, block-parallel, bit-identical to the serial partial-pivot LU + substitution (lu_inverse18 / the oracle).
+// Augmented elimination [A | I]: the forward substitution is folded into the LU -- element (i, c) of the right half receives
+//   s = s - l_ik * y_k   for k = 0, 1, ...  exactly in the order (and with the operands) of  y_i = b_i - sum_{j<i} L_ij y_j,
+// because a row's multipliers travel with it through the row swaps.  One thread per element of the 18 x 36 panel, one
+// __syncthreads per pivot step: ping-pong buffers make the row swap a re-indexed read (row k of the step = old row `bi`),
+// frozen rows go to U / Y.  The pivot is found redundantly by every thread (adjacent-pair tournament, left wins ties = first
+// maximum), so no broadcast is needed.  The back substitution keeps the serial order (j ascending) per column: 18 lanes,
+// registers only.  ~18 x (scan + div + update + barrier) + 18 x (div + short add chain) instead of one warp's 9 k
+// dependent instructions.
+#define INV_THREADS 672
+struct InvScratch {
+    double buf[2][18 * 37];
+    double U[18 * 19];
+    double Y[18 * 19];
+};
+__device__ __forceinline__ int pivot_row18(const double* m /*stride 37*/, int k) {
+    double v[18];
+    int id[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) { v[i] = (i >= k) ? fabs(m[i * 37 + k]) : -1.0; id[i] = i; }
+#define IM_PMERGE(a, b) if (v[b] > v[a]) { v[a] = v[b]; id[a] = id[b]; }
+    IM_PMERGE(0, 1) IM_PMERGE(2, 3) IM_PMERGE(4, 5) IM_PMERGE(6, 7) IM_PMERGE(8, 9) IM_PMERGE(10, 11) IM_PMERGE(12, 13) IM_PMERGE(14, 15) IM_PMERGE(16, 17)
+    IM_PMERGE(0, 2) IM_PMERGE(4, 6) IM_PMERGE(8, 10) IM_PMERGE(12, 14)
+    IM_PMERGE(0, 4) IM_PMERGE(8, 12)
+    IM_PMERGE(0, 8)
+    IM_PMERGE(0, 16)
+#undef IM_PMERGE
+    return id[0];
+}
+__device__ __noinline__ void block_lu_inverse18(const double* a_in /*[324] shared, row-major*/, InvScratch* W, double* inv_out /*[324] shared*/) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < 648; e += nt) {
+        const int i = e / 36, j = e - i * 36;
+        W->buf[0][i * 37 + j] = (j < 18) ? a_in[i * 18 + j] : ((j - 18 == i) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    int p = 0;
+    for (int k = 0; k < 18; ++k) {
+        const double* old = W->buf[p];
+        double* nw = W->buf[p ^ 1];
+        const int bi = pivot_row18(old, k);
+        const double pivv = old[bi * 37 + k];
+        for (int e = tid; e < 648; e += nt) {
+            const int i = e / 36, j = e - i * 36;
+            if (i < k || j < k) continue;            // frozen rows, eliminated columns
+            if (i == k) {                            // row k of this step (= old row bi) is final
+                const double v = old[bi * 37 + j];
+                if (j < 18) W->U[k * 19 + j] = v; else W->Y[k * 19 + (j - 18)] = v;
+            } else if (j > k) {
+                const int src = (i == bi) ? k : i;   // the swap, as a re-indexed read
+                const double l = old[src * 37 + k] / pivv;
+                nw[i * 37 + j] = old[src * 37 + j] - l * old[bi * 37 + j];
+            }
+        }
+        __syncthreads();
+        p ^= 1;
+    }
+    if (tid < 18) {
+        const int c = tid;
+        double x[18];
+#pragma unroll
+        for (int i = 17; i >= 0; --i) {
+            double s = W->Y[i * 19 + c];
+#pragma unroll
+            for (int j = i + 1; j < 18; ++j) s = s - W->U[i * 19 + j] * x[j];
+            x[i] = s / W->U[i * 19 + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 18; ++i) inv_out[i * 18 + c] = x[i];
+    }
+    __syncthreads();
+}
+
 // same arithmetic as ieskf_solve (lio_core.cuh), block-cooperative with the two LU inverses done by warp 0
-__device__ __noinline__ void ieskf_solve_block(const LioParams& P, LioCtrl* ctrl, int iter, SolveScratch* S) {
+__device__ __noinline__ void ieskf_solve_block(const LioParams& P, LioCtrl* ctrl, int iter, SolveScratch* S, InvScratch* W = nullptr) {
     const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: no divergence handling around the LU shuffles
     double* state = ctrl->state;
@@ -122,8 +196,12 @@ __device__ __noinline__ void ieskf_solve_block(const LioParams& P, LioCtrl* ctrl
         S->a[idx] = hth + ctrl->Pinv[idx];
     }
     __syncthreads();
-    if (warp == 0) warp_lu_inverse18(S->a, S->lu, S->piv, S->K1, lane);
-    __syncthreads();
+    if (W) {
+        block_lu_inverse18(S->a, W, S->K1);          // whole block (kernels launched with INV_THREADS threads)
+    } else {
+        if (warp == 0) warp_lu_inverse18(S->a, S->lu, S->piv, S->K1, lane);   // fused-solve tail of a 128-thread residual block
+        __syncthreads();
+    }
     for (int idx = tid; idx < 18 * 6; idx += nthreads) {
         const int i = idx / 6, j = idx % 6;
         double s = 0.0;
@@ -268,25 +346,146 @@ __global__ void __launch_bounds__(RES_THREADS) k_shard_pass2(VoxelMapDev map, Li
     }
 }
 
+// ---- sharded VoxelMap over peer windows (peer_win.cuh): the two exchanges of an iteration are fused into the kernels.
+// Window of one rank:  flag[2][8] u64 | acc[8][IM_NTERMS*2] u64 (one row per source rank) | bits[8][2][words_cap] u32
+struct LioPeers {
+    unsigned char* w[IM_MAX_RANKS];
+    int rank, n, words_cap, pad;
+};
+#define IM_LIOWIN_ACC_OFF 128
+#define IM_LIOWIN_BITS_OFF 4096
+__device__ __forceinline__ unsigned long long* liowin_flag(unsigned char* w, int phase, int src) { return (unsigned long long*)w + phase * IM_MAX_RANKS + src; }
+__device__ __forceinline__ unsigned long long* liowin_acc(unsigned char* w, int src) { return (unsigned long long*)(w + IM_LIOWIN_ACC_OFF) + src * (IM_NTERMS * 2); }
+__device__ __forceinline__ unsigned int* liowin_bits(unsigned char* w, int src, int which, int words_cap) { return (unsigned int*)(w + IM_LIOWIN_BITS_OFF) + (size_t)(src * 2 + which) * words_cap; }
+
+// pass 1 + publish: every warp ballots the two bits of its 32 consecutive points and lane r stores the two words into rank
+// r's window (row = this rank); the last block raises this rank's pass-1 flag in every peer window.
+__global__ void __launch_bounds__(RES_THREADS) k_shard_pass1_p2p(VoxelMapDev map, LioParams P, ScanBuf sb, LioCtrl* ctrl, int n, LioPeers pe, unsigned long long epoch) {
+    __shared__ double s_state[24 + 6 * 18];
+    __shared__ int s_last;
+    if (ctrl->stop) return;
+    for (int i = threadIdx.x; i < 24 + 6 * 18; i += blockDim.x) s_state[i] = ctrl->state[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int n32 = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += gridDim.x * blockDim.x) {
+        bool ex = false, ok1 = false;
+        if (i < n) shard_pass1_flags(map, P, sb, s_state, i, &ex, &ok1);
+        const unsigned int we = __ballot_sync(0xffffffffu, ex), wo = __ballot_sync(0xffffffffu, ok1);
+        if (lane < pe.n) {
+            liowin_bits(pe.w[lane], pe.rank, 0, pe.words_cap)[i >> 5] = we;
+            liowin_bits(pe.w[lane], pe.rank, 1, pe.words_cap)[i >> 5] = wo;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl->shard_cnt[0], 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x == 0) ctrl->shard_cnt[0] = 0;
+        __threadfence_system();
+        if (threadIdx.x < pe.n && threadIdx.x != pe.rank) immesh::st_release_sys(liowin_flag(pe.w[threadIdx.x], 0, pe.rank), epoch);
+    }
+}
+// wait for the peers' bits + pass 2 + integer block reduction + publish: the last block copies this rank's 60 partial sums
+// into row `rank` of every window and raises the pass-2 flag.
+__global__ void __launch_bounds__(RES_THREADS) k_shard_pass2_p2p(VoxelMapDev map, LioParams P, ScanBuf sb, LioCtrl* ctrl, int iter, int n, LioPeers pe, unsigned long long epoch) {
+    __shared__ double s_state[24 + 6 * 18];
+    __shared__ long long s_part[RES_THREADS / 32][IM_NTERMS];
+    __shared__ int s_last;
+    if (ctrl->stop) return;
+    if (threadIdx.x < pe.n && threadIdx.x != pe.rank) {
+        if (!immesh::wait_epoch(liowin_flag(pe.w[pe.rank], 0, threadIdx.x), epoch)) atomicOr(map.err, IM_ERR_PEER_TIMEOUT);
+    }
+    for (int i = threadIdx.x; i < 24 + 6 * 18; i += blockDim.x) s_state[i] = ctrl->state[i];
+    __syncthreads();
+    long long acc[IM_NTERMS];
+#pragma unroll
+    for (int k = 0; k < IM_NTERMS; ++k) acc[k] = 0;
+    unsigned char* mine = pe.w[pe.rank];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned int we = 0, wo = 0;
+        for (int r = 0; r < pe.n; ++r) {
+            we |= __ldcg(liowin_bits(mine, r, 0, pe.words_cap) + (i >> 5));
+            wo |= __ldcg(liowin_bits(mine, r, 1, pe.words_cap) + (i >> 5));
+        }
+        long long t[IM_NTERMS];
+        if (shard_pass2_flags(map, P, sb, s_state, i, (we >> (i & 31)) & 1u, (wo >> (i & 31)) & 1u, t, map.err)) {
+#pragma unroll
+            for (int k = 0; k < IM_NTERMS; ++k) acc[k] += t[k];
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < IM_NTERMS - 1; ++k) {
+        long long v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < IM_NTERMS - 1) {
+        long long v = 0;
+        for (int w = 0; w < RES_THREADS / 32; ++w) v += s_part[w][threadIdx.x];
+        if (v != 0) {
+            atomicAdd(&ctrl->acc[iter][2 * threadIdx.x], (unsigned long long)(v >> 32));
+            atomicAdd(&ctrl->acc[iter][2 * threadIdx.x + 1], (unsigned long long)(v & 0xffffffffLL));
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl->shard_cnt[1], 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (threadIdx.x == 0) ctrl->shard_cnt[1] = 0;
+        if (threadIdx.x < IM_NTERMS * 2) {
+            const unsigned long long v = *(volatile unsigned long long*)&ctrl->acc[iter][threadIdx.x];
+            for (int r = 0; r < pe.n; ++r) liowin_acc(pe.w[r], pe.rank)[threadIdx.x] = v;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < pe.n && threadIdx.x != pe.rank) immesh::st_release_sys(liowin_flag(pe.w[threadIdx.x], 1, pe.rank), epoch);
+    }
+}
+// wait for the peers' sums, add the rows (integers: order-free, identical on every rank), then the usual solve
+__global__ void __launch_bounds__(INV_THREADS) k_solve_warp_p2p(LioParams P, LioCtrl* ctrl, int iter, LioPeers pe, unsigned long long epoch, int* err) {
+    __shared__ SolveScratch S;
+    __shared__ InvScratch W;
+    if (ctrl->stop) return;
+    if (threadIdx.x < pe.n && threadIdx.x != pe.rank) {
+        if (!immesh::wait_epoch(liowin_flag(pe.w[pe.rank], 1, threadIdx.x), epoch)) atomicOr(err, IM_ERR_PEER_TIMEOUT);
+    }
+    __syncthreads();
+    if (threadIdx.x < IM_NTERMS * 2) {
+        unsigned long long v = 0;
+        for (int r = 0; r < pe.n; ++r) v += __ldcg(liowin_acc(pe.w[pe.rank], r) + threadIdx.x);
+        ctrl->acc[iter][threadIdx.x] = v;
+    }
+    __threadfence_block();
+    __syncthreads();
+    ieskf_solve_block(P, ctrl, iter, &S, &W);
+}
+
 #define SOLVE_THREADS 352
 __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(LioParams P, LioCtrl* ctrl, int iter) {
     __shared__ SolveScratch S;
     ieskf_solve(P, ctrl, iter, &S, threadIdx.x, blockDim.x);
 }
 
-__global__ void __launch_bounds__(32) k_pinv(LioCtrl* ctrl) {
-    __shared__ double a[324], lu[18 * 19], inv[324];
-    __shared__ int piv[18];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < 324; i += 32) a[i] = ctrl->state[24 + i];
-    __syncwarp();
-    warp_lu_inverse18(a, lu, piv, inv, lane);
-    for (int i = lane; i < 324; i += 32) ctrl->Pinv[i] = inv[i];
+__global__ void __launch_bounds__(INV_THREADS) k_pinv(LioCtrl* ctrl) {
+    __shared__ double a[324], inv[324];
+    __shared__ InvScratch W;
+    for (int i = threadIdx.x; i < 324; i += blockDim.x) a[i] = ctrl->state[24 + i];
+    __syncthreads();
+    block_lu_inverse18(a, &W, inv);
+    for (int i = threadIdx.x; i < 324; i += blockDim.x) ctrl->Pinv[i] = inv[i];
 }
-__global__ void __launch_bounds__(128) k_solve_warp(LioParams P, LioCtrl* ctrl, int iter) {
+__global__ void __launch_bounds__(INV_THREADS) k_solve_warp(LioParams P, LioCtrl* ctrl, int iter) {
     __shared__ SolveScratch S;
+    __shared__ InvScratch W;
     if (ctrl->stop) return;
-    ieskf_solve_block(P, ctrl, iter, &S);
+    ieskf_solve_block(P, ctrl, iter, &S, &W);
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS) k_predict(LioCtrl* ctrl, double dt, double cov_gyr, double cov_acc) {
@@ -471,6 +670,7 @@ int immesh_lio_destroy(immesh_lio_t* h) {
     if (!h) return IMMESH_OK;
     cudaStreamSynchronize(h->stream);
     h->graph.destroy();
+    if (h->win.local) immesh::peer_window_close(h->win);
     if (h->nccl_comm && nccl().CommDestroy) nccl().CommDestroy(h->nccl_comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_body) cudaFreeHost(h->h_body);
@@ -508,7 +708,24 @@ int immesh_lio_shard(immesh_lio_t* h, int rank, int nranks, const char* unique_i
     h->P.shard_rank = rank;
     h->P.shard_n = nranks;
     if (!h->d_bits) IM_CUDA(dev_alloc(h, &h->d_bits, (size_t)2 * (h->max_scan / 32 + 2), 0));
+    // peer window over NVLink (CUDA IPC): the exchanges of the residual pass are then fused into its kernels.  IMMESH_SHARD_NCCL=1
+    // keeps the NCCL all-reduce sequence (the baseline the fused path is measured against).
+    const char* force_nccl = std::getenv("IMMESH_SHARD_NCCL");
+    if (!(force_nccl && force_nccl[0] == '1')) {
+        h->words_cap = h->max_scan / 32 + 2;
+        const size_t bytes = IM_LIOWIN_BITS_OFF + (size_t)IM_MAX_RANKS * 2 * h->words_cap * sizeof(unsigned int);
+        const cudaError_t e = immesh::peer_window_open(h->win, bytes, rank, nranks, comm, h->stream);
+        if (e != cudaSuccess) {
+            std::fprintf(stderr, "[immesh_b200] rank %d: peer window unavailable (%s); sharded residual pass falls back to NCCL all-reduces\n", rank, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
     return IMMESH_OK;
+}
+int immesh_lio_shard_transport(immesh_lio_t* h) {   // 0 = not sharded, 1 = NCCL all-reduces, 2 = fused peer-window exchange
+    if (!h) return 0;
+    if (h->P.shard_n <= 1) return 0;
+    return h->win.ok ? 2 : 1;
 }
 
 int immesh_lio_set_state(immesh_lio_t* h, const double* s) {
@@ -549,6 +766,7 @@ static int check_flags(immesh_lio* h) {
     const int err = h->h_ints[4];
     if (err & (IM_ERR_NODE_POOL | IM_ERR_CHUNK_POOL | IM_ERR_HASH_FULL | IM_ERR_SEG_POOL)) return im_fail(IMMESH_E_CAPACITY, "device pool overflow (raise the capacities in immesh_lio_config)");
     if (err & (IM_ERR_KEY_RANGE | IM_ERR_FX_RANGE)) return im_fail(IMMESH_E_RANGE, "coordinate / normal-equation term outside the representable range");
+    if (err & IM_ERR_PEER_TIMEOUT) return im_fail(IMMESH_E_CUDA, "sharded mode: a peer rank did not publish its data in time (peer window epoch flag)");
     return IMMESH_OK;
 }
 static void launch_grow(immesh_lio* h, int n, int mode) {
@@ -564,7 +782,7 @@ static int launch_estimate_sharded(immesh_lio* h, int n) {
     const int words = (n + 31) / 32 + 1;
     cudaEventRecord(h->ev_fork, h->stream);
     cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-    IM_LAUNCH(k_pinv, 1, 32, 0, h->stream2, h->d_ctrl);
+    IM_LAUNCH(k_pinv, 1, INV_THREADS, 0, h->stream2, h->d_ctrl);
     cudaEventRecord(h->ev_join, h->stream2);
     IM_LAUNCH(k_reset_scan, 2, 256, 0, h->stream, h->sb, h->d_ctrl, 1);
     if (n > 0) IM_LAUNCH(k_prepare, grid_for(h, n, 128), 128, 0, h->stream, h->P, h->sb, n);
@@ -576,16 +794,40 @@ static int launch_estimate_sharded(immesh_lio* h, int n) {
         if (n > 0) IM_LAUNCH(k_shard_pass2, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n, h->d_bits, words);
         if (nccl().AllReduce(&h->d_ctrl->acc[it][0], &h->d_ctrl->acc[it][0], (size_t)IM_NTERMS * 2, kNcclUint64, kNcclSum, h->nccl_comm, h->stream)) return im_fail(IMMESH_E_CUDA, "ncclAllReduce(acc) failed");
         if (it == 0) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
-        IM_LAUNCH(k_solve_warp, 1, 128, 0, h->stream, h->P, h->d_ctrl, it);
+        IM_LAUNCH(k_solve_warp, 1, INV_THREADS, 0, h->stream, h->P, h->d_ctrl, it);
     }
     return IMMESH_OK;
 }
+// sharded VoxelMap over peer windows: per iteration  pass1(+publish bits) -> pass2(wait bits, +publish sums) -> solve(wait sums)
+static void launch_estimate_p2p(immesh_lio* h, int n) {
+    const bool replay = immesh::im_replaying();
+    if (n > 0) {
+        if (!replay) { cudaEventRecord(h->ev_fork, h->stream); cudaStreamWaitEvent(h->stream2, h->ev_fork, 0); }
+        IM_LAUNCH(k_pinv, 1, INV_THREADS, 0, h->stream2, h->d_ctrl);
+        if (!replay) cudaEventRecord(h->ev_join, h->stream2);
+    }
+    IM_LAUNCH(k_reset_scan, 2, 256, 0, h->stream, h->sb, h->d_ctrl, 1);
+    if (n <= 0) return;   // every rank sees the same (replicated) scan, so all of them skip the exchanges together
+    IM_LAUNCH(k_prepare, grid_for(h, n, 128), 128, 0, h->stream, h->P, h->sb, n);
+    LioPeers pe;
+    for (int r = 0; r < IM_MAX_RANKS; ++r) pe.w[r] = h->win.peer[r];
+    pe.rank = h->win.rank; pe.n = h->win.n; pe.words_cap = h->words_cap; pe.pad = 0;
+    const int g = grid_for(h, n, RES_THREADS, 4);
+    for (int it = 0; it < h->P.max_iter; ++it) {
+        const unsigned long long e = h->win.epoch + 1 + it;   // one epoch per iteration (base advanced once per scan by the caller); the two phases have separate flag rows
+        IM_LAUNCH(k_shard_pass1_p2p, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, n, pe, e);
+        IM_LAUNCH(k_shard_pass2_p2p, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n, pe, e);
+        if (it == 0 && !replay) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+        IM_LAUNCH(k_solve_warp_p2p, 1, INV_THREADS, 0, h->stream, h->P, h->d_ctrl, it, pe, e, h->map.err);
+    }
+}
 static void launch_estimate(immesh_lio* h, int n) {
+    if (h->P.shard_n > 1 && h->win.ok) { launch_estimate_p2p(h, n); return; }
     if (h->P.shard_n > 1) { launch_estimate_sharded(h, n); return; }
     const bool replay = immesh::im_replaying();   // graph replay: the fork/join edges are already part of the graph
     if (n > 0) {  // P^-1 on the side stream, overlapped with the scan preparation and the first residual pass
         if (!replay) { cudaEventRecord(h->ev_fork, h->stream); cudaStreamWaitEvent(h->stream2, h->ev_fork, 0); }
-        IM_LAUNCH(k_pinv, 1, 32, 0, h->stream2, h->d_ctrl);
+        IM_LAUNCH(k_pinv, 1, INV_THREADS, 0, h->stream2, h->d_ctrl);
         if (!replay) cudaEventRecord(h->ev_join, h->stream2);
     }
     IM_LAUNCH(k_reset_scan, 2, 256, 0, h->stream, h->sb, h->d_ctrl, 1);
@@ -599,7 +841,7 @@ static void launch_estimate(immesh_lio* h, int n) {
         } else {
             IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, n, 0);
             if (it == 0 && !replay) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
-            IM_LAUNCH(k_solve_warp, 1, 128, 0, h->stream, h->P, h->d_ctrl, it);
+            IM_LAUNCH(k_solve_warp, 1, INV_THREADS, 0, h->stream, h->P, h->d_ctrl, it);
         }
     }
 }
@@ -625,6 +867,7 @@ int immesh_lio_estimate(immesh_lio_t* h, const float* body, int n, int* iters_ru
     if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
     int rc = upload_scan(h, body, n);
     if (rc) return rc;
+    h->win.epoch += IM_MAX_ITER;   // epoch base of this scan (same sequence of calls on every rank)
     launch_estimate(h, n);
     IM_CUDA(cudaGetLastError());
     IM_CUDA(cudaMemcpyAsync(h->h_ints + 32, &h->d_ctrl->iters_run, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -643,6 +886,7 @@ int immesh_voxelmap_update(immesh_lio_t* h) {
 static int lio_flags_status(int err) {
     if (err & (IM_ERR_NODE_POOL | IM_ERR_CHUNK_POOL | IM_ERR_HASH_FULL | IM_ERR_SEG_POOL)) return im_fail(IMMESH_E_CAPACITY, "device pool overflow (raise the capacities in immesh_lio_config)");
     if (err & (IM_ERR_KEY_RANGE | IM_ERR_FX_RANGE)) return im_fail(IMMESH_E_RANGE, "coordinate / normal-equation term outside the representable range");
+    if (err & IM_ERR_PEER_TIMEOUT) return im_fail(IMMESH_E_CUDA, "sharded mode: a peer rank did not publish its data in time (peer window epoch flag)");
     return IMMESH_OK;
 }
 // queue predict + estimate + update for one scan; no host synchronisation unless both staging slots are busy
@@ -652,11 +896,12 @@ static int lio_enqueue(immesh_lio_t* h, const float* body, int n, int on_device,
     if (h->slot_busy[s]) { IM_CUDA(cudaEventSynchronize(h->ev_slot[s])); h->slot_busy[s] = 0; }
     int rc = upload_scan(h, body, n, on_device, s);
     if (rc) return rc;
+    h->win.epoch += IM_MAX_ITER;   // epoch base of this scan: advanced exactly once per scan, also when the graph body runs twice
     // The pipelined entry points replay the scan's launch sequence as one CUDA graph (the sequence is host-launch-bound
     // otherwise); the blocking ones launch directly, with stage timing events in between.
     bool queued = false;
-    if (allow_graph && h->use_graph && !profiler().enabled && h->P.shard_n <= 1 && n > 0) {
-        const unsigned sig = 1u | (dt > 0 ? 2u : 0u) | (h->fused_solve ? 4u : 0u) | ((unsigned)h->P.max_iter << 8);
+    if (allow_graph && h->use_graph && !profiler().enabled && (h->P.shard_n <= 1 || h->win.ok) && n > 0) {
+        const unsigned sig = 1u | (dt > 0 ? 2u : 0u) | (h->fused_solve ? 4u : 0u) | (h->win.ok ? 8u : 0u) | ((unsigned)h->P.max_iter << 8);
         queued = immesh::run_graphed(h->graph, sig, h->stream, [&] {
             if (dt > 0) IM_LAUNCH(k_predict, 1, SOLVE_THREADS, 0, h->stream, h->d_ctrl, dt, cov_gyr, cov_acc);
             launch_estimate(h, n);

@@ -42,6 +42,8 @@ struct LioCtrl {
     int rematch_num;
     int pad_;
     int blocks_done[IM_MAX_ITER];  // residual blocks that have published their sums (the last one runs the solve)
+    int shard_cnt[2];              // peer-window exchange: blocks of pass 1 / pass 2 that have finished (reset by the last one)
+    int pad2_[2];
 };
 
 struct ScanBuf {
@@ -185,9 +187,12 @@ IM_HDN inline bool residual_point(const VoxelMapDev& map, const LioParams& P, co
 // pass 2 lets exactly one rank contribute the point's normal-equation terms.  Integer sums => the all-reduced
 // accumulators, hence the state, are bit-identical to the single-GPU run for any number of ranks.
 //   sb.slot[i] : speculative neighbour match node (-1 none)      sb.seg[i] : its layer
-IM_HDN inline void shard_pass1_point(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, unsigned int* bits_exists, unsigned int* bits_ok) {
+// core of pass 1: returns the two bits of point i through *exists / *ok1 (false unless this rank owns the point's root voxel)
+IM_HDN inline void shard_pass1_flags(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, bool* exists, bool* ok1) {
     double pwd[3], pw[3], var6[6];
     residual_world(P, sb, state, i, pwd, pw, var6);
+    *exists = false;
+    *ok1 = false;
     sb.match_node[i] = -1;
     sb.match_layer[i] = 0;
     sb.slot[i] = -1;
@@ -206,20 +211,12 @@ IM_HDN inline void shard_pass1_point(const VoxelMapDev& map, const LioParams& P,
         const int slot = hash_find(map, key);
         const int root = slot >= 0 ? map.root_node[slot] : -1;
         if (root >= 0) {
-#if defined(__CUDA_ARCH__)
-            atomicOr(&bits_exists[i >> 5], 1u << (i & 31));
-#else
-            bits_exists[i >> 5] |= 1u << (i & 31);
-#endif
+            *exists = true;
             MatchResult best; best.node = -1; best.layer = 0; best.prob = 0.0;
             bool ok = false;
             match_in_voxel(map, P, root, pw, var6, &ok, &best);
             if (ok) {
-#if defined(__CUDA_ARCH__)
-                atomicOr(&bits_ok[i >> 5], 1u << (i & 31));
-#else
-                bits_ok[i >> 5] |= 1u << (i & 31);
-#endif
+                *ok1 = true;
                 sb.match_node[i] = best.node;
                 sb.match_layer[i] = best.layer;
             } else if (o2 == P.shard_rank) {
@@ -238,11 +235,22 @@ IM_HDN inline void shard_pass1_point(const VoxelMapDev& map, const LioParams& P,
         }
     }
 }
-// pass 2: after the bit words have been summed over the ranks
-IM_HDN inline bool shard_pass2_point(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, const unsigned int* bits_exists, const unsigned int* bits_ok, long long* terms, int* err) {
+// bit-word form (NCCL all-reduce / gloo variant): the two bits are OR-ed into per-scan words
+IM_HDN inline void shard_pass1_point(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, unsigned int* bits_exists, unsigned int* bits_ok) {
+    bool ex, ok1;
+    shard_pass1_flags(map, P, sb, state, i, &ex, &ok1);
+#if defined(__CUDA_ARCH__)
+    if (ex) atomicOr(&bits_exists[i >> 5], 1u << (i & 31));
+    if (ok1) atomicOr(&bits_ok[i >> 5], 1u << (i & 31));
+#else
+    if (ex) bits_exists[i >> 5] |= 1u << (i & 31);
+    if (ok1) bits_ok[i >> 5] |= 1u << (i & 31);
+#endif
+}
+// pass 2: after the bits of all ranks have been combined (ex / ok1 = the point's two global bits)
+IM_HDN inline bool shard_pass2_flags(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, bool ex, bool ok1, long long* terms, int* err) {
     int node = sb.match_node[i];
     if (node < 0 && sb.slot[i] >= 0) {
-        const bool ex = (bits_exists[i >> 5] >> (i & 31)) & 1u, ok1 = (bits_ok[i >> 5] >> (i & 31)) & 1u;
         if (ex && !ok1) { node = sb.slot[i]; sb.match_node[i] = node; sb.match_layer[i] = sb.seg[i]; }
     }
     if (node < 0) return false;
@@ -250,6 +258,10 @@ IM_HDN inline bool shard_pass2_point(const VoxelMapDev& map, const LioParams& P,
     const double pb[3] = {(double)sb.body[i * 3 + 0], (double)sb.body[i * 3 + 1], (double)sb.body[i * 3 + 2]};
     body_to_world(P, state, state + 9, pb, pwd);
     return residual_terms(map, P, sb, state, i, node, pwd, terms, err);
+}
+IM_HDN inline bool shard_pass2_point(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, const unsigned int* bits_exists, const unsigned int* bits_ok, long long* terms, int* err) {
+    const bool ex = (bits_exists[i >> 5] >> (i & 31)) & 1u, ok1 = (bits_ok[i >> 5] >> (i & 31)) & 1u;
+    return shard_pass2_flags(map, P, sb, state, i, ex, ok1, terms, err);
 }
 
 // ------------------------------------------------------------------ K4: 18x18 LU inverse, cooperative

@@ -410,6 +410,7 @@ int immesh_mesh_destroy(immesh_mesh_t* h) {
     if (!h) return IMMESH_OK;
     cudaStreamSynchronize(h->stream);
     h->graph.destroy();
+    if (h->win.local) immesh::peer_window_close(h->win);
     if (h->nccl_comm && immesh::nccl().CommDestroy) immesh::nccl().CommDestroy(h->nccl_comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_pts) cudaFreeHost(h->h_pts);
@@ -457,31 +458,80 @@ __global__ void k_xhdr(MeshDev M, FrameBuf F, XHeader* hdr) {
         hdr->pad = 0;
     }
 }
+// ---- the same exchange over peer windows (peer_win.cuh): k_xpush stores the USED part of this rank's segment straight into
+// slot `rank` of every rank's receive area (its own included) and the last block raises the epoch flag; the apply kernels
+// wait on the flags of their peers.  Window: flag[2][8] u64 | pad to 256 | recv1[n][seg1_bytes] | recv2[n][seg2_bytes].
+struct MeshPeers {
+    unsigned char* w[IM_MAX_RANKS];
+    int rank, n;          // n == 0: NCCL transport (no waiting inside the apply kernels)
+    unsigned long long recv_off[2], seg_bytes[2];
+};
+__device__ __forceinline__ unsigned long long* meshwin_flag(unsigned char* w, int which, int src) { return (unsigned long long*)w + which * IM_MAX_RANKS + src; }
+__device__ __forceinline__ void copy16(unsigned char* dst, const unsigned char* src, size_t n16, int tid, int nt) {
+    for (size_t i = tid; i < n16; i += nt) ((uint4*)dst)[i] = ((const uint4*)src)[i];
+}
+__global__ void __launch_bounds__(256) k_xpush(MeshDev M, FrameBuf F, const unsigned char* seg, int which, MeshPeers pe, unsigned long long epoch, int* done) {
+    __shared__ int s_last;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const int n_smooth = min(M.cnt[32], F.x_cap), n_face = min(M.cnt[30], F.x_cap), n_rem = min(M.cnt[31], F.x_cap);
+    for (int r = 0; r < pe.n; ++r) {
+        unsigned char* dst = pe.w[r] + pe.recv_off[which] + (size_t)pe.rank * pe.seg_bytes[which];
+        if (tid == 0) *(int4*)dst = make_int4(n_smooth, n_face, n_rem, 0);
+        if (which == 0) {
+            copy16(dst + 16, seg + 16, (size_t)n_smooth * 2, tid, nt);
+        } else {
+            copy16(dst + 16, seg + 16, (size_t)n_face, tid, nt);
+            const size_t woff = 16 + (size_t)F.x_cap * 16, roff = 16 + (size_t)F.x_cap * 24;
+            copy16(dst + woff, seg + woff, ((size_t)n_face + 1) / 2, tid, nt);
+            copy16(dst + roff, seg + roff, (size_t)n_rem, tid, nt);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(done, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x == 0) *done = 0;
+        __threadfence_system();
+        if (threadIdx.x < pe.n && threadIdx.x != pe.rank) immesh::st_release_sys(meshwin_flag(pe.w[threadIdx.x], which, pe.rank), epoch);
+    }
+}
+__device__ __forceinline__ void mesh_wait_peers(const MeshPeers& pe, int which, unsigned long long epoch, int* err) {
+    if (pe.n > 0) {
+        if (threadIdx.x < pe.n && threadIdx.x != pe.rank) {
+            if (!immesh::wait_epoch(meshwin_flag(pe.w[pe.rank], which, threadIdx.x), epoch)) atomicOr(err, IM_MERR_PEER_TIMEOUT);
+        }
+        __syncthreads();
+    }
+}
 // smoothed positions written by the other ranks' dilations -> this rank's replica
-__global__ void __launch_bounds__(256) k_apply_smooth(MeshDev M, FrameBuf F, const unsigned char* recv, size_t seg_bytes) {
+__global__ void __launch_bounds__(256) k_apply_smooth(MeshDev M, FrameBuf F, const unsigned char* recv, size_t seg_bytes, MeshPeers pe, unsigned long long epoch) {
+    mesh_wait_peers(pe, 0, epoch, &M.cnt[3]);
     for (int r = 0; r < F.shard_n; ++r) {
         if (r == F.shard_rank) continue;
         const unsigned char* seg = recv + (size_t)r * seg_bytes;
-        const int n = ((const XHeader*)seg)->n_smooth;
-        const XSmooth* e = (const XSmooth*)(seg + 16);
+        const int n = __ldcg((const int*)seg);
+        const double2* e = (const double2*)(seg + 16);
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-            const XSmooth v = e[i];
-            M.vsmooth[(size_t)v.id * 3 + 0] = v.x; M.vsmooth[(size_t)v.id * 3 + 1] = v.y; M.vsmooth[(size_t)v.id * 3 + 2] = v.z;
+            const double2 a = __ldcg(e + 2 * (size_t)i), b = __ldcg(e + 2 * (size_t)i + 1);   // {id|pad, x}, {y, z}
+            const int id = (int)(__double_as_longlong(a.x) & 0xffffffffLL);
+            M.vsmooth[(size_t)id * 3 + 0] = a.y; M.vsmooth[(size_t)id * 3 + 1] = b.x; M.vsmooth[(size_t)id * 3 + 2] = b.y;
         }
     }
 }
 // facets / removals of ALL ranks (own segment included) -> add / remove lists of this rank's replica
-__global__ void __launch_bounds__(256) k_apply_lists(MeshDev M, FrameBuf F, const unsigned char* recv, size_t seg_bytes) {
+__global__ void __launch_bounds__(256) k_apply_lists(MeshDev M, FrameBuf F, const unsigned char* recv, size_t seg_bytes, MeshPeers pe, unsigned long long epoch) {
+    mesh_wait_peers(pe, 1, epoch, &M.cnt[3]);
     for (int r = 0; r < F.shard_n; ++r) {
         const unsigned char* seg = recv + (size_t)r * seg_bytes;
-        const XHeader* h = (const XHeader*)seg;
+        const int4 h = __ldcg((const int4*)seg);   // n_smooth, n_face, n_rem, -
         const int4* face = (const int4*)(seg + 16);
         const unsigned long long* word = (const unsigned long long*)(seg + 16 + (size_t)F.x_cap * 16);
         const int4* rem = (const int4*)(seg + 16 + (size_t)F.x_cap * 24);
-        const int nf = h->n_face, nr = h->n_rem;
+        const int nf = h.y, nr = h.z;
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf + nr; i += gridDim.x * blockDim.x) {
-            if (i < nf) { const int4 f = face[i]; apply_face(M, F, f.x, f.y, f.z, word[i]); }
-            else { const int4 t = rem[i - nf]; apply_remove(M, F, t.x, t.y, t.z); }
+            if (i < nf) { const int4 f = __ldcg(face + i); apply_face(M, F, f.x, f.y, f.z, __ldcg(word + i)); }
+            else { const int4 t = __ldcg(rem + (i - nf)); apply_remove(M, F, t.x, t.y, t.z); }
         }
     }
 }
@@ -498,6 +548,7 @@ __global__ void k_pose_from_lio(const LioCtrl* ctrl, double res, FramePose* out)
 static int mesh_status(int err) {
     if (err & (IM_MERR_VERT_POOL | IM_MERR_TRI_POOL | IM_MERR_HASH_FULL | IM_MERR_LIST_CAP | IM_MERR_VOXEL_CAP)) return im_fail(IMMESH_E_CAPACITY, "mesh pool / per-voxel working-set overflow");
     if (err & (IM_MERR_KEY_RANGE | IM_MERR_PRIO_RANGE)) return im_fail(IMMESH_E_RANGE, "mesh key out of range");
+    if (err & IM_MERR_PEER_TIMEOUT) return im_fail(IMMESH_E_CUDA, "sharded mesher: a peer rank did not publish its segment in time (peer window epoch flag)");
     return IMMESH_OK;
 }
 // wait for the frame queued in slot s and take over its counters
@@ -565,6 +616,16 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
     }
     // the frame's launch sequence; replayed as one CUDA graph by the pipelined entry points (host-launch-bound otherwise)
     bool nccl_failed = false;
+    MeshPeers pe;
+    std::memset(&pe, 0, sizeof(pe));
+    unsigned long long epoch = 0;
+    if (F.shard_n > 1 && h->win.ok) {   // one epoch per frame; the two exchanges have separate flag rows
+        for (int r = 0; r < IM_MAX_RANKS; ++r) pe.w[r] = h->win.peer[r];
+        pe.rank = h->win.rank; pe.n = h->win.n;
+        pe.recv_off[0] = 256; pe.recv_off[1] = 256 + (unsigned long long)h->seg1_bytes * h->win.n;
+        pe.seg_bytes[0] = h->seg1_bytes; pe.seg_bytes[1] = h->seg2_bytes;
+        epoch = ++h->win.epoch;
+    }
     auto launch_frame = [&](bool timing) {
         const bool replay = immesh::im_replaying();
         IM_LAUNCH(k_frame_begin, mesh_grid(h, (int)std::max(F.cmask, F.fset_mask) + 1, 256), 256, 0, st, h->M, F);
@@ -582,10 +643,13 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         if (timing) cudaEventRecord(h->ev[2], st);
         if (F.m > 0) {
             IM_LAUNCH(k_voxel_dilate, h->n_sm * h->bps, 128, 0, st, h->M, P, F);
-            if (F.shard_n > 1) {   // smoothed positions of the other ranks' voxels (the facet orientation reads them)
+            if (F.shard_n > 1 && h->win.ok) {   // smoothed positions of the other ranks' voxels, pushed into their windows
+                IM_LAUNCH(k_xpush, h->n_sm, 256, 0, st, h->M, F, (const unsigned char*)h->d_seg1, 0, pe, epoch, h->d_xdone);
+                IM_LAUNCH(k_apply_smooth, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv1, h->seg1_bytes, pe, epoch);
+            } else if (F.shard_n > 1) {   // NCCL transport
                 IM_LAUNCH(k_xhdr, 1, 32, 0, st, h->M, F, (XHeader*)h->d_seg1);
                 if (immesh::nccl().AllGather(h->d_seg1, h->d_recv1, h->seg1_bytes, immesh::kNcclUint8, h->nccl_comm, st)) nccl_failed = true;
-                IM_LAUNCH(k_apply_smooth, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv1, h->seg1_bytes);
+                IM_LAUNCH(k_apply_smooth, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv1, h->seg1_bytes, pe, epoch);
             }
             // triangulation: small dilated sets warp-level on the side stream, mid-size ones block-level on the main stream,
             // concurrently; then the rare large / handed-over ones (monolithic: triangulate + commit in shared memory)
@@ -606,10 +670,13 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
             IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st, h->M, P, F, 256, 0);
             IM_LAUNCH(k_commit_faces, h->n_sm * 8, 128, 0, st, h->M, P, F);
             IM_LAUNCH(k_pull_check, h->n_sm * 8, 128, 0, st, h->M, F);
-            if (F.shard_n > 1) {   // every rank applies the facets / removals of all ranks to its replica of the store
+            if (F.shard_n > 1 && h->win.ok) {   // every rank applies the facets / removals of all ranks to its replica of the store
+                IM_LAUNCH(k_xpush, h->n_sm, 256, 0, st, h->M, F, (const unsigned char*)h->d_seg2, 1, pe, epoch, h->d_xdone + 1);
+                IM_LAUNCH(k_apply_lists, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv2, h->seg2_bytes, pe, epoch);
+            } else if (F.shard_n > 1) {
                 IM_LAUNCH(k_xhdr, 1, 32, 0, st, h->M, F, (XHeader*)h->d_seg2);
                 if (immesh::nccl().AllGather(h->d_seg2, h->d_recv2, h->seg2_bytes, immesh::kNcclUint8, h->nccl_comm, st)) nccl_failed = true;
-                IM_LAUNCH(k_apply_lists, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv2, h->seg2_bytes);
+                IM_LAUNCH(k_apply_lists, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv2, h->seg2_bytes, pe, epoch);
             }
         }
         if (timing) cudaEventRecord(h->ev[3], st);
@@ -620,8 +687,8 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         IM_LAUNCH(k_frame_end, 1, 1, 0, st, h->M);
     };
     bool queued = false;
-    if (allow_graph && h->use_graph && !profiler().enabled && F.m > 0 && F.shard_n <= 1) {
-        queued = immesh::run_graphed(h->graph, 1u, st, [&] { launch_frame(false); }) == cudaSuccess;
+    if (allow_graph && h->use_graph && !profiler().enabled && F.m > 0 && (F.shard_n <= 1 || h->win.ok)) {
+        queued = immesh::run_graphed(h->graph, h->win.ok ? 3u : 1u, st, [&] { launch_frame(false); }) == cudaSuccess;
         if (!queued) h->use_graph = 0;
     }
     if (!queued) launch_frame(true);
@@ -713,14 +780,33 @@ int immesh_mesh_shard(immesh_mesh_t* h, int rank, int nranks, const char* unique
     unsigned char *s1 = nullptr, *s2 = nullptr;
     IM_CUDA(mdev_alloc(h, &s1, h->seg1_bytes, 0));
     IM_CUDA(mdev_alloc(h, &s2, h->seg2_bytes, 0));
-    IM_CUDA(mdev_alloc(h, &h->d_recv1, h->seg1_bytes * nranks, 0));
-    IM_CUDA(mdev_alloc(h, &h->d_recv2, h->seg2_bytes * nranks, 0));
+    // receive areas: inside a peer window (other ranks store into it over NVLink) or, with NCCL transport, private buffers
+    const char* force_nccl = std::getenv("IMMESH_SHARD_NCCL");
+    if (!(force_nccl && force_nccl[0] == '1')) {
+        const cudaError_t e = immesh::peer_window_open(h->win, 256 + (h->seg1_bytes + h->seg2_bytes) * (size_t)nranks, rank, nranks, comm, h->stream);
+        if (e != cudaSuccess) {
+            std::fprintf(stderr, "[immesh_b200] rank %d: peer window unavailable (%s); sharded mesher falls back to NCCL all-gathers\n", rank, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    if (h->win.ok) {
+        h->d_recv1 = h->win.local + 256;
+        h->d_recv2 = h->win.local + 256 + h->seg1_bytes * (size_t)nranks;
+        IM_CUDA(mdev_alloc(h, &h->d_xdone, 2, 0));
+    } else {
+        IM_CUDA(mdev_alloc(h, &h->d_recv1, h->seg1_bytes * nranks, 0));
+        IM_CUDA(mdev_alloc(h, &h->d_recv2, h->seg2_bytes * nranks, 0));
+    }
     h->d_seg1 = s1; h->d_seg2 = s2;
     F.x_smooth = (immesh::XSmooth*)(s1 + 16);
     F.x_face = (int4*)(s2 + 16);
     F.x_word = (unsigned long long*)(s2 + 16 + (size_t)F.x_cap * 16);
     F.x_rem = (int4*)(s2 + 16 + (size_t)F.x_cap * 24);
     return IMMESH_OK;
+}
+int immesh_mesh_shard_transport(immesh_mesh_t* h) {
+    if (!h || h->F.shard_n <= 1) return 0;
+    return h->win.ok ? 2 : 1;
 }
 int immesh_graph_stats(immesh_lio_t* lio, immesh_mesh_t* mesh, int64_t* out) {
     if (!out) return im_fail(IMMESH_E_INVALID, "null argument");

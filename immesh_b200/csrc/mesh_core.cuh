@@ -62,6 +62,7 @@ enum : int {
     IM_MERR_LIST_CAP = 16,   // add/remove/work list overflow
     IM_MERR_KEY_RANGE = 32,
     IM_MERR_PRIO_RANGE = 64, // activated voxel farther than 1024 voxels from the sensor (flip priority)
+    IM_MERR_PEER_TIMEOUT = 128,   // sharded mode: a peer rank's epoch flag did not arrive (peer_win.cuh)
 };
 
 struct MeshDev {

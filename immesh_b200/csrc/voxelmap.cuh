@@ -93,6 +93,7 @@ enum : int {
     IM_ERR_HASH_FULL = 8,
     IM_ERR_FX_RANGE = 16,
     IM_ERR_SEG_POOL = 32,
+    IM_ERR_PEER_TIMEOUT = 64,   // sharded mode: a peer rank's epoch flag did not arrive (peer_win.cuh)
 };
 
 struct VoxelMapDev {

@@ -100,6 +100,13 @@ int immesh_lio_enqueue_memset(immesh_lio_t* h, void* d_buf, size_t bytes); /* be
  * immesh_comm_unique_id on rank 0 and distributed by the caller (e.g. torch.distributed broadcast). */
 int immesh_comm_unique_id(char* out128);
 int immesh_lio_shard(immesh_lio_t* h, int rank, int nranks, const char* unique_id128);
+/* Transport of a sharded handle's exchanges: 0 = handle not sharded, 1 = NCCL collectives, 2 = peer windows.  With peer
+ * windows (the default when the ranks' GPUs can map each other's memory through CUDA IPC / NVLink; IMMESH_SHARD_NCCL=1 in
+ * the environment forces NCCL) there is no collective call: the kernel that produces the data stores it directly into
+ * the consumer ranks' windows and raises an epoch flag, the consuming kernel waits on the flags -- the NCCL communicator
+ * is then only used once, to exchange the IPC handles. */
+int immesh_lio_shard_transport(immesh_lio_t* h);
+int immesh_mesh_shard_transport(immesh_mesh_t* h);
 /* Same for the mesher (its own communicator: use a second unique id).  Every rank is given the same frames and runs the
  * vertex append itself (replicated: identical vertex ids everywhere); the per-voxel stage -- dilation, triangulation
  * (mesh_rec_geometry.cpp:174-295), pull, commit -- runs only for the mesh voxels the rank owns.  Two all-gathers per frame

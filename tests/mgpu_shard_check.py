@@ -1,7 +1,7 @@
 """Multi-GPU parity check (run under torchrun, one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_shard_check.py
-Every rank runs the same scan stream twice on its GPU: once with the VoxelMap sharded over all ranks (NCCL all-reduces
-inside the C library) and once unsharded.  The sharded state must equal the unsharded one bit for bit on every rank,
+Every rank runs the same scan stream twice on its GPU: once with the VoxelMap sharded over all ranks (exchanges fused into
+the kernels over NVLink peer windows; IMMESH_SHARD_NCCL=1 selects the NCCL all-reduce / all-gather baseline) and once unsharded.  The sharded state must equal the unsharded one bit for bit on every rank,
 and the union of the ranks' map shards must equal the unsharded map.  The mesher runs sharded (per-voxel stage by voxel
 owner, two all-gathers per frame) next to an unsharded instance: vertices, facet set and flags must be identical."""
 import os
@@ -77,7 +77,8 @@ def main():
     sizes = [len(d) for d in dumps]
     if rank == 0:
         print(f"ranks={world} state_bit_exact={ok} map_union_bit_exact={map_ok} shard_rows={sizes} single_rows={len(ref)} "
-              f"mesh_replicas_bit_exact={mesh_ok} facets={n_facets} voxels_meshed_last_frame_rank0={owned}", flush=True)
+              f"mesh_replicas_bit_exact={mesh_ok} facets={n_facets} voxels_meshed_last_frame_rank0={owned} "
+              f"transport_voxelmap={handles['sharded'].shard_transport()} transport_mesher={meshes['sharded'].shard_transport()}", flush=True)
     flag = torch.tensor([int(ok and map_ok and mesh_ok)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
