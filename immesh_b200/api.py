@@ -124,9 +124,15 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_mesh_snapshot", [vp, fp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         ("immesh_knn", [vp, fp, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int32), fp]),
         ("immesh_mesh_last_timing", [vp, dp]),
+        ("immesh_voxelgrid_create", [C.c_int, C.POINTER(vp)]),
+        ("immesh_voxelgrid_destroy", [vp]),
+        ("immesh_voxelgrid_filter", [vp, vp, C.c_int, C.c_int, C.c_float, vp, ip, ip]),
+        ("immesh_voxelgrid_device_points", [vp]),
     ):
         if hasattr(lib, name):
             getattr(lib, name).argtypes = args
+    if hasattr(lib, "immesh_voxelgrid_device_points"):
+        lib.immesh_voxelgrid_device_points.restype = C.c_void_p
     if hasattr(lib, "immesh_launch_count"):
         lib.immesh_launch_count.restype = C.c_longlong
     if hasattr(lib, "immesh_last_error"):
@@ -400,6 +406,45 @@ class Mesh:
         o = np.zeros(4)
         self.lib.immesh_mesh_last_timing(self._h, o.ctypes.data_as(C.POINTER(C.c_double)))
         return o
+
+
+class VoxelGrid:
+    """pcl::VoxelGrid front-end on the device (immesh_voxelgrid_*): filter(points, leaf) -> centroids, leaves in PCL index order."""
+
+    def __init__(self, max_points: int = 1 << 20, lib: Optional[C.CDLL] = None):
+        self.lib = lib or load_library()
+        self._h = C.c_void_p()
+        _check(self.lib, self.lib.immesh_voxelgrid_create(max_points, C.byref(self._h)), "voxelgrid_create")
+        self.leaf_too_small = False
+        self.m = 0
+
+    def close(self):
+        if self._h:
+            self.lib.immesh_voxelgrid_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def filter(self, pts, leaf: float, n=None, on_device=False, fetch=True):
+        """pts: float32[n,3] host array, or a device pointer (int) with n and on_device=True.  Returns float32[m,3] (or m if not fetch)."""
+        if on_device:
+            ptr, cnt = C.c_void_p(int(pts)), int(n)
+        else:
+            a = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)
+            ptr, cnt = a.ctypes.data_as(C.c_void_p), a.shape[0]
+        out = np.zeros((max(cnt, 1), 3), dtype=np.float32) if fetch else None
+        m, small = C.c_int(0), C.c_int(0)
+        _check(self.lib, self.lib.immesh_voxelgrid_filter(self._h, ptr, cnt, 1 if on_device else 0, C.c_float(leaf),
+                                                          out.ctypes.data_as(C.c_void_p) if fetch else None, C.byref(m), C.byref(small)), "voxelgrid_filter")
+        self.m, self.leaf_too_small = m.value, bool(small.value)
+        return out[:m.value].copy() if fetch else m.value
+
+    def device_points(self) -> int:
+        return int(self.lib.immesh_voxelgrid_device_points(self._h) or 0)
 
 
 def profile_enable(on: bool, lib: Optional[C.CDLL] = None):

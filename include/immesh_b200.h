@@ -33,6 +33,7 @@ extern "C" {
 
 typedef struct immesh_lio immesh_lio_t;
 typedef struct immesh_mesh immesh_mesh_t;
+typedef struct immesh_voxelgrid immesh_voxelgrid_t;
 
 /* Parameters of Voxel_mapping that the path reads (src/voxel_mapping.hpp:149-191,
  * read_ros_parameters src/voxel_mapping_common.cpp:625-707). */
@@ -186,6 +187,20 @@ int immesh_knn(immesh_mesh_t* h, const float* query_xyz /*[nq][3]*/, int nq, int
  * dilated vertices, facets produced, voxels meshed, add-list entries, remove-list entries] */
 int immesh_mesh_work_stats(immesh_mesh_t* h, int64_t* out /*[8]*/);
 int immesh_mesh_last_timing(immesh_mesh_t* h, double* ms /*[4]: whole frame incl. H2D, append, per-voxel, push*/);
+
+/* ---- front-end: pcl::VoxelGrid centroid down-sampling of a scan on the device.  Replaces
+ *   m_downSizeFilterSurf.setLeafSize(l, l, l); m_downSizeFilterSurf.setInputCloud(m_feats_undistort);
+ *   m_downSizeFilterSurf.filter(*m_feats_down_body);      (src/voxel_mapping.cpp:1715, :1888-1889)
+ * and the mesher's copy (src/ImMesh_mesh_reconstruction.cpp:335-338).  xyz: [n][3] floats like pcl::PointXYZI's x, y, z
+ * (host pointer, or device pointer with on_device = 1).  Output: one centroid per occupied leaf, leaves in ascending
+ * PCL cell index, [m][3]; it stays on the device (immesh_voxelgrid_device_points, valid until the next call on the
+ * handle -- pass it to immesh_lio_step_async(..., on_device = 1)) and is copied to out_xyz when that is not NULL.
+ * leaf_too_small mirrors PCL's "Leaf size is too small for the input dataset" branch (output = input, m = n). */
+int immesh_voxelgrid_create(int max_points, immesh_voxelgrid_t** out);
+int immesh_voxelgrid_destroy(immesh_voxelgrid_t* h);
+int immesh_voxelgrid_filter(immesh_voxelgrid_t* h, const float* xyz, int n, int on_device, float leaf, float* out_xyz /*[n][3] or NULL*/,
+                            int* m_out, int* leaf_too_small /*or NULL*/);
+const float* immesh_voxelgrid_device_points(immesh_voxelgrid_t* h);
 
 /* optional per-kernel CUDA-event profiler (off by default) and launch accounting, process-wide */
 int immesh_profile_enable(int on);   /* 0 off, 1 per-kernel totals, 2 totals + timeline */

@@ -6,6 +6,7 @@
 
 #include "orc_lio.hpp"
 #include "orc_mesh.hpp"
+#include "orc_frontend.hpp"
 
 using namespace orc;
 
@@ -217,6 +218,14 @@ void orc_math_probe(const double* x, int n, double* s, double* c, double* e, dou
         e[i] = det_exp(-std::fabs(x[i]));
         ac[i] = det_acos(std::fmax(-1.0, std::fmin(1.0, x[i])));
     }
+}
+// pcl::VoxelGrid restatement (orc_frontend.hpp).  out: [cap][3]; returns m (or -m-1 when PCL's leaf-too-small branch copied the input)
+int orc_voxel_grid(const float* pts, int n, float leaf, float* out, int cap, int* grid6) {
+    const VoxelGridResult r = voxel_grid_filter(pts, n, leaf);
+    const int m = (int)(r.out.size() / 3);
+    for (int i = 0; i < m && i < cap; ++i) { out[3 * i] = r.out[3 * i]; out[3 * i + 1] = r.out[3 * i + 1]; out[3 * i + 2] = r.out[3 * i + 2]; }
+    if (grid6) { for (int a = 0; a < 3; ++a) { grid6[a] = r.min_b[a]; grid6[3 + a] = r.div_b[a]; } }
+    return r.leaf_too_small ? -m - 1 : m;
 }
 void orc_jacobi_eig3(const double* a6, double* d, double* V) { jacobi_eig3(a6, d, V); }
 void orc_lu_inverse18(const double* A, double* Ainv) { lu_inverse<18>(A, Ainv); }

@@ -162,6 +162,20 @@ class OracleMesh:
         return idx, d2
 
 
+def voxel_grid(pts, leaf):
+    """pcl::VoxelGrid restatement: returns (out float32[m,3], leaf_too_small, (min_b, div_b))."""
+    L = lib()
+    a = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros((max(a.shape[0], 1), 3), dtype=np.float32)
+    grid = np.zeros(6, dtype=np.int32)
+    L.orc_voxel_grid.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p]
+    m = L.orc_voxel_grid(_p(a), a.shape[0], C.c_float(leaf), _p(out), out.shape[0], _p(grid))
+    small = m < 0
+    if small:
+        m = -m - 1
+    return out[:m].copy(), small, (grid[:3].copy(), grid[3:].copy())
+
+
 def delaunay2d_int(pts):
     L = lib()
     a = np.ascontiguousarray(pts, dtype=np.int64)

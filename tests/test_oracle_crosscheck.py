@@ -184,3 +184,29 @@ def test_fixed_point_sums_close_to_serial_double():
         ia, ib = a.iter_stats(0), b.iter_stats(0)
         assert np.allclose(ia["HTH"], ib["HTH"], rtol=1e-9, atol=1e-4)
         assert np.allclose(a.get_state()[:12], b.get_state()[:12], rtol=1e-9, atol=1e-10)
+
+
+def test_voxel_grid_oracle_vs_numpy_restatement():
+    """orc_frontend.hpp (pcl::VoxelGrid restatement) against an independent numpy statement of the same published algorithm:
+    float32 inverse leaf / box / cell index, leaves in ascending index, float32 sums in scan order."""
+    rng = np.random.default_rng(2)
+    for pts, leaf in ((synth.make_stream("avia", 1, seed=1)[1][0]["body_full"], 0.4),
+                      (rng.normal(0, 5, (20000, 3)).astype(np.float32), 0.5),
+                      ((rng.integers(-30, 30, (5000, 3)) * 0.25).astype(np.float32), 0.25)):
+        out, small, (min_b, div_b) = oa.voxel_grid(pts, leaf)
+        assert not small
+        inv = np.float32(1.0) / np.float32(leaf)
+        mb = np.floor(pts.min(axis=0) * inv).astype(np.int32)
+        assert np.array_equal(mb, min_b)
+        ijk = (np.floor(pts * inv) - mb.astype(np.float32)).astype(np.int32)
+        idx = ijk[:, 0] + ijk[:, 1] * div_b[0] + ijk[:, 2] * div_b[0] * div_b[1]
+        order = np.argsort(idx, kind="stable")
+        uniq, start = np.unique(idx[order], return_index=True)
+        assert len(uniq) == len(out)
+        ends = list(start[1:]) + [len(order)]
+        for r in rng.integers(0, len(uniq), 300):
+            run = pts[order[start[r]:ends[r]]]
+            s = np.zeros(3, np.float32)
+            for p in run:
+                s = (s + p).astype(np.float32)
+            assert np.array_equal(out[r], s / np.float32(len(run)))
