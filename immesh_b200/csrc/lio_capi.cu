@@ -119,7 +119,70 @@ __device__ __forceinline__ int pivot_row18(const double* m /*stride 37*/, int k)
 #undef IM_PMERGE
     return id[0];
 }
-__device__ __noinline__ void block_lu_inverse18(const double* a_in /*[324] shared, row-major*/, InvScratch* W, double* inv_out /*[324] shared*/) {
+// variant 1 ("lean"): no redundant double-precision work -- the pivot is found by warp 0 alone (shuffle tournament, lower lane wins
+// ties), the 17-k multipliers l_i are divided once per row, then every thread updates its element; three barriers per step.
+__device__ __noinline__ void block_lu_inverse18_lean(const double* a_in, InvScratch* W, double* inv_out) {
+    __shared__ int s_bi;
+    __shared__ double s_l[18];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    for (int e = tid; e < 648; e += nt) {
+        const int i = e / 36, j = e - i * 36;
+        W->buf[0][i * 37 + j] = (j < 18) ? a_in[i * 18 + j] : ((j - 18 == i) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    int p = 0;
+    for (int k = 0; k < 18; ++k) {
+        const double* old = W->buf[p];
+        double* nw = W->buf[p ^ 1];
+        if (tid < 32) {   // first maximum of |old[i][k]|, i >= k
+            double bv = (lane >= k && lane < 18) ? fabs(old[lane * 37 + k]) : -1.0;
+            int bi = lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) s_bi = bi;
+        }
+        __syncthreads();
+        const int bi = s_bi;
+        if (tid > k && tid < 18) {   // multiplier of (post-swap) row tid
+            const int src = (tid == bi) ? k : tid;
+            s_l[tid] = old[src * 37 + k] / old[bi * 37 + k];
+        }
+        __syncthreads();
+        for (int e = tid; e < 648; e += nt) {
+            const int i = e / 36, j = e - i * 36;
+            if (i < k || j < k) continue;
+            if (i == k) {
+                const double v = old[bi * 37 + j];
+                if (j < 18) W->U[k * 19 + j] = v; else W->Y[k * 19 + (j - 18)] = v;
+            } else if (j > k) {
+                const int src = (i == bi) ? k : i;
+                nw[i * 37 + j] = old[src * 37 + j] - s_l[i] * old[bi * 37 + j];
+            }
+        }
+        __syncthreads();
+        p ^= 1;
+    }
+    if (tid < 18) {
+        const int c = tid;
+        double x[18];
+#pragma unroll
+        for (int i = 17; i >= 0; --i) {
+            double s = W->Y[i * 19 + c];
+#pragma unroll
+            for (int j = i + 1; j < 18; ++j) s = s - W->U[i * 19 + j] * x[j];
+            x[i] = s / W->U[i * 19 + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 18; ++i) inv_out[i * 18 + c] = x[i];
+    }
+    __syncthreads();
+}
+__device__ __noinline__ void block_lu_inverse18_redundant(const double* a_in /*[324] shared, row-major*/, InvScratch* W, double* inv_out /*[324] shared*/) {
+
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int e = tid; e < 648; e += nt) {
         const int i = e / 36, j = e - i * 36;
@@ -161,6 +224,12 @@ __device__ __noinline__ void block_lu_inverse18(const double* a_in /*[324] share
         for (int i = 0; i < 18; ++i) inv_out[i * 18 + c] = x[i];
     }
     __syncthreads();
+}
+
+__device__ int g_lu_variant = 1;   // 0: redundant (one barrier per step), 1: lean (three barriers, no redundant f64 work)
+__device__ __forceinline__ void block_lu_inverse18(const double* a_in, InvScratch* W, double* inv_out) {
+    if (g_lu_variant == 0) block_lu_inverse18_redundant(a_in, W, inv_out);
+    else block_lu_inverse18_lean(a_in, W, inv_out);
 }
 
 // same arithmetic as ieskf_solve (lio_core.cuh), block-cooperative with the two LU inverses done by warp 0
@@ -662,6 +731,10 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     for (int i = 0; i < 18; ++i) h->h_state[24 + i * 18 + i] = 0.0000001;
     IM_CUDA(cudaMemcpy(h->d_ctrl->state, h->h_state, IM_STATE_DOUBLES * sizeof(double), cudaMemcpyHostToDevice));
     IM_CUDA(cudaDeviceSynchronize());
+    if (const char* v = std::getenv("IMMESH_LU_VARIANT")) {   // experiments: 0 = redundant-pivot variant, 1 = lean (default)
+        const int iv = std::atoi(v);
+        IM_CUDA(cudaMemcpyToSymbol(g_lu_variant, &iv, sizeof(int)));
+    }
     *out = h;
     return IMMESH_OK;
 }

@@ -689,21 +689,34 @@ IM_HDN inline void tri_add(const MeshDev& M, int a, int b, int c, unsigned long 
     if (t < 0) { im_atomic_or(&M.cnt[3], IM_MERR_HASH_FULL); return; }
     if (t == mine) {
         const int vs[3] = {a, b, c};
-        for (int k = 0; k < 3; ++k) {
 #if defined(__CUDA_ARCH__)
-            int old = M.v_tri_head[vs[k]];
-            while (true) {
-                M.tri_next[(size_t)t * 3 + k] = old;
-                __threadfence();
-                const int prev = atomicCAS(&M.v_tri_head[vs[k]], old, t);
-                if (prev == old) break;
-                old = prev;
-            }
+        // the three list insertions are independent: their next-pointer stores, ONE fence and the three CAS are issued
+        // together, so a round costs one memory round trip instead of three; only the lists whose CAS lost a race (another
+        // facet of the same vertex was linked in between -- ~6 facets meet at a vertex) go into the next round
+        int old[3] = {M.v_tri_head[a], M.v_tri_head[b], M.v_tri_head[c]};
+        unsigned int pending = 7u;
+        while (pending) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (pending & (1u << k)) M.tri_next[(size_t)t * 3 + k] = old[k];
+            __threadfence();
+            int prev[3] = {0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (pending & (1u << k)) prev[k] = atomicCAS(&M.v_tri_head[vs[k]], old[k], t);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (pending & (1u << k)) {
+                    if (prev[k] == old[k]) pending &= ~(1u << k);
+                    else old[k] = prev[k];
+                }
+        }
 #else
+        for (int k = 0; k < 3; ++k) {
             M.tri_next[(size_t)t * 3 + k] = M.v_tri_head[vs[k]];
             M.v_tri_head[vs[k]] = t;
-#endif
         }
+#endif
     }
     // (a record allocated by a thread that lost the publication race stays unused: a leaked slot, never linked)
     if (im_atomic_exch(&M.tri[t].w, 1) == 0) im_atomic_add(&M.cnt[2], 1);

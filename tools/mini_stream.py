@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""A few scans through both pipelines with the blocking API: small target for `ncu -k regex:...` captures.
+    python tools/mini_stream.py [n_scans] [kind]"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from immesh_b200 import api, synth  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+kind = sys.argv[2] if len(sys.argv) > 2 else "avia100k"
+cfg = api.AVIA
+sensor, scans = synth.make_stream(kind, n + 1, seed=0, leaf=cfg.filter_size_surf, ext_T=cfg.ext_T)
+lio, mesh = api.Lio(cfg), api.Mesh(api.MeshConfig())
+lio.set_pose(scans[0]["R_true"], scans[0]["t_true"])
+lio.voxel_map_init(scans[0]["body_full"])
+vg = api.VoxelGrid(1 << 20)
+for sc in scans[1:]:
+    ds = vg.filter(sc["body_full"], cfg.filter_size_surf)
+    s, it = lio.step(ds, sc["dt"])
+    mesh.push_frame_from_lio(lio, sc["body_full"])
+print("ok", lio.counts(), mesh.counts(), "ds points", len(ds))
