@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -198,8 +199,9 @@ __global__ void __launch_bounds__(VG_THREADS) k_vg_heads(const unsigned int* __r
     __syncthreads();
     if (threadIdx.x == 0) tile_heads[blockIdx.x] = s_cnt;
 }
+// head_pos != nullptr: only record where run `slot` starts (the sums are then taken by k_vg_centroid_warp)
 __global__ void __launch_bounds__(VG_THREADS) k_vg_centroid(const float* __restrict__ pts, const unsigned int* __restrict__ keys, const unsigned int* __restrict__ vals, int n,
-                                                             const int* __restrict__ tile_base, float* out) {
+                                                             const int* __restrict__ tile_base, float* out, int* head_pos) {
     __shared__ int s_warp[VG_THREADS / 32];
     __shared__ int s_run;
     if (threadIdx.x == 0) s_run = tile_base[blockIdx.x];
@@ -216,7 +218,9 @@ __global__ void __launch_bounds__(VG_THREADS) k_vg_centroid(const float* __restr
         __syncthreads();
         int slot = s_run + __popc(hb & ((1u << lane) - 1u));
         for (int w = 0; w < warp; ++w) slot += s_warp[w];
-        if (head) {   // CentroidPoint: float sums in run order, divided by (float)count
+        if (head && head_pos) {
+            head_pos[slot] = i;
+        } else if (head) {   // CentroidPoint: float sums in run order, divided by (float)count
             float sx = 0.f, sy = 0.f, sz = 0.f;
             int e = i;
             while (e < n && keys[e] == k) {
@@ -230,6 +234,32 @@ __global__ void __launch_bounds__(VG_THREADS) k_vg_centroid(const float* __restr
         __syncthreads();
         if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < VG_THREADS / 32; ++w) t += s_warp[w]; s_run += t; }
         __syncthreads();
+    }
+}
+// one warp per run: the lanes fetch 32 points of the run at once (the loads are what made the thread-per-run loop slow: a dense
+// leaf near the sensor holds hundreds of points, ~1 us of dependent misses each), then every lane adds the 32 values in
+// run order from shuffles -- the float sum keeps the serial order of CentroidPoint, only the memory latency is taken off the chain.
+__global__ void __launch_bounds__(VG_THREADS) k_vg_centroid_warp(const float* __restrict__ pts, const unsigned int* __restrict__ vals, const int* __restrict__ head_pos,
+                                                                  const int* __restrict__ total_heads, const VgGrid* g, float* out) {
+    const int lane = threadIdx.x & 31;
+    const int m = *total_heads, n_valid = g->n_finite;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); slot < m; slot += nwarps) {
+        const int b = head_pos[slot], e = (slot + 1 < m) ? head_pos[slot + 1] : n_valid;
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int c = b; c < e; c += 32) {
+            const int i = c + lane;
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (i < e) { const unsigned int p = vals[i]; x = pts[3 * (size_t)p]; y = pts[3 * (size_t)p + 1]; z = pts[3 * (size_t)p + 2]; }
+            const int cnt = min(32, e - c);
+            for (int t = 0; t < cnt; ++t) {
+                sx += __shfl_sync(0xffffffffu, x, t); sy += __shfl_sync(0xffffffffu, y, t); sz += __shfl_sync(0xffffffffu, z, t);
+            }
+        }
+        if (lane == 0) {
+            const float cnt = (float)(e - b);
+            out[3 * (size_t)slot] = sx / cnt; out[3 * (size_t)slot + 1] = sy / cnt; out[3 * (size_t)slot + 2] = sz / cnt;
+        }
     }
 }
 __global__ void k_vg_finish(VgGrid* g, const int* total_heads, int n) {
@@ -250,6 +280,8 @@ struct immesh_voxelgrid {
     unsigned int *d_k[2] = {nullptr, nullptr}, *d_v[2] = {nullptr, nullptr};
     int* d_hist = nullptr;       // [256 * nblocks_max]
     int* d_tile = nullptr;       // [nblocks_max + 1]
+    int* d_head = nullptr;       // [max_points] start of every run in the sorted order
+    int warp_centroid = 1;       // 1: warp-per-run sums (k_vg_centroid_warp); 0: thread-per-run (IMMESH_VG_THREAD_CENTROID=1)
     VgGrid* d_grid = nullptr;
     VgGrid* h_grid = nullptr;    // pinned
     float* h_pts = nullptr;      // pinned staging [max_points][3]
@@ -278,6 +310,8 @@ int immesh_voxelgrid_create(int max_points, immesh_voxelgrid_t** out) {
     }
     IM_CUDA(cudaMalloc((void**)&h->d_hist, (size_t)256 * h->nblocks_max * sizeof(int)));
     IM_CUDA(cudaMalloc((void**)&h->d_tile, ((size_t)h->nblocks_max + 1) * sizeof(int)));
+    IM_CUDA(cudaMalloc((void**)&h->d_head, n * sizeof(int)));
+    if (const char* e = std::getenv("IMMESH_VG_THREAD_CENTROID")) h->warp_centroid = (e[0] == '1') ? 0 : 1;
     IM_CUDA(cudaMalloc((void**)&h->d_grid, sizeof(VgGrid)));
     IM_CUDA(cudaMallocHost((void**)&h->h_grid, sizeof(VgGrid)));
     IM_CUDA(cudaMallocHost((void**)&h->h_pts, n * 3 * sizeof(float)));
@@ -290,7 +324,7 @@ int immesh_voxelgrid_destroy(immesh_voxelgrid_t* h) {
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_in); cudaFree(h->d_out);
     for (int i = 0; i < 2; ++i) { cudaFree(h->d_k[i]); cudaFree(h->d_v[i]); }
-    cudaFree(h->d_hist); cudaFree(h->d_tile); cudaFree(h->d_grid);
+    cudaFree(h->d_hist); cudaFree(h->d_tile); cudaFree(h->d_head); cudaFree(h->d_grid);
     cudaFreeHost(h->h_grid); cudaFreeHost(h->h_pts);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -329,7 +363,13 @@ int immesh_voxelgrid_filter(immesh_voxelgrid_t* h, const float* xyz, int n, int 
     }
     IM_LAUNCH(k_vg_heads, nb, VG_THREADS, 0, st, (const unsigned int*)h->d_k[cur], n, h->d_tile);
     IM_LAUNCH(k_rs_scan, 1, 1024, 0, st, h->d_tile, nb, h->d_tile + h->nblocks_max);
-    IM_LAUNCH(k_vg_centroid, nb, VG_THREADS, 0, st, d_pts, (const unsigned int*)h->d_k[cur], (const unsigned int*)h->d_v[cur], n, (const int*)h->d_tile, h->d_out);
+    if (h->warp_centroid) {
+        IM_LAUNCH(k_vg_centroid, nb, VG_THREADS, 0, st, d_pts, (const unsigned int*)h->d_k[cur], (const unsigned int*)h->d_v[cur], n, (const int*)h->d_tile, h->d_out, h->d_head);
+        IM_LAUNCH(k_vg_centroid_warp, h->n_sm * 4, VG_THREADS, 0, st, d_pts, (const unsigned int*)h->d_v[cur], (const int*)h->d_head,
+                  (const int*)(h->d_tile + h->nblocks_max), (const VgGrid*)h->d_grid, h->d_out);
+    } else {
+        IM_LAUNCH(k_vg_centroid, nb, VG_THREADS, 0, st, d_pts, (const unsigned int*)h->d_k[cur], (const unsigned int*)h->d_v[cur], n, (const int*)h->d_tile, h->d_out, (int*)nullptr);
+    }
     IM_LAUNCH(k_vg_finish, 1, 32, 0, st, h->d_grid, (const int*)(h->d_tile + h->nblocks_max), n);
     IM_LAUNCH(k_vg_copy_if_small, gs, VG_THREADS, 0, st, d_pts, n, (const VgGrid*)h->d_grid, h->d_out);
     IM_CUDA(cudaGetLastError());

@@ -121,7 +121,7 @@ __device__ __forceinline__ int pivot_row18(const double* m /*stride 37*/, int k)
 }
 // variant 1 ("lean"): no redundant double-precision work -- the pivot is found by warp 0 alone (shuffle tournament, lower lane wins
 // ties), the 17-k multipliers l_i are divided once per row, then every thread updates its element; three barriers per step.
-__device__ __noinline__ void block_lu_inverse18_lean(const double* a_in, InvScratch* W, double* inv_out) {
+__device__ __noinline__ void block_lu_inverse18_lean(const double* a_in, InvScratch* W, double* inv_out, bool rolled) {
     __shared__ int s_bi;
     __shared__ double s_l[18];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
@@ -165,6 +165,22 @@ __device__ __noinline__ void block_lu_inverse18_lean(const double* a_in, InvScra
         }
         __syncthreads();
         p ^= 1;
+    }
+    if (rolled) {
+        // compact code (a straight-line unrolled substitution is ~900 instructions executed once: instruction fetch, not
+        // arithmetic, then sets the pace).  x lives in inv_out (column c is private to thread c), j ascending as in the oracle.
+        if (tid < 18) {
+            const int c = tid;
+#pragma unroll 1
+            for (int i = 17; i >= 0; --i) {
+                double s = W->Y[i * 19 + c];
+#pragma unroll 2
+                for (int j = i + 1; j < 18; ++j) s = s - W->U[i * 19 + j] * inv_out[j * 18 + c];
+                inv_out[i * 18 + c] = s / W->U[i * 19 + i];
+            }
+        }
+        __syncthreads();
+        return;
     }
     if (tid < 18) {
         const int c = tid;
@@ -226,10 +242,11 @@ __device__ __noinline__ void block_lu_inverse18_redundant(const double* a_in /*[
     __syncthreads();
 }
 
-__device__ int g_lu_variant = 1;   // 0: redundant (one barrier per step), 1: lean (three barriers, no redundant f64 work)
+__device__ int g_lu_variant = 1;   // 0: redundant (one barrier per step), 1: lean (three barriers, no redundant f64 work), 2: lean + rolled back substitution
 __device__ __forceinline__ void block_lu_inverse18(const double* a_in, InvScratch* W, double* inv_out) {
-    if (g_lu_variant == 0) block_lu_inverse18_redundant(a_in, W, inv_out);
-    else block_lu_inverse18_lean(a_in, W, inv_out);
+    const int v = g_lu_variant;
+    if (v == 0) block_lu_inverse18_redundant(a_in, W, inv_out);
+    else block_lu_inverse18_lean(a_in, W, inv_out, v == 2);
 }
 
 // same arithmetic as ieskf_solve (lio_core.cuh), block-cooperative with the two LU inverses done by warp 0
@@ -464,7 +481,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_shard_pass2_p2p(VoxelMapDev map
     __shared__ int s_last;
     if (ctrl->stop) return;
     if (threadIdx.x < pe.n && threadIdx.x != pe.rank) {
-        if (!immesh::wait_epoch(liowin_flag(pe.w[pe.rank], 0, threadIdx.x), epoch)) atomicOr(map.err, IM_ERR_PEER_TIMEOUT);
+        immesh::wait_epoch(liowin_flag(pe.w[pe.rank], 0, threadIdx.x), epoch, map.err, IM_ERR_PEER_TIMEOUT);
     }
     for (int i = threadIdx.x; i < 24 + 6 * 18; i += blockDim.x) s_state[i] = ctrl->state[i];
     __syncthreads();
@@ -523,7 +540,7 @@ __global__ void __launch_bounds__(INV_THREADS) k_solve_warp_p2p(LioParams P, Lio
     __shared__ InvScratch W;
     if (ctrl->stop) return;
     if (threadIdx.x < pe.n && threadIdx.x != pe.rank) {
-        if (!immesh::wait_epoch(liowin_flag(pe.w[pe.rank], 1, threadIdx.x), epoch)) atomicOr(err, IM_ERR_PEER_TIMEOUT);
+        immesh::wait_epoch(liowin_flag(pe.w[pe.rank], 1, threadIdx.x), epoch, err, IM_ERR_PEER_TIMEOUT);
     }
     __syncthreads();
     if (threadIdx.x < IM_NTERMS * 2) {

@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(256) k_xpush(MeshDev M, FrameBuf F, const unsi
 __device__ __forceinline__ void mesh_wait_peers(const MeshPeers& pe, int which, unsigned long long epoch, int* err) {
     if (pe.n > 0) {
         if (threadIdx.x < pe.n && threadIdx.x != pe.rank) {
-            if (!immesh::wait_epoch(meshwin_flag(pe.w[pe.rank], which, threadIdx.x), epoch)) atomicOr(err, IM_MERR_PEER_TIMEOUT);
+            immesh::wait_epoch(meshwin_flag(pe.w[pe.rank], which, threadIdx.x), epoch, err, IM_MERR_PEER_TIMEOUT);
         }
         __syncthreads();
     }

@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "nccl_api.hpp"
@@ -30,12 +31,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// spin until *flag >= epoch.  Bounded (~2 s at 2 GHz): a dead peer must not hang the GPU; the caller reports the error.
-__device__ __forceinline__ bool wait_epoch(const unsigned long long* flag, unsigned long long epoch) {
-    const long long t0 = clock64();
+// spin until *flag >= epoch.  Bounded (default ~10 s of SM clocks, IMMESH_PEER_TIMEOUT_MS): a dead peer must not hang the
+// GPU.  On expiry `bit` is OR-ed into *err (the handle's error word, reported by the next wait/step call); once it is set,
+// later waits return at once, so a lost peer costs ONE timeout, not one per kernel.
+static __device__ long long g_peer_timeout_cycles = 20000000000LL;
+__device__ __forceinline__ bool wait_epoch(const unsigned long long* flag, unsigned long long epoch, int* err, int bit) {
+    if (*(volatile int*)err & bit) return false;
+    const long long t0 = clock64(), limit = g_peer_timeout_cycles;
     while (ld_acquire_sys(flag) < epoch) {
         __nanosleep(40);
-        if (clock64() - t0 > 4000000000LL) return false;
+        if (clock64() - t0 > limit) { atomicOr(err, bit); return false; }
     }
     return true;
 }
@@ -78,6 +83,12 @@ inline cudaError_t peer_window_open(PeerWindow& w, size_t bytes, int rank, int n
         if ((e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) return e;
         w.peer[r] = (unsigned char*)p;
     }
+#if defined(__CUDACC__)
+    if (const char* t = std::getenv("IMMESH_PEER_TIMEOUT_MS")) {
+        const long long cyc = (long long)(std::atof(t) * 2.0e6);   // ~2 GHz SM clock
+        if (cyc > 0) cudaMemcpyToSymbol(g_peer_timeout_cycles, &cyc, sizeof(cyc));
+    }
+#endif
     w.ok = true;
     return cudaSuccess;
 }

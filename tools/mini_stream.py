@@ -22,4 +22,13 @@ for sc in scans[1:]:
     ds = vg.filter(sc["body_full"], cfg.filter_size_surf)
     s, it = lio.step(ds, sc["dt"])
     mesh.push_frame_from_lio(lio, sc["body_full"])
+import time
+full = scans[-1]["body_full"]
+for on_dev in (False,):
+    vg.filter(full, cfg.filter_size_surf, fetch=False)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        m = vg.filter(full, cfg.filter_size_surf, fetch=False)
+    dt = (time.perf_counter() - t0) / 50
+    print(f"voxelgrid front-end: {len(full)} -> {m} points, {dt * 1e3:.3f} ms per call (host input: memcpy + H2D + 20 kernels + D2H of the count)")
 print("ok", lio.counts(), mesh.counts(), "ds points", len(ds))
