@@ -281,7 +281,7 @@ struct immesh_voxelgrid {
     int* d_hist = nullptr;       // [256 * nblocks_max]
     int* d_tile = nullptr;       // [nblocks_max + 1]
     int* d_head = nullptr;       // [max_points] start of every run in the sorted order
-    int warp_centroid = 1;       // 1: warp-per-run sums (k_vg_centroid_warp); 0: thread-per-run (IMMESH_VG_THREAD_CENTROID=1)
+    int warp_centroid = 0;       // 1: warp-per-run sums (k_vg_centroid_warp, IMMESH_VG_WARP_CENTROID=1); 0: thread-per-run
     VgGrid* d_grid = nullptr;
     VgGrid* h_grid = nullptr;    // pinned
     float* h_pts = nullptr;      // pinned staging [max_points][3]
@@ -311,7 +311,7 @@ int immesh_voxelgrid_create(int max_points, immesh_voxelgrid_t** out) {
     IM_CUDA(cudaMalloc((void**)&h->d_hist, (size_t)256 * h->nblocks_max * sizeof(int)));
     IM_CUDA(cudaMalloc((void**)&h->d_tile, ((size_t)h->nblocks_max + 1) * sizeof(int)));
     IM_CUDA(cudaMalloc((void**)&h->d_head, n * sizeof(int)));
-    if (const char* e = std::getenv("IMMESH_VG_THREAD_CENTROID")) h->warp_centroid = (e[0] == '1') ? 0 : 1;
+    if (const char* e = std::getenv("IMMESH_VG_WARP_CENTROID")) h->warp_centroid = (e[0] == '1') ? 1 : 0;
     IM_CUDA(cudaMalloc((void**)&h->d_grid, sizeof(VgGrid)));
     IM_CUDA(cudaMallocHost((void**)&h->h_grid, sizeof(VgGrid)));
     IM_CUDA(cudaMallocHost((void**)&h->h_pts, n * 3 * sizeof(float)));
