@@ -281,7 +281,7 @@ struct immesh_voxelgrid {
     int* d_hist = nullptr;       // [256 * nblocks_max]
     int* d_tile = nullptr;       // [nblocks_max + 1]
     int* d_head = nullptr;       // [max_points] start of every run in the sorted order
-    int warp_centroid = 0;       // 1: warp-per-run sums (k_vg_centroid_warp, IMMESH_VG_WARP_CENTROID=1); 0: thread-per-run
+    int warp_centroid = 1;       // 1: warp-per-run sums (k_vg_centroid_warp); 0: thread-per-run loop (IMMESH_VG_WARP_CENTROID=0)
     VgGrid* d_grid = nullptr;
     VgGrid* h_grid = nullptr;    // pinned
     float* h_pts = nullptr;      // pinned staging [max_points][3]
