@@ -53,16 +53,60 @@ def init_state_vec(scans):
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed regions.  NVML in a thread (about 1 ms per sample: the timed
+    region of a default run is only ~15 ms, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index=0, uuid=None):
+        self.index, self.uuid, self.rows, self.proc = index, uuid, [], None
+        self.samples, self.max_mhz, self.mask, self.stop_flag, self.thread, self.how = [], None, 0, False, None, None
+
+    def _nvml_handle(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = None
+        if self.uuid:
+            for cand in (self.uuid, "GPU-" + self.uuid):
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")) and self.index < len(vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+        return nv, h
 
     def start(self):
+        try:
+            nv, h = self._nvml_handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        self.mask |= int(reasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.001)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            self.how = "nvidia-smi"
         except Exception:
             self.proc = None
 
@@ -71,6 +115,12 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            reasons = [n for n, bit in self.BITS.items() if self.mask & bit]
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(self.samples), "how": "nvml, 1 ms period, across both timed regions"}
         if self.proc:
             self.proc.terminate()
             try:
@@ -81,7 +131,7 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm), "how": "nvidia-smi -lms 20"}
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
@@ -258,7 +308,11 @@ def run_gpu(args, rank, world):
     # overlaps meshing of scan k on a second stream (the reference's own LIO || mesh-thread pipeline).  A 256 MB write is
     # queued in front of every scan as the L2 flush and is INSIDE the timed region (conservative).  Time = CUDA events
     # from the first queued operation to the completion of both streams.
-    sampler = ClockSampler(local_rank)
+    try:
+        dev_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local_rank, dev_uuid)
     sampler.start()
     launches0 = api.launch_count(lib)
     barrier()
