@@ -121,8 +121,10 @@ __device__ __forceinline__ int pivot_row18(const double* m /*stride 37*/, int k)
 }
 // variant 1 ("lean"): no redundant double-precision work -- the pivot is found by warp 0 alone (shuffle tournament, lower lane wins
 // ties), the 17-k multipliers l_i are divided once per row, then every thread updates its element; three barriers per step.
-__device__ __noinline__ void block_lu_inverse18_lean(const double* a_in, InvScratch* W, double* inv_out, bool rolled) {
+__device__ long long g_inv_stamps[16];   // diagnostic: clock64 at the phase boundaries of the last block_lu_inverse18_lean call
+__device__ __noinline__ void block_lu_inverse18_lean(const double* a_in, InvScratch* W, double* inv_out, bool rolled, bool redux) {
     __shared__ int s_bi;
+    if (threadIdx.x == 0) g_inv_stamps[0] = clock64();
     __shared__ double s_l[18];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     for (int e = tid; e < 648; e += nt) {
@@ -130,11 +132,28 @@ __device__ __noinline__ void block_lu_inverse18_lean(const double* a_in, InvScra
         W->buf[0][i * 37 + j] = (j < 18) ? a_in[i * 18 + j] : ((j - 18 == i) ? 1.0 : 0.0);
     }
     __syncthreads();
+    if (threadIdx.x == 0) g_inv_stamps[1] = clock64();
     int p = 0;
     for (int k = 0; k < 18; ++k) {
         const double* old = W->buf[p];
         double* nw = W->buf[p ^ 1];
-        if (tid < 32) {   // first maximum of |old[i][k]|, i >= k
+        const bool stamp = (k == 5 && tid == 0);
+        if (stamp) g_inv_stamps[8] = clock64();
+        if (tid < 32 && redux) {
+            // measured (clock64 stamps, profiles/README.md): the shuffle tournament below is a ~105-instruction dependent chain,
+            // ~1.5 k cycles per step -- most of the kernel.  Non-negative doubles order like their bit patterns, so the first
+            // maximum is three warp REDUX operations: max of the high words, max of the low words among the lanes that hold
+            // that high word, min lane among the lanes that hold both.
+            const bool act = lane >= k && lane < 18;
+            const unsigned long long bits = act ? (unsigned long long)__double_as_longlong(fabs(old[lane * 37 + k])) : 0ull;
+            const unsigned int hi = (unsigned int)(bits >> 32), lo = (unsigned int)bits;
+            const unsigned int mhi = __reduce_max_sync(0xffffffffu, act ? hi : 0u);
+            const bool c1 = act && hi == mhi;
+            const unsigned int mlo = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+            const bool c2 = c1 && lo == mlo;
+            const unsigned int bl = __reduce_min_sync(0xffffffffu, c2 ? (unsigned int)lane : 0xffffffffu);
+            if (lane == 0) s_bi = (int)bl;
+        } else if (tid < 32) {   // first maximum of |old[i][k]|, i >= k
             double bv = (lane >= k && lane < 18) ? fabs(old[lane * 37 + k]) : -1.0;
             int bi = lane;
 #pragma unroll
@@ -145,13 +164,17 @@ __device__ __noinline__ void block_lu_inverse18_lean(const double* a_in, InvScra
             }
             if (lane == 0) s_bi = bi;
         }
+        if (stamp) g_inv_stamps[9] = clock64();
         __syncthreads();
+        if (stamp) g_inv_stamps[10] = clock64();
         const int bi = s_bi;
         if (tid > k && tid < 18) {   // multiplier of (post-swap) row tid
             const int src = (tid == bi) ? k : tid;
             s_l[tid] = old[src * 37 + k] / old[bi * 37 + k];
         }
+        if (stamp) g_inv_stamps[11] = clock64();
         __syncthreads();
+        if (stamp) g_inv_stamps[12] = clock64();
         for (int e = tid; e < 648; e += nt) {
             const int i = e / 36, j = e - i * 36;
             if (i < k || j < k) continue;
@@ -163,9 +186,13 @@ __device__ __noinline__ void block_lu_inverse18_lean(const double* a_in, InvScra
                 nw[i * 37 + j] = old[src * 37 + j] - s_l[i] * old[bi * 37 + j];
             }
         }
+        if (stamp) g_inv_stamps[13] = clock64();
         __syncthreads();
+        if (stamp) g_inv_stamps[14] = clock64();
         p ^= 1;
+        if (k == 0 && threadIdx.x == 0) g_inv_stamps[2] = clock64();
     }
+    if (threadIdx.x == 0) g_inv_stamps[3] = clock64();
     if (rolled) {
         // compact code (a straight-line unrolled substitution is ~900 instructions executed once: instruction fetch, not
         // arithmetic, then sets the pace).  x lives in inv_out (column c is private to thread c), j ascending as in the oracle.
@@ -180,6 +207,7 @@ __device__ __noinline__ void block_lu_inverse18_lean(const double* a_in, InvScra
             }
         }
         __syncthreads();
+        if (threadIdx.x == 0) g_inv_stamps[4] = clock64();
         return;
     }
     if (tid < 18) {
@@ -196,6 +224,7 @@ __device__ __noinline__ void block_lu_inverse18_lean(const double* a_in, InvScra
         for (int i = 0; i < 18; ++i) inv_out[i * 18 + c] = x[i];
     }
     __syncthreads();
+    if (threadIdx.x == 0) g_inv_stamps[4] = clock64();
 }
 __device__ __noinline__ void block_lu_inverse18_redundant(const double* a_in /*[324] shared, row-major*/, InvScratch* W, double* inv_out /*[324] shared*/) {
 
@@ -242,11 +271,12 @@ __device__ __noinline__ void block_lu_inverse18_redundant(const double* a_in /*[
     __syncthreads();
 }
 
-__device__ int g_lu_variant = 1;   // 0: redundant (one barrier per step), 1: lean (three barriers, no redundant f64 work), 2: lean + rolled back substitution
+__device__ int g_lu_variant = 1;   // 0: redundant (one barrier per step), 1: lean (three barriers, no redundant f64 work), 2: lean + rolled back substitution,
+                                   // 3: lean + REDUX pivot search (compiled, NOT yet run on a GPU: first item of the next round)
 __device__ __forceinline__ void block_lu_inverse18(const double* a_in, InvScratch* W, double* inv_out) {
     const int v = g_lu_variant;
     if (v == 0) block_lu_inverse18_redundant(a_in, W, inv_out);
-    else block_lu_inverse18_lean(a_in, W, inv_out, v == 2);
+    else block_lu_inverse18_lean(a_in, W, inv_out, v == 2, v == 3);
 }
 
 // same arithmetic as ieskf_solve (lio_core.cuh), block-cooperative with the two LU inverses done by warp 0
@@ -562,10 +592,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(LioParams P, LioCtrl* c
 __global__ void __launch_bounds__(INV_THREADS) k_pinv(LioCtrl* ctrl) {
     __shared__ double a[324], inv[324];
     __shared__ InvScratch W;
+    const long long t_in = clock64();
     for (int i = threadIdx.x; i < 324; i += blockDim.x) a[i] = ctrl->state[24 + i];
     __syncthreads();
     block_lu_inverse18(a, &W, inv);
     for (int i = threadIdx.x; i < 324; i += blockDim.x) ctrl->Pinv[i] = inv[i];
+    if (threadIdx.x == 0) { g_inv_stamps[5] = t_in; g_inv_stamps[6] = clock64(); }
 }
 __global__ void __launch_bounds__(INV_THREADS) k_solve_warp(LioParams P, LioCtrl* ctrl, int iter) {
     __shared__ SolveScratch S;
@@ -810,6 +842,13 @@ int immesh_lio_shard(immesh_lio_t* h, int rank, int nranks, const char* unique_i
             cudaGetLastError();
         }
     }
+    return IMMESH_OK;
+}
+// diagnostic: clock64 stamps of the last 18x18 inverse (k_pinv): [enter, after init, after step 0, after LU, after back substitution, kernel start, kernel end]
+int immesh_debug_inverse_stamps(long long* out8 /*[16]*/) {
+    if (!out8) return im_fail(IMMESH_E_INVALID, "null argument");
+    IM_CUDA(cudaDeviceSynchronize());
+    IM_CUDA(cudaMemcpyFromSymbol(out8, g_inv_stamps, 16 * sizeof(long long)));
     return IMMESH_OK;
 }
 int immesh_lio_shard_transport(immesh_lio_t* h) {   // 0 = not sharded, 1 = NCCL all-reduces, 2 = fused peer-window exchange

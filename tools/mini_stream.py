@@ -32,3 +32,13 @@ for on_dev in (False,):
     dt = (time.perf_counter() - t0) / 50
     print(f"voxelgrid front-end: {len(full)} -> {m} points, {dt * 1e3:.3f} ms per call (host input: memcpy + H2D + 20 kernels + D2H of the count)")
 print("ok", lio.counts(), mesh.counts(), "ds points", len(ds))
+
+import ctypes as C
+st = (C.c_longlong * 16)()
+lib = api.load_library()
+if hasattr(lib, "immesh_debug_inverse_stamps"):
+    lib.immesh_debug_inverse_stamps.argtypes = [C.c_void_p]
+    lib.immesh_debug_inverse_stamps(st)
+    s = list(st)
+    print("k_pinv cycles: kernel", s[6] - s[5], "| load+enter", s[0] - s[5], "init", s[1] - s[0], "step0", s[2] - s[1], "steps1-17", s[3] - s[2], "back-subst", s[4] - s[3], "store+exit", s[6] - s[4])
+    print("step 5 (thread 0): pivot", s[9] - s[8], "barrier1", s[10] - s[9], "read+div(idle for t0)", s[11] - s[10], "barrier2", s[12] - s[11], "update", s[13] - s[12], "barrier3", s[14] - s[13])
