@@ -31,6 +31,11 @@ class _MeshCfg(C.Structure):
     ]
 
 
+class _ImuCfg(C.Structure):
+    _fields_ = [("cov_gyr", C.c_double * 3), ("cov_acc", C.c_double * 3), ("cov_bias_gyr", C.c_double * 3), ("cov_bias_acc", C.c_double * 3),
+                ("mean_acc_norm", C.c_double), ("lid_R", C.c_double * 9), ("lid_T", C.c_double * 3), ("max_points", C.c_int), ("max_imu", C.c_int)]
+
+
 @dataclasses.dataclass
 class LioConfig:
     """Hot-path parameters of Voxel_mapping (config/*.yaml of the reference)."""
@@ -128,9 +133,17 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_voxelgrid_destroy", [vp]),
         ("immesh_voxelgrid_filter", [vp, vp, C.c_int, C.c_int, C.c_float, vp, ip, ip]),
         ("immesh_voxelgrid_device_points", [vp]),
+        ("immesh_imu_create", [C.POINTER(_ImuCfg), C.POINTER(vp)]),
+        ("immesh_imu_destroy", [vp]),
+        ("immesh_imu_reset", [vp, dp, C.c_double, C.c_double, dp, dp]),
+        ("immesh_imu_undistort", [vp, vp, dp, C.c_int, vp, C.c_int, C.c_int, C.c_double, vp]),
+        ("immesh_imu_device_points", [vp]),
+        ("immesh_imu_get_poses", [vp, dp, C.c_int]),
     ):
         if hasattr(lib, name):
             getattr(lib, name).argtypes = args
+    if hasattr(lib, "immesh_imu_device_points"):
+        lib.immesh_imu_device_points.restype = C.c_void_p
     if hasattr(lib, "immesh_voxelgrid_device_points"):
         lib.immesh_voxelgrid_device_points.restype = C.c_void_p
     if hasattr(lib, "immesh_launch_count"):
@@ -445,6 +458,56 @@ class VoxelGrid:
 
     def device_points(self) -> int:
         return int(self.lib.immesh_voxelgrid_device_points(self._h) or 0)
+
+
+class Imu:
+    """ImuProcess::UndistortPcl on the device (immesh_imu_*): forward propagation of the localization handle's state over the IMU
+    samples of a scan + per-point motion compensation.  cfg: dict with cov_gyr, cov_acc, cov_bias_gyr, cov_bias_acc, mean_acc_norm,
+    lid_R (3x3), lid_T."""
+
+    def __init__(self, cfg: dict, max_points: int = 1 << 18, max_imu: int = 128, lib: Optional[C.CDLL] = None):
+        self.lib = lib or load_library()
+        c = _ImuCfg()
+        for k in ("cov_gyr", "cov_acc", "cov_bias_gyr", "cov_bias_acc", "lid_T"):
+            for i in range(3):
+                getattr(c, k)[i] = float(np.asarray(cfg[k]).reshape(-1)[i])
+        for i in range(9):
+            c.lid_R[i] = float(np.asarray(cfg["lid_R"]).reshape(-1)[i])
+        c.mean_acc_norm = float(cfg["mean_acc_norm"])
+        c.max_points, c.max_imu = max_points, max_imu
+        self._h = C.c_void_p()
+        _check(self.lib, self.lib.immesh_imu_create(C.byref(c), C.byref(self._h)), "imu_create")
+
+    def close(self):
+        if self._h:
+            self.lib.immesh_imu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, last_imu7, last_lidar_end_time, last_update_time=0.0, acc_s_last=None, angvel_last=None):
+        a = np.ascontiguousarray(last_imu7, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        f = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64).ctypes.data_as(dp)  # noqa: E731
+        _check(self.lib, self.lib.immesh_imu_reset(self._h, a.ctypes.data_as(dp), last_lidar_end_time, last_update_time, f(acc_s_last), f(angvel_last)), "imu_reset")
+
+    def undistort(self, lio: "Lio", imu, pts_xyzt, lidar_beg_time):
+        """imu: float64[n_imu,7] (stamp, gyr, acc); pts_xyzt: float32[n,4] (x, y, z, curvature ms).  Returns the time-sorted, compensated cloud."""
+        im = np.ascontiguousarray(imu, dtype=np.float64).reshape(-1, 7)
+        p = np.ascontiguousarray(pts_xyzt, dtype=np.float32).reshape(-1, 4)
+        out = np.zeros_like(p)
+        _check(self.lib, self.lib.immesh_imu_undistort(self._h, lio._h, im.ctypes.data_as(C.POINTER(C.c_double)), im.shape[0], p.ctypes.data_as(C.c_void_p), p.shape[0], 0,
+                                                       lidar_beg_time, out.ctypes.data_as(C.c_void_p)), "imu_undistort")
+        return out
+
+    def poses(self, cap=300):
+        o = np.zeros((cap, 22))
+        m = self.lib.immesh_imu_get_poses(self._h, o.ctypes.data_as(C.POINTER(C.c_double)), cap)
+        return o[:m].copy()
 
 
 def profile_enable(on: bool, lib: Optional[C.CDLL] = None):

@@ -34,6 +34,7 @@ extern "C" {
 typedef struct immesh_lio immesh_lio_t;
 typedef struct immesh_mesh immesh_mesh_t;
 typedef struct immesh_voxelgrid immesh_voxelgrid_t;
+typedef struct immesh_imu immesh_imu_t;
 
 /* Parameters of Voxel_mapping that the path reads (src/voxel_mapping.hpp:149-191,
  * read_ros_parameters src/voxel_mapping_common.cpp:625-707). */
@@ -203,6 +204,38 @@ int immesh_voxelgrid_destroy(immesh_voxelgrid_t* h);
 int immesh_voxelgrid_filter(immesh_voxelgrid_t* h, const float* xyz, int n, int on_device, float leaf, float* out_xyz /*[n][3] or NULL*/,
                             int* m_out, int* leaf_too_small /*or NULL*/);
 const float* immesh_voxelgrid_device_points(immesh_voxelgrid_t* h);
+
+/* ---- front-end: IMU forward propagation + per-point motion compensation on the device.  Replaces
+ *   ImuProcess::UndistortPcl(lidar_meas, state_inout, pcl_out)            (src/IMU_Processing.cpp:755-958)
+ * for the LiDAR-only flow (is_lidar_end == true).  The handle carries the ImuProcess members the function reads and writes
+ * (cov_gyr / cov_acc / bias covariances :56-61, mean_acc from IMU_init :127-181, Lid_rot_to_IMU / Lid_offset_to_IMU :108-112,
+ * last_imu_, last_lidar_end_time_, acc_s_last, angvel_last, lidar_meas.last_update_time); `state_inout` is the localization
+ * handle's device-resident state: its rot / pos / vel are moved to the scan end and its 18x18 covariance is propagated
+ * (F P F^T + Q per IMU interval).
+ *   imu      : meas.imu of this scan, [n_imu][7] = stamp (s), angular_velocity xyz, linear_acceleration xyz
+ *   pts_xyzt : [n][4] = x, y, z, curvature (ms since lidar_beg_time), float like pcl::PointXYZINormal; host pointer, or device
+ *              pointer (16-byte aligned) with on_device = 1
+ * Output: the scan sorted by time stamp (stable) and compensated into the scan-end frame, [n][4]; it stays on the device
+ * (immesh_imu_device_points) and is copied to out_xyzt when that is not NULL.  Defined where the reference is not: points
+ * with equal stamps keep their input order.  Work is queued on the localization handle's stream. */
+typedef struct immesh_imu_config {
+    double cov_gyr[3], cov_acc[3], cov_bias_gyr[3], cov_bias_acc[3];
+    double mean_acc_norm;
+    double lid_R[9]; /* row-major */
+    double lid_T[3];
+    int max_points;  /* capacity of one scan */
+    int max_imu;     /* capacity of one IMU batch (<= 256) */
+} immesh_imu_config;
+int immesh_imu_create(const immesh_imu_config* cfg, immesh_imu_t** out);
+int immesh_imu_destroy(immesh_imu_t* h);
+/* seed the members IMU_init / the previous scan leave behind; acc_s_last / angvel_last may be NULL (zeros) */
+int immesh_imu_reset(immesh_imu_t* h, const double* last_imu7, double last_lidar_end_time, double last_update_time, const double* acc_s_last,
+                     const double* angvel_last);
+int immesh_imu_undistort(immesh_imu_t* h, immesh_lio_t* lio, const double* imu, int n_imu, const float* pts_xyzt, int n, int on_device,
+                         double lidar_beg_time, float* out_xyzt /*[n][4] or NULL*/);
+const float* immesh_imu_device_points(immesh_imu_t* h);
+/* IMUpose of the last call (Pose6D: offset_time, acc, gyr, vel, pos, rot = 22 doubles each); returns their number */
+int immesh_imu_get_poses(immesh_imu_t* h, double* out, int cap_poses);
 
 /* optional per-kernel CUDA-event profiler (off by default) and launch accounting, process-wide */
 int immesh_profile_enable(int on);   /* 0 off, 1 per-kernel totals, 2 totals + timeline */

@@ -7,6 +7,7 @@
 #include "orc_lio.hpp"
 #include "orc_mesh.hpp"
 #include "orc_frontend.hpp"
+#include "orc_imu.hpp"
 
 using namespace orc;
 
@@ -218,6 +219,41 @@ void orc_math_probe(const double* x, int n, double* s, double* c, double* e, dou
         e[i] = det_exp(-std::fabs(x[i]));
         ac[i] = det_acos(std::fmax(-1.0, std::fmin(1.0, x[i])));
     }
+}
+// ImuProcess::UndistortPcl restatement (orc_imu.hpp).  cfg: cov_gyr 3, cov_acc 3, cov_bias_gyr 3, cov_bias_acc 3, mean_acc_norm, lid_R 9, lid_T 3 (25)
+void* orc_imu_create(const double* cfg) {
+    ImuOracle* o = new ImuOracle();
+    for (int i = 0; i < 3; ++i) { o->cov_gyr[i] = cfg[i]; o->cov_acc[i] = cfg[3 + i]; o->cov_bias_gyr[i] = cfg[6 + i]; o->cov_bias_acc[i] = cfg[9 + i]; o->lid_T[i] = cfg[22 + i]; }
+    o->mean_acc_norm = cfg[12];
+    for (int i = 0; i < 9; ++i) o->lid_R[i] = cfg[13 + i];
+    return o;
+}
+void orc_imu_destroy(void* h) { delete (ImuOracle*)h; }
+void orc_imu_reset(void* h, const double* last_imu7, double last_lidar_end_time, double last_update_time, const double* acc_s_last, const double* angvel_last) {
+    ImuOracle* o = (ImuOracle*)h;
+    o->last_imu.t = last_imu7[0];
+    for (int i = 0; i < 3; ++i) { o->last_imu.gyr[i] = last_imu7[1 + i]; o->last_imu.acc[i] = last_imu7[4 + i]; o->acc_s_last[i] = acc_s_last ? acc_s_last[i] : 0.0; o->angvel_last[i] = angvel_last ? angvel_last[i] : 0.0; }
+    o->last_lidar_end_time = last_lidar_end_time;
+    o->last_update_time = last_update_time;
+}
+// state348 in/out; pts [n][4] in/out (sorted + compensated); returns the number of IMUpose records, copied to poses (22 doubles each)
+int orc_imu_undistort(void* h, double* state348, const double* imu, int n_imu, float* pts, int n, double lidar_beg_time, double* poses, int cap_poses) {
+    ImuOracle* o = (ImuOracle*)h;
+    State st;
+    unpack_state(state348, st);
+    std::vector<ImuSample> v(n_imu);
+    for (int i = 0; i < n_imu; ++i) { v[i].t = imu[7 * i]; for (int k = 0; k < 3; ++k) { v[i].gyr[k] = imu[7 * i + 1 + k]; v[i].acc[k] = imu[7 * i + 4 + k]; } }
+    o->undistort_pcl(st, v, pts, n, lidar_beg_time);
+    pack_state(st, state348);
+    const int m = (int)o->IMUpose.size();
+    for (int i = 0; i < m && i < cap_poses; ++i) {
+        const Pose6D& p = o->IMUpose[i];
+        double* q = poses + 22 * (size_t)i;
+        q[0] = p.offset_time;
+        for (int k = 0; k < 3; ++k) { q[1 + k] = p.acc[k]; q[4 + k] = p.gyr[k]; q[7 + k] = p.vel[k]; q[10 + k] = p.pos[k]; }
+        for (int k = 0; k < 9; ++k) q[13 + k] = p.rot[k];
+    }
+    return m;
 }
 // pcl::VoxelGrid restatement (orc_frontend.hpp).  out: [cap][3]; returns m (or -m-1 when PCL's leaf-too-small branch copied the input)
 int orc_voxel_grid(const float* pts, int n, float leaf, float* out, int cap, int* grid6) {

@@ -222,3 +222,84 @@ int emu_shard_solve(immesh_lio_t* h, int it) {
     return h->ctrl.stop;
 }
 }
+
+// ---- IMU front-end (imu_core.cuh bodies, one thread): same entry points as immesh_b200/csrc/imu_capi.cu
+#include "../../immesh_b200/csrc/imu_core.cuh"
+struct immesh_imu {
+    ImuParams P;
+    double last_imu[7] = {0, 0, 0, 0, 0, 0, 0};
+    double last_lidar_end_time = -1.0, last_update_time = 0.0;
+    double run[IM_IMU_RUN];
+    std::vector<double> poses;
+    std::vector<float> out;
+    int last_poses = 0;
+};
+extern "C" {
+int immesh_imu_create(const immesh_imu_config* c, immesh_imu_t** out) {
+    immesh_imu* h = new immesh_imu();
+    for (int i = 0; i < 3; ++i) { h->P.cov_gyr[i] = c->cov_gyr[i]; h->P.cov_acc[i] = c->cov_acc[i]; h->P.cov_bias_gyr[i] = c->cov_bias_gyr[i]; h->P.cov_bias_acc[i] = c->cov_bias_acc[i]; h->P.lid_T[i] = c->lid_T[i]; }
+    for (int i = 0; i < 9; ++i) h->P.lid_R[i] = c->lid_R[i];
+    h->P.mean_acc_norm = c->mean_acc_norm;
+    for (int i = 0; i < IM_IMU_RUN; ++i) h->run[i] = 0.0;
+    *out = h;
+    return 0;
+}
+int immesh_imu_destroy(immesh_imu_t* h) { delete h; return 0; }
+int immesh_imu_reset(immesh_imu_t* h, const double* last_imu7, double last_lidar_end_time, double last_update_time, const double* acc_s_last, const double* angvel_last) {
+    std::memcpy(h->last_imu, last_imu7, 56);
+    h->last_lidar_end_time = last_lidar_end_time; h->last_update_time = last_update_time;
+    for (int i = 0; i < 3; ++i) { h->run[i] = acc_s_last ? acc_s_last[i] : 0.0; h->run[3 + i] = angvel_last ? angvel_last[i] : 0.0; }
+    return 0;
+}
+int immesh_imu_undistort(immesh_imu_t* h, immesh_lio_t* lio, const double* imu, int n_imu, const float* pts, int n, int, double lidar_beg_time, float* out_xyzt) {
+    std::vector<const double*> v;
+    v.push_back(h->last_imu);
+    for (int i = 0; i < n_imu; ++i) v.push_back(imu + 7 * (size_t)i);
+    const double imu_end_time = v.back()[0];
+    const double pcl_beg_time = std::max(lidar_beg_time, h->last_update_time);
+    const double pcl_end_time = lidar_beg_time + (double)pts[4 * (size_t)(n - 1) + 3] / double(1000);
+    h->last_update_time = pcl_end_time;
+    std::vector<ImuStep> steps;
+    for (size_t k = 0; k + 1 < v.size(); ++k) {
+        const double *head = v[k], *tail = v[k + 1];
+        if (tail[0] < h->last_lidar_end_time) continue;
+        ImuStep s;
+        for (int i = 0; i < 3; ++i) { s.gyr_avg[i] = 0.5 * (head[1 + i] + tail[1 + i]); s.acc_avg[i] = 0.5 * (head[4 + i] + tail[4 + i]); }
+        s.dt = (head[0] < h->last_lidar_end_time) ? tail[0] - h->last_lidar_end_time : tail[0] - head[0];
+        s.offs_t = tail[0] - pcl_beg_time;
+        steps.push_back(s);
+    }
+    double note, dt_end;
+    if (imu_end_time > pcl_beg_time) { note = pcl_end_time > imu_end_time ? 1.0 : -1.0; dt_end = note * (pcl_end_time - imu_end_time); }
+    else { note = pcl_end_time > pcl_beg_time ? 1.0 : -1.0; dt_end = note * (pcl_end_time - pcl_beg_time); }
+    double last[7];
+    std::memcpy(last, v.back(), 56);
+    std::memcpy(h->last_imu, last, 56);
+    h->last_lidar_end_time = pcl_end_time;
+    double* st = lio->ctrl.state;
+    for (int i = 0; i < 3; ++i) { h->run[6 + i] = st[12 + i]; h->run[9 + i] = st[9 + i]; }
+    for (int i = 0; i < 9; ++i) h->run[12 + i] = st[i];
+    h->poses.assign((steps.size() + 1) * IM_POSE_DOUBLES, 0.0);
+    imu_write_pose(h->poses.data(), 0.0, h->run);
+    std::vector<double> Fx(324), T(324);
+    for (size_t k = 0; k < steps.size(); ++k) imu_forward_step(h->P, st, h->run, steps[k], h->poses.data() + (k + 1) * IM_POSE_DOUBLES, Fx.data(), T.data(), 0, 1);
+    imu_predict_end(st, h->run, note, dt_end);
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pts[4 * (size_t)a + 3] < pts[4 * (size_t)b + 3]; });
+    h->out.resize(4 * (size_t)n);
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c < 4; ++c) h->out[4 * (size_t)i + c] = pts[4 * (size_t)order[i] + c];
+    const int n_pose = (int)steps.size() + 1;
+    for (int s = 0; s < n; ++s) imu_undistort_point(h->P, st, h->poses.data(), n_pose, h->out.data(), s);
+    h->last_poses = n_pose;
+    if (out_xyzt) std::memcpy(out_xyzt, h->out.data(), 4 * (size_t)n * sizeof(float));
+    return 0;
+}
+const float* immesh_imu_device_points(immesh_imu_t* h) { return h->out.data(); }
+int immesh_imu_get_poses(immesh_imu_t* h, double* out, int cap) {
+    const int m = std::min(cap, h->last_poses);
+    std::memcpy(out, h->poses.data(), (size_t)m * IM_POSE_DOUBLES * sizeof(double));
+    return h->last_poses;
+}
+}  // extern "C"

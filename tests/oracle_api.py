@@ -162,6 +162,44 @@ class OracleMesh:
         return idx, d2
 
 
+class OracleImu:
+    """orc_imu.hpp: ImuProcess::UndistortPcl restatement."""
+
+    def __init__(self, cfg: dict):
+        self.L = lib()
+        v = np.zeros(25)
+        v[0:3], v[3:6], v[6:9], v[9:12] = cfg["cov_gyr"], cfg["cov_acc"], cfg["cov_bias_gyr"], cfg["cov_bias_acc"]
+        v[12] = cfg["mean_acc_norm"]
+        v[13:22] = np.asarray(cfg["lid_R"]).reshape(9)
+        v[22:25] = cfg["lid_T"]
+        self.L.orc_imu_create.restype = C.c_void_p
+        self.L.orc_imu_create.argtypes = [C.c_void_p]
+        self.L.orc_imu_destroy.argtypes = [C.c_void_p]
+        self.L.orc_imu_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        self.L.orc_imu_undistort.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int]
+        self.h = C.c_void_p(self.L.orc_imu_create(_p(v)))
+
+    def __del__(self):
+        try:
+            self.L.orc_imu_destroy(self.h)
+        except Exception:
+            pass
+
+    def reset(self, last_imu7, last_lidar_end_time, last_update_time=0.0, acc_s_last=None, angvel_last=None):
+        a = np.ascontiguousarray(last_imu7, dtype=np.float64)
+        f = lambda x: None if x is None else _p(np.ascontiguousarray(x, dtype=np.float64))  # noqa: E731
+        self.L.orc_imu_reset(self.h, _p(a), last_lidar_end_time, last_update_time, f(acc_s_last), f(angvel_last))
+
+    def undistort(self, state348, imu, pts_xyzt, lidar_beg_time):
+        """Returns (state348 after, sorted + compensated cloud, IMUpose[m,22])."""
+        st = np.ascontiguousarray(state348, dtype=np.float64).copy()
+        im = np.ascontiguousarray(imu, dtype=np.float64).reshape(-1, 7)
+        p = np.ascontiguousarray(pts_xyzt, dtype=np.float32).reshape(-1, 4).copy()
+        poses = np.zeros((im.shape[0] + 2, 22))
+        m = self.L.orc_imu_undistort(self.h, _p(st), _p(im), im.shape[0], _p(p), p.shape[0], lidar_beg_time, _p(poses), poses.shape[0])
+        return st, p, poses[:m].copy()
+
+
 def voxel_grid(pts, leaf):
     """pcl::VoxelGrid restatement: returns (out float32[m,3], leaf_too_small, (min_b, div_b))."""
     L = lib()

@@ -210,3 +210,89 @@ def test_voxel_grid_oracle_vs_numpy_restatement():
             for p in run:
                 s = (s + p).astype(np.float32)
             assert np.array_equal(out[r], s / np.float32(len(run)))
+
+
+def test_imu_oracle_vs_numpy_propagation():
+    """orc_imu.hpp against an independent numpy/scipy statement of the same equations (IMU_Processing.cpp:809-896, 930-950):
+    matrix exponential from scipy, dense F P F^T + Q, closed-form compensation -- agreement to rounding."""
+    from scipy.linalg import expm
+
+    def skew(v):
+        return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0.0]])
+
+    rng = np.random.default_rng(5)
+    cfg = dict(cov_gyr=[0.1, 0.12, 0.09], cov_acc=[0.4, 0.5, 0.45], cov_bias_gyr=[1e-4, 1e-4, 2e-4], cov_bias_acc=[1e-3, 2e-3, 1e-3],
+               mean_acc_norm=9.78, lid_R=np.eye(3), lid_T=[0.04, 0.02, -0.03])
+    o = oa.OracleImu(cfg)
+    t0 = 50.0
+    last = np.array([t0 - 0.004, 0.02, -0.01, 0.03, 0.1, 0.2, 9.7])
+    o.reset(last, t0 - 0.001, 0.0, None, None)
+    st = np.zeros(348)
+    st[0:9] = np.eye(3).reshape(9)
+    st[12:15] = [1.0, 0.2, -0.1]
+    st[15:18] = [0.001, 0.002, -0.001]
+    st[18:21] = [0.02, -0.01, 0.03]
+    st[21:24] = [0, 0, -9.81]
+    P0 = rng.normal(size=(18, 18))
+    P0 = P0 @ P0.T * 1e-4
+    st[24:] = P0.reshape(-1)
+    tt = t0 + 0.005 * np.arange(1, 21)
+    imu = np.concatenate([tt[:, None], rng.normal(0, 0.2, (20, 3)), np.array([0.1, -0.2, 9.78]) + rng.normal(0, 0.3, (20, 3))], axis=1)
+    n = 500
+    pts = np.concatenate([rng.normal(0, 5, (n, 3)), rng.uniform(0, 100.0, (n, 1))], axis=1).astype(np.float32)
+    st1, out, poses = o.undistort(st, imu, pts, t0)
+    # numpy restatement
+    R, p, v, bg, ba, g = np.eye(3), st[9:12].copy(), st[12:15].copy(), st[15:18], st[18:21], st[21:24]
+    P = P0.copy()
+    v_imu = np.vstack([last, imu])
+    lle = t0 - 0.001
+    ref_poses = [(0.0, np.zeros(3), np.zeros(3), v.copy(), p.copy(), R.copy())]
+    for k in range(len(v_imu) - 1):
+        head, tail = v_imu[k], v_imu[k + 1]
+        if tail[0] < lle:
+            continue
+        w = 0.5 * (head[1:4] + tail[1:4]) - bg
+        a = 0.5 * (head[4:7] + tail[4:7]) * 9.81 / 9.78 - ba
+        dt = tail[0] - lle if head[0] < lle else tail[0] - head[0]
+        F = np.eye(18)
+        F[0:3, 0:3] = expm(skew(w) * (-dt))
+        F[0:3, 9:12] = -np.eye(3) * dt
+        F[3:6, 6:9] = np.eye(3) * dt
+        F[6:9, 0:3] = -R @ skew(a) * dt
+        F[6:9, 12:15] = -R * dt
+        F[6:9, 15:18] = np.eye(3) * dt
+        Q = np.zeros((18, 18))
+        Q[0:3, 0:3] = np.diag(cfg["cov_gyr"]) * dt * dt
+        Q[6:9, 6:9] = R @ np.diag(cfg["cov_acc"]) @ R.T * dt * dt
+        Q[9:12, 9:12] = np.diag(cfg["cov_bias_gyr"]) * dt * dt
+        Q[12:15, 12:15] = np.diag(cfg["cov_bias_acc"]) * dt * dt
+        P = F @ P @ F.T + Q
+        R = R @ expm(skew(w) * dt)
+        acc = R @ a + g
+        p = p + v * dt + 0.5 * acc * dt * dt
+        v = v + acc * dt
+        ref_poses.append((tail[0] - t0, acc.copy(), w.copy(), v.copy(), p.copy(), R.copy()))
+    pcl_end = t0 + float(pts[-1, 3]) / 1000.0
+    imu_end = v_imu[-1, 0]
+    note = 1.0 if pcl_end > imu_end else -1.0
+    dte = note * (pcl_end - imu_end)
+    v_end = v + note * acc * dte
+    R_end = R @ expm(skew(note * w) * dte)
+    p_end = p + note * v * dte + note * 0.5 * acc * dte * dte
+    assert len(poses) == len(ref_poses)
+    assert np.allclose(st1[24:].reshape(18, 18), P, rtol=1e-9, atol=1e-15)
+    assert np.allclose(st1[0:9].reshape(3, 3), R_end, atol=1e-12) and np.allclose(st1[9:12], p_end, atol=1e-12) and np.allclose(st1[12:15], v_end, atol=1e-12)
+    # compensation of a few interior points
+    order = np.argsort(pts[:, 3], kind="stable")
+    offs = np.array([q[0] for q in ref_poses])
+    lT = np.asarray(cfg["lid_T"])
+    for s in rng.integers(1, n, 40):
+        x = pts[order[s]].astype(np.float64)
+        t = x[3] / 1000.0
+        j = np.max(np.nonzero(offs[:-1] < t)[0])
+        _, a_h, w_h, v_h, p_h, R_h = ref_poses[j]
+        dt = t - offs[j]
+        R_i = R_h @ expm(skew(w_h) * dt)
+        T_ei = p_h + v_h * dt + 0.5 * a_h * dt * dt - p_end
+        ref = R_end.T @ (R_i @ (x[:3] + lT) + T_ei) - lT
+        assert np.allclose(out[s, :3], ref, atol=2e-5), (s, out[s, :3], ref)
