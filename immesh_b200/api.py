@@ -129,6 +129,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_mesh_snapshot", [vp, fp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         ("immesh_knn", [vp, fp, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int32), fp]),
         ("immesh_mesh_last_timing", [vp, dp]),
+        ("immesh_write_ply", [C.c_char_p, fp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
         ("immesh_voxelgrid_create", [C.c_int, C.POINTER(vp)]),
         ("immesh_voxelgrid_destroy", [vp]),
         ("immesh_voxelgrid_filter", [vp, vp, C.c_int, C.c_int, C.c_float, vp, ip, ip]),
@@ -508,6 +509,16 @@ class Imu:
         o = np.zeros((cap, 22))
         m = self.lib.immesh_imu_get_poses(self._h, o.ctypes.data_as(C.POINTER(C.c_double)), cap)
         return o[:m].copy()
+
+
+def write_ply(path: str, vertices, triangles, flips=None, lib: Optional[C.CDLL] = None):
+    """save_to_ply_file layout for a snapshot (vertices float32[nv,3], triangles int32[nt,3], flips int32[nt])."""
+    lib = lib or load_library()
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
+    fl = None if flips is None else np.ascontiguousarray(flips, dtype=np.int32)
+    _check(lib, lib.immesh_write_ply(path.encode(), v.ctypes.data_as(C.POINTER(C.c_float)), v.shape[0], t.ctypes.data_as(C.POINTER(C.c_int32)),
+                                     None if fl is None else fl.ctypes.data_as(C.POINTER(C.c_int32)), t.shape[0]), "write_ply")
 
 
 def profile_enable(on: bool, lib: Optional[C.CDLL] = None):

@@ -182,6 +182,10 @@ int immesh_mesh_counts(immesh_mesh_t* h, int64_t* out /*[8]*/);
  * live triangles as ascending sorted (i<j<k) id triples with their m_index_flip. */
 int immesh_mesh_snapshot(immesh_mesh_t* h, float* vertices /*[nv][3] or NULL*/, int32_t* triangles /*[nt][3] or NULL*/,
                          int32_t* flips /*[nt] or NULL*/);
+/* save_to_ply_file (src/meshing/mesh_rec_geometry.cpp:71-131, smooth_factor == 0): binary little-endian PLY of a snapshot -- float x y z
+ * per vertex, one face per triangle oriented by the reference's rule (m_index_flip != 0: p0 p1 p2, else p0 p2 p1).  Host-side only. */
+int immesh_write_ply(const char* path, const float* vertices /*[nv][3]*/, int nv, const int32_t* triangles /*[nt][3]*/,
+                     const int32_t* flips /*[nt] or NULL*/, int nt);
 /* KD_TREE::Nearest_Search(point, k, ..., max_dist) (include/ikd-Tree/ikd_Tree.h:306) over the mesh vertices:
  * exact k nearest by float squared distance, ascending, ties by lower id; idx = -1 / d2 = inf when fewer exist. */
 int immesh_knn(immesh_mesh_t* h, const float* query_xyz /*[nq][3]*/, int nq, int k, double max_dist, int32_t* idx /*[nq][k]*/,
