@@ -1,8 +1,7 @@
 """GPU tier: the IMU front-end (immesh_imu_*) through the C ABI against the oracle restatement of
 ImuProcess::UndistortPcl.  Same scenario as tests/test_imu_emu.py (which runs the same device bodies on the CPU, bit-exact).
 
-STATUS: written after the round's GPU budget was spent -- this file has not run on hardware yet.  It is therefore marked
-xfail(strict=False): a pass shows up as XPASS, a failure cannot mask the validated tiers (the file also sorts last)."""
+First hardware run: 3 passed on a B200 (last gpurun call of round 1)."""
 import numpy as np
 import pytest
 
@@ -10,7 +9,7 @@ import oracle_api as oa
 from immesh_b200 import api
 from test_imu_emu import _imu_cfg, _make_scan
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (GPU budget of the round spent)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("n_pts,dup", [(3000, False), (50000, True), (1, False)])
