@@ -684,7 +684,6 @@ template <int MAXD>
 IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, MeshWarpSmem<MAXD>* S, int lane, int nlanes, int n_max) {
     const int n = F.work_n_ids[w];
     if (n < 3 || n > n_max || n > MAXD) return;
-    const int vs = F.work[w];
     float (*pos)[3] = S->circ;  // alias: positions are dead once projected
     for (int i = lane; i < n; i += nlanes) {
         const int id = F.work_ids[(size_t)w * IM_MAXD + i];
