@@ -186,6 +186,34 @@ inline cudaError_t run_graphed(GraphCtx& g, unsigned sig, cudaStream_t st, Body&
     }
     return cudaErrorUnknown;
 }
+// Static form: the body's launches take every per-call value from device memory, so once captured the graph is replayed by a
+// bare cudaGraphLaunch -- the body is not run again and no node is touched.  `sig` must cover everything that changes the
+// sequence or its arguments (handle pointers, modes, iteration counts).
+template <typename Body>
+inline cudaError_t run_graphed_static(GraphCtx& g, unsigned sig, cudaStream_t st, Body&& body) {
+    if (g.exec && g.sig != sig) g.destroy();
+    if (!g.exec) {
+        g.err = cudaSuccess;
+        g.nodes.clear();
+        graph_ctx() = &g;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) { graph_ctx() = nullptr; return e; }
+        g.mode = 1;
+        body();
+        g.mode = 0;
+        graph_ctx() = nullptr;
+        e = cudaStreamEndCapture(st, &g.graph);
+        if (e == cudaSuccess && g.err != cudaSuccess) e = g.err;
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&g.exec, g.graph, 0);
+        if (e != cudaSuccess) { g.destroy(); cudaGetLastError(); g.failures++; return e; }
+        g.sig = sig;
+        g.captures++;
+    } else {
+        g.replays++;
+        profiler().launches += (long long)g.nodes.size();   // launch accounting: every kernel node of the graph runs
+    }
+    return cudaGraphLaunch(g.exec, st);
+}
 }  // namespace immesh
 
 // kernel launch with accounting; wrap template kernels in parentheses: IM_LAUNCH((k<256>), grid, block, smem, stream, args...)

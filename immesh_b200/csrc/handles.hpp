@@ -26,9 +26,13 @@ struct immesh_lio {
     cudaEvent_t ev_slot[2] = {nullptr, nullptr};  // completion of the step that used staging slot s
     int slot_busy[2] = {0, 0};
     int step_counter = 0;
-    int pending_rc = 0;
-    cudaStream_t stream2 = nullptr;   // side stream: P^-1 of the propagated covariance, concurrent with the first residual pass
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    immesh::ScanDyn* h_dyn = nullptr;   // pinned, 2 slots: per-scan inputs of the launch sequence (one H2D per scan)
+    immesh::ScanDyn dyn_last = {};         // host copy of the block last uploaded
+    immesh::LioOut* h_out = nullptr;    // pinned, 2 slots: what a scan returns to the host (one D2H per scan)
+    int scan_counter = 0;               // scans queued through the step entry points; pose ring slot = scan_counter & 7
+    int pose_pub_idx = -1;              // scan index whose converged pose is in LioCtrl::pose_ring (-1: not published)
+    int timed_last = 0;                 // the last step recorded its stage timing events
+    cudaEvent_t ev_pose = nullptr;      // "pose of the last scan published" (the mesher's stream waits on it)
     cudaEvent_t ev_mark = nullptr;   // pipeline timing mark (begin)
     void* nccl_comm = nullptr;       // ncclComm_t when the VoxelMap is sharded over several GPUs
     unsigned int* d_bits = nullptr;  // [2][words] exists / matched-in-own-voxel bit words of the sharded residual pass
@@ -44,7 +48,6 @@ struct immesh_lio {
     immesh::GraphCtx graph;   // replay of the per-scan launch sequence (pipelined API)
     int use_graph = 1;
     int bps = 4;              // (mesh: 3 by default, see immesh_mesh_create) resident blocks per SM of the persistent per-voxel kernels (headroom for the other stream)
-    int fused_solve = 0;  // 1: the last residual block of an iteration runs the solve (no separate launch)
     double last_ms[3] = {0, 0, 0};
     std::vector<void*> allocs;
 };
@@ -61,6 +64,9 @@ struct immesh_mesh {
     int* h_cnt = nullptr;     // pinned, 2 slots of 32
     FramePose* d_fp = nullptr;  // 2 slots
     FramePose* h_fp = nullptr;  // pinned, 2 slots
+    immesh::FrameDyn* h_dyn = nullptr;  // pinned, 2 slots: per-frame inputs of the launch sequence
+    immesh::FrameDyn* d_dyn = nullptr;  // device copy read by every kernel of the frame (F.dyn)
+    int timed_last = 0;
     cudaEvent_t ev_in[2] = {nullptr, nullptr};    // inputs of slot s ready (recorded on the producer stream)
     cudaEvent_t ev_done[2] = {nullptr, nullptr};  // frame of slot s finished (mesh stream)
     int inflight[2] = {0, 0};

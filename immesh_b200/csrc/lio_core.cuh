@@ -30,11 +30,33 @@ struct IterStats {
     double converged;
 };
 
+// Per-scan inputs of the launch sequence.  They live in device memory (one small H2D per scan) instead of kernel arguments so
+// that the captured CUDA graph of a scan is replayed WITHOUT touching any of its nodes: kernel arguments, grids and
+// dependencies are constant from scan to scan.
+struct ScanDyn {
+    const float* body;        // [n][3] body-frame scan (device pointer)
+    int n;
+    int scan_idx;             // running scan counter; the converged pose goes to LioCtrl::pose_ring[scan_idx & 7]
+    double dt, cov_gyr, cov_acc;   // Forward_without_imu inputs; dt <= 0: no prediction
+    unsigned long long epoch; // peer-window epoch base of this scan (sharded mode)
+    int mode, pad_;
+};
+// what the host reads back after a scan, one D2H copy
+struct LioOut {
+    double state[IM_STATE_DOUBLES];
+    int iters_run;
+    int scan_idx;
+    int counters[16];
+    int pad_[2];
+};
+#define IM_POSE_RING 8
+
 struct LioCtrl {
     double state[IM_STATE_DOUBLES];
     double state_prop[IM_STATE_DOUBLES];
-    double G[324];
-    double Pinv[324];  // inverse of the propagated covariance: constant over the iterations of one scan
+    double pose_ring[IM_POSE_RING][12];   // rot_end, pos_end each scan converged to (read by the mesher's frame, which runs behind)
+    LioOut out;
+    ScanDyn dyn;
     unsigned long long acc[IM_MAX_ITER][IM_NTERMS * 2];  // (hi, lo) pairs, two's complement sums
     IterStats stats[IM_MAX_ITER];
     int stop;
@@ -49,6 +71,7 @@ struct LioCtrl {
 struct ScanBuf {
     int n;
     const float* body;   // [n][3] body-frame (LiDAR) points, float like pcl::PointXYZI
+    const ScanDyn* dyn;  // device: n / body of the current scan are taken from here (scan_load_dyn), see ScanDyn
     double* body_cov;    // [n][6]
     double* p_imu;       // [n][3]  R_ext p + t_ext (z==0 -> 0.001 rule applied first, :1305-1312)
     double* bv_imu;      // [n][6]  calcBodyVar at the IMU-frame point of the raw scan point (weights, :1498-1521); state independent
@@ -68,6 +91,13 @@ struct ScanBuf {
     int* n_touched;
     int* seg_top;
 };
+
+// kernels work on a copy of their ScanBuf argument whose per-scan fields come from the device-resident block
+IM_HD ScanBuf scan_load_dyn(const ScanBuf& sb) {
+    ScanBuf o = sb;
+    if (sb.dyn) { o.n = sb.dyn->n; o.body = sb.dyn->body; }
+    return o;
+}
 
 // ------------------------------------------------------------------ K1
 IM_HDN inline void prepare_point(const LioParams& P, const ScanBuf& sb, int i) {
@@ -264,66 +294,64 @@ IM_HDN inline bool shard_pass2_point(const VoxelMapDev& map, const LioParams& P,
     return shard_pass2_flags(map, P, sb, state, i, ex, ok1, terms, err);
 }
 
-// ------------------------------------------------------------------ K4: 18x18 LU inverse, cooperative
-// a: 18x18 working copy (shared), piv: 18 ints (shared), inv: 18x18 output.  Same elimination order as a
-// textbook serial partial-pivot LU, every element's update sequence is serial in k.
-IM_HDN inline void lu_inverse18(double* a, int* piv, double* inv, int tid, int nthreads) {
-    for (int i = tid; i < 18; i += nthreads) piv[i] = i;
-    IM_SYNCBLOCK();
-    for (int k = 0; k < 18; ++k) {
-        if (tid == 0) {
-            int best = k;
-            double bv = fabs(a[k * 18 + k]);
-            for (int i = k + 1; i < 18; ++i) {
-                const double v = fabs(a[i * 18 + k]);
-                if (v > bv) { bv = v; best = i; }
-            }
-            if (best != k) {
-                for (int j = 0; j < 18; ++j) { const double tv = a[k * 18 + j]; a[k * 18 + j] = a[best * 18 + j]; a[best * 18 + j] = tv; }
-                const int tp = piv[k]; piv[k] = piv[best]; piv[best] = tp;
-            }
-        }
-        IM_SYNCBLOCK();
-        const double pivv = a[k * 18 + k];
-        IM_SYNCBLOCK();
-        for (int i = k + 1 + tid; i < 18; i += nthreads) a[i * 18 + k] = a[i * 18 + k] / pivv;
-        IM_SYNCBLOCK();
-        for (int idx = tid; idx < 324; idx += nthreads) {
-            const int i = idx / 18, j = idx % 18;
-            if (i > k && j > k) a[i * 18 + j] = a[i * 18 + j] - a[i * 18 + k] * a[k * 18 + j];
-        }
-        IM_SYNCBLOCK();
-    }
-    for (int c = tid; c < 18; c += nthreads) {
-        double y[18];
-        for (int i = 0; i < 18; ++i) {
-            double s = (piv[i] == c) ? 1.0 : 0.0;
-            for (int j = 0; j < i; ++j) s = s - a[i * 18 + j] * y[j];
-            y[i] = s;
-        }
-        for (int i = 17; i >= 0; --i) {
-            double s = y[i];
-            for (int j = i + 1; j < 18; ++j) s = s - a[i * 18 + j] * y[j];
-            y[i] = s / a[i * 18 + i];
-        }
-        for (int i = 0; i < 18; ++i) inv[i * 18 + c] = y[i];
-    }
-    IM_SYNCBLOCK();
-}
-
+// ------------------------------------------------------------------ K4: IESKF update
+// The reference forms K1 = (H^T R^-1 H (+) 0_12 + P^-1)^-1 with two 18x18 inverses per iteration (voxel_mapping.cpp:1588-1592).
+// H^T R^-1 H is non-zero only in its 6x6 pose block A, and K1 is only ever used through its first six columns, for which the
+// matrix inversion lemma gives
+//     K1[:, :6] = P[:, :6] (I6 + A P11)^-1,          P11 = P[:6, :6]
+// (G = K1[:, :6] A, solution = K1[:, :6] H^T z + v - G v[:6], final P = P - G[:, :6] P[:6, :]).  One 6x6 partial-pivot LU instead
+// of two 18x18 ones, no P^-1 at all; better conditioned than the double inversion.  The oracle evaluates the same expressions
+// in the same order (orc_lio.hpp, solve_mode 0) and bounds the distance to the literal reference form (solve_mode 1).
 struct SolveScratch {
-    double a[324];
-    double Pinv[324];
-    double K1[324];
-    double ncov[324];
-    double lu[18 * 19];
     double HTH[36];
     double HTz[6];
+    double B[36];     // I + A P11, LU-factorised in place
+    double S[36];     // its inverse
+    double K1c[108];  // K1[:, :6]
+    double G6[108];   // G[:, :6]
     double vec[18];
     double sol[18];
-    int piv[18];
-    int flags[4];
+    double ncov[324];
+    int piv[6];
+    int flags[2];
 };
+
+// 6x6 partial-pivot LU (one thread) + substitution (one thread per column); same operation order as orc::lu_inverse<6>
+IM_HDN inline void lu_factor6(double* a, int* piv) {
+    for (int i = 0; i < 6; ++i) piv[i] = i;
+    for (int k = 0; k < 6; ++k) {
+        int best = k;
+        double bv = fabs(a[k * 6 + k]);
+        for (int i = k + 1; i < 6; ++i) {
+            const double v = fabs(a[i * 6 + k]);
+            if (v > bv) { bv = v; best = i; }
+        }
+        if (best != k) {
+            for (int j = 0; j < 6; ++j) { const double tv = a[k * 6 + j]; a[k * 6 + j] = a[best * 6 + j]; a[best * 6 + j] = tv; }
+            const int tp = piv[k]; piv[k] = piv[best]; piv[best] = tp;
+        }
+        const double pivv = a[k * 6 + k];
+        for (int i = k + 1; i < 6; ++i) a[i * 6 + k] = a[i * 6 + k] / pivv;
+        for (int i = k + 1; i < 6; ++i) {
+            const double lik = a[i * 6 + k];
+            for (int j = k + 1; j < 6; ++j) a[i * 6 + j] = a[i * 6 + j] - lik * a[k * 6 + j];
+        }
+    }
+}
+IM_HDN inline void lu_solve_col6(const double* a, const int* piv, int c, double* inv) {
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+        double s = (piv[i] == c) ? 1.0 : 0.0;
+        for (int j = 0; j < i; ++j) s = s - a[i * 6 + j] * y[j];
+        y[i] = s;
+    }
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+        for (int j = i + 1; j < 6; ++j) s = s - a[i * 6 + j] * y[j];
+        y[i] = s / a[i * 6 + i];
+    }
+    for (int i = 0; i < 6; ++i) inv[i * 6 + c] = y[i];
+}
 
 // state_propagat (-) state, include/common_lib.h:249-260
 IM_HDN inline void state_minus(const double* a, const double* b, double* out) {
@@ -342,14 +370,18 @@ IM_HDN inline void state_plus(double* s, const double* add) {
     for (int i = 0; i < 15; ++i) s[9 + i] = s[9 + i] + add[3 + i];
 }
 
-// one IESKF update (voxel_mapping.cpp:1586-1650) executed by one thread block
+// one IESKF update (voxel_mapping.cpp:1586-1650) executed by one thread block (>= 32 threads; 1 thread in the host emulation)
 IM_HDN inline void ieskf_solve(const LioParams& P, LioCtrl* ctrl, int iter, SolveScratch* S, int tid, int nthreads) {
-    if (ctrl->stop) return;  // block-uniform
     double* state = ctrl->state;
     double* cov = state + 24;
     // normal equations from the fixed-point accumulators
     for (int e = tid; e < 29; e += nthreads) {
+#if defined(__CUDA_ARCH__)
+        const long long hi = (long long)*(volatile unsigned long long*)&ctrl->acc[iter][2 * e];
+        const long long lo = (long long)*(volatile unsigned long long*)&ctrl->acc[iter][2 * e + 1];
+#else
         const long long hi = (long long)ctrl->acc[iter][2 * e], lo = (long long)ctrl->acc[iter][2 * e + 1];
+#endif
         // hi/lo were accumulated from block sums: total = hi * 2^32 + lo (two's complement, exact)
         const double v = fx_value(hi, lo);
         if (e < 21) {
@@ -366,60 +398,70 @@ IM_HDN inline void ieskf_solve(const LioParams& P, LioCtrl* ctrl, int iter, Solv
             ctrl->stats[iter].n_match = (double)((hi << 32) + lo);
         }
     }
-    for (int i = tid; i < 324; i += nthreads) S->a[i] = cov[i];
+    // v = state_propagat (-) state: independent of the gain, done by the last thread while thread 0 factorises
+    if (tid == nthreads - 1) state_minus(ctrl->state_prop, state, S->vec);
     IM_SYNCBLOCK();
-    lu_inverse18(S->a, S->piv, S->Pinv, tid, nthreads);
-    for (int idx = tid; idx < 324; idx += nthreads) {
-        const int i = idx / 18, j = idx % 18;
-        const double hth = (i < 6 && j < 6) ? S->HTH[i * 6 + j] : 0.0;
-        S->a[idx] = hth + S->Pinv[idx];
+    for (int idx = tid; idx < 36; idx += nthreads) {
+        const int i = idx / 6, j = idx % 6;
+        double s = (i == j) ? 1.0 : 0.0;
+        for (int k = 0; k < 6; ++k) s = s + S->HTH[i * 6 + k] * cov[k * 18 + j];
+        S->B[idx] = s;
     }
     IM_SYNCBLOCK();
-    lu_inverse18(S->a, S->piv, S->K1, tid, nthreads);
-    // G[:, :6] = K1[:, :6] * HTH
-    for (int idx = tid; idx < 18 * 6; idx += nthreads) {
+    if (tid == 0) lu_factor6(S->B, S->piv);
+    IM_SYNCBLOCK();
+    for (int c = tid; c < 6; c += nthreads) lu_solve_col6(S->B, S->piv, c, S->S);
+    IM_SYNCBLOCK();
+    for (int idx = tid; idx < 108; idx += nthreads) {
         const int i = idx / 6, j = idx % 6;
         double s = 0.0;
-        for (int k = 0; k < 6; ++k) s = s + S->K1[i * 18 + k] * S->HTH[k * 6 + j];
-        ctrl->G[i * 18 + j] = s;
+        for (int k = 0; k < 6; ++k) s = s + cov[i * 18 + k] * S->S[k * 6 + j];
+        S->K1c[idx] = s;
     }
-    if (tid == 0) state_minus(ctrl->state_prop, state, S->vec);
+    IM_SYNCBLOCK();
+    for (int idx = tid; idx < 108; idx += nthreads) {
+        const int i = idx / 6, j = idx % 6;
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) s = s + S->K1c[i * 6 + k] * S->HTH[k * 6 + j];
+        S->G6[idx] = s;
+    }
     IM_SYNCBLOCK();
     for (int i = tid; i < 18; i += nthreads) {
         double s1 = 0.0, s2 = 0.0;
-        for (int k = 0; k < 6; ++k) s1 = s1 + S->K1[i * 18 + k] * S->HTz[k];
-        for (int k = 0; k < 6; ++k) s2 = s2 + ctrl->G[i * 18 + k] * S->vec[k];
+        for (int k = 0; k < 6; ++k) s1 = s1 + S->K1c[i * 6 + k] * S->HTz[k];
+        for (int k = 0; k < 6; ++k) s2 = s2 + S->G6[i * 6 + k] * S->vec[k];
         S->sol[i] = (s1 + S->vec[i]) - s2;
     }
     IM_SYNCBLOCK();
     if (tid == 0) {
-        state_plus(state, S->sol);
         const double* sol = S->sol;
         const double rn = sqrt((sol[0] * sol[0] + sol[1] * sol[1]) + sol[2] * sol[2]);
         const double tn = sqrt((sol[3] * sol[3] + sol[4] * sol[4]) + sol[5] * sol[5]);
         const int converged = ((rn * 57.3 < 0.01) && (tn * 100 < 0.015)) ? 1 : 0;
-        IterStats& st = ctrl->stats[iter];
-        for (int i = 0; i < 36; ++i) st.HTH[i] = S->HTH[i];
-        for (int i = 0; i < 6; ++i) st.HTz[i] = S->HTz[i];
-        for (int i = 0; i < 18; ++i) st.solution[i] = sol[i];
-        st.converged = converged;
-        ctrl->iters_run = iter + 1;
         int rematch = ctrl->rematch_num;
         if (converged || ((rematch == 0) && (iter == P.max_iter - 2))) rematch++;
         ctrl->rematch_num = rematch;
+        ctrl->iters_run = iter + 1;
         S->flags[0] = (rematch >= 2 || iter == P.max_iter - 1) ? 1 : 0;
+        S->flags[1] = converged;
+        state_plus(state, S->sol);
+    }
+    // diagnostics of the iteration (parity tests)
+    {
+        IterStats& st = ctrl->stats[iter];
+        for (int i = tid; i < 36; i += nthreads) st.HTH[i] = S->HTH[i];
+        for (int i = tid; i < 6; i += nthreads) st.HTz[i] = S->HTz[i];
+        for (int i = tid; i < 18; i += nthreads) st.solution[i] = S->sol[i];
     }
     IM_SYNCBLOCK();
+    if (tid == 0) ctrl->stats[iter].converged = S->flags[1];
     if (S->flags[0]) {
-        // cov = (I - G) * cov
+        // cov = (I - G) cov = cov - G[:, :6] cov[:6, :]  (rows 0-5 of cov are operands of every element: staged, then stored)
         for (int idx = tid; idx < 324; idx += nthreads) {
             const int i = idx / 18, j = idx % 18;
             double s = 0.0;
-            for (int k = 0; k < 18; ++k) {
-                const double ig = ((i == k) ? 1.0 : 0.0) - ((k < 6) ? ctrl->G[i * 18 + k] : 0.0);
-                s = s + ig * cov[k * 18 + j];
-            }
-            S->ncov[idx] = s;
+            for (int k = 0; k < 6; ++k) s = s + S->G6[i * 6 + k] * cov[k * 18 + j];
+            S->ncov[idx] = cov[idx] - s;
         }
         IM_SYNCBLOCK();
         for (int idx = tid; idx < 324; idx += nthreads) cov[idx] = S->ncov[idx];

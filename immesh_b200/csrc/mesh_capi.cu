@@ -17,7 +17,8 @@
 using namespace immesh;
 
 // ------------------------------------------------------------------ kernels
-__global__ void k_frame_begin(MeshDev M, FrameBuf F) {
+__global__ void k_frame_begin(MeshDev M, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     for (unsigned int i = tid; i <= F.cmask; i += nt) { F.ckeys[i] = IM_EMPTY_KEY; F.chead[i] = -1; }
     for (unsigned int i = tid; i <= F.fset_mask; i += nt) F.fset[i] = -1;
@@ -29,16 +30,19 @@ __global__ void k_frame_begin(MeshDev M, FrameBuf F) {
         M.cnt[30] = 0; M.cnt[31] = 0; M.cnt[32] = 0;
     }
 }
-__global__ void __launch_bounds__(128) k_cand_init(MeshDev M, MeshParams P, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_cand_init(MeshDev M, MeshParams P, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F.m; c += gridDim.x * blockDim.x) cand_init(M, P, F, c);
 }
-__global__ void __launch_bounds__(128) k_cand_conflicts(MeshDev M, MeshParams P, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_cand_conflicts(MeshDev M, MeshParams P, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F.m; c += gridDim.x * blockDim.x) cand_conflicts(M, P, F, c);
 }
 // Priority polling: candidate c waits only on candidates with a smaller index.  Blocks take tickets so that the
 // block holding the smallest undecided candidate is always resident; a poll cap turns a (never observed) livelock
 // into an error flag instead of a hang.
-__global__ void __launch_bounds__(128) k_cand_resolve(MeshDev M, MeshParams P, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_cand_resolve(MeshDev M, MeshParams P, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     __shared__ int s_ticket;
     const int nblocks = (F.m + blockDim.x - 1) / blockDim.x;
     while (true) {
@@ -59,7 +63,8 @@ __global__ void __launch_bounds__(128) k_cand_resolve(MeshDev M, MeshParams P, F
     }
 }
 // exclusive scan of the accept flags by one block in ONE pass: thread t owns a contiguous chunk of ceil(m/1024) candidates
-__global__ void __launch_bounds__(1024) k_cand_scan(MeshDev M, FrameBuf F) {
+__global__ void __launch_bounds__(1024) k_cand_scan(MeshDev M, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     __shared__ int s_warp[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = (F.m + 1023) / 1024;
@@ -90,20 +95,24 @@ __global__ void __launch_bounds__(1024) k_cand_scan(MeshDev M, FrameBuf F) {
         run += (F.cand_status[c] == CAND_ACCEPT) ? 1 : 0;
     }
 }
-__global__ void __launch_bounds__(128) k_cand_commit(MeshDev M, MeshParams P, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_cand_commit(MeshDev M, MeshParams P, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     const int base = M.cnt[0];
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F.m; c += gridDim.x * blockDim.x) cand_commit(M, P, F, c, base);
 }
-__global__ void __launch_bounds__(128) k_cand_place(MeshDev M, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_cand_place(MeshDev M, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     const int base = M.cnt[0];
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F.m; c += gridDim.x * blockDim.x) cand_place(M, F, c, base);
 }
-__global__ void __launch_bounds__(128) k_voxel_select(MeshDev M, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_voxel_select(MeshDev M, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     const int na = min(M.cnt[5], F.max_act);
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < na; a += gridDim.x * blockDim.x) voxel_select(M, F, a);
 }
 // stage A: dilation (exact 20-NN of the in-voxel vertices + smoothing); one block per (voxel, group of <= 8 queries)
-__global__ void __launch_bounds__(128) k_voxel_dilate(MeshDev M, MeshParams P, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_voxel_dilate(MeshDev M, MeshParams P, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     __shared__ DilateSmem S;
     __shared__ int s_item;
     const int ni = min(M.cnt[29], F.max_ditem);
@@ -119,7 +128,8 @@ __global__ void __launch_bounds__(128) k_voxel_dilate(MeshDev M, MeshParams P, F
 }
 // stage B, small dilated sets: one warp per voxel (four independent voxels per block), voxels claimed dynamically
 #define IM_WARP_NMAX 96
-__global__ void __launch_bounds__(128) k_voxel_tri_warp(MeshDev M, MeshParams P, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_voxel_tri_warp(MeshDev M, MeshParams P, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -135,20 +145,24 @@ __global__ void __launch_bounds__(128) k_voxel_tri_warp(MeshDev M, MeshParams P,
     }
 }
 // stage C (flat): after every voxel's smoothing is final
-__global__ void __launch_bounds__(128) k_commit_faces(MeshDev M, MeshParams P, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_commit_faces(MeshDev M, MeshParams P, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     const int nf = min(M.cnt[25], F.max_list);
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) commit_face(M, P, F, f);
 }
-__global__ void __launch_bounds__(128) k_pull_vertices(MeshDev M, MeshParams P, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_pull_vertices(MeshDev M, MeshParams P, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     const int nr = min(M.cnt[26], F.max_vref);
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nr; r += gridDim.x * blockDim.x) pull_vertex(M, P, F, r);
 }
-__global__ void __launch_bounds__(128) k_pull_check(MeshDev M, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_pull_check(MeshDev M, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     const int ne = min(M.cnt[28], F.max_list);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) pull_check(M, F, e);
 }
 template <int MAXD>
-__global__ void __launch_bounds__(128) k_voxel_mesh(MeshDev M, MeshParams P, FrameBuf F, int lo, int store_only) {
+__global__ void __launch_bounds__(128) k_voxel_mesh(MeshDev M, MeshParams P, FrameBuf F_, int lo, int store_only) {
+    const FrameBuf F = frame_load_dyn(F_);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MeshSmem<MAXD>* S = reinterpret_cast<MeshSmem<MAXD>*>(smem_raw);
     const int nw = work_total(M, F);
@@ -160,11 +174,13 @@ __global__ void __launch_bounds__(128) k_voxel_mesh(MeshDev M, MeshParams P, Fra
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(128) k_push_remove(MeshDev M, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_push_remove(MeshDev M, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     const int n = min(M.cnt[8], F.max_list);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) tri_remove(M, F.rem_tri[e]);
 }
-__global__ void __launch_bounds__(128) k_push_add(MeshDev M, FrameBuf F) {
+__global__ void __launch_bounds__(128) k_push_add(MeshDev M, FrameBuf F_) {
+    const FrameBuf F = frame_load_dyn(F_);
     const int n = min(M.cnt[7], F.max_list);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
         tri_add(M, F.add_tri[(size_t)e * 3 + 0], F.add_tri[(size_t)e * 3 + 1], F.add_tri[(size_t)e * 3 + 2], F.add_flip[e]);
@@ -392,6 +408,10 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(cudaMallocHost((void**)&h->h_pts, 2 * mc * 3 * sizeof(float)));
     IM_CUDA(cudaMallocHost((void**)&h->h_cnt, 2 * 32 * sizeof(int)));
     IM_CUDA(cudaMallocHost((void**)&h->h_fp, 2 * sizeof(FramePose)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_dyn, 2 * sizeof(FrameDyn)));
+    IM_CUDA(mdev_alloc(h, &h->d_dyn, 1, 0));
+    F.dyn = h->d_dyn;
+    F.epoch = 0;
     IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<1024>)));
     IM_CUDA(cudaFuncSetAttribute(k_voxel_tri_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(MeshWarpSmem<128>))));
     IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<256>)));
@@ -416,6 +436,7 @@ int immesh_mesh_destroy(immesh_mesh_t* h) {
     if (h->h_pts) cudaFreeHost(h->h_pts);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     if (h->h_fp) cudaFreeHost(h->h_fp);
+    if (h->h_dyn) cudaFreeHost(h->h_dyn);
     for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -435,11 +456,23 @@ static int mesh_grid(const immesh_mesh* h, int n, int threads, int waves = 8) {
 }
 
 // transformLidar of the full-resolution scan with the converged state (ImMesh_mesh_reconstruction.cpp:413 ->
-// voxel_mapping_common.cpp:709-726): p_w = (float)( R (R_ext p + t_ext) + t )
-__global__ void __launch_bounds__(128) k_transform_full(LioParams P, const LioCtrl* ctrl, const float* body, int n, float* world) {
+// voxel_mapping_common.cpp:709-726): p_w = (float)( R (R_ext p + t_ext) + t ).  First kernel of a frame handed over by the
+// localization handle: the pose is the one that scan converged to (LioCtrl::pose_ring, written by the last kernel of the
+// scan's sequence; the localization stream may already be working on later scans).  Block 0 also derives the frame's sensor
+// position + the origin of the flip-priority rank.
+__global__ void __launch_bounds__(128) k_transform_full(LioParams P, const LioCtrl* ctrl, FrameBuf F_, double res) {
     __shared__ double s[12];
-    if (threadIdx.x < 12) s[threadIdx.x] = ctrl->state[threadIdx.x];
+    const FrameDyn d = *F_.dyn;
+    if (threadIdx.x < 12) s[threadIdx.x] = ctrl->pose_ring[d.pose_idx][threadIdx.x];
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < 3) {
+        const double t = s[9 + threadIdx.x];
+        d.fp->pose_t[threadIdx.x] = t;
+        d.fp->prio_origin[threadIdx.x] = (long long)floor(t / res) - 1024;
+    }
+    const float* body = d.body;
+    float* world = const_cast<float*>(d.pts);
+    const int n = d.n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double pb[3] = {(double)body[(size_t)i * 3 + 0], (double)body[(size_t)i * 3 + 1], (double)body[(size_t)i * 3 + 2]};
         double pw[3];
@@ -447,10 +480,15 @@ __global__ void __launch_bounds__(128) k_transform_full(LioParams P, const LioCt
         world[(size_t)i * 3 + 0] = (float)pw[0]; world[(size_t)i * 3 + 1] = (float)pw[1]; world[(size_t)i * 3 + 2] = (float)pw[2];
     }
 }
+// blocking localization calls (immesh_lio_estimate, set_state, ...) do not publish a pose: done on request, on the localization stream
+__global__ void k_pose_publish(LioCtrl* ctrl, int idx) {
+    if (threadIdx.x < 12) ctrl->pose_ring[idx][threadIdx.x] = ctrl->state[threadIdx.x];
+}
 
 // ---- multi-GPU exchange of the per-voxel stage (sharded mesher).  A segment = [16-B header: counts][entries, x_cap each].
 struct XHeader { int n_smooth, n_face, n_rem, pad; };
-__global__ void k_xhdr(MeshDev M, FrameBuf F, XHeader* hdr) {
+__global__ void k_xhdr(MeshDev M, FrameBuf F_, XHeader* hdr) {
+    const FrameBuf F = frame_load_dyn(F_);
     if (threadIdx.x == 0) {
         hdr->n_smooth = min(M.cnt[32], F.x_cap);
         hdr->n_face = min(M.cnt[30], F.x_cap);
@@ -470,7 +508,9 @@ __device__ __forceinline__ unsigned long long* meshwin_flag(unsigned char* w, in
 __device__ __forceinline__ void copy16(unsigned char* dst, const unsigned char* src, size_t n16, int tid, int nt) {
     for (size_t i = tid; i < n16; i += nt) ((uint4*)dst)[i] = ((const uint4*)src)[i];
 }
-__global__ void __launch_bounds__(256) k_xpush(MeshDev M, FrameBuf F, const unsigned char* seg, int which, MeshPeers pe, unsigned long long epoch, int* done) {
+__global__ void __launch_bounds__(256) k_xpush(MeshDev M, FrameBuf F_, const unsigned char* seg, int which, MeshPeers pe, int* done) {
+    const FrameBuf F = frame_load_dyn(F_);
+    const unsigned long long epoch = F.epoch;
     __shared__ int s_last;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     const int n_smooth = min(M.cnt[32], F.x_cap), n_face = min(M.cnt[30], F.x_cap), n_rem = min(M.cnt[31], F.x_cap);
@@ -505,7 +545,9 @@ __device__ __forceinline__ void mesh_wait_peers(const MeshPeers& pe, int which, 
     }
 }
 // smoothed positions written by the other ranks' dilations -> this rank's replica
-__global__ void __launch_bounds__(256) k_apply_smooth(MeshDev M, FrameBuf F, const unsigned char* recv, size_t seg_bytes, MeshPeers pe, unsigned long long epoch) {
+__global__ void __launch_bounds__(256) k_apply_smooth(MeshDev M, FrameBuf F_, const unsigned char* recv, size_t seg_bytes, MeshPeers pe) {
+    const FrameBuf F = frame_load_dyn(F_);
+    const unsigned long long epoch = F.epoch;
     mesh_wait_peers(pe, 0, epoch, &M.cnt[3]);
     for (int r = 0; r < F.shard_n; ++r) {
         if (r == F.shard_rank) continue;
@@ -520,7 +562,9 @@ __global__ void __launch_bounds__(256) k_apply_smooth(MeshDev M, FrameBuf F, con
     }
 }
 // facets / removals of ALL ranks (own segment included) -> add / remove lists of this rank's replica
-__global__ void __launch_bounds__(256) k_apply_lists(MeshDev M, FrameBuf F, const unsigned char* recv, size_t seg_bytes, MeshPeers pe, unsigned long long epoch) {
+__global__ void __launch_bounds__(256) k_apply_lists(MeshDev M, FrameBuf F_, const unsigned char* recv, size_t seg_bytes, MeshPeers pe) {
+    const FrameBuf F = frame_load_dyn(F_);
+    const unsigned long long epoch = F.epoch;
     mesh_wait_peers(pe, 1, epoch, &M.cnt[3]);
     for (int r = 0; r < F.shard_n; ++r) {
         const unsigned char* seg = recv + (size_t)r * seg_bytes;
@@ -533,15 +577,6 @@ __global__ void __launch_bounds__(256) k_apply_lists(MeshDev M, FrameBuf F, cons
             if (i < nf) { const int4 f = __ldcg(face + i); apply_face(M, F, f.x, f.y, f.z, __ldcg(word + i)); }
             else { const int4 t = __ldcg(rem + (i - nf)); apply_remove(M, F, t.x, t.y, t.z); }
         }
-    }
-}
-
-// sensor position of the frame + origin of the flip-priority rank, taken from the state the localization converged to
-__global__ void k_pose_from_lio(const LioCtrl* ctrl, double res, FramePose* out) {
-    if (threadIdx.x < 3) {
-        const double t = ctrl->state[9 + threadIdx.x];
-        out->pose_t[threadIdx.x] = t;
-        out->prio_origin[threadIdx.x] = (long long)floor(t / res) - 1024;
     }
 }
 
@@ -562,8 +597,20 @@ static int mesh_harvest(immesh_mesh* h, int s) {
     return rc;
 }
 
+static bool mesh_host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+static int mesh_grid_fixed(const immesh_mesh* h, long long n_cap, int threads, int waves = 8) {
+    long long g = (n_cap + threads - 1) / threads;
+    if (g > (long long)h->n_sm * waves) g = (long long)h->n_sm * waves;
+    return g < 1 ? 1 : (int)g;
+}
 // src_mode: 0 host world points, 1 device world points, 2 host body points + lio state, 3 device body points + lio state.
-// Queues one frame (no host synchronisation except when both staging slots are still busy).
+// Queues one frame (no host synchronisation except when both staging slots are still busy).  Host work per frame in the
+// pipelined form: (memcpy into the pinned slot unless the caller's buffer is pinned) + H2D scan + H2D FrameDyn + one stream
+// wait + ONE cudaGraphLaunch (no node is touched: every per-frame value is read from the FrameDyn) + one D2H of the counters.
 static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double* pose_t, int src_mode, immesh_lio* lio, bool allow_graph = false) {
     if (!h || (!xyz && n > 0) || n < 0 || (src_mode < 2 && !pose_t)) return im_fail(IMMESH_E_INVALID, "bad argument");
     if (n > h->max_frame_points) return im_fail(IMMESH_E_CAPACITY, "frame larger than max_frame_points");
@@ -585,37 +632,43 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
     F.fp = d_fp;
     F.cmask = (unsigned)(pow2_at_least((size_t)std::max(F.m, 1) * 2) - 1);
     cudaStream_t st = h->stream;
-    IM_CUDA(cudaEventRecord(h->ev[0], st));
+    const bool graphed = allow_graph && h->use_graph && !profiler().enabled && (F.shard_n <= 1 || h->win.ok);
+    if (!graphed) IM_CUDA(cudaEventRecord(h->ev[0], st));
     F.pts = d_pts;
+    const float* d_body = nullptr;
+    int pose_idx = 0;
     if (src_mode < 2) {
         FramePose* hp = h->h_fp + s;
         for (int j = 0; j < 3; ++j) { hp->pose_t[j] = pose_t[j]; hp->prio_origin[j] = (long long)std::floor(pose_t[j] / P.res) - 1024; }
         IM_CUDA(cudaMemcpyAsync(d_fp, hp, sizeof(FramePose), cudaMemcpyHostToDevice, st));
         if (n > 0) {
             if (src_mode == 0) {
-                std::memcpy(h_pts, xyz, (size_t)n * 3 * sizeof(float));
-                IM_CUDA(cudaMemcpyAsync(d_pts, h_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+                const float* src = xyz;
+                if (!mesh_host_ptr_is_pinned(xyz)) { std::memcpy(h_pts, xyz, (size_t)n * 3 * sizeof(float)); src = h_pts; }
+                IM_CUDA(cudaMemcpyAsync(d_pts, src, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
             } else {
                 F.pts = xyz;
             }
         }
     } else {
-        // producer side runs on the localization stream, right behind the step that produced the state
-        cudaStream_t ls = lio->stream;
-        const float* d_body = xyz;
+        // the body-frame scan does not depend on the localization: it is uploaded on the mesh stream right away
+        d_body = xyz;
         if (src_mode == 2 && n > 0) {
             if (!h->d_body) IM_CUDA(mdev_alloc(h, &h->d_body, 2 * slot_pts));
-            std::memcpy(h_pts, xyz, (size_t)n * 3 * sizeof(float));
-            IM_CUDA(cudaMemcpyAsync(h->d_body + s * slot_pts, h_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ls));
+            const float* src = xyz;
+            if (!mesh_host_ptr_is_pinned(xyz)) { std::memcpy(h_pts, xyz, (size_t)n * 3 * sizeof(float)); src = h_pts; }
+            IM_CUDA(cudaMemcpyAsync(h->d_body + s * slot_pts, src, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
             d_body = h->d_body + s * slot_pts;
         }
-        if (n > 0) IM_LAUNCH(k_transform_full, mesh_grid(h, n, 128), 128, 0, ls, lio->P, lio->d_ctrl, d_body, n, d_pts);
-        IM_LAUNCH(k_pose_from_lio, 1, 32, 0, ls, lio->d_ctrl, P.res, d_fp);
-        IM_CUDA(cudaEventRecord(h->ev_in[s], ls));
-        IM_CUDA(cudaStreamWaitEvent(st, h->ev_in[s], 0));
+        // the pose: published by the last kernel of the scan's sequence (step entry points), else on request
+        if (lio->pose_pub_idx < 0) {
+            lio->pose_pub_idx = ++lio->scan_counter;
+            IM_LAUNCH(k_pose_publish, 1, 32, 0, lio->stream, lio->d_ctrl, lio->pose_pub_idx & (IM_POSE_RING - 1));
+        }
+        pose_idx = lio->pose_pub_idx & (IM_POSE_RING - 1);
+        IM_CUDA(cudaEventRecord(lio->ev_pose, lio->stream));
+        IM_CUDA(cudaStreamWaitEvent(st, lio->ev_pose, 0));
     }
-    // the frame's launch sequence; replayed as one CUDA graph by the pipelined entry points (host-launch-bound otherwise)
-    bool nccl_failed = false;
     MeshPeers pe;
     std::memset(&pe, 0, sizeof(pe));
     unsigned long long epoch = 0;
@@ -626,78 +679,82 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         pe.seg_bytes[0] = h->seg1_bytes; pe.seg_bytes[1] = h->seg2_bytes;
         epoch = ++h->win.epoch;
     }
+    F.epoch = epoch;
+    {   // the frame's device-resident inputs
+        FrameDyn& d = h->h_dyn[s];
+        d.pts = F.pts; d.body = d_body; d.fp = d_fp;
+        d.n = F.n; d.step = F.step; d.m = F.m; d.frame = F.frame; d.cmask = F.cmask; d.pose_idx = pose_idx; d.epoch = epoch;
+        IM_CUDA(cudaMemcpyAsync(h->d_dyn, &d, sizeof(FrameDyn), cudaMemcpyHostToDevice, st));
+    }
+    // the frame's launch sequence (fixed grids: grid-stride loops over the counts the kernels read on the device)
+    bool nccl_failed = false;
+    const int g_pts = mesh_grid_fixed(h, h->max_frame_points, 128);
+    const int g_cand = mesh_grid_fixed(h, std::min<long long>(h->max_frame_points, 2LL * P.append_target), 128);
     auto launch_frame = [&](bool timing) {
-        const bool replay = immesh::im_replaying();
-        IM_LAUNCH(k_frame_begin, mesh_grid(h, (int)std::max(F.cmask, F.fset_mask) + 1, 256), 256, 0, st, h->M, F);
+        if (src_mode >= 2) IM_LAUNCH(k_transform_full, g_pts, 128, 0, st, lio->P, (const LioCtrl*)lio->d_ctrl, F, P.res);
+        IM_LAUNCH(k_frame_begin, h->n_sm * 8, 256, 0, st, h->M, F);
         if (timing) cudaEventRecord(h->ev[1], st);
-        if (F.m > 0) {
-            const int g = mesh_grid(h, F.m, 128);
-            IM_LAUNCH(k_cand_init, g, 128, 0, st, h->M, P, F);
-            IM_LAUNCH(k_cand_conflicts, g, 128, 0, st, h->M, P, F);
-            IM_LAUNCH(k_cand_resolve, mesh_grid(h, F.m, 128, 16), 128, 0, st, h->M, P, F);
-            IM_LAUNCH(k_cand_scan, 1, 1024, 0, st, h->M, F);
-            IM_LAUNCH(k_cand_commit, g, 128, 0, st, h->M, P, F);
-            IM_LAUNCH(k_cand_place, g, 128, 0, st, h->M, F);
-            IM_LAUNCH(k_voxel_select, mesh_grid(h, F.m, 128), 128, 0, st, h->M, F);
-        }
+        IM_LAUNCH(k_cand_init, g_cand, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_cand_conflicts, g_cand, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_cand_resolve, h->n_sm * 4, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_cand_scan, 1, 1024, 0, st, h->M, F);
+        IM_LAUNCH(k_cand_commit, g_cand, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_cand_place, g_cand, 128, 0, st, h->M, F);
+        IM_LAUNCH(k_voxel_select, g_cand, 128, 0, st, h->M, F);
         if (timing) cudaEventRecord(h->ev[2], st);
-        if (F.m > 0) {
-            IM_LAUNCH(k_voxel_dilate, h->n_sm * h->bps, 128, 0, st, h->M, P, F);
-            if (F.shard_n > 1 && h->win.ok) {   // smoothed positions of the other ranks' voxels, pushed into their windows
-                IM_LAUNCH(k_xpush, h->n_sm, 256, 0, st, h->M, F, (const unsigned char*)h->d_seg1, 0, pe, epoch, h->d_xdone);
-                IM_LAUNCH(k_apply_smooth, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv1, h->seg1_bytes, pe, epoch);
-            } else if (F.shard_n > 1) {   // NCCL transport
-                IM_LAUNCH(k_xhdr, 1, 32, 0, st, h->M, F, (XHeader*)h->d_seg1);
-                if (immesh::nccl().AllGather(h->d_seg1, h->d_recv1, h->seg1_bytes, immesh::kNcclUint8, h->nccl_comm, st)) nccl_failed = true;
-                IM_LAUNCH(k_apply_smooth, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv1, h->seg1_bytes, pe, epoch);
-            }
-            // triangulation: small dilated sets warp-level on the side stream, mid-size ones block-level on the main stream,
-            // concurrently; then the rare large / handed-over ones (monolithic: triangulate + commit in shared memory)
-            if (!replay) {
-                cudaEventRecord(h->ev_fork, st);
-                cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-                cudaStreamWaitEvent(h->stream3, h->ev_fork, 0);
-            }
-            IM_LAUNCH(k_voxel_tri_warp, h->n_sm * h->bps, 128, 4 * sizeof(MeshWarpSmem<128>), h->stream2, h->M, P, F);
-            if (!replay) cudaEventRecord(h->ev_join, h->stream2);
-            IM_LAUNCH(k_pull_vertices, h->n_sm * 8, 128, 0, h->stream3, h->M, P, F);   // incidence-list walk: only needs the dilation
-            if (!replay) cudaEventRecord(h->ev_join3, h->stream3);
-            IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * h->bps, 128, sizeof(MeshSmem<256>), st, h->M, P, F, IM_WARP_NMAX, 1);
-            if (!replay) {
-                cudaStreamWaitEvent(st, h->ev_join, 0);
-                cudaStreamWaitEvent(st, h->ev_join3, 0);
-            }
-            IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st, h->M, P, F, 256, 0);
-            IM_LAUNCH(k_commit_faces, h->n_sm * 8, 128, 0, st, h->M, P, F);
-            IM_LAUNCH(k_pull_check, h->n_sm * 8, 128, 0, st, h->M, F);
-            if (F.shard_n > 1 && h->win.ok) {   // every rank applies the facets / removals of all ranks to its replica of the store
-                IM_LAUNCH(k_xpush, h->n_sm, 256, 0, st, h->M, F, (const unsigned char*)h->d_seg2, 1, pe, epoch, h->d_xdone + 1);
-                IM_LAUNCH(k_apply_lists, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv2, h->seg2_bytes, pe, epoch);
-            } else if (F.shard_n > 1) {
-                IM_LAUNCH(k_xhdr, 1, 32, 0, st, h->M, F, (XHeader*)h->d_seg2);
-                if (immesh::nccl().AllGather(h->d_seg2, h->d_recv2, h->seg2_bytes, immesh::kNcclUint8, h->nccl_comm, st)) nccl_failed = true;
-                IM_LAUNCH(k_apply_lists, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv2, h->seg2_bytes, pe, epoch);
-            }
+        IM_LAUNCH(k_voxel_dilate, h->n_sm * h->bps, 128, 0, st, h->M, P, F);
+        if (F.shard_n > 1 && h->win.ok) {   // smoothed positions of the other ranks' voxels, pushed into their windows
+            IM_LAUNCH(k_xpush, h->n_sm, 256, 0, st, h->M, F, (const unsigned char*)h->d_seg1, 0, pe, h->d_xdone);
+            IM_LAUNCH(k_apply_smooth, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv1, h->seg1_bytes, pe);
+        } else if (F.shard_n > 1) {   // NCCL transport
+            IM_LAUNCH(k_xhdr, 1, 32, 0, st, h->M, F, (XHeader*)h->d_seg1);
+            if (immesh::nccl().AllGather(h->d_seg1, h->d_recv1, h->seg1_bytes, immesh::kNcclUint8, h->nccl_comm, st)) nccl_failed = true;
+            IM_LAUNCH(k_apply_smooth, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv1, h->seg1_bytes, pe);
+        }
+        // triangulation: small dilated sets warp-level on the side stream, mid-size ones block-level on the main stream,
+        // concurrently; then the rare large / handed-over ones (monolithic: triangulate + commit in shared memory)
+        cudaEventRecord(h->ev_fork, st);
+        cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+        cudaStreamWaitEvent(h->stream3, h->ev_fork, 0);
+        IM_LAUNCH(k_voxel_tri_warp, h->n_sm * h->bps, 128, 4 * sizeof(MeshWarpSmem<128>), h->stream2, h->M, P, F);
+        cudaEventRecord(h->ev_join, h->stream2);
+        IM_LAUNCH(k_pull_vertices, h->n_sm * 8, 128, 0, h->stream3, h->M, P, F);   // incidence-list walk: only needs the dilation
+        cudaEventRecord(h->ev_join3, h->stream3);
+        IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * h->bps, 128, sizeof(MeshSmem<256>), st, h->M, P, F, IM_WARP_NMAX, 1);
+        cudaStreamWaitEvent(st, h->ev_join, 0);
+        cudaStreamWaitEvent(st, h->ev_join3, 0);
+        IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st, h->M, P, F, 256, 0);
+        IM_LAUNCH(k_commit_faces, h->n_sm * 8, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_pull_check, h->n_sm * 8, 128, 0, st, h->M, F);
+        if (F.shard_n > 1 && h->win.ok) {   // every rank applies the facets / removals of all ranks to its replica of the store
+            IM_LAUNCH(k_xpush, h->n_sm, 256, 0, st, h->M, F, (const unsigned char*)h->d_seg2, 1, pe, h->d_xdone + 1);
+            IM_LAUNCH(k_apply_lists, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv2, h->seg2_bytes, pe);
+        } else if (F.shard_n > 1) {
+            IM_LAUNCH(k_xhdr, 1, 32, 0, st, h->M, F, (XHeader*)h->d_seg2);
+            if (immesh::nccl().AllGather(h->d_seg2, h->d_recv2, h->seg2_bytes, immesh::kNcclUint8, h->nccl_comm, st)) nccl_failed = true;
+            IM_LAUNCH(k_apply_lists, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv2, h->seg2_bytes, pe);
         }
         if (timing) cudaEventRecord(h->ev[3], st);
-        if (F.m > 0) {
-            IM_LAUNCH(k_push_remove, h->n_sm * 2, 128, 0, st, h->M, F);
-            IM_LAUNCH(k_push_add, h->n_sm * 2, 128, 0, st, h->M, F);
-        }
+        IM_LAUNCH(k_push_remove, h->n_sm * 2, 128, 0, st, h->M, F);
+        IM_LAUNCH(k_push_add, h->n_sm * 2, 128, 0, st, h->M, F);
         IM_LAUNCH(k_frame_end, 1, 1, 0, st, h->M);
     };
     bool queued = false;
-    if (allow_graph && h->use_graph && !profiler().enabled && F.m > 0 && (F.shard_n <= 1 || h->win.ok)) {
-        queued = immesh::run_graphed(h->graph, h->win.ok ? 3u : 1u, st, [&] { launch_frame(false); }) == cudaSuccess;
-        if (!queued) h->use_graph = 0;
+    if (graphed) {
+        // signature: everything that changes the sequence or its (static) arguments
+        const unsigned long long lp = (unsigned long long)(uintptr_t)lio;
+        const unsigned sig = (h->win.ok ? 2u : 0u) | 1u | ((unsigned)src_mode << 2) | ((unsigned)F.shard_n << 5) | ((unsigned)((lp >> 4) ^ (lp >> 36)) << 9);
+        queued = immesh::run_graphed_static(h->graph, sig, st, [&] { launch_frame(false); }) == cudaSuccess;
+        if (!queued) { h->use_graph = 0; IM_CUDA(cudaEventRecord(h->ev[0], st)); }
     }
     if (!queued) launch_frame(true);
     if (nccl_failed) return im_fail(IMMESH_E_CUDA, "ncclAllGather failed");
     IM_CUDA(cudaGetLastError());
     IM_CUDA(cudaMemcpyAsync(h->h_cnt + 32 * s, h->M.cnt, 32 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    IM_CUDA(cudaEventRecord(h->ev[4], st));
+    if (!queued) IM_CUDA(cudaEventRecord(h->ev[4], st));
     IM_CUDA(cudaEventRecord(h->ev_done[s], st));
     h->inflight[s] = 1;
+    h->timed_last = queued ? 0 : 1;
     return IMMESH_OK;
 }
 // drain the queue; returns the status of the frames harvested since the last call
@@ -709,7 +766,7 @@ static int mesh_wait_impl(immesh_mesh_t* h, bool timings) {
         cudaStreamSynchronize(h->stream);
         profiler().collect();
     }
-    if (timings) {
+    if (timings && h->timed_last) {
         float a = 0, b = 0, c = 0, d = 0;
         cudaEventElapsedTime(&a, h->ev[0], h->ev[4]);
         cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);

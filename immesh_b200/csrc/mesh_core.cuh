@@ -104,11 +104,24 @@ struct FramePose {        // per-frame sensor position (device resident so that 
     long long prio_origin[3];  // floor(pose_t / res) - 1024: origin of the 11-bit-per-axis voxel rank used by the flip priority
 };
 struct XSmooth { int id, pad; double x, y, z; };   // 32 B
+// Per-frame inputs of the launch sequence, device resident (one small H2D per frame): the captured CUDA graph of a frame is
+// replayed without touching its nodes, every kernel takes the frame's values from here (frame_load_dyn).
+struct FrameDyn {
+    const float* pts;     // world-frame scan of this frame (staging slot, or the caller's device buffer)
+    const float* body;    // body-frame scan when the frame is handed over by the localization handle (transformed into pts first)
+    FramePose* fp;
+    int n, step, m, frame;
+    unsigned int cmask;
+    int pose_idx;         // slot of LioCtrl::pose_ring holding the pose the scan converged to
+    unsigned long long epoch;   // peer-window epoch of this frame (sharded mode)
+};
 struct FrameBuf {
     const float* pts;     // [n][3] world-frame scan
     int n, step, m;       // m = number of candidates = ceil(n / step)
     int frame;            // internal monotonically increasing frame counter
     const FramePose* fp;
+    const FrameDyn* dyn;  // device: the seven per-frame fields above + cmask + epoch are taken from here by the kernels
+    unsigned long long epoch;
     // candidates
     unsigned long long* cand_gkey;
     int* cand_vslot;
@@ -154,6 +167,15 @@ struct FrameBuf {
     unsigned long long* x_word;   // their flip-priority words
     int4* x_rem;          // triangles (a, b, c, -) this rank's voxels want removed    (count: cnt[31])
 };
+
+IM_HD FrameBuf frame_load_dyn(const FrameBuf& F) {
+    FrameBuf o = F;
+    if (F.dyn) {
+        const FrameDyn d = *F.dyn;
+        o.pts = d.pts; o.n = d.n; o.step = d.step; o.m = d.m; o.frame = d.frame; o.fp = d.fp; o.cmask = d.cmask; o.epoch = d.epoch;
+    }
+    return o;
+}
 
 // ------------------------------------------------------------------ keys
 IM_HD int round_key(float x, double cell) { return (int)round((double)x / cell); }  // std::round, pointcloud_rgbd.cpp:467-472

@@ -55,33 +55,67 @@ struct PeerWindow {
     unsigned long long epoch = 0;   // host counter, advanced once per exchange
 };
 
+inline void peer_window_close(PeerWindow& w);
 // Allocates the local window, exchanges the IPC handles through the (already initialised) NCCL communicator and maps the
-// peers' windows.  Returns cudaSuccess or the failing CUDA error; `w.ok` is only set when every peer is mapped.
+// peers' windows.  The decision "peer windows or NCCL" must be the SAME on every rank (a rank spinning on epoch flags while
+// another sits in an all-reduce would hang both), so every rank always takes part in both collectives below, a local failure
+// travels as a marker, and `w.ok` is set only when EVERY rank mapped EVERY peer; otherwise everything opened here is released
+// again on all ranks and they all use the NCCL transport.  Returns cudaSuccess or the first local CUDA error
+// (cudaErrorNotReady: this rank was fine but a peer was not).
 inline cudaError_t peer_window_open(PeerWindow& w, size_t bytes, int rank, int n, nccl_comm_t comm, cudaStream_t st) {
+    struct Msg { cudaIpcMemHandle_t h; int ok; int pad_[15]; };
     w.ok = false;
     w.rank = rank;
     w.n = n;
     w.bytes = bytes;
-    if (n > IM_MAX_RANKS) return cudaErrorInvalidValue;
-    cudaError_t e = cudaMalloc((void**)&w.local, bytes);
-    if (e != cudaSuccess) return e;
-    if ((e = cudaMemset(w.local, 0, bytes)) != cudaSuccess) return e;
-    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
-    cudaIpcMemHandle_t mine;
-    if ((e = cudaIpcGetMemHandle(&mine, w.local)) != cudaSuccess) return e;
+    if (n > IM_MAX_RANKS) return cudaErrorInvalidValue;          // same n on every rank: a uniform decision
+    cudaError_t first = cudaSuccess;
+    auto note = [&](cudaError_t e) { if (e != cudaSuccess && first == cudaSuccess) first = e; return e == cudaSuccess; };
+    // exchange buffer first: without it this rank could not even report its failure (a 1 KB allocation; if it fails the
+    // process is out of device memory and the caller's create/shard call fails as a whole)
     unsigned char* d_x = nullptr;
-    if ((e = cudaMalloc((void**)&d_x, sizeof(mine) * (size_t)(n + 1))) != cudaSuccess) return e;
+    cudaError_t e = cudaMalloc((void**)&d_x, sizeof(Msg) * (size_t)(n + 1) + 16);
+    if (e != cudaSuccess) return e;
+    Msg mine;
+    std::memset(&mine, 0, sizeof(mine));
+    if (note(cudaMalloc((void**)&w.local, bytes)) && note(cudaMemset(w.local, 0, bytes)) && note(cudaDeviceSynchronize()) &&
+        note(cudaIpcGetMemHandle(&mine.h, w.local)))
+        mine.ok = 1;
     cudaMemcpy(d_x, &mine, sizeof(mine), cudaMemcpyHostToDevice);
-    if (nccl().AllGather(d_x, d_x + sizeof(mine), sizeof(mine), kNcclUint8, comm, st)) { cudaFree(d_x); return cudaErrorUnknown; }
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { cudaFree(d_x); return e; }
-    cudaIpcMemHandle_t all[IM_MAX_RANKS];
-    cudaMemcpy(all, d_x + sizeof(mine), sizeof(mine) * (size_t)n, cudaMemcpyDeviceToHost);
+    bool coll_ok = nccl().AllGather(d_x, d_x + sizeof(Msg), sizeof(Msg), kNcclUint8, comm, st) == 0;
+    coll_ok = coll_ok && cudaStreamSynchronize(st) == cudaSuccess;
+    Msg all[IM_MAX_RANKS];
+    std::memset(all, 0, sizeof(all));
+    if (coll_ok) cudaMemcpy(all, d_x + sizeof(Msg), sizeof(Msg) * (size_t)n, cudaMemcpyDeviceToHost);
+    bool everyone = coll_ok;
+    for (int r = 0; r < n && everyone; ++r) everyone = all[r].ok != 0;
+    unsigned int failed = 0;
+    if (everyone) {
+        for (int r = 0; r < n; ++r) {
+            if (r == rank) { w.peer[r] = w.local; continue; }
+            void* p = nullptr;
+            if (!note(cudaIpcOpenMemHandle(&p, all[r].h, cudaIpcMemLazyEnablePeerAccess))) { failed = 1; break; }
+            w.peer[r] = (unsigned char*)p;
+        }
+    } else {
+        failed = 1;
+    }
+    // second round: did every rank map every peer?  (sum of the failure markers)
+    if (coll_ok) {
+        unsigned int* d_f = (unsigned int*)(d_x + sizeof(Msg) * (size_t)(n + 1));
+        cudaMemcpy(d_f, &failed, sizeof(failed), cudaMemcpyHostToDevice);
+        unsigned int total = 1;
+        if (nccl().AllReduce(d_f, d_f, 1, kNcclUint32, kNcclSum, comm, st) == 0 && cudaStreamSynchronize(st) == cudaSuccess)
+            cudaMemcpy(&total, d_f, sizeof(total), cudaMemcpyDeviceToHost);
+        failed = total;
+    }
     cudaFree(d_x);
-    for (int r = 0; r < n; ++r) {
-        if (r == rank) { w.peer[r] = w.local; continue; }
-        void* p = nullptr;
-        if ((e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) return e;
-        w.peer[r] = (unsigned char*)p;
+    if (failed) {
+        const int keep_rank = w.rank, keep_n = w.n;
+        peer_window_close(w);
+        w.rank = keep_rank; w.n = keep_n;
+        cudaGetLastError();
+        return first != cudaSuccess ? first : cudaErrorNotReady;
     }
 #if defined(__CUDACC__)
     if (const char* t = std::getenv("IMMESH_PEER_TIMEOUT_MS")) {

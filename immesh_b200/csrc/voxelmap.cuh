@@ -587,7 +587,7 @@ IM_HDN inline void update_octo_tree(const VoxelMapDev& m, const LioParams& P, in
                 node_append(m, nd, x, y, z, var6);
             }
             IM_SYNCWARP();
-            if (m.nodes[nd].n_pts > P.layer_init[m.nodes[nd].layer]) init_octo_tree(m, P, nd, lane, nlanes);
+            if (IM_BCAST_I(m.nodes[nd].n_pts > P.layer_init[m.nodes[nd].layer] ? 1 : 0)) init_octo_tree(m, P, nd, lane, nlanes);
             return;
         }
         if (m.planes[nd].is_plane) {
@@ -597,12 +597,12 @@ IM_HDN inline void update_octo_tree(const VoxelMapDev& m, const LioParams& P, in
                     node_append(m, nd, x, y, z, var6);
                 }
                 IM_SYNCWARP();
-                if (m.nodes[nd].new_points > 5) {
+                if (IM_BCAST_I(m.nodes[nd].new_points > 5 ? 1 : 0)) {
                     init_plane(m, P, nd, lane, nlanes);
                     if (lane == 0) m.nodes[nd].new_points = 0;
                     IM_SYNCWARP();
                 }
-                if (m.nodes[nd].n_pts >= P.max_points) {
+                if (IM_BCAST_I(m.nodes[nd].n_pts >= P.max_points ? 1 : 0)) {
                     if (lane == 0) {
                         m.nodes[nd].update_enable = 0;
                         node_free_points(m, nd);
@@ -614,7 +614,7 @@ IM_HDN inline void update_octo_tree(const VoxelMapDev& m, const LioParams& P, in
             return;
         }
         if (n.layer < P.max_layer) {
-            if (n.n_pts != 0) {
+            if (IM_BCAST_I(n.n_pts != 0 ? 1 : 0)) {
                 if (lane == 0) node_free_points(m, nd);
                 IM_SYNCWARP();
             }
@@ -632,12 +632,12 @@ IM_HDN inline void update_octo_tree(const VoxelMapDev& m, const LioParams& P, in
                 node_append(m, nd, x, y, z, var6);
             }
             IM_SYNCWARP();
-            if (m.nodes[nd].new_points > 5) {
+            if (IM_BCAST_I(m.nodes[nd].new_points > 5 ? 1 : 0)) {
                 init_plane(m, P, nd, lane, nlanes);
                 if (lane == 0) m.nodes[nd].new_points = 0;
                 IM_SYNCWARP();
             }
-            if (m.nodes[nd].n_pts > 1000) {  // g_max_points, voxel_loc.cpp:45
+            if (IM_BCAST_I(m.nodes[nd].n_pts > 1000 ? 1 : 0)) {  // g_max_points, voxel_loc.cpp:45
                 if (lane == 0) {
                     m.nodes[nd].update_enable = 0;
                     node_free_points(m, nd);

@@ -108,8 +108,6 @@ int immesh_lio_shard(immesh_lio_t* h, int rank, int nranks, const char* unique_i
  * the consumer ranks' windows and raises an epoch flag, the consuming kernel waits on the flags -- the NCCL communicator
  * is then only used once, to exchange the IPC handles. */
 int immesh_lio_shard_transport(immesh_lio_t* h);
-/* diagnostic (profiles/README.md): clock64 stamps at the phase boundaries of the last 18x18 inverse kernel */
-int immesh_debug_inverse_stamps(long long* out16);
 int immesh_mesh_shard_transport(immesh_mesh_t* h);
 /* Same for the mesher (its own communicator: use a second unique id).  Every rank is given the same frames and runs the
  * vertex append itself (replicated: identical vertex ids everywhere); the per-voxel stage -- dilation, triangulation

@@ -26,6 +26,7 @@ struct LioCfg {
     int sum_mode;               // 0: fixed-point order-free sums (matches the CUDA product bit for bit)
                                 // 1: plain serial double sums (closest to the reference's Eigen GEMM)
     int omp_threads;            // threads for the residual loop (reference: MP_PROC_NUM = 4)
+    int solve_mode;             // 0: 6x6 matrix-inversion-lemma form of the IESKF gain (matches the CUDA product); 1: the reference's two 18x18 inverses
 };
 
 struct PV {  // Point_with_var, voxel_loc.hpp:75-80
@@ -697,17 +698,42 @@ class LioOracle {
                 st.n_match = m;
                 st.total_residual = cfg.sum_mode == 0 ? fx_res.value() : sres;
             }
-            // (e) :1586-1592
-            for (int a = 0; a < 6; ++a)
-                for (int b = 0; b < 6; ++b) HTH18[a * 18 + b] = st.HTH[a * 6 + b];
-            double Pinv[324], M[324], K1[324];
-            lu_inverse<18>(state.cov, Pinv);
-            for (int i = 0; i < 324; ++i) M[i] = HTH18[i] + Pinv[i];
-            lu_inverse<18>(M, K1);
+            // (e) :1586-1592.  The reference forms K1 = (H^T R^-1 H (+) 0_12 + P^-1)^-1 with two 18x18 Eigen inverses.  H^T R^-1 H
+            // is non-zero only in its 6x6 pose block A, so by the matrix inversion lemma
+            //     K1[:, :6] = P[:, :6] (I6 + A P11)^-1,     P11 = P[:6, :6],
+            // and K1 is only ever used through its first six columns (G = K1[:, :6] A, the solution, (I - G) P).  solve_mode 0
+            // (default, what the CUDA product computes, bit for bit): that 6x6 form; solve_mode 1: the reference's literal two
+            // inversions (Eigen's .inverse() is unpinned either way; tests/test_oracle_crosscheck.py bounds the gap between the two).
+            double K1c[108];   // K1[:, :6], 18 x 6
+            if (cfg.solve_mode == 0) {
+                double B[36], S[36];
+                for (int i = 0; i < 6; ++i)
+                    for (int j = 0; j < 6; ++j) {
+                        double s = (i == j) ? 1.0 : 0.0;
+                        for (int k = 0; k < 6; ++k) s = s + st.HTH[i * 6 + k] * state.cov[k * 18 + j];
+                        B[i * 6 + j] = s;
+                    }
+                lu_inverse<6>(B, S);
+                for (int i = 0; i < 18; ++i)
+                    for (int j = 0; j < 6; ++j) {
+                        double s = 0.0;
+                        for (int k = 0; k < 6; ++k) s = s + state.cov[i * 18 + k] * S[k * 6 + j];
+                        K1c[i * 6 + j] = s;
+                    }
+            } else {
+                for (int a = 0; a < 6; ++a)
+                    for (int b = 0; b < 6; ++b) HTH18[a * 18 + b] = st.HTH[a * 6 + b];
+                double Pinv[324], M[324], K1[324];
+                lu_inverse<18>(state.cov, Pinv);
+                for (int i = 0; i < 324; ++i) M[i] = HTH18[i] + Pinv[i];
+                lu_inverse<18>(M, K1);
+                for (int i = 0; i < 18; ++i)
+                    for (int j = 0; j < 6; ++j) K1c[i * 6 + j] = K1[i * 18 + j];
+            }
             for (int i = 0; i < 18; ++i)
                 for (int j = 0; j < 6; ++j) {
                     double s = 0.0;
-                    for (int k = 0; k < 6; ++k) s = s + K1[i * 18 + k] * st.HTH[k * 6 + j];
+                    for (int k = 0; k < 6; ++k) s = s + K1c[i * 6 + k] * st.HTH[k * 6 + j];
                     G[i * 18 + j] = s;
                 }
             double vec[18];
@@ -715,7 +741,7 @@ class LioOracle {
             double solution[18];
             for (int i = 0; i < 18; ++i) {
                 double s1 = 0.0, s2 = 0.0;
-                for (int k = 0; k < 6; ++k) s1 = s1 + K1[i * 18 + k] * st.HTz[k];
+                for (int k = 0; k < 6; ++k) s1 = s1 + K1c[i * 6 + k] * st.HTz[k];
                 for (int k = 0; k < 6; ++k) s2 = s2 + G[i * 18 + k] * vec[k];
                 solution[i] = (s1 + vec[i]) - s2;
             }
@@ -733,16 +759,22 @@ class LioOracle {
             for (const Ptpl& p : ptpl_list) { last_match_idx.push_back(p.src_index); last_match_layer.push_back(p.layer); }
             if (converged || ((rematch_num == 0) && (iter == cfg.max_iteration - 2))) rematch_num++;
             if (rematch_num >= 2 || iter == cfg.max_iteration - 1) {
-                // cov = (I - G) * cov
+                // cov = (I - G) * cov (:1646).  G has six non-zero columns: solve_mode 0 evaluates P - G[:, :6] P[:6, :]
                 double ncov[324];
                 for (int i = 0; i < 18; ++i)
                     for (int j = 0; j < 18; ++j) {
-                        double s = 0.0;
-                        for (int k = 0; k < 18; ++k) {
-                            const double ig = ((i == k) ? 1.0 : 0.0) - G[i * 18 + k];
-                            s = s + ig * state.cov[k * 18 + j];
+                        if (cfg.solve_mode == 0) {
+                            double s = 0.0;
+                            for (int k = 0; k < 6; ++k) s = s + G[i * 18 + k] * state.cov[k * 18 + j];
+                            ncov[i * 18 + j] = state.cov[i * 18 + j] - s;
+                        } else {
+                            double s = 0.0;
+                            for (int k = 0; k < 18; ++k) {
+                                const double ig = ((i == k) ? 1.0 : 0.0) - G[i * 18 + k];
+                                s = s + ig * state.cov[k * 18 + j];
+                            }
+                            ncov[i * 18 + j] = s;
                         }
-                        ncov[i * 18 + j] = s;
                     }
                 for (int i = 0; i < 324; ++i) state.cov[i] = ncov[i];
                 break;

@@ -80,6 +80,7 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     h->match_node.assign(ms, -1); h->match_layer.assign(ms, 0); h->slot.resize(ms); h->seg.resize(ms); h->seg2.resize(ms); h->touched.resize(ms);
     h->slot_count.assign(cap, 0); h->slot_offset.assign(cap, 0); h->slot_cursor.assign(cap, 0);
     ScanBuf& sb = h->sb;
+    sb.dyn = nullptr;
     sb.n = 0; sb.body = h->body.data(); sb.body_cov = h->body_cov.data(); sb.p_imu = h->p_imu.data(); sb.bv_imu = h->bv_imu.data();
     sb.match_node = h->match_node.data(); sb.match_layer = h->match_layer.data(); sb.pw = h->pw.data(); sb.var = h->var.data();
     sb.sortkey = h->sortkey.data(); sb.slot = h->slot.data(); sb.seg = h->seg.data();

@@ -186,6 +186,43 @@ def test_fixed_point_sums_close_to_serial_double():
         assert np.allclose(a.get_state()[:12], b.get_state()[:12], rtol=1e-9, atol=1e-10)
 
 
+def test_ieskf_gain_6x6_form_equals_reference_form():
+    """The IESKF update is evaluated through the matrix inversion lemma, K1[:, :6] = P[:, :6] (I + A P11)^-1 (solve_mode 0: what the
+    CUDA product computes), instead of the reference's two 18x18 inverses (voxel_mapping.cpp:1588-1592, solve_mode 1).  Same
+    stream through both forms: identical iteration counts / match sets, state and covariance within 1e-9 relative; plus the
+    solution of one iteration against numpy's literal  (H^T R^-1 H (+) 0 + P^-1)^-1."""
+    cfg = api.AVIA
+    sensor, scans = synth.make_stream("avia", 6, seed=21, ext_T=cfg.ext_T)
+    a, b = oa.OracleLio(cfg, sum_mode=0, solve_mode=0), oa.OracleLio(cfg, sum_mode=0, solve_mode=1)
+    for h in (a, b):
+        h.set_pose(scans[0]["R_true"], scans[0]["t_true"])
+        s = h.get_state()
+        s[12:15] = (scans[1]["t_true"] - scans[0]["t_true"]) / scans[0]["dt"]
+        h.set_state(s)
+        h.voxel_map_init(scans[0]["body_full"])
+    for k in range(1, 6):
+        for h in (a, b):
+            h.predict(scans[k]["dt"])
+        prop = a.get_state()
+        ia, ib = a.lio_state_estimation(scans[k]["body_ds"]), b.lio_state_estimation(scans[k]["body_ds"])
+        assert ia == ib
+        assert np.array_equal(a.matches(), b.matches())
+        sa, sb = a.get_state(), b.get_state()
+        assert np.allclose(sa[:24], sb[:24], rtol=1e-9, atol=1e-12), np.abs(sa[:24] - sb[:24]).max()
+        Pa, Pb = sa[24:].reshape(18, 18), sb[24:].reshape(18, 18)
+        assert np.abs(Pa - Pb).max() <= 1e-9 * np.abs(Pb).max()
+        # first iteration against numpy: state == propagated state there, so v = 0 and solution = K1[:, :6] H^T z
+        st = a.iter_stats(0)
+        P = prop[24:].reshape(18, 18)
+        M = np.linalg.inv(P)
+        M[:6, :6] += st["HTH"]
+        sol = np.linalg.inv(M)[:, :6] @ st["HTz"]
+        assert np.allclose(st["solution"], sol, rtol=1e-7, atol=1e-12)
+        for h in (a, b):
+            h.map_incremental_grow(scans[k]["body_ds"])
+    assert a.dump_map().shape == b.dump_map().shape
+
+
 def test_voxel_grid_oracle_vs_numpy_restatement():
     """orc_frontend.hpp (pcl::VoxelGrid restatement) against an independent numpy statement of the same published algorithm:
     float32 inverse leaf / box / cell index, leaves in ascending index, float32 sums in scan order."""
