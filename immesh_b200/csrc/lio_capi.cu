@@ -394,7 +394,8 @@ static cudaError_t dev_alloc(immesh_lio* h, T** p, size_t count, int memset_byte
 // Grids are fixed per handle (sized for max_scan_points, at most 8 waves of blocks; every per-point kernel is a grid-stride
 // loop over the n it reads from the device-resident ScanDyn), so that the captured launch sequence is identical for every scan.
 static int grid_fixed(const immesh_lio* h, int threads, int max_waves = 8) {
-    long long g = ((long long)h->max_scan + threads - 1) / threads;
+    static const int by_n = std::getenv("IMMESH_DEBUG_GRID_N") ? std::atoi(std::getenv("IMMESH_DEBUG_GRID_N")) : 0;   // experiments: size the grids by the scan
+    long long g = ((long long)(by_n ? (h->last_n > 0 ? h->last_n : 1) : h->max_scan) + threads - 1) / threads;
     const long long cap = (long long)h->n_sm * max_waves;
     if (g > cap) g = cap;
     if (g < 1) g = 1;

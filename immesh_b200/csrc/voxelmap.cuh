@@ -28,6 +28,10 @@
 #define IM_SYNCWARP()
 #define IM_BCAST_I(x) (x)
 #endif
+// Predicates of the per-node state machine are evaluated by every lane on data that only lane 0 writes, always behind a warp
+// barrier.  (Taking lane 0's value through a shuffle instead was tried and changed results on the B200 -- tools/debug/lio_diff.py,
+// profiles/README.md round 2 -- so the per-lane evaluation, validated bit for bit against the oracle, stays.)
+#define IM_UPRED(x) (x)
 
 namespace immesh {
 
@@ -587,7 +591,7 @@ IM_HDN inline void update_octo_tree(const VoxelMapDev& m, const LioParams& P, in
                 node_append(m, nd, x, y, z, var6);
             }
             IM_SYNCWARP();
-            if (IM_BCAST_I(m.nodes[nd].n_pts > P.layer_init[m.nodes[nd].layer] ? 1 : 0)) init_octo_tree(m, P, nd, lane, nlanes);
+            if (IM_UPRED(m.nodes[nd].n_pts > P.layer_init[m.nodes[nd].layer] ? 1 : 0)) init_octo_tree(m, P, nd, lane, nlanes);
             return;
         }
         if (m.planes[nd].is_plane) {
@@ -597,12 +601,12 @@ IM_HDN inline void update_octo_tree(const VoxelMapDev& m, const LioParams& P, in
                     node_append(m, nd, x, y, z, var6);
                 }
                 IM_SYNCWARP();
-                if (IM_BCAST_I(m.nodes[nd].new_points > 5 ? 1 : 0)) {
+                if (IM_UPRED(m.nodes[nd].new_points > 5 ? 1 : 0)) {
                     init_plane(m, P, nd, lane, nlanes);
                     if (lane == 0) m.nodes[nd].new_points = 0;
                     IM_SYNCWARP();
                 }
-                if (IM_BCAST_I(m.nodes[nd].n_pts >= P.max_points ? 1 : 0)) {
+                if (IM_UPRED(m.nodes[nd].n_pts >= P.max_points ? 1 : 0)) {
                     if (lane == 0) {
                         m.nodes[nd].update_enable = 0;
                         node_free_points(m, nd);
@@ -614,7 +618,7 @@ IM_HDN inline void update_octo_tree(const VoxelMapDev& m, const LioParams& P, in
             return;
         }
         if (n.layer < P.max_layer) {
-            if (IM_BCAST_I(n.n_pts != 0 ? 1 : 0)) {
+            if (IM_UPRED(n.n_pts != 0 ? 1 : 0)) {
                 if (lane == 0) node_free_points(m, nd);
                 IM_SYNCWARP();
             }
@@ -632,12 +636,12 @@ IM_HDN inline void update_octo_tree(const VoxelMapDev& m, const LioParams& P, in
                 node_append(m, nd, x, y, z, var6);
             }
             IM_SYNCWARP();
-            if (IM_BCAST_I(m.nodes[nd].new_points > 5 ? 1 : 0)) {
+            if (IM_UPRED(m.nodes[nd].new_points > 5 ? 1 : 0)) {
                 init_plane(m, P, nd, lane, nlanes);
                 if (lane == 0) m.nodes[nd].new_points = 0;
                 IM_SYNCWARP();
             }
-            if (IM_BCAST_I(m.nodes[nd].n_pts > 1000 ? 1 : 0)) {  // g_max_points, voxel_loc.cpp:45
+            if (IM_UPRED(m.nodes[nd].n_pts > 1000 ? 1 : 0)) {  // g_max_points, voxel_loc.cpp:45
                 if (lane == 0) {
                     m.nodes[nd].update_enable = 0;
                     node_free_points(m, nd);
