@@ -102,6 +102,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_mesh_push_frame_dev", [vp, vp, C.c_int, dp, C.c_int]),
         ("immesh_mesh_push_frame_from_lio", [vp, vp, vp, C.c_int, C.c_int]),
         ("immesh_lio_match_nodes", [vp, ip, C.c_int]),
+        ("immesh_voxelmap_build_pv", [vp, dp, dp, C.c_int]),
+        ("immesh_voxelmap_update_pv", [vp, dp, dp, C.c_int]),
+        ("immesh_residual_build_pv", [vp, dp, dp, dp, C.c_int, ip, dp, C.c_int, ip]),
         ("immesh_comm_unique_id", [C.c_char_p]),
         ("immesh_lio_shard", [vp, C.c_int, C.c_int, C.c_char_p]),
         ("immesh_mesh_shard", [vp, C.c_int, C.c_int, C.c_char_p]),
@@ -115,6 +118,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_pipeline_mark_begin", [vp]),
         ("immesh_pipeline_mark_end", [vp, vp, dp]),
         ("immesh_mesh_work_stats", [vp, C.POINTER(C.c_int64)]),
+        ("immesh_host_wait_ms", [vp, vp, dp]),
+        ("immesh_lio_work_stats", [vp, C.POINTER(C.c_int64)]),
         ("immesh_profile_enable", [C.c_int]),
         ("immesh_profile_reset", []),
         ("immesh_profile_report", [C.c_char_p, C.c_int]),
@@ -290,6 +295,29 @@ class Lio:
         _check(self.lib, self.lib.immesh_residual_build(self._h, p, n, il.ctypes.data_as(C.POINTER(C.c_int)), vals.ctypes.data_as(C.POINTER(C.c_double)), n, C.byref(m)), "residual_build")
         return il[: m.value], vals[: m.value]
 
+    # --- the three free functions of src/voxel_mapping.hpp:80-105 on caller-built Point_with_var lists
+    @staticmethod
+    def _f64(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+    def voxelmap_build_pv(self, pts_world, var9):
+        (pw, ppw), (v9, pv9) = self._f64(pts_world), self._f64(var9)
+        _check(self.lib, self.lib.immesh_voxelmap_build_pv(self._h, ppw, pv9, pw.shape[0]), "voxelmap_build_pv")
+
+    def voxelmap_update_pv(self, pts_world, var9):
+        (pw, ppw), (v9, pv9) = self._f64(pts_world), self._f64(var9)
+        _check(self.lib, self.lib.immesh_voxelmap_update_pv(self._h, ppw, pv9, pw.shape[0]), "voxelmap_update_pv")
+
+    def residual_build_pv(self, pts_body, pts_world, var9):
+        (pb, ppb), (pw, ppw), (v9, pv9) = self._f64(pts_body), self._f64(pts_world), self._f64(var9)
+        n = pb.shape[0]
+        il = np.zeros((max(n, 1), 2), dtype=np.int32)
+        vals = np.zeros((max(n, 1), 31))
+        m = C.c_int(0)
+        _check(self.lib, self.lib.immesh_residual_build_pv(self._h, ppb, ppw, pv9, n, il.ctypes.data_as(C.POINTER(C.c_int)), vals.ctypes.data_as(C.POINTER(C.c_double)), n, C.byref(m)), "residual_build_pv")
+        return il[: m.value], vals[: m.value]
+
     # --- diagnostics
     def iter_stats(self, it):
         o = np.zeros(63)
@@ -319,6 +347,11 @@ class Lio:
         o = np.zeros(4, dtype=np.int64)
         self.lib.immesh_voxelmap_counts(self._h, o.ctypes.data_as(C.POINTER(C.c_int64)))
         return dict(roots=int(o[0]), nodes=int(o[1]), chunks=int(o[2]), err=int(o[3]))
+
+    def work_stats(self):
+        o = np.zeros(4, dtype=np.int64)
+        _check(self.lib, self.lib.immesh_lio_work_stats(self._h, o.ctypes.data_as(C.POINTER(C.c_int64))), "lio_work_stats")
+        return dict(n=int(o[0]), roots=int(o[1]), refits=int(o[2]), refit_points=int(o[3]))
 
     def last_timing(self):
         o = np.zeros(3)
@@ -567,6 +600,14 @@ def graph_stats(lio: Optional["Lio"], mesh: Optional["Mesh"]) -> dict:
     _check(lib, lib.immesh_graph_stats(lio._h if lio else None, mesh._h if mesh else None, out), "graph_stats")
     keys = ("lio_captures", "lio_replays", "lio_failures", "mesh_captures", "mesh_replays", "mesh_failures")
     return dict(zip(keys, [int(v) for v in out]))
+
+
+def host_wait_ms(lio: Optional["Lio"], mesh: Optional["Mesh"]):
+    """Host milliseconds the enqueue calls spent blocked on busy staging slots since the last call: (lio, mesh)."""
+    lib = (lio or mesh).lib
+    out = (C.c_double * 2)()
+    _check(lib, lib.immesh_host_wait_ms(lio._h if lio else None, mesh._h if mesh else None, out), "host_wait_ms")
+    return float(out[0]), float(out[1])
 
 
 def pipeline_mark_begin(lio: Lio):

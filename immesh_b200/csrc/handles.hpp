@@ -32,6 +32,7 @@ struct immesh_lio {
     int scan_counter = 0;               // scans queued through the step entry points; pose ring slot = scan_counter & 7
     int pose_pub_idx = -1;              // scan index whose converged pose is in LioCtrl::pose_ring (-1: not published)
     int timed_last = 0;                 // the last step recorded its stage timing events
+    double host_wait_ms = 0;            // host time spent blocked on a busy staging slot inside the enqueue calls (back-pressure, not work)
     cudaEvent_t ev_pose = nullptr;      // "pose of the last scan published" (the mesher's stream waits on it)
     cudaEvent_t ev_mark = nullptr;   // pipeline timing mark (begin)
     void* nccl_comm = nullptr;       // ncclComm_t when the VoxelMap is sharded over several GPUs
@@ -67,6 +68,7 @@ struct immesh_mesh {
     immesh::FrameDyn* h_dyn = nullptr;  // pinned, 2 slots: per-frame inputs of the launch sequence
     immesh::FrameDyn* d_dyn = nullptr;  // device copy read by every kernel of the frame (F.dyn)
     int timed_last = 0;
+    double host_wait_ms = 0;
     cudaEvent_t ev_in[2] = {nullptr, nullptr};    // inputs of slot s ready (recorded on the producer stream)
     cudaEvent_t ev_done[2] = {nullptr, nullptr};  // frame of slot s finished (mesh stream)
     int inflight[2] = {0, 0};

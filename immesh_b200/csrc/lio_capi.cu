@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -332,6 +333,8 @@ __global__ void k_grow_finish(VoxelMapDev map, ScanBuf sb, int* work_counter, Li
         if (threadIdx.x < 16) ctrl->out.counters[threadIdx.x] = counters[threadIdx.x];
         if (threadIdx.x == 0) { ctrl->out.iters_run = ctrl->iters_run; ctrl->out.scan_idx = si; }
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && map.stat) { map.stat[0] = 0; map.stat[1] = 0; }   // per-scan work counters (reported through LioOut::counters[9..10])
 }
 // BuildResidualListOMP on caller-supplied Point_with_var data (world point + covariance per point)
 __global__ void __launch_bounds__(128) k_match_pv(VoxelMapDev map, LioParams P, ScanBuf sb, const double* pw, int n) {   // API call: explicit n
@@ -448,7 +451,7 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     IM_CREATE(dev_alloc(h, &m.pending, (size_t)h->max_chunks));
     IM_CREATE(dev_alloc(h, &h->d_counters, 16, 0));
     m.node_count = h->d_counters + 0; m.chunk_bump = h->d_counters + 1; m.avail_top = h->d_counters + 2; m.pending_n = h->d_counters + 3;
-    m.err = h->d_counters + 4; m.n_roots = h->d_counters + 5;
+    m.err = h->d_counters + 4; m.n_roots = h->d_counters + 5; m.stat = h->d_counters + 9;
     m.max_nodes = h->max_nodes; m.max_chunks = h->max_chunks;
     ScanBuf& sb = h->sb;
     const size_t ms = (size_t)h->max_scan;
@@ -728,7 +731,12 @@ int immesh_voxelmap_update(immesh_lio_t* h) {
 static int lio_enqueue(immesh_lio_t* h, const float* body, int n, int on_device, double dt, double cov_gyr, double cov_acc, bool allow_graph) {
     if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
     const int s = (++h->step_counter) & 1;
-    if (h->slot_busy[s]) { IM_CUDA(cudaEventSynchronize(h->ev_slot[s])); h->slot_busy[s] = 0; }
+    if (h->slot_busy[s]) {
+        const auto t0 = std::chrono::steady_clock::now();
+        IM_CUDA(cudaEventSynchronize(h->ev_slot[s]));
+        h->host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        h->slot_busy[s] = 0;
+    }
     h->win.epoch += IM_MAX_ITER + 1;   // epoch base of this scan: advanced exactly once per scan
     ++h->scan_counter;
     const bool timing = !(allow_graph && h->use_graph && !profiler().enabled && (h->P.shard_n <= 1 || h->win.ok));
@@ -805,6 +813,13 @@ int immesh_lio_enqueue_memset(immesh_lio_t* h, void* d_buf, size_t bytes) {
     return IMMESH_OK;
 }
 
+// work counters of the last step (roofline byte model): [n, touched root voxels are not kept, plane refits, points read by the refits]
+int immesh_lio_work_stats(immesh_lio_t* h, int64_t* out /*[4]*/) {
+    if (!h || !out) return im_fail(IMMESH_E_INVALID, "null argument");
+    const LioOut& o = h->h_out[h->step_counter & 1];
+    out[0] = h->last_n; out[1] = o.counters[5]; out[2] = o.counters[9]; out[3] = o.counters[10];
+    return IMMESH_OK;
+}
 int immesh_lio_last_timing(immesh_lio_t* h, double* ms) {
     if (!h || !ms) return im_fail(IMMESH_E_INVALID, "null argument");
     ms[0] = h->last_ms[0]; ms[1] = h->last_ms[1]; ms[2] = h->last_ms[2];

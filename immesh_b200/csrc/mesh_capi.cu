@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -589,7 +590,12 @@ static int mesh_status(int err) {
 // wait for the frame queued in slot s and take over its counters
 static int mesh_harvest(immesh_mesh* h, int s) {
     if (!h->inflight[s]) return IMMESH_OK;
-    IM_CUDA(cudaEventSynchronize(h->ev_done[s]));
+    if (cudaEventQuery(h->ev_done[s]) != cudaSuccess) {
+        cudaGetLastError();
+        const auto t0 = std::chrono::steady_clock::now();
+        IM_CUDA(cudaEventSynchronize(h->ev_done[s]));
+        h->host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
     h->inflight[s] = 0;
     std::memcpy(h->last_cnt, h->h_cnt + 32 * s, 32 * sizeof(int));
     const int rc = mesh_status(h->last_cnt[3]);
@@ -870,6 +876,16 @@ int immesh_graph_stats(immesh_lio_t* lio, immesh_mesh_t* mesh, int64_t* out) {
     for (int i = 0; i < 6; ++i) out[i] = 0;
     if (lio) { out[0] = lio->graph.captures; out[1] = lio->graph.replays; out[2] = lio->graph.failures; }
     if (mesh) { out[3] = mesh->graph.captures; out[4] = mesh->graph.replays; out[5] = mesh->graph.failures; }
+    return IMMESH_OK;
+}
+// host time (ms) the enqueue calls spent blocked on busy staging slots since the last call of this function: [lio, mesh].
+// Queueing a scan costs (wall time of the call) - (this): the rest is back-pressure from the device.
+int immesh_host_wait_ms(immesh_lio_t* lio, immesh_mesh_t* mesh, double* out) {
+    if (!out) return im_fail(IMMESH_E_INVALID, "null argument");
+    out[0] = lio ? lio->host_wait_ms : 0.0;
+    out[1] = mesh ? mesh->host_wait_ms : 0.0;
+    if (lio) lio->host_wait_ms = 0;
+    if (mesh) mesh->host_wait_ms = 0;
     return IMMESH_OK;
 }
 int immesh_mesh_wait(immesh_mesh_t* h) {

@@ -117,6 +117,7 @@ struct VoxelMapDev {
     int* pending_n;
     int* err;
     int* n_roots;
+    int* stat;   // optional work counters of the current scan: [0] plane refits, [1] points read by them (roofline byte model); may be null
 };
 
 #define IM_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
@@ -313,6 +314,7 @@ IM_HDN inline void init_plane(const VoxelMapDev& m, const LioParams& P, int nd, 
     const NodeRec& n = m.nodes[nd];
     PlaneRec& pl = m.planes[nd];
     const int np = n.n_pts;
+    if (lane == 0 && m.stat) { im_atomic_add(m.stat, 1); im_atomic_add(m.stat + 1, np); }
     // centre / covariance sums are kept incrementally by node_append in append order: bit-identical to the
     // reference's loop over m_temp_points_ (voxel_loc.cpp:55-59)
     double cov[6], c[3];

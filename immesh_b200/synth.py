@@ -140,6 +140,10 @@ def make_sensor(kind: str, n_points: int | None = None) -> SensorModel:
         s = Spinning("hdl64", n_points or 131072, 2.0, 120.0, 0.04, 0.1, 10.0, 10.0)
         s.rings, s.el_hi, s.el_lo = 64, 2.0, -24.8
         return s
+    if kind == "hdl64loop":
+        s = Spinning("hdl64loop", n_points or 131072, 2.0, 120.0, 0.04, 0.1, 10.0, 10.0)
+        s.rings, s.el_hi, s.el_lo = 64, 2.0, -24.8
+        return s
     if kind == "ouster1m":
         s = Spinning("ouster1m", n_points or 1048576, 0.5, 120.0, 0.02, 0.05, 10.0, 2.0)
         s.rings, s.el_hi, s.el_lo = 128, 22.5, -22.5
@@ -147,10 +151,32 @@ def make_sensor(kind: str, n_points: int | None = None) -> SensorModel:
     raise ValueError(kind)
 
 
+def _loop_pose(s: float) -> tuple[np.ndarray, np.ndarray]:
+    """Closed race-track loop inside the scene (two 58 m straights at y = -5 / +5 joined by half circles): the KITTI-seq-00-shape
+    stream (BASELINE config C4, 4541 scans) revisits its own map lap after lap."""
+    L, r = 58.0, 5.0
+    per = 2 * L + 2 * np.pi * r
+    u = s % per
+    if u < L:                       # lower straight, heading +x
+        x, y, yaw = -26.0 + u, -r, 0.0
+    elif u < L + np.pi * r:         # right turn-around
+        a = (u - L) / r
+        x, y, yaw = 32.0 + r * np.sin(a), -r * np.cos(a), a
+    elif u < 2 * L + np.pi * r:     # upper straight, heading -x
+        x, y, yaw = 32.0 - (u - L - np.pi * r), r, np.pi
+    else:
+        a = (u - 2 * L - np.pi * r) / r
+        x, y, yaw = -26.0 - r * np.sin(a), r * np.cos(a), np.pi + a
+    z = 1.73 + 0.03 * np.sin(0.5 * s)
+    return _rot_z(yaw) @ _rot_y(0.008 * np.sin(0.3 * s)), np.array([x, y, z])
+
+
 def trajectory_pose(sensor: SensorModel, k: int) -> tuple[np.ndarray, np.ndarray]:
     """Ground-truth IMU/body pose of scan k (R, t): smooth forward motion with a gentle weave."""
     dt = 1.0 / sensor.hz
     s = sensor.speed * dt * k
+    if sensor.name.endswith("loop"):
+        return _loop_pose(s)
     x = -30.0 + s
     y = 1.2 * np.sin(0.15 * s)
     z = 1.6 + 0.05 * np.sin(0.4 * s)

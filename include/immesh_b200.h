@@ -91,6 +91,8 @@ int immesh_lio_step_dev(immesh_lio_t* h, const float* d_body_xyz, int n, double 
 /* Pipelined form (the reference runs LIO and meshing concurrently: LIO thread || mesh thread pool):
  * immesh_lio_step_async queues a scan on the localization stream and returns; immesh_lio_wait blocks until everything
  * queued has finished and returns the latest state.  on_device != 0: body_xyz is a device pointer. */
+/* Host buffers: page-locked memory (cudaMallocHost / cudaHostRegister) is read by the copy engine directly and must stay
+ * unchanged until the matching wait; pageable memory is staged through the handle's pinned slots at once. */
 int immesh_lio_step_async(immesh_lio_t* h, const float* body_xyz, int n, int on_device, double dt, double cov_gyr, double cov_acc);
 int immesh_lio_wait(immesh_lio_t* h, double* state_out /*[348] or NULL*/, int* iters_run /*or NULL*/);
 int immesh_lio_enqueue_memset(immesh_lio_t* h, void* d_buf, size_t bytes); /* benchmark helper: in-stream L2 flush */
@@ -142,6 +144,9 @@ int immesh_voxelmap_counts(immesh_lio_t* h, int64_t* out /*[4]: roots, nodes, ch
 /* device time (ms, CUDA events on the handle's stream) of the stages of the last immesh_lio_step call:
  * [0] whole step incl. H2D, [1] residual+solve iterations, [2] map update */
 int immesh_lio_last_timing(immesh_lio_t* h, double* ms /*[3]*/);
+/* work accounting of the last immesh_lio_step* call, used for the roofline arithmetic: [points in the scan, root voxels in the map,
+ * plane refits (init_plane calls) of the map update, stored points those refits read] */
+int immesh_lio_work_stats(immesh_lio_t* h, int64_t* out /*[4]*/);
 
 /* ---- meshing handle: Global_map + Triangle_manager of the voxel-wise mesher ---------------------------- */
 typedef struct immesh_mesh_config {
@@ -171,6 +176,9 @@ int immesh_mesh_push_frame_from_lio(immesh_mesh_t* h, immesh_lio_t* lio, const f
  * localization stream) and meshed on the mesh stream while the next scan is being localised; immesh_mesh_wait drains. */
 int immesh_mesh_push_frame_from_lio_async(immesh_mesh_t* h, immesh_lio_t* lio, const float* body_xyz, int n, int on_device);
 int immesh_mesh_wait(immesh_mesh_t* h);
+/* host time (ms) the queueing calls spent blocked on a busy staging slot (back-pressure from the device, not work) since the
+ * last call: out[0] localization handle, out[1] meshing handle; either handle may be NULL */
+int immesh_host_wait_ms(immesh_lio_t* lio, immesh_mesh_t* h, double* out /*[2]*/);
 /* CUDA-event time (ms) of everything queued on both handles between the two marks */
 int immesh_pipeline_mark_begin(immesh_lio_t* lio);
 int immesh_pipeline_mark_end(immesh_lio_t* lio, immesh_mesh_t* h, double* ms);

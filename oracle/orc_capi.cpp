@@ -116,6 +116,81 @@ int orc_lio_residual_list(void* h, const float* body, int n, int* idx_layer, dou
     return m;
 }
 
+// transformLidar of a full-resolution scan with the current state (ImMesh_mesh_reconstruction.cpp:413 -> voxel_mapping_common.cpp:709-726)
+void orc_lio_transform_full(void* h, const float* body, int n, float* world) {
+    LioOracle* o = (LioOracle*)h;
+    for (int i = 0; i < n; ++i) {
+        const double pb[3] = {(double)body[i * 3 + 0], (double)body[i * 3 + 1], (double)body[i * 3 + 2]};
+        double pw[3];
+        o->body_to_world_f(o->state.rot, o->state.pos, pb, pw);
+        for (int j = 0; j < 3; ++j) world[i * 3 + j] = (float)pw[j];
+    }
+}
+// The three free functions of voxel_mapping.hpp:80-105 on caller-built Point_with_var lists (parity tests of the *_pv entry points)
+static void fill_pv(std::vector<PV>& pv, const double* pts_body, const double* pts_world, const double* var9, int n) {
+    pv.resize(n);
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < 3; ++j) { pv[i].pb[j] = pts_body[i * 3 + j]; pv[i].pw[j] = pts_world[i * 3 + j]; }
+        const double* v = var9 + (size_t)i * 9;
+        pv[i].var[0] = v[0]; pv[i].var[1] = v[1]; pv[i].var[2] = v[2]; pv[i].var[3] = v[4]; pv[i].var[4] = v[5]; pv[i].var[5] = v[8];
+    }
+}
+void orc_lio_build_pv(void* h, const double* pts_world, const double* var9, int n) {
+    std::vector<PV> pv;
+    fill_pv(pv, pts_world, pts_world, var9, n);   // insert path: m_point carries the world point
+    ((LioOracle*)h)->build_voxel_map(pv);
+}
+void orc_lio_update_pv(void* h, const double* pts_world, const double* var9, int n) {
+    std::vector<PV> pv;
+    fill_pv(pv, pts_world, pts_world, var9, n);
+    ((LioOracle*)h)->update_voxel_map(pv);
+}
+int orc_lio_residual_pv(void* h, const double* pts_body, const double* pts_world, const double* var9, int n, int* idx_layer, double* vals, int cap) {
+    std::vector<PV> pv;
+    fill_pv(pv, pts_body, pts_world, var9, n);
+    std::vector<Ptpl> out;
+    ((LioOracle*)h)->build_residual_list(pv, 3.0, out);
+    const int m = (int)out.size();
+    for (int i = 0; i < m && i < cap; ++i) {
+        idx_layer[2 * i] = out[i].src_index;
+        idx_layer[2 * i + 1] = out[i].layer;
+        double* v = vals + (size_t)i * 31;
+        for (int j = 0; j < 3; ++j) { v[j] = out[i].point[j]; v[3 + j] = out[i].normal[j]; v[6 + j] = out[i].center[j]; }
+        v[9] = out[i].d;
+        for (int j = 0; j < 21; ++j) v[10 + j] = out[i].plane_var[j];
+    }
+    return m;
+}
+// per-point world covariance lists exactly as the reference builds them before calling the free functions (tests build their
+// Point_with_var inputs from these): mode 0 = map_incremental_grow (ImMesh_mesh_reconstruction.cpp:393-404), 1 = matching (:1344-1359)
+void orc_lio_pv_lists(void* h, const float* body, int n, int mode, double* pts_world, double* var9) {
+    LioOracle* o = (LioOracle*)h;
+    o->prepare_scan(body, n);
+    double RRe[9];
+    mat3_mul(o->state.rot, o->cfg.extR, RRe);
+    for (int i = 0; i < n; ++i) {
+        const double pb[3] = {(double)body[i * 3 + 0], (double)body[i * 3 + 1], (double)body[i * 3 + 2]};
+        double pw[3], v6[6];
+        o->body_to_world_f(o->state.rot, o->state.pos, pb, pw);
+        if (mode == 1) {
+            o->world_cov_match(o->state.rot, o->state.cov, i, v6);
+        } else {
+            double Sb[9], T1[6], T2[6], C[9], nC[9], rot_var[9];
+            sym6_to_full(&o->body_cov[(size_t)i * 6], Sb);
+            congr_sym6(RRe, Sb, T1);
+            for (int k = 0; k < 9; ++k) { C[k] = o->cross_mat[(size_t)i * 9 + k]; nC[k] = -C[k]; }
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) rot_var[a * 3 + b] = o->state.cov[a * 18 + b];
+            congr_sym6(nC, rot_var, T2);
+            for (int a = 0; a < 3; ++a)
+                for (int b = a; b < 3; ++b) v6[sym6_idx(a, b)] = (T1[sym6_idx(a, b)] + T2[sym6_idx(a, b)]) + o->state.cov[(3 + a) * 18 + (3 + b)];
+        }
+        for (int j = 0; j < 3; ++j) pts_world[i * 3 + j] = pw[j];
+        double* v = var9 + (size_t)i * 9;
+        v[0] = v6[0]; v[1] = v6[1]; v[2] = v6[2]; v[3] = v6[1]; v[4] = v6[3]; v[5] = v6[4]; v[6] = v6[2]; v[7] = v6[4]; v[8] = v6[5];
+    }
+}
+
 // ------------------------------------------------------------------ mesh
 void* orc_mesh_create(double minimum_pts, double voxel_res, int append_target, int threads) {
     MeshCfg c;

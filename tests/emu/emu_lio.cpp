@@ -73,7 +73,7 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     m.nodes = h->nodes.data(); m.planes = h->planes.data(); m.node_count = &h->counters[0]; m.max_nodes = max_nodes;
     m.chunks = h->chunks.data(); m.chunk_bump = &h->counters[1]; m.max_chunks = max_chunks;
     m.avail = h->avail.data(); m.avail_top = &h->counters[2]; m.pending = h->pending.data(); m.pending_n = &h->counters[3];
-    m.err = &h->counters[4]; m.n_roots = &h->counters[5];
+    m.err = &h->counters[4]; m.n_roots = &h->counters[5]; m.stat = nullptr;
     const int ms = h->max_scan;
     h->body.resize((size_t)ms * 3); h->pw.resize((size_t)ms * 3);
     h->body_cov.resize((size_t)ms * 6); h->p_imu.resize((size_t)ms * 3); h->bv_imu.resize((size_t)ms * 6); h->var.resize((size_t)ms * 6); h->sortkey.resize(ms);

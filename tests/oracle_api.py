@@ -102,6 +102,34 @@ class OracleLio:
         m = self.L.orc_lio_residual_list(self.h, _p(a), C.c_int(n), _p(il), _p(vals), C.c_int(n))
         return il[:m], vals[:m]
 
+    def transform_full(self, body):
+        a = np.ascontiguousarray(body, dtype=np.float32)
+        out = np.zeros_like(a)
+        self.L.orc_lio_transform_full(self.h, _p(a), C.c_int(a.shape[0]), _p(out))
+        return out
+
+    def pv_lists(self, body, mode=0):
+        """(pts_world f64[n,3], var f64[n,9]) as the reference builds its Point_with_var lists (mode 0: map growth, 1: matching)."""
+        a = np.ascontiguousarray(body, dtype=np.float32)
+        pw, v9 = np.zeros((a.shape[0], 3)), np.zeros((a.shape[0], 9))
+        self.L.orc_lio_pv_lists(self.h, _p(a), C.c_int(a.shape[0]), C.c_int(mode), _p(pw), _p(v9))
+        return pw, v9
+
+    def build_pv(self, pts_world, var9):
+        pw, v9 = np.ascontiguousarray(pts_world, dtype=np.float64), np.ascontiguousarray(var9, dtype=np.float64)
+        self.L.orc_lio_build_pv(self.h, _p(pw), _p(v9), C.c_int(pw.shape[0]))
+
+    def update_pv(self, pts_world, var9):
+        pw, v9 = np.ascontiguousarray(pts_world, dtype=np.float64), np.ascontiguousarray(var9, dtype=np.float64)
+        self.L.orc_lio_update_pv(self.h, _p(pw), _p(v9), C.c_int(pw.shape[0]))
+
+    def residual_pv(self, pts_body, pts_world, var9):
+        pb, pw, v9 = (np.ascontiguousarray(x, dtype=np.float64) for x in (pts_body, pts_world, var9))
+        n = pb.shape[0]
+        il, vals = np.zeros((n, 2), dtype=np.int32), np.zeros((n, 31))
+        m = self.L.orc_lio_residual_pv(self.h, _p(pb), _p(pw), _p(v9), C.c_int(n), _p(il), _p(vals), C.c_int(n))
+        return il[:m], vals[:m]
+
     def dump_map(self):
         rows = self.L.orc_lio_dump_map(self.h, None, C.c_long(0))
         out = np.zeros((rows, 45))
