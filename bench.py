@@ -200,7 +200,7 @@ def run_cpu(wl, scans, n_warm, n_timed, t_loc, t_mesh):
     """The reference algorithm on the host cores (oracle port): returns per-scan (t_loc, t_mesh) seconds."""
     from oracle_api import OracleLio, OracleMesh
     cfg = wl["lio"]
-    lio = OracleLio(cfg, sum_mode=1, omp_threads=t_loc)
+    lio = OracleLio(cfg, sum_mode=1, omp_threads=t_loc, solve_mode=1, plane_var_mode=1)   # the reference's literal formulation: serial double sums, two 18x18 inverses, per-point plane covariance loop
     mesh = OracleMesh(wl["mesh"], threads=t_mesh)
     lio.set_state(init_state_vec(scans))
     lio.voxel_map_init(scans[0]["body_full"])

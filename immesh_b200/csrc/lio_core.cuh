@@ -603,12 +603,14 @@ IM_HDN inline void grow_voxel(const VoxelMapDev& map, const LioParams& P, const 
             }
         } else {
             // buildVoxelMap: append everything, then one init_octo_tree (voxel_mapping.cpp:115-150)
-            if (lane == 0) {
-                for (int a = 0; a < cnt; ++a) {
-                    const int i = sorted_scratch[off + a];
-                    node_append(map, root, sb.pw[(size_t)i * 3 + 0], sb.pw[(size_t)i * 3 + 1], sb.pw[(size_t)i * 3 + 2], sb.var + (size_t)i * 6);
+            for (int a = 0; a < cnt; ++a) {
+                const int i = sorted_scratch[off + a];
+                const float px = sb.pw[(size_t)i * 3 + 0], py = sb.pw[(size_t)i * 3 + 1], pz = sb.pw[(size_t)i * 3 + 2];
+                if (lane == 0) {
+                    node_append(map, root, px, py, pz, sb.var + (size_t)i * 6);
                     map.nodes[root].new_points += 1;
                 }
+                node_moments_add(map, root, px, py, pz, sb.var + (size_t)i * 6, lane, nlanes);
             }
             IM_SYNCWARP();
             init_octo_tree(map, P, root, lane, nlanes);

@@ -79,6 +79,14 @@ struct alignas(16) NodeRec {
     double sum_p[3];   // running sum of the stored points, in append order (= the reference's loop order in init_plane)
     double sum_pp[6];  // running sum of p p^T, upper triangle
     double pad_;
+    // Running moments of the stored points' covariances about the node's FIXED voxel centre, q = p - vc, in append order:
+    //   mq[p*6+s]      = sum_i q_j q_k Sigma_i[s]   p = pair (j<=k) in the order 00 01 02 11 12 22, s = symmetric 3x3 index
+    //   mq[36+j*6+s]   = sum_i q_j Sigma_i[s]
+    //   mq[54+s]       = sum_i Sigma_i[s]
+    // plane_var = sum_i J_i Sigma_i J_i^T with J_i linear in (p_i - c) is a fixed contraction of these 60 sums (init_plane): a
+    // refit costs O(1) instead of a pass over all stored points (the reference recomputes from every stored point on each of
+    // its refits, voxel_loc.cpp:76-121: O(n^2/5) per node lifetime, ~4 ms per KITTI-shape scan on this GPU before).
+    double mq[60];
 };
 struct alignas(16) Chunk {
     float x[8], y[8], z[8];
@@ -87,7 +95,7 @@ struct alignas(16) Chunk {
     double var[6][8];
 };
 static_assert(sizeof(PlaneRec) == 256, "PlaneRec must be 256 B");
-static_assert(sizeof(NodeRec) == 176, "NodeRec must be 176 B");
+static_assert(sizeof(NodeRec) == 656, "NodeRec must be 656 B");
 static_assert(sizeof(Chunk) == 512, "Chunk must be 512 B");
 
 enum : int {
@@ -242,6 +250,7 @@ IM_HD void init_node(const VoxelMapDev& m, int id, int layer, const double* vc, 
     n.root_slot = root_slot;
     for (int i = 0; i < 3; ++i) n.sum_p[i] = 0.0;
     for (int i = 0; i < 6; ++i) n.sum_pp[i] = 0.0;
+    for (int i = 0; i < 60; ++i) n.mq[i] = 0.0;
     PlaneRec& p = m.planes[id];
     p.center[0] = p.center[1] = p.center[2] = 0.0;
     p.normal[0] = p.normal[1] = p.normal[2] = 0.0;
@@ -284,6 +293,30 @@ IM_HD void node_append(const VoxelMapDev& m, int nd, float x, float y, float z, 
     n.sum_pp[3] += dy * dy; n.sum_pp[4] += dy * dz; n.sum_pp[5] += dz * dz;
     n.sum_p[0] += dx; n.sum_p[1] += dy; n.sum_p[2] += dz;
 }
+// moment update of an appended point, spread over the lanes (entry e of 60 by lane e % nlanes); call with all lanes, right
+// next to the lane-0 node_append of the same point
+IM_HDN inline void node_moments_add(const VoxelMapDev& m, int nd, float x, float y, float z, const double* var6, int lane, int nlanes) {
+    NodeRec& n = m.nodes[nd];
+    const double q[3] = {(double)x - n.vc[0], (double)y - n.vc[1], (double)z - n.vc[2]};
+    for (int e = lane; e < 60; e += nlanes) {
+        double w;
+        int sidx;
+        if (e < 36) {
+            const int pr = e / 6;
+            sidx = e - pr * 6;
+            const int j = pr < 3 ? 0 : (pr < 5 ? 1 : 2), k = pr < 3 ? pr : (pr < 5 ? pr - 2 : 2);
+            w = q[j] * q[k];
+        } else if (e < 54) {
+            const int j = (e - 36) / 6;
+            sidx = (e - 36) - j * 6;
+            w = q[j];
+        } else {
+            sidx = e - 54;
+            w = 1.0;
+        }
+        n.mq[e] = n.mq[e] + w * var6[sidx];
+    }
+}
 // std::vector<Point_with_var>().swap(m_temp_points_): chunks go to the pending-free list (recycled between scans)
 IM_HD void node_free_points(const VoxelMapDev& m, int nd) {
     NodeRec& n = m.nodes[nd];
@@ -299,12 +332,22 @@ IM_HD void node_free_points(const VoxelMapDev& m, int nd) {
     n.n_pts = 0;
     for (int i = 0; i < 3; ++i) n.sum_p[i] = 0.0;
     for (int i = 0; i < 6; ++i) n.sum_pp[i] = 0.0;
+    for (int i = 0; i < 60; ++i) n.mq[i] = 0.0;
 }
 
 // ------------------------------------------------------------------ init_plane (voxel_loc.cpp:47-139)
-// Cooperative over `nlanes` lanes (32 on the GPU, 1 in the host emulation).  Every lane recomputes the
-// sequential centre / covariance sums and the eigen-decomposition (identical bits in all lanes); lane e owns
-// plane_var entry e of 21.  No reduction is ever split across lanes.
+// Cooperative over `nlanes` lanes (32 on the GPU, 1 in the host emulation).  Every lane recomputes the centre / covariance
+// and the eigen-decomposition from the node's running sums (identical bits in all lanes); lane e owns plane_var entry e of 21.
+//
+// plane_var = sum_i J_i Sigma_i J_i^T,  J_i = [U F_i ; I/n],  F_i[m,:] = (p_i - c)^T s_m M_m  (m != min; s_m = 1/(n (l_min - l_m)),
+// M_m = u_m u_min^T + u_min u_m^T).  U F_i = sum_j d_ij G_j with d_i = p_i - c and the 27 constants
+//     G_j[a][b] = U[a][m0] (s0 M0[j][b]) + U[a][m1] (s1 M1[j][b]),
+// so with W_jk = sum_i d_ij d_ik Sigma_i, V_j = sum_i d_ij Sigma_i, S0 = sum_i Sigma_i:
+//     top-left  = sum_jk G_j W_jk G_k^T      top-right = (sum_j G_j V_j) / n      bottom-right = S0 / n^2,
+// and W, V follow from the node's moments about its voxel centre (NodeRec::mq) with e = c - vc:
+//     W_jk = ((Q2_jk - e_j Q1_k) - e_k Q1_j) + (e_j e_k) S0,      V_j = Q1_j - e_j S0.
+// The oracle evaluates the same expressions in the same order (orc_lio.hpp, plane_var_mode 0) and bounds the distance to the
+// reference's literal per-point loop (plane_var_mode 1; tests/test_oracle_crosscheck.py).
 #if defined(__CUDA_ARCH__)
 #define IM_ENT_PER_LANE 1
 #else
@@ -338,125 +381,59 @@ IM_HDN inline void init_plane(const VoxelMapDev& m, const LioParams& P, int nd, 
         const double invn = 1.0 / dn;
         const int m0 = (imin == 0) ? 1 : 0;            // the two rows of F that are not identically zero
         const int m1 = (imin == 2) ? 1 : 2;
-        // (p - c) / (n (lambda_min - lambda_m)) as a multiplication by the reciprocal
         const double s0 = 1.0 / (dn * (ev[imin] - ev[m0])), s1 = 1.0 / (dn * (ev[imin] - ev[m1]));
-        double M0[9], M1[9];
-        for (int j = 0; j < 3; ++j)
-            for (int k = 0; k < 3; ++k) {
-                M0[j * 3 + k] = U[j * 3 + m0] * U[k * 3 + imin] + U[j * 3 + imin] * U[k * 3 + m0];
-                M1[j * 3 + k] = U[j * 3 + m1] * U[k * 3 + imin] + U[j * 3 + imin] * U[k * 3 + m1];
-            }
-#if defined(__CUDA_ARCH__)
-        {
-            // Warp-cooperative evaluation of J Sigma J^T: per point, lanes 0-5 produce the six non-zero entries of F, lanes
-            // 0-8 the entries of A = U F and of T = A Sigma, every lane e < 21 its own covariance entry; operands travel by
-            // warp shuffles.  Every value is produced by the same expression as in the generic path below (which the host
-            // emulation runs): bit-identical results, ~2.5x fewer instructions per point than recomputing A and T per lane.
-            const int b3 = lane % 3, a3 = (lane / 3) % 3;
-            // lane constants, selected without dynamic register indexing
-            const bool fl1 = lane >= 3;                                   // F row: m0 (lanes 0-2) or m1 (lanes 3-5)
-            const double fs = fl1 ? s1 : s0;
-            double fm0, fm1, fm2;                                         // column b3 of M0 / M1
-            {
-                const double* Mx = fl1 ? M1 : M0;
-                fm0 = b3 == 0 ? Mx[0] : (b3 == 1 ? Mx[1] : Mx[2]);
-                fm1 = b3 == 0 ? Mx[3] : (b3 == 1 ? Mx[4] : Mx[5]);
-                fm2 = b3 == 0 ? Mx[6] : (b3 == 1 ? Mx[7] : Mx[8]);
-            }
-            const double ua0 = a3 == 0 ? U[0] : (a3 == 1 ? U[3] : U[6]);  // row a3 of U
-            const double ua1 = a3 == 0 ? U[1] : (a3 == 1 ? U[4] : U[7]);
-            const double ua2 = a3 == 0 ? U[2] : (a3 == 1 ? U[5] : U[8]);
-            // which F row feeds rows 0,1,2 of the product: 0 -> zero row (imin), 1 -> m0 (lanes b), 2 -> m1 (lanes 3+b)
-            const int r0 = (imin == 0) ? 0 : ((m0 == 0) ? 1 : 2);
-            const int r1 = (imin == 1) ? 0 : ((m0 == 1) ? 1 : 2);
-            const int r2 = (imin == 2) ? 0 : ((m0 == 2) ? 1 : 2);
-            // covariance entry of this lane
-            int ei = 0, ej = 0;
-            {
-                const int e = lane < 21 ? lane : 0;
-                int base = 0;
-                while (e >= base + (6 - ei)) { base += 6 - ei; ++ei; }
-                ej = ei + (e - base);
-            }
-            const int ti = ei < 3 ? ei : 0;            // T row needed (TL / TR entries)
-            const int aj = ej < 3 ? ej : 0;            // A row needed (TL entries)
-            const int trk = (ej >= 3 && ei < 3) ? (ej - 3) : 0;
-            int ch = n.first_chunk;
-            double accv = 0.0;
-            for (int i = 0; i < np; ++i) {
-                const int s = i & 7;
-                if (i && s == 0) ch = m.chunks[ch].next;
-                const Chunk& ck = m.chunks[ch];
-                const double px = (double)ck.x[s], py = (double)ck.y[s], pz = (double)ck.z[s];
-                const double S0 = ck.var[0][s], S1 = ck.var[1][s], S2 = ck.var[2][s], S4 = ck.var[3][s], S5 = ck.var[4][s], S8 = ck.var[5][s];
-                // F entry (lanes 0-5)
-                const double v0 = (px - c[0]) * fs, v1 = (py - c[1]) * fs, v2 = (pz - c[2]) * fs;
-                const double Fv = (v0 * fm0 + v1 * fm1) + v2 * fm2;
-                const double f_m0b = __shfl_sync(0xffffffffu, Fv, b3), f_m1b = __shfl_sync(0xffffffffu, Fv, 3 + b3);
-                const double F0b = r0 == 0 ? 0.0 : (r0 == 1 ? f_m0b : f_m1b);
-                const double F1b = r1 == 0 ? 0.0 : (r1 == 1 ? f_m0b : f_m1b);
-                const double F2b = r2 == 0 ? 0.0 : (r2 == 1 ? f_m0b : f_m1b);
-                // A entry (a3, b3) (lanes 0-8)
-                const double Av = (ua0 * F0b + ua1 * F1b) + ua2 * F2b;
-                // T entry (a3, b3) = row a3 of A times column b3 of Sigma
-                const double Aa0 = __shfl_sync(0xffffffffu, Av, a3 * 3 + 0), Aa1 = __shfl_sync(0xffffffffu, Av, a3 * 3 + 1), Aa2 = __shfl_sync(0xffffffffu, Av, a3 * 3 + 2);
-                const double Sc0 = b3 == 0 ? S0 : (b3 == 1 ? S1 : S2);   // Sigma[0][b3]
-                const double Sc1 = b3 == 0 ? S1 : (b3 == 1 ? S4 : S5);   // Sigma[1][b3]
-                const double Sc2 = b3 == 0 ? S2 : (b3 == 1 ? S5 : S8);   // Sigma[2][b3]
-                const double Tv = (Aa0 * Sc0 + Aa1 * Sc1) + Aa2 * Sc2;
-                // this lane's covariance entry
-                const double Ti0 = __shfl_sync(0xffffffffu, Tv, ti * 3 + 0), Ti1 = __shfl_sync(0xffffffffu, Tv, ti * 3 + 1), Ti2 = __shfl_sync(0xffffffffu, Tv, ti * 3 + 2);
-                const double Aj0 = __shfl_sync(0xffffffffu, Av, aj * 3 + 0), Aj1 = __shfl_sync(0xffffffffu, Av, aj * 3 + 1), Aj2 = __shfl_sync(0xffffffffu, Av, aj * 3 + 2);
-                double term;
-                if (ej < 3) term = (Ti0 * Aj0 + Ti1 * Aj1) + Ti2 * Aj2;
-                else if (ei < 3) term = (trk == 0 ? Ti0 : (trk == 1 ? Ti1 : Ti2)) * invn;
-                else {
-                    const int k3 = ei - 3, l3 = ej - 3;   // Sigma[k3][l3], k3 <= l3
-                    const double Skl = k3 == 0 ? (l3 == 0 ? S0 : (l3 == 1 ? S1 : S2)) : (k3 == 1 ? (l3 == 1 ? S4 : S5) : S8);
-                    term = (invn * Skl) * invn;
+        const double e3[3] = {c[0] - n.vc[0], c[1] - n.vc[1], c[2] - n.vc[2]};
+        const double* mq = n.mq;
+        for (int k = 0; k < IM_ENT_PER_LANE; ++k) {
+            const int e = lane + k * nlanes;
+            if (e >= 21) break;
+            int ei = 0, base = 0;
+            while (e >= base + (6 - ei)) { base += 6 - ei; ++ei; }
+            const int ej = ei + (e - base);
+            double r;
+            if (ei >= 3) {
+                r = (invn * mq[54 + s6(ei - 3, ej - 3)]) * invn;
+            } else {
+                // G_j[a][.] for this entry's row a = ei, and (top-left only) G_k[b][.] for b = ej
+                double Ga[9], Gb[9];
+                for (int j = 0; j < 3; ++j)
+                    for (int x = 0; x < 3; ++x) {
+                        const double M0jx = U[j * 3 + m0] * U[x * 3 + imin] + U[j * 3 + imin] * U[x * 3 + m0];
+                        const double M1jx = U[j * 3 + m1] * U[x * 3 + imin] + U[j * 3 + imin] * U[x * 3 + m1];
+                        Ga[j * 3 + x] = U[ei * 3 + m0] * (s0 * M0jx) + U[ei * 3 + m1] * (s1 * M1jx);
+                        const int bb = ej < 3 ? ej : 0;
+                        Gb[j * 3 + x] = U[bb * 3 + m0] * (s0 * M0jx) + U[bb * 3 + m1] * (s1 * M1jx);
+                    }
+                if (ej >= 3) {
+                    // top-right (ei, 3 + l): (sum_j sum_x G_j[ei][x] V_j[x][l]) / n
+                    const int l = ej - 3;
+                    double a2 = 0.0;
+                    for (int j = 0; j < 3; ++j)
+                        for (int x = 0; x < 3; ++x) {
+                            const int sx = s6(x, l);
+                            const double v = mq[36 + j * 6 + sx] - e3[j] * mq[54 + sx];
+                            a2 = a2 + Ga[j * 3 + x] * v;
+                        }
+                    r = a2 * invn;
+                } else {
+                    // top-left (ei, ej): sum_jk sum_xy G_j[ei][x] W_jk[x][y] G_k[ej][y]
+                    double a2 = 0.0;
+                    for (int j = 0; j < 3; ++j)
+                        for (int k2 = 0; k2 < 3; ++k2) {
+                            const int pr = s6(j, k2);
+                            const double ejk = e3[j] * e3[k2];
+                            for (int x = 0; x < 3; ++x)
+                                for (int y = 0; y < 3; ++y) {
+                                    const int sx = s6(x, y);
+                                    const double w = ((mq[pr * 6 + sx] - e3[j] * mq[36 + k2 * 6 + sx]) - e3[k2] * mq[36 + j * 6 + sx]) + ejk * mq[54 + sx];
+                                    a2 = a2 + (Ga[j * 3 + x] * w) * Gb[k2 * 3 + y];
+                                }
+                        }
+                    r = a2;
                 }
-                accv += term;
             }
-            acc[0] = accv;
+            acc[k] = r;
         }
-#else
-        int ch = n.first_chunk;
-        for (int i = 0; i < np; ++i) {
-            const int s = i & 7;
-            if (i && s == 0) ch = m.chunks[ch].next;
-            const Chunk& ck = m.chunks[ch];
-            const double px = (double)ck.x[s], py = (double)ck.y[s], pz = (double)ck.z[s];
-            double F[9];
-            F[imin * 3 + 0] = 0.0; F[imin * 3 + 1] = 0.0; F[imin * 3 + 2] = 0.0;
-            {
-                const double v0 = (px - c[0]) * s0, v1 = (py - c[1]) * s0, v2 = (pz - c[2]) * s0;
-                for (int k = 0; k < 3; ++k) F[m0 * 3 + k] = (v0 * M0[0 * 3 + k] + v1 * M0[1 * 3 + k]) + v2 * M0[2 * 3 + k];
-            }
-            {
-                const double v0 = (px - c[0]) * s1, v1 = (py - c[1]) * s1, v2 = (pz - c[2]) * s1;
-                for (int k = 0; k < 3; ++k) F[m1 * 3 + k] = (v0 * M1[0 * 3 + k] + v1 * M1[1 * 3 + k]) + v2 * M1[2 * 3 + k];
-            }
-            double A[9], S[9], T[9];
-            m3_mul(U, F, A);
-            S[0] = ck.var[0][s]; S[1] = ck.var[1][s]; S[2] = ck.var[2][s];
-            S[3] = S[1]; S[4] = ck.var[3][s]; S[5] = ck.var[4][s];
-            S[6] = S[2]; S[7] = S[5]; S[8] = ck.var[5][s];
-            m3_mul(A, S, T);
-            for (int k = 0; k < IM_ENT_PER_LANE; ++k) {
-                const int e = lane + k * nlanes;
-                if (e >= 21) break;
-                // decode e -> (i,j), i <= j
-                int ei = 0, base = 0;
-                while (e >= base + (6 - ei)) { base += 6 - ei; ++ei; }
-                const int ej = ei + (e - base);
-                double term;
-                if (ej < 3) term = (T[ei * 3 + 0] * A[ej * 3 + 0] + T[ei * 3 + 1] * A[ej * 3 + 1]) + T[ei * 3 + 2] * A[ej * 3 + 2];
-                else if (ei < 3) term = T[ei * 3 + (ej - 3)] * invn;
-                else term = (invn * S[(ei - 3) * 3 + (ej - 3)]) * invn;
-                acc[k] += term;
-            }
-        }
-#endif
     }
     IM_SYNCWARP();  // all lanes have finished reading the old record
     for (int k = 0; k < IM_ENT_PER_LANE; ++k) {
@@ -532,12 +509,13 @@ IM_HDN inline void cut_octo_tree(const VoxelMapDev& m, const LioParams& P, int n
                 int child = m.nodes[nd].children[leaf];
                 if (child < 0) child = make_child(m, nd, leaf, lane);
                 if (child < 0) break;
+                double v6[6];
+                for (int k = 0; k < 6; ++k) v6[k] = m.chunks[ch].var[k][s];
                 if (lane == 0) {
-                    double v6[6];
-                    for (int k = 0; k < 6; ++k) v6[k] = m.chunks[ch].var[k][s];
                     node_append(m, child, x, y, z, v6);
                     m.nodes[child].new_points += 1;
                 }
+                node_moments_add(m, child, x, y, z, v6, lane, nlanes);
                 IM_SYNCWARP();
             }
             st_child[sp - 1] = 0;
@@ -592,6 +570,7 @@ IM_HDN inline void update_octo_tree(const VoxelMapDev& m, const LioParams& P, in
                 m.nodes[nd].new_points += 1;
                 node_append(m, nd, x, y, z, var6);
             }
+            node_moments_add(m, nd, x, y, z, var6, lane, nlanes);
             IM_SYNCWARP();
             if (IM_UPRED(m.nodes[nd].n_pts > P.layer_init[m.nodes[nd].layer] ? 1 : 0)) init_octo_tree(m, P, nd, lane, nlanes);
             return;
@@ -602,6 +581,7 @@ IM_HDN inline void update_octo_tree(const VoxelMapDev& m, const LioParams& P, in
                     m.nodes[nd].new_points += 1;
                     node_append(m, nd, x, y, z, var6);
                 }
+                node_moments_add(m, nd, x, y, z, var6, lane, nlanes);
                 IM_SYNCWARP();
                 if (IM_UPRED(m.nodes[nd].new_points > 5 ? 1 : 0)) {
                     init_plane(m, P, nd, lane, nlanes);
@@ -637,6 +617,7 @@ IM_HDN inline void update_octo_tree(const VoxelMapDev& m, const LioParams& P, in
                 m.nodes[nd].new_points += 1;
                 node_append(m, nd, x, y, z, var6);
             }
+            node_moments_add(m, nd, x, y, z, var6, lane, nlanes);
             IM_SYNCWARP();
             if (IM_UPRED(m.nodes[nd].new_points > 5 ? 1 : 0)) {
                 init_plane(m, P, nd, lane, nlanes);

@@ -33,7 +33,7 @@ static void unpack_state(const double* o, State& s) {
 extern "C" {
 
 // cfg_d: [voxel_size, min_eigen_value, dept_err, beam_err, extR[9], extT[3]]  (16)
-// cfg_i: [max_layer, layer_init_size[5], max_points_size, max_iteration, calib_laser, sum_mode, omp_threads, solve_mode] (12)
+// cfg_i: [max_layer, layer_init_size[5], max_points_size, max_iteration, calib_laser, sum_mode, omp_threads, solve_mode, plane_var_mode] (13)
 void* orc_lio_create(const double* cfg_d, const int* cfg_i) {
     LioCfg c;
     c.voxel_size = cfg_d[0];
@@ -50,6 +50,7 @@ void* orc_lio_create(const double* cfg_d, const int* cfg_i) {
     c.sum_mode = cfg_i[9];
     c.omp_threads = cfg_i[10];
     c.solve_mode = cfg_i[11];
+    c.plane_var_mode = cfg_i[12];
     return new LioOracle(c);
 }
 void orc_lio_destroy(void* h) { delete (LioOracle*)h; }

@@ -26,6 +26,7 @@ struct LioCfg {
     int sum_mode;               // 0: fixed-point order-free sums (matches the CUDA product bit for bit)
                                 // 1: plain serial double sums (closest to the reference's Eigen GEMM)
     int omp_threads;            // threads for the residual loop (reference: MP_PROC_NUM = 4)
+    int plane_var_mode;         // 0: plane covariance from running moments (matches the CUDA product); 1: the reference's per-point loop (voxel_loc.cpp:76-121)
     int solve_mode;             // 0: 6x6 matrix-inversion-lemma form of the IESKF gain (matches the CUDA product); 1: the reference's two 18x18 inverses
 };
 
@@ -191,7 +192,7 @@ class LioOracle {
     }
 
     // ------------------------------------------------------------------ init_plane, voxel_loc.cpp:47-139
-    void init_plane(const std::vector<PV>& pts, Plane* pl) {
+    void init_plane(const std::vector<PV>& pts, Plane* pl, const double* vc) {
         for (double& v : pl->plane_var) v = 0;
         double cov[6] = {0, 0, 0, 0, 0, 0}, c[3] = {0, 0, 0};
         pl->normal[0] = pl->normal[1] = pl->normal[2] = 0;
@@ -230,7 +231,86 @@ class LioOracle {
                     for (int k = 0; k < 3; ++k)
                         Mm[m][j * 3 + k] = U[j * 3 + m] * U[k * 3 + imin] + U[j * 3 + imin] * U[k * 3 + m];
             }
-            for (int ip = 0; ip < n; ++ip) {
+            if (cfg.plane_var_mode == 0) {
+                // plane_var_mode 0 (what the CUDA product computes, bit for bit): J_i is linear in d_i = p_i - c, so
+                // sum_i J_i Sigma_i J_i^T is a fixed contraction of the moments  Q2_jk = sum q_j q_k Sigma_i,  Q1_j = sum q_j Sigma_i,
+                // S0 = sum Sigma_i  about the node's fixed voxel centre (q = p - vc; the product keeps them as running sums in
+                // append order -> refits cost O(1)).  With e = c - vc, G_j[a][b] = U[a][m0] (s0 M0[j][b]) + U[a][m1] (s1 M1[j][b]):
+                //   W_jk = ((Q2_jk - e_j Q1_k) - e_k Q1_j) + (e_j e_k) S0,  V_j = Q1_j - e_j S0,
+                //   top-left = sum_jk G_j W_jk G_k^T,  top-right = (sum_j G_j V_j)/n,  bottom-right = (S0/n)/n.
+                // plane_var_mode 1 below is the reference's literal per-point loop; tests bound the gap between the two.
+                double mq[60];
+                for (double& v : mq) v = 0.0;
+                for (int ip = 0; ip < n; ++ip) {
+                    const PV& pv = pts[ip];
+                    const double q[3] = {pv.pb[0] - vc[0], pv.pb[1] - vc[1], pv.pb[2] - vc[2]};
+                    for (int e = 0; e < 60; ++e) {
+                        double w;
+                        int sidx;
+                        if (e < 36) {
+                            const int pr = e / 6;
+                            sidx = e - pr * 6;
+                            const int j = pr < 3 ? 0 : (pr < 5 ? 1 : 2), k = pr < 3 ? pr : (pr < 5 ? pr - 2 : 2);
+                            w = q[j] * q[k];
+                        } else if (e < 54) {
+                            const int j = (e - 36) / 6;
+                            sidx = (e - 36) - j * 6;
+                            w = q[j];
+                        } else {
+                            sidx = e - 54;
+                            w = 1.0;
+                        }
+                        mq[e] = mq[e] + w * pv.var[sidx];
+                    }
+                }
+                int m0 = -1, m1 = -1;
+                for (int m = 0; m < 3; ++m)
+                    if (m != imin) { if (m0 < 0) m0 = m; else m1 = m; }
+                const double s0 = sm[m0], s1 = sm[m1];
+                const double e3[3] = {c[0] - vc[0], c[1] - vc[1], c[2] - vc[2]};
+                for (int ei = 0; ei < 6; ++ei)
+                    for (int ej = ei; ej < 6; ++ej) {
+                        double r;
+                        if (ei >= 3) {
+                            r = (invn * mq[54 + sym6_idx(ei - 3, ej - 3)]) * invn;
+                        } else {
+                            double Ga[9], Gb[9];
+                            const int bb = ej < 3 ? ej : 0;
+                            for (int j = 0; j < 3; ++j)
+                                for (int x = 0; x < 3; ++x) {
+                                    Ga[j * 3 + x] = U[ei * 3 + m0] * (s0 * Mm[m0][j * 3 + x]) + U[ei * 3 + m1] * (s1 * Mm[m1][j * 3 + x]);
+                                    Gb[j * 3 + x] = U[bb * 3 + m0] * (s0 * Mm[m0][j * 3 + x]) + U[bb * 3 + m1] * (s1 * Mm[m1][j * 3 + x]);
+                                }
+                            if (ej >= 3) {
+                                const int l = ej - 3;
+                                double a2 = 0.0;
+                                for (int j = 0; j < 3; ++j)
+                                    for (int x = 0; x < 3; ++x) {
+                                        const int sx = sym6_idx(x, l);
+                                        const double v = mq[36 + j * 6 + sx] - e3[j] * mq[54 + sx];
+                                        a2 = a2 + Ga[j * 3 + x] * v;
+                                    }
+                                r = a2 * invn;
+                            } else {
+                                double a2 = 0.0;
+                                for (int j = 0; j < 3; ++j)
+                                    for (int k2 = 0; k2 < 3; ++k2) {
+                                        const int pr = sym6_idx(j, k2);
+                                        const double ejk = e3[j] * e3[k2];
+                                        for (int x = 0; x < 3; ++x)
+                                            for (int y = 0; y < 3; ++y) {
+                                                const int sx = sym6_idx(x, y);
+                                                const double w = ((mq[pr * 6 + sx] - e3[j] * mq[36 + k2 * 6 + sx]) - e3[k2] * mq[36 + j * 6 + sx]) + ejk * mq[54 + sx];
+                                                a2 = a2 + (Ga[j * 3 + x] * w) * Gb[k2 * 3 + y];
+                                            }
+                                    }
+                                r = a2;
+                            }
+                        }
+                        pl->plane_var[pv21_idx(ei, ej)] = r;
+                    }
+            }
+            for (int ip = 0; ip < n && cfg.plane_var_mode != 0; ++ip) {
                 const PV& pv = pts[ip];
                 double F[9];
                 for (int m = 0; m < 3; ++m) {
@@ -299,7 +379,7 @@ class LioOracle {
             OctoTree* ch = nd->leaves[i];
             if (ch == nullptr) continue;
             if ((int)ch->temp_points.size() > init_size(ch)) {
-                init_plane(ch->temp_points, &ch->plane);
+                init_plane(ch->temp_points, &ch->plane, ch->voxel_center);
                 if (ch->plane.is_plane) {
                     ch->octo_state = 0;
                 } else {
@@ -314,7 +394,7 @@ class LioOracle {
     // voxel_loc.cpp:141-159
     void init_octo_tree(OctoTree* nd) {
         if ((int)nd->temp_points.size() > init_size(nd)) {
-            init_plane(nd->temp_points, &nd->plane);
+            init_plane(nd->temp_points, &nd->plane, nd->voxel_center);
             if (nd->plane.is_plane) {
                 nd->octo_state = 0;
             } else {
@@ -338,7 +418,7 @@ class LioOracle {
                 nd->new_points++;
                 nd->temp_points.push_back(pv);
                 if (nd->new_points > 5) {  // m_update_size_threshold_
-                    init_plane(nd->temp_points, &nd->plane);
+                    init_plane(nd->temp_points, &nd->plane, nd->voxel_center);
                     nd->new_points = 0;
                 }
                 if ((int)nd->temp_points.size() >= cfg.max_points_size) {
@@ -362,7 +442,7 @@ class LioOracle {
                 nd->new_points++;
                 nd->temp_points.push_back(pv);
                 if (nd->new_points > 5) {
-                    init_plane(nd->temp_points, &nd->plane);
+                    init_plane(nd->temp_points, &nd->plane, nd->voxel_center);
                     nd->new_points = 0;
                 }
                 if ((int)nd->temp_points.size() > 1000) {  // g_max_points, voxel_loc.cpp:45,298

@@ -36,10 +36,10 @@ def _p(a):
 
 
 class OracleLio:
-    def __init__(self, cfg, sum_mode=0, omp_threads=1, solve_mode=0):
+    def __init__(self, cfg, sum_mode=0, omp_threads=1, solve_mode=0, plane_var_mode=0):
         L = lib()
         cd = np.array([cfg.voxel_size, cfg.min_eigen_value, cfg.dept_err, cfg.beam_err, *cfg.ext_R, *cfg.ext_T], dtype=np.float64)
-        ci = np.array([cfg.max_layer, *cfg.layer_init_size, cfg.max_points_size, cfg.max_iteration, cfg.calib_laser, sum_mode, omp_threads, solve_mode], dtype=np.int32)
+        ci = np.array([cfg.max_layer, *cfg.layer_init_size, cfg.max_points_size, cfg.max_iteration, cfg.calib_laser, sum_mode, omp_threads, solve_mode, plane_var_mode], dtype=np.int32)
         self.h = C.c_void_p(L.orc_lio_create(_p(cd), _p(ci)))
         self.L = L
 

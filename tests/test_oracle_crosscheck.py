@@ -223,6 +223,35 @@ def test_ieskf_gain_6x6_form_equals_reference_form():
     assert a.dump_map().shape == b.dump_map().shape
 
 
+def test_plane_covariance_from_moments_equals_per_point_loop():
+    """plane_var = sum_i J_i Sigma_i J_i^T is evaluated from 60 running moments of the stored points (plane_var_mode 0: what the
+    CUDA product computes, O(1) per refit) instead of the reference's loop over every stored point (voxel_loc.cpp:76-121,
+    plane_var_mode 1).  Same streams through both: identical octree shape and match sets, plane covariances within 1e-9
+    (relative to the largest entry of the matrix), states within 1e-9."""
+    for kind, cfg, n_pts in (("avia", api.AVIA, None), ("hdl64", api.VELODYNE, 32768)):
+        sensor, scans = synth.make_stream(kind, 5, seed=23, leaf=cfg.filter_size_surf, ext_T=cfg.ext_T, n_points=n_pts)
+        a, b = oa.OracleLio(cfg, plane_var_mode=0), oa.OracleLio(cfg, plane_var_mode=1)
+        for h in (a, b):
+            h.set_pose(scans[0]["R_true"], scans[0]["t_true"])
+            h.voxel_map_init(scans[0]["body_full"])
+        for k in range(1, 5):
+            for h in (a, b):
+                h.predict(scans[k]["dt"])
+            ia, ib = a.lio_state_estimation(scans[k]["body_ds"]), b.lio_state_estimation(scans[k]["body_ds"])
+            assert ia == ib
+            assert np.array_equal(a.matches(), b.matches())
+            assert np.allclose(a.get_state()[:24], b.get_state()[:24], rtol=1e-9, atol=1e-12)
+            for h in (a, b):
+                h.map_incremental_grow(scans[k]["body_ds"])
+            da, db = a.dump_map(), b.dump_map()
+            assert da.shape == db.shape
+            assert np.array_equal(da[:, :24], db[:, :24])          # keys, octree shape, centres, normals, d, radius, eigenvalue, counts
+            pa, pb = da[:, 24:], db[:, 24:]
+            scale = np.abs(pb).max(axis=1, keepdims=True) + 1e-300
+            assert (np.abs(pa - pb) / scale).max() < 1e-9
+        assert (da[:, 6] == 1).sum() > 50
+
+
 def test_voxel_grid_oracle_vs_numpy_restatement():
     """orc_frontend.hpp (pcl::VoxelGrid restatement) against an independent numpy statement of the same published algorithm:
     float32 inverse leaf / box / cell index, leaves in ascending index, float32 sums in scan order."""
