@@ -20,7 +20,9 @@ struct immesh_lio {
     int* d_counters = nullptr;  // node_count, chunk_bump, avail_top, pending_n, err, n_roots, n_touched, seg_top, work_counter
     int* d_sorted = nullptr;
     double* d_ptpl = nullptr;
-    float* d_body_own = nullptr;  // scan buffer owned by the handle (sb.body points here unless the caller passed a device pointer)
+    float* d_body_own = nullptr;  // scan buffers owned by the handle, 2 slots of max_scan*3 (sb.body points into them unless the caller passed a device pointer)
+    cudaStream_t stream_up = nullptr;   // upload stream: the H2D copy of scan k+1 overlaps the kernels of scan k
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};
     float* h_body = nullptr;   // pinned staging, 2 slots
     double* h_state = nullptr; // pinned, 2 slots of (IM_STATE_DOUBLES + 64)
     cudaEvent_t ev_slot[2] = {nullptr, nullptr};  // completion of the step that used staging slot s
@@ -75,6 +77,8 @@ struct immesh_mesh {
     cudaEvent_t ev_mark = nullptr, ev_sync = nullptr;  // pipeline timing mark (end) / cross-stream join
     cudaStream_t stream2 = nullptr;   // side stream: warp-level triangulation, concurrent with the block-level one
     cudaStream_t stream3 = nullptr;   // side stream: pull (incidence-list walk), concurrent with the triangulation
+    cudaStream_t stream_up = nullptr; // upload stream: the H2D copy of frame k+1 overlaps the kernels of frame k
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
     int pending_rc = 0;
     void* nccl_comm = nullptr;        // ncclComm_t when the per-voxel stage is sharded over several GPUs

@@ -456,7 +456,9 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     ScanBuf& sb = h->sb;
     const size_t ms = (size_t)h->max_scan;
     float* d_body = nullptr;
-    IM_CREATE(dev_alloc(h, &d_body, ms * 3));
+    IM_CREATE(dev_alloc(h, &d_body, 2 * ms * 3));
+    IM_CREATE(cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) IM_CREATE(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
     sb.body = d_body;
     h->d_body_own = d_body;
     IM_CREATE(dev_alloc(h, &sb.body_cov, ms * 6));
@@ -509,6 +511,8 @@ int immesh_lio_destroy(immesh_lio_t* h) {
     if (h->h_out) cudaFreeHost(h->h_out);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->ev_pose) cudaEventDestroy(h->ev_pose);
+    for (int i = 0; i < 2; ++i) if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
+    if (h->stream_up) cudaStreamDestroy(h->stream_up);
     if (h->ev_mark) cudaEventDestroy(h->ev_mark);
     if (h->stream) cudaStreamDestroy(h->stream);
     for (int i = 0; i < 2; ++i) if (h->ev_slot[i]) cudaEventDestroy(h->ev_slot[i]);
@@ -595,7 +599,8 @@ static int upload_scan(immesh_lio* h, const float* body, int n, int on_device = 
     if (on_device) {
         h->sb.body = body;  // caller-owned device buffer, must stay valid until the next call on this handle
     } else {
-        h->sb.body = h->d_body_own;
+        float* dst = h->d_body_own + (size_t)slot * h->max_scan * 3;   // the slot's previous user has finished (ev_slot waited on by the caller)
+        h->sb.body = dst;
         if (n > 0) {
             const float* src = body;
             if (!host_ptr_is_pinned(body)) {
@@ -603,7 +608,10 @@ static int upload_scan(immesh_lio* h, const float* body, int n, int on_device = 
                 std::memcpy(stage, body, (size_t)n * 3 * sizeof(float));
                 src = stage;
             }
-            IM_CUDA(cudaMemcpyAsync((void*)h->d_body_own, src, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            // on the upload stream, so that the copy overlaps the kernels of the scan before; the compute stream joins it
+            IM_CUDA(cudaMemcpyAsync((void*)dst, src, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream_up));
+            IM_CUDA(cudaEventRecord(h->ev_up[slot], h->stream_up));
+            IM_CUDA(cudaStreamWaitEvent(h->stream, h->ev_up[slot], 0));
         }
     }
     return push_dyn(h, n, slot, dt, cov_gyr, cov_acc);

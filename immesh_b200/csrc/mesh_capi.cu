@@ -418,6 +418,8 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<256>)));
     IM_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
     IM_CUDA(cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
+    IM_CUDA(cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) IM_CUDA(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
@@ -443,6 +445,8 @@ int immesh_mesh_destroy(immesh_mesh_t* h) {
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream3) cudaStreamDestroy(h->stream3);
+    if (h->stream_up) cudaStreamDestroy(h->stream_up);
+    for (int i = 0; i < 2; ++i) if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_join3) cudaEventDestroy(h->ev_join3);
@@ -651,7 +655,9 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
             if (src_mode == 0) {
                 const float* src = xyz;
                 if (!mesh_host_ptr_is_pinned(xyz)) { std::memcpy(h_pts, xyz, (size_t)n * 3 * sizeof(float)); src = h_pts; }
-                IM_CUDA(cudaMemcpyAsync(d_pts, src, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+                IM_CUDA(cudaMemcpyAsync(d_pts, src, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream_up));
+                IM_CUDA(cudaEventRecord(h->ev_up[s], h->stream_up));
+                IM_CUDA(cudaStreamWaitEvent(st, h->ev_up[s], 0));
             } else {
                 F.pts = xyz;
             }
@@ -663,7 +669,10 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
             if (!h->d_body) IM_CUDA(mdev_alloc(h, &h->d_body, 2 * slot_pts));
             const float* src = xyz;
             if (!mesh_host_ptr_is_pinned(xyz)) { std::memcpy(h_pts, xyz, (size_t)n * 3 * sizeof(float)); src = h_pts; }
-            IM_CUDA(cudaMemcpyAsync(h->d_body + s * slot_pts, src, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+            // upload stream: overlaps the kernels of the frame before (slot s was released by mesh_harvest above)
+            IM_CUDA(cudaMemcpyAsync(h->d_body + s * slot_pts, src, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream_up));
+            IM_CUDA(cudaEventRecord(h->ev_up[s], h->stream_up));
+            IM_CUDA(cudaStreamWaitEvent(st, h->ev_up[s], 0));
             d_body = h->d_body + s * slot_pts;
         }
         // the pose: published by the last kernel of the scan's sequence (step entry points), else on request
