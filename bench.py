@@ -228,6 +228,18 @@ def cpu_summary(tt):
             "mesh_ms_median_p95": [round(float(np.median(mesh)) * 1e3, 3), round(float(np.percentile(mesh, 95)) * 1e3, 3)]}
 
 
+def cpu_frontend_ms(wl, scans, n):
+    """The CPU arm's own front-end (what the GPU arm's e2e_raw includes): [calibration] + VoxelGrid of the raw scan, oracle port."""
+    import oracle_api as oa
+    ts = []
+    for sc in scans[1:1 + n]:
+        t0 = time.perf_counter()
+        pts = oa.kitti_calib(sc["body_full"]) if wl["lio"].calib_laser else sc["body_full"]
+        oa.voxel_grid(pts, wl["lio"].filter_size_surf)
+        ts.append(time.perf_counter() - t0)
+    return round(float(np.mean(ts)) * 1e3, 3)
+
+
 def cpu_baseline_block(wl, scans, n_warm, n_timed, what):
     res = {}
     for label, tl, tm in cpu_thread_sets():
@@ -236,7 +248,7 @@ def cpu_baseline_block(wl, scans, n_warm, n_timed, what):
     best = res["all"]
     return {"value": best["pipelined_scans_s"], "unit": "scans/s", "cores": max(best["threads_loc_mesh"]), "host_cores": os.cpu_count() or 1, "kind": "port",
             "sample": f"{n_timed} scans of the same stream after {n_warm} untimed scans; {what}; value = pipelined rate 1/max(t_loc, t_mesh) at the fastest thread setting ('all')",
-            "all_cores": res["all"], "reference_4_threads": res["ref4"],
+            "all_cores": res["all"], "reference_4_threads": res["ref4"], "frontend_ms_single_thread": cpu_frontend_ms(wl, scans, min(4, n_timed)),
             "reference_published": "Avia 24k-pt scans on i9-10900: localization 16.6 ms, meshing 25.3 ms; KITTI HDL-64: 42.2 / 31.3 ms (T-RO Table IV)"}
 
 
@@ -406,7 +418,8 @@ def run_gpu(args, rank, world):
     MW = wl["map_warm"]
     n_prof = min(K, 10)
     n_stage = min(K, 10)
-    n_scans = 1 + MW + W + 2 * K + n_stage + n_prof + 1
+    K_raw = 0 if args.no_raw_leg else min(K, 20)
+    n_scans = 1 + MW + W + 2 * K + K_raw + n_stage + n_prof + 1
     scans = get_stream(wl, n_scans, seed=rank if args.independent_streams else 0)
     lib = api.load_library()
     dev = torch.device("cuda", local_rank)
@@ -515,8 +528,41 @@ def run_gpu(args, rank, world):
     mesh.wait()
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()
     del pinned
+    # ---- timed region 3 (`e2e_raw`): the device-resident front-end chain.  RAW full-resolution scans in pinned host memory ->
+    # [KITTI laser calibration when the config sets it] -> pcl::VoxelGrid -> localization, and the (calibrated) full-resolution
+    # cloud -> meshing; the down-sampled cloud and its size never leave the device.  Wall clock as for e2e.
+    e2e_raw = None
+    if K_raw > 0:
+        vg = api.VoxelGrid(max(1 << 17, max(s["body_full"].shape[0] for s in scans) + 1024), lib=lib)
+        calib = bool(wl["lio"].calib_laser)
+        leaf = float(wl["lio"].filter_size_surf)
+        pinned = [pin(scans[k + j]["body_full"]) for j in range(K_raw)]
+        for j in range(2):    # front-end warm-up (not timed): first launches of its kernels
+            vg.prepare(pinned[j][0], calib_laser=calib, fetch=False)
+        barrier()
+        t0 = time.perf_counter()
+        raw_bytes = 0
+        for j in range(K_raw):
+            full, _ = pinned[j]
+            vg.step_async_raw(lio, full, leaf, dt=scans[k]["dt"], calib_laser=calib)
+            mesh.push_frame_from_lio_async(lio, vg.input_points(), full.shape[0], on_device=True)
+            raw_bytes += full.nbytes + 128
+            k += 1
+        lio.wait()
+        mesh.wait()
+        barrier()
+        raw_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([raw_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            raw_s = float(t[0])
+        e2e_raw = {"value": round(K_raw * (world if args.independent_streams else 1) / raw_s, 3), "unit": "scans/s", "ms_per_step": round(raw_s / K_raw * 1e3, 4), "steps": K_raw,
+                   "h2d_bytes_per_step": int(raw_bytes / K_raw), "calib_laser": calib,
+                   "what": "raw full-resolution scan (pinned host) -> [KITTI calibration] -> VoxelGrid down-sampling -> localization -> meshing, all on the device; only the raw scan goes up, state + counters come back"}
+        del pinned
+        vg.close()
+    clocks = sampler.stop()
     # ---- blocking per-stage timing (one scan at a time, L2 flushed before each): explains where the time goes
     dev_ms, stage = [], []
     for _ in range(n_stage):
@@ -601,6 +647,7 @@ def run_gpu(args, rank, world):
         "e2e": {"value": round(scans_done / e2e_s, 3), "unit": "scans/s", "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
                 "ms_per_step": round(e2e_s / K * 1e3, 4), "host_buffers": "pinned (cudaHostAlloc); the C ABI copies straight from them",
                 "host_work_ms_per_step": round((e2e_enq_ms - sum(e2e_waits)) / K, 4)},
+        "e2e_raw": e2e_raw,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "parity_gate": gate,
@@ -691,6 +738,7 @@ def main():
                     help="N>1: 'replicas' (default) = every rank runs its own independent stream, weak scaling; 'sharded' = one scan stream, "
                          "VoxelMap + mesher sharded over the ranks (exchanges fused into the kernels over NVLink peer windows), strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-raw-leg", action="store_true", help="skip the e2e_raw region (device-resident front-end chain)")
     ap.add_argument("--no-parity-gate", action="store_true", help="experiments only: skip the GPU-vs-oracle check that precedes the timed regions")
     ap.add_argument("--streams", type=int, default=None, help="N=1: also measure this many independent streams interleaved on the one GPU (reported as `multi_stream`; 1 = skip)")
     ap.add_argument("--no-sharded-extra", action="store_true", help="N>1, replicas mode: skip the additional sharded single-stream measurement")

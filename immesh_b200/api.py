@@ -139,6 +139,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_voxelgrid_destroy", [vp]),
         ("immesh_voxelgrid_filter", [vp, vp, C.c_int, C.c_int, C.c_float, vp, ip, ip]),
         ("immesh_voxelgrid_device_points", [vp]),
+        ("immesh_frontend_prepare", [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+        ("immesh_voxelgrid_input_points", [vp]),
+        ("immesh_lio_step_async_raw", [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_double]),
+        ("immesh_lio_step_async_dev_n", [vp, vp, C.c_int, vp, C.c_double, C.c_double, C.c_double]),
         ("immesh_imu_create", [C.POINTER(_ImuCfg), C.POINTER(vp)]),
         ("immesh_imu_destroy", [vp]),
         ("immesh_imu_reset", [vp, dp, C.c_double, C.c_double, dp, dp]),
@@ -152,6 +156,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         lib.immesh_imu_device_points.restype = C.c_void_p
     if hasattr(lib, "immesh_voxelgrid_device_points"):
         lib.immesh_voxelgrid_device_points.restype = C.c_void_p
+    if hasattr(lib, "immesh_voxelgrid_input_points"):
+        lib.immesh_voxelgrid_input_points.restype = C.c_void_p
     if hasattr(lib, "immesh_launch_count"):
         lib.immesh_launch_count.restype = C.c_longlong
     if hasattr(lib, "immesh_last_error"):
@@ -492,6 +498,30 @@ class VoxelGrid:
 
     def device_points(self) -> int:
         return int(self.lib.immesh_voxelgrid_device_points(self._h) or 0)
+
+    def prepare(self, pts, calib_laser=False, fetch=True):
+        """KITTI laser calibration (optional) + repack of a float32[n,3] or [n,4] cloud; the packed cloud stays on the device
+        (input_points()).  Returns it as float32[n,3] when fetch."""
+        a = np.ascontiguousarray(pts, dtype=np.float32)
+        n, stride = a.shape[0], a.shape[1]
+        out = np.zeros((n, 3), dtype=np.float32) if fetch else None
+        _check(self.lib, self.lib.immesh_frontend_prepare(self._h, a.ctypes.data_as(C.c_void_p), n, stride, 0, 1 if calib_laser else 0,
+                                                          out.ctypes.data_as(C.c_void_p) if fetch else None), "frontend_prepare")
+        return out
+
+    def input_points(self) -> int:
+        return int(self.lib.immesh_voxelgrid_input_points(self._h) or 0)
+
+    def step_async_raw(self, lio: "Lio", pts, leaf: float, dt=0.0, calib_laser=False, cov_gyr=0.1, cov_acc=0.1, n=None, stride=3, on_device=False):
+        """The device-resident front-end chain: [calibration] -> VoxelGrid -> lio.step_async, no host round trip in between."""
+        if on_device:
+            ptr, cnt = C.c_void_p(int(pts)), int(n)
+        else:
+            a = np.ascontiguousarray(pts, dtype=np.float32)
+            ptr, cnt, stride = a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1]
+        _check(self.lib, self.lib.immesh_lio_step_async_raw(lio._h, self._h, ptr, cnt, stride, 1 if on_device else 0, 1 if calib_laser else 0, C.c_float(leaf),
+                                                            dt, cov_gyr, cov_acc), "lio_step_async_raw")
+        lio._last_n = cnt
 
 
 class Imu:

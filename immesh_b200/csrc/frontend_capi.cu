@@ -24,6 +24,7 @@
 
 #include "../../include/immesh_b200.h"
 #include "common_host.hpp"
+#include "handles.hpp"
 
 using immesh::im_fail;
 
@@ -194,12 +195,28 @@ __global__ void __launch_bounds__(VG_THREADS) k_vg_copy_if_small(const float* __
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 3 * (size_t)n; i += (size_t)gridDim.x * blockDim.x) out[i] = pts[i];
 }
 
+// front of the front-end: strided input (3 floats xyz, or 4 as the IMU stage emits: xyz + curvature) -> packed [n][3], with the
+// KITTI laser calibration (voxel_mapping.cpp:1844-1859) applied on the way when preprocess/calib_laser is set
+__global__ void __launch_bounds__(VG_THREADS) k_frontend_pack(const float* __restrict__ src, int n, int stride, int calib, float* __restrict__ dst) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float x = src[(size_t)i * stride], y = src[(size_t)i * stride + 1], z = src[(size_t)i * stride + 2];
+        if (calib) immesh::kitti_calib_point(&x, &y, &z);
+        dst[3 * (size_t)i] = x; dst[3 * (size_t)i + 1] = y; dst[3 * (size_t)i + 2] = z;
+    }
+}
+
 }  // namespace
 
 struct immesh_voxelgrid {
     int max_points = 0, nblocks_max = 0, n_sm = 148;
     cudaStream_t stream = nullptr;
-    float* d_in = nullptr;       // staging for host input
+    float* d_in = nullptr;       // staging for host input / packed (calibrated) cloud of immesh_frontend_prepare: the current slot of
+    float* d_in_ring[4] = {nullptr, nullptr, nullptr, nullptr};   // a ring of 4 (a mesh frame may still be reading the cloud of 2-3 scans ago)
+    int in_idx = 0;
+    float* d_raw = nullptr;      // [max_points][4] strided input of immesh_frontend_prepare
+    float* h_raw = nullptr;      // pinned staging for it
+    cudaEvent_t ev_raw = nullptr; // the H2D copy out of h_raw has completed
+    int raw_pending = 0;
     float* d_out = nullptr;      // [max_points][3]
     unsigned int *d_k[2] = {nullptr, nullptr}, *d_v[2] = {nullptr, nullptr};
     int* d_hist = nullptr;       // [256 * nblocks_max]
@@ -226,8 +243,12 @@ int immesh_voxelgrid_create(int max_points, immesh_voxelgrid_t** out) {
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
     IM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     const size_t n = (size_t)max_points;
-    IM_CUDA(cudaMalloc((void**)&h->d_in, n * 3 * sizeof(float)));
+    for (int i = 0; i < 4; ++i) IM_CUDA(cudaMalloc((void**)&h->d_in_ring[i], n * 3 * sizeof(float)));
+    h->d_in = h->d_in_ring[0];
     IM_CUDA(cudaMalloc((void**)&h->d_out, n * 3 * sizeof(float)));
+    IM_CUDA(cudaMalloc((void**)&h->d_raw, n * 4 * sizeof(float)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_raw, n * 4 * sizeof(float)));
+    IM_CUDA(cudaEventCreateWithFlags(&h->ev_raw, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         IM_CUDA(cudaMalloc((void**)&h->d_k[i], n * sizeof(unsigned int)));
         IM_CUDA(cudaMalloc((void**)&h->d_v[i], n * sizeof(unsigned int)));
@@ -246,7 +267,9 @@ int immesh_voxelgrid_create(int max_points, immesh_voxelgrid_t** out) {
 int immesh_voxelgrid_destroy(immesh_voxelgrid_t* h) {
     if (!h) return IMMESH_OK;
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_in); cudaFree(h->d_out);
+    for (int i = 0; i < 4; ++i) cudaFree(h->d_in_ring[i]);
+    cudaFree(h->d_out); cudaFree(h->d_raw); cudaFreeHost(h->h_raw);
+    if (h->ev_raw) cudaEventDestroy(h->ev_raw);
     for (int i = 0; i < 2; ++i) { cudaFree(h->d_k[i]); cudaFree(h->d_v[i]); }
     cudaFree(h->d_hist); cudaFree(h->d_tile); cudaFree(h->d_head); cudaFree(h->d_grid);
     cudaFreeHost(h->h_grid); cudaFreeHost(h->h_pts);
@@ -255,20 +278,8 @@ int immesh_voxelgrid_destroy(immesh_voxelgrid_t* h) {
     return IMMESH_OK;
 }
 
-int immesh_voxelgrid_filter(immesh_voxelgrid_t* h, const float* xyz, int n, int on_device, float leaf, float* out_xyz, int* m_out, int* leaf_too_small) {
-    if (!h || (!xyz && n > 0) || n < 0 || !(leaf > 0.f)) return im_fail(IMMESH_E_INVALID, "bad argument");
-    if (n > h->max_points) return im_fail(IMMESH_E_CAPACITY, "cloud larger than max_points");
-    if (m_out) *m_out = 0;
-    if (leaf_too_small) *leaf_too_small = 0;
-    h->last_m = 0;
-    if (n == 0) return IMMESH_OK;
-    cudaStream_t st = h->stream;
-    const float* d_pts = xyz;
-    if (!on_device) {
-        std::memcpy(h->h_pts, xyz, (size_t)n * 3 * sizeof(float));
-        IM_CUDA(cudaMemcpyAsync(h->d_in, h->h_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-        d_pts = h->d_in;
-    }
+// queue the filter's launch sequence for the packed device cloud d_pts on stream st (no host synchronisation)
+static int vg_enqueue(immesh_voxelgrid* h, const float* d_pts, int n, float leaf, cudaStream_t st) {
     const float inv = 1.0f / leaf;
     const int nb = (n + VG_TILE - 1) / VG_TILE;
     const int gs = std::min(nb * (VG_TILE / VG_THREADS), h->n_sm * 8);
@@ -297,6 +308,25 @@ int immesh_voxelgrid_filter(immesh_voxelgrid_t* h, const float* xyz, int n, int 
     IM_LAUNCH(k_vg_finish, 1, 32, 0, st, h->d_grid, (const int*)(h->d_tile + h->nblocks_max), n);
     IM_LAUNCH(k_vg_copy_if_small, gs, VG_THREADS, 0, st, d_pts, n, (const VgGrid*)h->d_grid, h->d_out);
     IM_CUDA(cudaGetLastError());
+    return IMMESH_OK;
+}
+
+int immesh_voxelgrid_filter(immesh_voxelgrid_t* h, const float* xyz, int n, int on_device, float leaf, float* out_xyz, int* m_out, int* leaf_too_small) {
+    if (!h || (!xyz && n > 0) || n < 0 || !(leaf > 0.f)) return im_fail(IMMESH_E_INVALID, "bad argument");
+    if (n > h->max_points) return im_fail(IMMESH_E_CAPACITY, "cloud larger than max_points");
+    if (m_out) *m_out = 0;
+    if (leaf_too_small) *leaf_too_small = 0;
+    h->last_m = 0;
+    if (n == 0) return IMMESH_OK;
+    cudaStream_t st = h->stream;
+    const float* d_pts = xyz;
+    if (!on_device) {
+        std::memcpy(h->h_pts, xyz, (size_t)n * 3 * sizeof(float));
+        IM_CUDA(cudaMemcpyAsync(h->d_in, h->h_pts, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_pts = h->d_in;
+    }
+    const int rc = vg_enqueue(h, d_pts, n, leaf, st);
+    if (rc) return rc;
     IM_CUDA(cudaMemcpyAsync(h->h_grid, h->d_grid, sizeof(VgGrid), cudaMemcpyDeviceToHost, st));
     IM_CUDA(cudaStreamSynchronize(st));
     const int m = h->h_grid->m_out;
@@ -309,6 +339,61 @@ int immesh_voxelgrid_filter(immesh_voxelgrid_t* h, const float* xyz, int n, int 
         std::memcpy(out_xyz, h->h_pts, (size_t)m * 3 * sizeof(float));
     }
     return IMMESH_OK;
+}
+
+// upload (host input) + pack / calibrate into d_in on stream st
+static int frontend_pack(immesh_voxelgrid* h, const float* pts, int n, int stride, int on_device, int calib_laser, cudaStream_t st) {
+    h->in_idx = (h->in_idx + 1) & 3;
+    h->d_in = h->d_in_ring[h->in_idx];
+    const float* d_src = pts;
+    if (!on_device) {
+        cudaPointerAttributes a;
+        const float* src = pts;
+        if (cudaPointerGetAttributes(&a, pts) != cudaSuccess || a.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            if (h->raw_pending) { IM_CUDA(cudaEventSynchronize(h->ev_raw)); h->raw_pending = 0; }   // the previous copy out of the staging buffer
+            std::memcpy(h->h_raw, pts, (size_t)n * stride * sizeof(float));
+            src = h->h_raw;
+        }
+        IM_CUDA(cudaMemcpyAsync(h->d_raw, src, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (src == h->h_raw) { IM_CUDA(cudaEventRecord(h->ev_raw, st)); h->raw_pending = 1; }
+        d_src = h->d_raw;
+    }
+    IM_LAUNCH(k_frontend_pack, std::min((n + VG_THREADS - 1) / VG_THREADS, h->n_sm * 8), VG_THREADS, 0, st, d_src, n, stride, calib_laser, h->d_in);
+    return IMMESH_OK;
+}
+
+int immesh_frontend_prepare(immesh_voxelgrid_t* h, const float* pts, int n, int stride, int on_device, int calib_laser, float* out_xyz) {
+    if (!h || (!pts && n > 0) || n < 0 || (stride != 3 && stride != 4)) return im_fail(IMMESH_E_INVALID, "bad argument (stride must be 3 or 4)");
+    if (n > h->max_points) return im_fail(IMMESH_E_CAPACITY, "cloud larger than max_points");
+    if (n == 0) return IMMESH_OK;
+    int rc = frontend_pack(h, pts, n, stride, on_device, calib_laser, h->stream);
+    if (rc) return rc;
+    IM_CUDA(cudaGetLastError());
+    if (out_xyz) {
+        IM_CUDA(cudaMemcpyAsync(h->h_pts, h->d_in, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        IM_CUDA(cudaStreamSynchronize(h->stream));
+        std::memcpy(out_xyz, h->h_pts, (size_t)n * 3 * sizeof(float));
+    } else {
+        IM_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return IMMESH_OK;
+}
+const float* immesh_voxelgrid_input_points(immesh_voxelgrid_t* h) { return h ? h->d_in : nullptr; }
+
+// The device-resident front-end chain of one scan, queued on the localization handle's stream with no host round
+// trip: [KITTI laser calibration] -> pcl::VoxelGrid -> predict + IESKF iterations + map update.  The down-sampled cloud and its
+// size never leave the device (the step reads the count from the filter's result block).
+int immesh_lio_step_async_raw(immesh_lio_t* lio, immesh_voxelgrid_t* h, const float* pts, int n, int stride, int on_device, int calib_laser, float leaf,
+                              double dt, double cov_gyr, double cov_acc) {
+    if (!lio || !h || (!pts && n > 0) || n < 1 || (stride != 3 && stride != 4) || !(leaf > 0.f)) return im_fail(IMMESH_E_INVALID, "bad argument");
+    if (n > h->max_points) return im_fail(IMMESH_E_CAPACITY, "cloud larger than max_points");
+    cudaStream_t st = lio->stream;
+    int rc = frontend_pack(h, pts, n, stride, on_device, calib_laser, st);
+    if (rc) return rc;
+    rc = vg_enqueue(h, h->d_in, n, leaf, st);
+    if (rc) return rc;
+    return immesh_lio_step_async_dev_n(lio, h->d_out, n < lio->max_scan ? n : lio->max_scan, &h->d_grid->m_out, dt, cov_gyr, cov_acc);
 }
 
 const float* immesh_voxelgrid_device_points(immesh_voxelgrid_t* h) { return h ? h->d_out : nullptr; }

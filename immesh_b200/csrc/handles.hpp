@@ -31,6 +31,7 @@ struct immesh_lio {
     immesh::ScanDyn* h_dyn = nullptr;   // pinned, 2 slots: per-scan inputs of the launch sequence (one H2D per scan)
     immesh::ScanDyn dyn_last = {};         // host copy of the block last uploaded
     immesh::LioOut* h_out = nullptr;    // pinned, 2 slots: what a scan returns to the host (one D2H per scan)
+    const int* next_n_dev = nullptr;    // device-resident point count for the next upload (immesh_lio_step_async_dev_n)
     int scan_counter = 0;               // scans queued through the step entry points; pose ring slot = scan_counter & 7
     int pose_pub_idx = -1;              // scan index whose converged pose is in LioCtrl::pose_ring (-1: not published)
     int timed_last = 0;                 // the last step recorded its stage timing events

@@ -121,6 +121,44 @@ IM_HD double im_acos(double x) {
     return (1.57079632673412561417e+00 - asin_series(x)) + 6.07710050650619224932e-11;
 }
 
+// asin on [-1, 1] and atan2 (through asin on |argument| <= 0.7072), arithmetic only like the functions above
+IM_HD double im_asin(double x) {
+    const double ax = fabs(x);
+    double r;
+    if (ax <= 0.5) r = asin_series(ax);
+    else r = (1.57079632673412561417e+00 - 2.0 * asin_series(sqrt((1.0 - ax) * 0.5))) + 6.07710050650619224932e-11;
+    return x < 0 ? -r : r;
+}
+IM_HD double im_atan2(double y, double x) {
+    if (x == 0.0 && y == 0.0) return 0.0;
+    const double r = sqrt(x * x + y * y);
+    const double kPi = 3.14159265358979311600e+00, kPio2 = 1.57079632679489655800e+00;
+    if (fabs(x) >= fabs(y)) {
+        const double a = im_asin(y / r);
+        if (x > 0) return a;
+        return (y >= 0 ? kPi : -kPi) - a;
+    }
+    const double a = im_asin(x / r);
+    return y > 0 ? (kPio2 - a) : (a - kPio2);
+}
+// KITTI laser calibration of one point (voxel_mapping.cpp:1844-1859, preprocess/calib_laser): the vertical angle of every return
+// is raised by 0.15 degrees.  float fields like PointType; range and the horizon angle go through float as in the reference
+// (std::sqrt / std::atan2 on float arguments under `using namespace std`, include/common_lib.h:23).
+IM_HD void kitti_calib_point(float* x, float* y, float* z) {
+    const float fx = *x, fy = *y, fz = *z;
+    const double range = (double)sqrtf((fx * fx + fy * fy) + fz * fz);
+    const double calib_vertical_angle = 0.15 * 3.14159265358 / 180.0;   // deg2rad(0.15) with PI_M (common_lib.h:34,297-300)
+    const double vertical_angle = im_asin((double)fz / range) + calib_vertical_angle;
+    const double horizon_angle = (double)(float)im_atan2((double)fy, (double)fx);
+    double sv, cv, sh, ch;
+    im_sincos(vertical_angle, &sv, &cv);
+    im_sincos(horizon_angle, &sh, &ch);
+    *z = (float)(range * sv);
+    const double project_len = range * cv;
+    *x = (float)(project_len * ch);
+    *y = (float)(project_len * sh);
+}
+
 // ------------------------------------------------------------------ small dense helpers (row-major 3x3)
 IM_HD void m3_mul(const double* A, const double* B, double* C) {
 #pragma unroll

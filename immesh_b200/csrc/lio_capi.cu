@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_shard_pass2_p2p(VoxelMapDev map
 #define SOLVE_THREADS 128
 __global__ void __launch_bounds__(SOLVE_THREADS) k_solve_p2p(LioParams P, LioCtrl* ctrl, int iter, LioPeers pe, int epoch_off, int* err) {
     __shared__ SolveScratch S;
-    if (ctrl->stop || ctrl->dyn.n <= 0) return;
+    if (ctrl->stop || (ctrl->dyn.n_dev ? *ctrl->dyn.n_dev : ctrl->dyn.n) <= 0) return;
     const unsigned long long epoch = ctrl->dyn.epoch + (unsigned long long)epoch_off;
     if (threadIdx.x < pe.n && threadIdx.x != pe.rank) {
         immesh::wait_epoch(liowin_flag(pe.w[pe.rank], 1, threadIdx.x), epoch, err, IM_ERR_PEER_TIMEOUT);
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve_p2p(LioParams P, LioCtr
 // stand-alone solve (NCCL-sharded path: the sums are complete only after the all-reduce)
 __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(LioParams P, LioCtrl* ctrl, int iter) {
     __shared__ SolveScratch S;
-    if (ctrl->stop || ctrl->dyn.n <= 0) return;
+    if (ctrl->stop || (ctrl->dyn.n_dev ? *ctrl->dyn.n_dev : ctrl->dyn.n) <= 0) return;
     ieskf_solve(P, ctrl, iter, &S, threadIdx.x, blockDim.x);
 }
 
@@ -626,6 +626,8 @@ static int push_dyn(immesh_lio* h, int n, int slot, double dt, double cov_gyr, d
     d.dt = dt; d.cov_gyr = cov_gyr; d.cov_acc = cov_acc;
     d.epoch = h->win.epoch;
     d.mode = 0; d.pad_ = 0;
+    d.n_dev = h->next_n_dev;
+    h->next_n_dev = nullptr;
     h->dyn_last = d;
     h->dyn_last.dt = 0.0;
     IM_CUDA(cudaMemcpyAsync(&h->d_ctrl->dyn, &d, sizeof(ScanDyn), cudaMemcpyHostToDevice, h->stream));
@@ -812,6 +814,12 @@ int immesh_lio_step_dev(immesh_lio_t* h, const float* d_body, int n, double dt, 
 }
 int immesh_lio_step_async(immesh_lio_t* h, const float* body, int n, int on_device, double dt, double cov_gyr, double cov_acc) {
     return lio_enqueue(h, body, n, on_device, dt, cov_gyr, cov_acc, true);
+}
+// the scan AND its point count are device resident (e.g. produced by the device front-end): n is read at execution time
+int immesh_lio_step_async_dev_n(immesh_lio_t* h, const float* d_body_xyz, int n_max, const int* d_n, double dt, double cov_gyr, double cov_acc) {
+    if (!h || !d_n || n_max < 0) return im_fail(IMMESH_E_INVALID, "bad argument");
+    h->next_n_dev = d_n;
+    return lio_enqueue(h, d_body_xyz, n_max, 1, dt, cov_gyr, cov_acc, true);
 }
 int immesh_lio_wait(immesh_lio_t* h, double* state_out, int* iters_run) { return lio_wait_impl(h, state_out, iters_run, false); }
 // queue a write of `bytes` bytes over a caller-provided device buffer on the localization stream (benchmark L2 flush)

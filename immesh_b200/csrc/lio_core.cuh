@@ -40,6 +40,8 @@ struct ScanDyn {
     double dt, cov_gyr, cov_acc;   // Forward_without_imu inputs; dt <= 0: no prediction
     unsigned long long epoch; // peer-window epoch base of this scan (sharded mode)
     int mode, pad_;
+    const int* n_dev;         // when not null: the number of points is read from here at execution time (a device-resident
+                              // front-end produced the scan: no host round trip of the count)
 };
 // what the host reads back after a scan, one D2H copy
 struct LioOut {
@@ -95,7 +97,7 @@ struct ScanBuf {
 // kernels work on a copy of their ScanBuf argument whose per-scan fields come from the device-resident block
 IM_HD ScanBuf scan_load_dyn(const ScanBuf& sb) {
     ScanBuf o = sb;
-    if (sb.dyn) { o.n = sb.dyn->n; o.body = sb.dyn->body; }
+    if (sb.dyn) { o.n = sb.dyn->n_dev ? *sb.dyn->n_dev : sb.dyn->n; o.body = sb.dyn->body; }
     return o;
 }
 
@@ -220,13 +222,19 @@ IM_HDN inline bool residual_point(const VoxelMapDev& map, const LioParams& P, co
 // core of pass 1: returns the two bits of point i through *exists / *ok1 (false unless this rank owns the point's root voxel)
 IM_HDN inline void shard_pass1_flags(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, bool* exists, bool* ok1) {
     double pwd[3], pw[3], var6[6];
-    residual_world(P, sb, state, i, pwd, pw, var6);
     *exists = false;
     *ok1 = false;
     sb.match_node[i] = -1;
     sb.match_layer[i] = 0;
     sb.slot[i] = -1;
     sb.seg[i] = 0;
+    // owner-computes: the world point alone decides which ranks need this point (its root voxel's owner and the owner of the
+    // one retry neighbour); everybody else is done after ~40 flops, without the covariance propagation and without a probe
+    {
+        const double pb[3] = {(double)sb.body[i * 3 + 0], (double)sb.body[i * 3 + 1], (double)sb.body[i * 3 + 2]};
+        body_to_world(P, state, state + 9, pb, pwd);
+        pw[0] = (double)(float)pwd[0]; pw[1] = (double)(float)pwd[1]; pw[2] = (double)(float)pwd[2];
+    }
     long long k[3];
     float loc[3];
     if (!voxel_key3_loc(pw, P.voxel_size, k, loc)) return;
@@ -237,6 +245,8 @@ IM_HDN inline void shard_pass1_flags(const VoxelMapDev& map, const LioParams& P,
     const unsigned long long nkey = nk_ok ? pack_key(nk[0], nk[1], nk[2]) : 0ull;
     const int o1 = voxel_owner(key, P.shard_n);
     const int o2 = nk_ok ? voxel_owner(nkey, P.shard_n) : -1;
+    if (o1 != P.shard_rank && o2 != P.shard_rank) return;
+    world_cov(state, sb.body_cov + (size_t)i * 6, sb.p_imu + (size_t)i * 3, state + 24, var6);
     if (o1 == P.shard_rank) {
         const int slot = hash_find(map, key);
         const int root = slot >= 0 ? map.root_node[slot] : -1;

@@ -94,6 +94,9 @@ int immesh_lio_step_dev(immesh_lio_t* h, const float* d_body_xyz, int n, double 
 /* Host buffers: page-locked memory (cudaMallocHost / cudaHostRegister) is read by the copy engine directly and must stay
  * unchanged until the matching wait; pageable memory is staged through the handle's pinned slots at once. */
 int immesh_lio_step_async(immesh_lio_t* h, const float* body_xyz, int n, int on_device, double dt, double cov_gyr, double cov_acc);
+/* same with the point COUNT device resident too (d_n: device pointer to an int <= n_max, read when the step executes): the scan
+ * produced by a device front-end is localised without a host round trip of its size */
+int immesh_lio_step_async_dev_n(immesh_lio_t* h, const float* d_body_xyz, int n_max, const int* d_n, double dt, double cov_gyr, double cov_acc);
 int immesh_lio_wait(immesh_lio_t* h, double* state_out /*[348] or NULL*/, int* iters_run /*or NULL*/);
 int immesh_lio_enqueue_memset(immesh_lio_t* h, void* d_buf, size_t bytes); /* benchmark helper: in-stream L2 flush */
 
@@ -214,6 +217,17 @@ int immesh_voxelgrid_destroy(immesh_voxelgrid_t* h);
 int immesh_voxelgrid_filter(immesh_voxelgrid_t* h, const float* xyz, int n, int on_device, float leaf, float* out_xyz /*[n][3] or NULL*/,
                             int* m_out, int* leaf_too_small /*or NULL*/);
 const float* immesh_voxelgrid_device_points(immesh_voxelgrid_t* h);
+/* KITTI laser calibration (src/voxel_mapping.cpp:1844-1859, preprocess/calib_laser: the vertical angle of every return is raised
+ * by 0.15 deg) + repacking: reads n points of `stride` floats (3: x y z; 4: x y z curvature, what immesh_imu_undistort emits),
+ * applies the calibration when calib_laser != 0 and leaves the packed [n][3] cloud on the device (immesh_voxelgrid_input_points:
+ * pass it to immesh_voxelgrid_filter with on_device = 1); copied to out_xyz when that is not NULL. */
+int immesh_frontend_prepare(immesh_voxelgrid_t* h, const float* pts, int n, int stride, int on_device, int calib_laser, float* out_xyz /*[n][3] or NULL*/);
+const float* immesh_voxelgrid_input_points(immesh_voxelgrid_t* h);
+/* The whole front-end chain of one scan on the device, queued on the localization handle's stream without any host round trip:
+ * [calibration] -> VoxelGrid down-sampling -> immesh_lio_step_async on the down-sampled cloud (its size stays on the device).
+ * Replaces src/voxel_mapping.cpp:1844-1859 + :1888-1889 + lio_state_estimation + map_incremental_grow for the scan. */
+int immesh_lio_step_async_raw(immesh_lio_t* lio, immesh_voxelgrid_t* h, const float* pts, int n, int stride, int on_device, int calib_laser, float leaf,
+                              double dt, double cov_gyr, double cov_acc);
 
 /* ---- front-end: IMU forward propagation + per-point motion compensation on the device.  Replaces
  *   ImuProcess::UndistortPcl(lidar_meas, state_inout, pcl_out)            (src/IMU_Processing.cpp:755-958)

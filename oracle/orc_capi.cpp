@@ -340,6 +340,7 @@ int orc_voxel_grid(const float* pts, int n, float leaf, float* out, int cap, int
     if (grid6) { for (int a = 0; a < 3; ++a) { grid6[a] = r.min_b[a]; grid6[3 + a] = r.div_b[a]; } }
     return r.leaf_too_small ? -m - 1 : m;
 }
+void orc_kitti_calib(float* pts, int n) { kitti_calib(pts, n); }
 void orc_jacobi_eig3(const double* a6, double* d, double* V) { jacobi_eig3(a6, d, V); }
 void orc_lu_inverse18(const double* A, double* Ainv) { lu_inverse<18>(A, Ainv); }
 void orc_calc_body_var(const double* pb, double dept_err, double beam_err, double* var6) {

@@ -22,7 +22,35 @@
 #include <cstdint>
 #include <vector>
 
+#include "orc_math.hpp"
+
 namespace orc {
+
+// KITTI laser calibration, voxel_mapping.cpp:1844-1859 (preprocess/calib_laser): in place on packed float xyz.
+//   range = sqrt(x*x + y*y + z*z)   float products and sum, std::sqrt(float) (the file is compiled under `using namespace std`,
+//                                   include/common_lib.h:23, so the float overloads are selected), then widened to double
+//   vertical_angle = asin(z / range) + deg2rad(0.15)        double; deg2rad(x) = x * PI_M / 180.0, PI_M = 3.14159265358 (common_lib.h:34)
+//   horizon_angle  = atan2(y, x)                            float arguments -> float result, widened
+//   z = range * sin(vertical_angle); project_len = range * cos(vertical_angle); x = project_len * cos(horizon_angle); y = ... sin(...)
+// sin / cos / asin / atan2 are the arithmetic-only implementations of orc_math.hpp (libm results differ in the last ulp between
+// glibc and CUDA); tests/test_oracle_crosscheck.py compares with numpy / glibc.  PARITY UNPINNED (no reference fixture exists).
+inline void kitti_calib(float* pts, int n) {
+    for (int i = 0; i < n; ++i) {
+        float* p = pts + 3 * (size_t)i;
+        const float fx = p[0], fy = p[1], fz = p[2];
+        const double range = (double)std::sqrt((fx * fx + fy * fy) + fz * fz);
+        const double calib_vertical_angle = 0.15 * 3.14159265358 / 180.0;
+        const double vertical_angle = det_asin((double)fz / range) + calib_vertical_angle;
+        const double horizon_angle = (double)(float)det_atan2((double)fy, (double)fx);
+        double sv, cv, sh, ch;
+        det_sincos(vertical_angle, &sv, &cv);
+        det_sincos(horizon_angle, &sh, &ch);
+        p[2] = (float)(range * sv);
+        const double project_len = range * cv;
+        p[0] = (float)(project_len * ch);
+        p[1] = (float)(project_len * sh);
+    }
+}
 
 struct VoxelGridResult {
     std::vector<float> out;   // [m][3]

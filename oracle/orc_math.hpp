@@ -120,6 +120,26 @@ inline double det_acos(double x) {
     return (kPio2Hi - asin_small(x)) + kPio2Lo;
 }
 
+inline double det_asin(double x) {
+    const double ax = std::fabs(x);
+    double r;
+    if (ax <= 0.5) r = asin_small(ax);
+    else r = (kPio2Hi - 2.0 * asin_small(std::sqrt((1.0 - ax) * 0.5))) + kPio2Lo;
+    return x < 0 ? -r : r;
+}
+inline double det_atan2(double y, double x) {
+    if (x == 0.0 && y == 0.0) return 0.0;
+    const double r = std::sqrt(x * x + y * y);
+    const double pio2 = 1.57079632679489655800e+00;
+    if (std::fabs(x) >= std::fabs(y)) {
+        const double a = det_asin(y / r);
+        if (x > 0) return a;
+        return (y >= 0 ? kPi : -kPi) - a;
+    }
+    const double a = det_asin(x / r);
+    return y > 0 ? (pio2 - a) : (a - pio2);
+}
+
 // ---------------------------------------------------------------- 3x3 helpers (row-major)
 inline void mat3_mul(const double* A, const double* B, double* C) {  // C = A*B
     for (int i = 0; i < 3; ++i)

@@ -257,3 +257,10 @@ def voxel_triangulate(pts, voxel_res=0.4):
     sa = np.zeros(3)
     n = L.orc_voxel_triangulate(_p(a), a.shape[0], voxel_res, _p(out), out.shape[0], _p(sa))
     return out[:n], sa
+
+
+def kitti_calib(pts):
+    """KITTI laser calibration (voxel_mapping.cpp:1844-1859) of a packed float32[n,3] cloud; returns a new array."""
+    a = np.ascontiguousarray(pts, dtype=np.float32).copy()
+    lib().orc_kitti_calib(_p(a), C.c_int(a.shape[0]))
+    return a

@@ -66,3 +66,47 @@ def test_device_output_feeds_localization(cuda_lib):
             s, _ = lio.wait()
         states.append(s)
     assert np.array_equal(states[0], states[1])
+
+
+def test_kitti_calib_and_strided_input_bit_exact(cuda_lib):
+    """immesh_frontend_prepare: KITTI laser calibration (voxel_mapping.cpp:1844-1859) + repack of [n][3] and [n][4] clouds."""
+    sensor, scans = synth.make_stream("hdl64", 1, seed=11, n_points=65536)
+    pts = scans[0]["body_full"]
+    vg = api.VoxelGrid(1 << 17, lib=cuda_lib)
+    ref = oa.kitti_calib(pts)
+    assert np.array_equal(vg.prepare(pts, calib_laser=True), ref)
+    p4 = np.concatenate([pts, np.arange(len(pts), dtype=np.float32)[:, None]], axis=1)      # xyz + curvature, as the IMU stage emits
+    assert np.array_equal(vg.prepare(p4, calib_laser=True), ref)
+    assert np.array_equal(vg.prepare(p4, calib_laser=False), pts)
+    # chained on the device: calibrated cloud -> VoxelGrid
+    ds = vg.filter(vg.input_points(), 0.5, n=len(pts), on_device=True)
+    vg.prepare(pts, calib_laser=True, fetch=False)
+    ds = vg.filter(vg.input_points(), 0.5, n=len(pts), on_device=True)
+    ref_ds, _, _ = oa.voxel_grid(ref, 0.5)
+    assert np.array_equal(ds, ref_ds)
+
+
+def test_device_resident_frontend_chain_equals_staged_calls(cuda_lib):
+    """immesh_lio_step_async_raw: raw scan -> [calibration] -> VoxelGrid -> localization without a host round trip of the down-sampled
+    cloud or its size, against the same steps through the host (oracle front-end + oracle localization)."""
+    import dataclasses
+    from oracle_api import OracleLio
+    from lio_common import init_velocity
+    cfg = dataclasses.replace(api.VELODYNE, calib_laser=1)
+    sensor, scans = synth.make_stream("hdl64", 4, seed=12, leaf=cfg.filter_size_surf, n_points=65536)
+    g, o = api.Lio(cfg, lib=cuda_lib), OracleLio(cfg)
+    vg = api.VoxelGrid(1 << 17, lib=cuda_lib)
+    for h in (g, o):
+        h.set_pose(scans[0]["R_true"], scans[0]["t_true"])
+        init_velocity(h, sensor, scans)
+        h.voxel_map_init(oa.kitti_calib(scans[0]["body_full"]))
+    for k in (1, 2, 3):
+        raw = scans[k]["body_full"]
+        vg.step_async_raw(g, raw, cfg.filter_size_surf, dt=scans[k]["dt"], calib_laser=True)
+        ds, _, _ = oa.voxel_grid(oa.kitti_calib(raw), cfg.filter_size_surf)
+        o.predict(scans[k]["dt"])
+        o.lio_state_estimation(ds)
+        o.map_incremental_grow(ds)
+    s, it = g.wait()
+    assert np.array_equal(s, o.get_state())
+    assert np.array_equal(g.dump_map(), o.dump_map())

@@ -252,6 +252,29 @@ def test_plane_covariance_from_moments_equals_per_point_loop():
         assert (da[:, 6] == 1).sum() > 50
 
 
+def test_kitti_calib_oracle_vs_numpy():
+    """orc_frontend.hpp: kitti_calib (voxel_mapping.cpp:1844-1859) against the same formulas through numpy / glibc: the arithmetic-only
+    asin / atan2 / sin / cos agree to a few ulp, so the float outputs may differ in the last bit only."""
+    rng = np.random.default_rng(5)
+    d = rng.normal(size=(20000, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pts = (d * rng.uniform(2.0, 120.0, (20000, 1))).astype(np.float32)
+    got = oa.kitti_calib(pts)
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    rng_f = np.sqrt((x * x + y * y) + z * z).astype(np.float64)          # float32 arithmetic, float sqrt
+    va = np.arcsin(z.astype(np.float64) / rng_f) + 0.15 * 3.14159265358 / 180.0
+    ha = np.arctan2(y, x).astype(np.float32).astype(np.float64)            # atan2f
+    ref = np.stack([rng_f * np.cos(va) * np.cos(ha), rng_f * np.cos(va) * np.sin(ha), rng_f * np.sin(va)], axis=1)
+    err = np.abs(got.astype(np.float64) - ref)
+    # the horizon angle goes through float (atan2f): its last bit (2.4e-7 rad near pi) moves x / y by that times the range
+    assert np.all(err <= 3.0e-7 * rng_f[:, None] + 4e-6)
+    assert (got == ref.astype(np.float32)).mean() > 0.7
+    # the calibration raises every elevation angle by 0.15 degrees and keeps the range
+    el0 = np.degrees(np.arcsin(z.astype(np.float64) / rng_f))
+    el1 = np.degrees(np.arcsin(got[:, 2].astype(np.float64) / np.linalg.norm(got.astype(np.float64), axis=1)))
+    assert np.allclose(el1 - el0, 0.15, atol=2e-4)
+
+
 def test_voxel_grid_oracle_vs_numpy_restatement():
     """orc_frontend.hpp (pcl::VoxelGrid restatement) against an independent numpy statement of the same published algorithm:
     float32 inverse leaf / box / cell index, leaves in ascending index, float32 sums in scan order."""

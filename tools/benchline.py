@@ -20,6 +20,6 @@ for f in sys.argv[1:]:
     if d.get("cpu_baseline"):
         c = d["cpu_baseline"]
         print("   cpu", c["value"], "all", c.get("all_cores"), "ref4", c.get("reference_4_threads"))
-    for key in ("multi_stream", "sharded_single_stream"):
+    for key in ("e2e_raw", "multi_stream", "sharded_single_stream"):
         if d.get(key):
             print("  ", key, d[key])
