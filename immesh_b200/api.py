@@ -135,6 +135,11 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_knn", [vp, fp, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int32), fp]),
         ("immesh_mesh_last_timing", [vp, dp]),
         ("immesh_write_ply", [C.c_char_p, fp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
+        ("immesh_write_pcd", [C.c_char_p, fp, C.c_int]),
+        ("immesh_mesh_reconstruct_from_pointcloud", [vp, vp, vp, C.c_int, C.c_int, C.c_double, ip]),
+        ("immesh_mesh_smooth_all", [vp, C.c_double, C.c_int, dp]),
+        ("immesh_mesh_region_stream", [vp, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), ip]),
+        ("immesh_kitti_pose_line", [dp, C.c_double, C.c_char_p, C.c_int]),
         ("immesh_voxelgrid_create", [C.c_int, C.POINTER(vp)]),
         ("immesh_voxelgrid_destroy", [vp]),
         ("immesh_voxelgrid_filter", [vp, vp, C.c_int, C.c_int, C.c_float, vp, ip, ip]),
@@ -455,6 +460,30 @@ class Mesh:
         _check(self.lib, self.lib.immesh_knn(self._h, p, nq, k, max_dist, idx.ctypes.data_as(C.POINTER(C.c_int32)), d2.ctypes.data_as(C.POINTER(C.c_float))), "knn")
         return idx, d2
 
+    def reconstruct_from_pointcloud(self, vg: "VoxelGrid", pts, minimum_pts_distance: float) -> int:
+        """reconstruct_mesh_from_pointcloud: VoxelGrid(leaf = minimum_pts_distance) + one frame with the identity pose; returns the down-sampled size."""
+        a, p = _f32(pts)
+        m = C.c_int(0)
+        _check(self.lib, self.lib.immesh_mesh_reconstruct_from_pointcloud(self._h, vg._h, C.cast(p, C.c_void_p), a.shape[0], 0, minimum_pts_distance, C.byref(m)), "mesh_reconstruct_from_pointcloud")
+        return m.value
+
+    def smooth_all(self, smooth_factor=0.1, knn=20):
+        """smooth_all_pts: returns the smoothed positions float64[nv,3] (and stores them as the vertices' smoothed positions)."""
+        nv = self.counts()["n_vertices"]
+        out = np.zeros((nv, 3))
+        _check(self.lib, self.lib.immesh_mesh_smooth_all(self._h, smooth_factor, knn, out.ctypes.data_as(C.POINTER(C.c_double))), "mesh_smooth_all")
+        return out
+
+    def region_stream(self, region_size=10.0, cap=1 << 16):
+        """(region_keys int32[nr,3], region_offsets int32[nr+1], triangles int32[nt,3]) -- the viewer's region-bucketed triangle sets."""
+        nt = self.counts()["n_triangles"]
+        keys, offs = np.zeros((cap, 3), dtype=np.int32), np.zeros(cap + 1, dtype=np.int32)
+        tri = np.zeros((max(nt, 1), 3), dtype=np.int32)
+        nr = C.c_int(0)
+        i32 = C.POINTER(C.c_int32)
+        _check(self.lib, self.lib.immesh_mesh_region_stream(self._h, region_size, keys.ctypes.data_as(i32), offs.ctypes.data_as(i32), cap, tri.ctypes.data_as(i32), C.byref(nr)), "mesh_region_stream")
+        return keys[:nr.value].copy(), offs[:nr.value + 1].copy(), tri[:nt].copy()
+
     def last_timing(self):
         o = np.zeros(4)
         self.lib.immesh_mesh_last_timing(self._h, o.ctypes.data_as(C.POINTER(C.c_double)))
@@ -582,6 +611,20 @@ def write_ply(path: str, vertices, triangles, flips=None, lib: Optional[C.CDLL] 
     fl = None if flips is None else np.ascontiguousarray(flips, dtype=np.int32)
     _check(lib, lib.immesh_write_ply(path.encode(), v.ctypes.data_as(C.POINTER(C.c_float)), v.shape[0], t.ctypes.data_as(C.POINTER(C.c_int32)),
                                      None if fl is None else fl.ctypes.data_as(C.POINTER(C.c_int32)), t.shape[0]), "write_ply")
+
+
+def write_pcd(path: str, vertices, lib: Optional[C.CDLL] = None):
+    lib = lib or load_library()
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    _check(lib, lib.immesh_write_pcd(path.encode(), v.ctypes.data_as(C.POINTER(C.c_float)), v.shape[0]), "write_pcd")
+
+
+def kitti_pose_line(state, stamp: float, lib: Optional[C.CDLL] = None) -> str:
+    lib = lib or load_library()
+    s = np.ascontiguousarray(state, dtype=np.float64)
+    buf = C.create_string_buffer(512)
+    _check(lib, lib.immesh_kitti_pose_line(s.ctypes.data_as(C.POINTER(C.c_double)), stamp, buf, 512), "kitti_pose_line")
+    return buf.value.decode()
 
 
 def profile_enable(on: bool, lib: Optional[C.CDLL] = None):

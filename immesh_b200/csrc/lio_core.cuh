@@ -532,16 +532,27 @@ IM_HDN inline void grow_point(const VoxelMapDev& map, const LioParams& P, const 
     const double* cov = state + 24;
     float wx, wy, wz;
     double* v6 = sb.var + (size_t)i * 6;
+    double pb[3] = {0.0, 0.0, 0.0};
     if (mode & 2) {
         wx = sb.pw[(size_t)i * 3 + 0]; wy = sb.pw[(size_t)i * 3 + 1]; wz = sb.pw[(size_t)i * 3 + 2];
-        sb.sortkey[i] = (double)i;
     } else {
-    const double pb[3] = {(double)sb.body[i * 3 + 0], (double)sb.body[i * 3 + 1], (double)sb.body[i * 3 + 2]};
-    double pwd[3];
-    body_to_world(P, R, t, pb, pwd);
-    wx = (float)pwd[0]; wy = (float)pwd[1]; wz = (float)pwd[2];
-    sb.pw[(size_t)i * 3 + 0] = wx; sb.pw[(size_t)i * 3 + 1] = wy; sb.pw[(size_t)i * 3 + 2] = wz;
-    if (mode == 0) {
+        pb[0] = (double)sb.body[i * 3 + 0]; pb[1] = (double)sb.body[i * 3 + 1]; pb[2] = (double)sb.body[i * 3 + 2];
+        double pwd[3];
+        body_to_world(P, R, t, pb, pwd);
+        wx = (float)pwd[0]; wy = (float)pwd[1]; wz = (float)pwd[2];
+        sb.pw[(size_t)i * 3 + 0] = wx; sb.pw[(size_t)i * 3 + 1] = wy; sb.pw[(size_t)i * 3 + 2] = wz;
+    }
+    // the root voxel (and with it the owning rank) follows from the world point alone: a sharded rank is done with the points of
+    // other ranks' voxels here, before the covariance propagation
+    const double pw[3] = {(double)wx, (double)wy, (double)wz};
+    long long k[3];
+    sb.slot[i] = -1;
+    if (!voxel_key3(pw, P.voxel_size_ins, k)) { im_atomic_or(map.err, IM_ERR_KEY_RANGE); return; }
+    const unsigned long long key = pack_key(k[0], k[1], k[2]);
+    if (P.shard_n > 1 && voxel_owner(key, P.shard_n) != P.shard_rank) return;   // another rank owns this root voxel
+    if (mode & 2) {
+        sb.sortkey[i] = (double)i;
+    } else if (mode == 0) {
         double RRe[9];
         m3_mul(R, P.extR, RRe);
         world_cov(RRe, sb.body_cov + (size_t)i * 6, sb.p_imu + (size_t)i * 3, cov, v6);
@@ -553,14 +564,7 @@ IM_HDN inline void grow_point(const VoxelMapDev& map, const LioParams& P, const 
         world_cov(R, bv, pt, cov, v6);
         sb.sortkey[i] = (double)i;
     }
-    }
-    const double pw[3] = {(double)wx, (double)wy, (double)wz};
-    long long k[3];
-    sb.slot[i] = -1;
-    if (!voxel_key3(pw, P.voxel_size_ins, k)) { im_atomic_or(map.err, IM_ERR_KEY_RANGE); return; }
     int created = 0;
-    const unsigned long long key = pack_key(k[0], k[1], k[2]);
-    if (P.shard_n > 1 && voxel_owner(key, P.shard_n) != P.shard_rank) return;   // another rank owns this root voxel
     const int slot = hash_insert(map, key, &created);
     if (slot < 0) return;
     if (created) {

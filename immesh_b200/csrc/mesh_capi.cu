@@ -203,12 +203,12 @@ __global__ void __launch_bounds__(128) k_snapshot(MeshDev M, int n_alloc, int* o
 // exact kNN over the mesh vertices for arbitrary queries (KD_TREE::Nearest_Search): one warp per query, ring
 // expansion over the mesh-voxel hash, per-lane sorted top-k lists merged with warp shuffles.
 #define KNN_KMAX 32
-__global__ void __launch_bounds__(128) k_knn(MeshDev M, MeshParams P, const float* q, int nq, int k, double max_dist, int* out_idx, float* out_d2) {
+__global__ void __launch_bounds__(128) k_knn(MeshDev M, MeshParams P, const float* q, int qstride, int nq, int k, double max_dist, int* out_idx, float* out_d2) {
     const int lane = threadIdx.x & 31;
     const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const double max_d2 = max_dist * max_dist;
     for (int qi = wglobal; qi < nq; qi += nw) {
-        const float qx = q[qi * 3 + 0], qy = q[qi * 3 + 1], qz = q[qi * 3 + 2];
+        const float qx = q[(size_t)qi * qstride + 0], qy = q[(size_t)qi * qstride + 1], qz = q[(size_t)qi * qstride + 2];
         const int cx = round_key(qx, P.res), cy = round_key(qy, P.res), cz = round_key(qz, P.res);
         float ld[KNN_KMAX];
         int lid[KNN_KMAX];
@@ -281,6 +281,41 @@ __global__ void __launch_bounds__(128) k_knn(MeshDev M, MeshParams P, const floa
                 out_d2[(size_t)qi * k + r] = bid == 0x7fffffff ? INFINITY : bd;
             }
         }
+    }
+}
+
+// Global_map::smooth_pts (pointcloud_rgbd.cpp:932-958) on every vertex = smooth_all_pts (mesh_rec_geometry.cpp:60-69): from the
+// vertex's knn nearest vertices (k_knn, ascending; the first is the vertex itself and is skipped) those with sqrt(d2) < max_dis
+// are averaged, smoothed = p (1 - f) + sum f / valid; stored as the smoothed position (set_smooth_pos) and written to out.
+__global__ void __launch_bounds__(128) k_smooth_all(MeshDev M, int nv, int k, const int* __restrict__ idx, const float* __restrict__ d2, double sf, double max_dis, double* out) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+        const float4 p = M.vpos[v];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, valid = 0.0;
+        for (int j = 1; j < k; ++j) {
+            const int id = idx[(size_t)v * k + j];
+            if (id < 0) break;
+            if ((double)sqrtf(d2[(size_t)v * k + j]) < max_dis) {
+                const float4 q = M.vpos[id];
+                s0 = s0 + (double)q.x; s1 = s1 + (double)q.y; s2 = s2 + (double)q.z;
+                valid += 1.0;
+            }
+        }
+        const double r0 = (double)p.x * (1.0 - sf) + s0 * sf / valid, r1 = (double)p.y * (1.0 - sf) + s1 * sf / valid, r2 = (double)p.z * (1.0 - sf) + s2 * sf / valid;
+        M.vsmooth[(size_t)v * 3 + 0] = r0; M.vsmooth[(size_t)v * 3 + 1] = r1; M.vsmooth[(size_t)v * 3 + 2] = r2;
+        if (out) { out[(size_t)v * 3 + 0] = r0; out[(size_t)v * 3 + 1] = r1; out[(size_t)v * 3 + 2] = r2; }
+    }
+}
+// Triangle_manager::insert_triangle_to_list (triangle.cpp:35-53): region = round(centre / region_size) of every live triangle
+__global__ void __launch_bounds__(128) k_region_keys(MeshDev M, int n_alloc, double region_size, int* out_tri, int* out_key, int* out_n) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_alloc; t += gridDim.x * blockDim.x) {
+        const int4 r = M.tri[t];
+        if (!r.w) continue;
+        const float4 a = M.vpos[r.x], b = M.vpos[r.y], c = M.vpos[r.z];
+        const int e = atomicAdd(out_n, 1);
+        out_tri[(size_t)e * 3 + 0] = r.x; out_tri[(size_t)e * 3 + 1] = r.y; out_tri[(size_t)e * 3 + 2] = r.z;
+        out_key[(size_t)e * 3 + 0] = (int)round((((double)a.x + (double)b.x) + (double)c.x) / 3.0 / region_size);
+        out_key[(size_t)e * 3 + 1] = (int)round((((double)a.y + (double)b.y) + (double)c.y) / 3.0 / region_size);
+        out_key[(size_t)e * 3 + 2] = (int)round((((double)a.z + (double)b.z) + (double)c.z) / 3.0 / region_size);
     }
 }
 
@@ -964,13 +999,95 @@ int immesh_knn(immesh_mesh_t* h, const float* query_xyz, int nq, int k, double m
     IM_CUDA(cudaMalloc(&di, (size_t)nq * k * sizeof(int)));
     IM_CUDA(cudaMalloc(&dd, (size_t)nq * k * sizeof(float)));
     IM_CUDA(cudaMemcpyAsync(dq, query_xyz, (size_t)nq * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    IM_LAUNCH(k_knn, mesh_grid(h, nq * 32, 128), 128, 0, h->stream, h->M, h->P, dq, nq, k, max_dist, di, dd);
+    IM_LAUNCH(k_knn, mesh_grid(h, nq * 32, 128), 128, 0, h->stream, h->M, h->P, (const float*)dq, 3, nq, k, max_dist, di, dd);
     IM_CUDA(cudaGetLastError());
     IM_CUDA(cudaMemcpyAsync(idx, di, (size_t)nq * k * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     IM_CUDA(cudaMemcpyAsync(d2, dd, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     IM_CUDA(cudaStreamSynchronize(h->stream));
     cudaFree(dq); cudaFree(di); cudaFree(dd);
     return IMMESH_OK;
+}
+
+int immesh_mesh_smooth_all(immesh_mesh_t* h, double smooth_factor, int knn, double* smoothed) {
+    if (!h || knn < 1 || knn > KNN_KMAX) return im_fail(IMMESH_E_INVALID, "bad argument (knn must be in [1,32])");
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    int cnt[32];
+    IM_CUDA(cudaMemcpy(cnt, h->M.cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
+    const int nv = cnt[0];
+    if (nv == 0) return IMMESH_OK;
+    int* di = nullptr;
+    float* dd = nullptr;
+    double* dout = nullptr;
+    IM_CUDA(cudaMalloc(&di, (size_t)nv * knn * sizeof(int)));
+    IM_CUDA(cudaMalloc(&dd, (size_t)nv * knn * sizeof(float)));
+    if (smoothed) IM_CUDA(cudaMalloc(&dout, (size_t)nv * 3 * sizeof(double)));
+    IM_LAUNCH(k_knn, mesh_grid(h, nv, 4), 128, 0, h->stream, h->M, h->P, (const float*)h->M.vpos, 4, nv, knn, (double)INFINITY, di, dd);
+    IM_LAUNCH(k_smooth_all, mesh_grid(h, nv, 128), 128, 0, h->stream, h->M, nv, knn, (const int*)di, (const float*)dd, smooth_factor, h->P.accept, dout);
+    IM_CUDA(cudaGetLastError());
+    if (smoothed) IM_CUDA(cudaMemcpyAsync(smoothed, dout, (size_t)nv * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(di); cudaFree(dd); if (dout) cudaFree(dout);
+    return IMMESH_OK;
+}
+
+int immesh_mesh_region_stream(immesh_mesh_t* h, double region_size, int32_t* region_keys, int32_t* region_offsets, int cap_regions, int32_t* triangles, int* n_regions) {
+    if (!h || !(region_size > 0) || !n_regions) return im_fail(IMMESH_E_INVALID, "bad argument");
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    int cnt[32];
+    IM_CUDA(cudaMemcpy(cnt, h->M.cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
+    const int nalloc = std::min(cnt[1], h->M.max_t), nlive = cnt[2];
+    *n_regions = 0;
+    if (nlive == 0) { if (region_offsets && cap_regions >= 0) region_offsets[0] = 0; return IMMESH_OK; }
+    int *d_tri = nullptr, *d_key = nullptr, *d_n = nullptr;
+    IM_CUDA(cudaMalloc(&d_tri, (size_t)nlive * 3 * sizeof(int)));
+    IM_CUDA(cudaMalloc(&d_key, (size_t)nlive * 3 * sizeof(int)));
+    IM_CUDA(cudaMalloc(&d_n, sizeof(int)));
+    IM_CUDA(cudaMemset(d_n, 0, sizeof(int)));
+    IM_LAUNCH(k_region_keys, mesh_grid(h, nalloc, 128), 128, 0, h->stream, h->M, nalloc, region_size, d_tri, d_key, d_n);
+    std::vector<int> t((size_t)nlive * 3), kx((size_t)nlive * 3);
+    IM_CUDA(cudaMemcpyAsync(t.data(), d_tri, t.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaMemcpyAsync(kx.data(), d_key, kx.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(d_tri); cudaFree(d_key); cudaFree(d_n);
+    std::vector<int> order(nlive);
+    for (int i = 0; i < nlive; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {   // regions by ascending key, triangles by ascending triple inside a region
+        for (int j = 0; j < 3; ++j)
+            if (kx[(size_t)a * 3 + j] != kx[(size_t)b * 3 + j]) return kx[(size_t)a * 3 + j] < kx[(size_t)b * 3 + j];
+        for (int j = 0; j < 3; ++j)
+            if (t[(size_t)a * 3 + j] != t[(size_t)b * 3 + j]) return t[(size_t)a * 3 + j] < t[(size_t)b * 3 + j];
+        return false;
+    });
+    int nr = 0;
+    for (int i = 0; i < nlive; ++i) {
+        const int o = order[i];
+        const bool first = (i == 0) || kx[(size_t)o * 3] != kx[(size_t)order[i - 1] * 3] || kx[(size_t)o * 3 + 1] != kx[(size_t)order[i - 1] * 3 + 1] ||
+                           kx[(size_t)o * 3 + 2] != kx[(size_t)order[i - 1] * 3 + 2];
+        if (first) {
+            if (nr < cap_regions) {
+                if (region_keys) for (int j = 0; j < 3; ++j) region_keys[(size_t)nr * 3 + j] = kx[(size_t)o * 3 + j];
+                if (region_offsets) region_offsets[nr] = i;
+            }
+            ++nr;
+        }
+        if (triangles) for (int j = 0; j < 3; ++j) triangles[(size_t)i * 3 + j] = t[(size_t)o * 3 + j];
+    }
+    if (region_offsets && nr <= cap_regions) region_offsets[nr] = nlive;
+    *n_regions = nr;
+    return nr <= cap_regions ? IMMESH_OK : im_fail(IMMESH_E_CAPACITY, "more regions than cap_regions");
+}
+
+// reconstruct_mesh_from_pointcloud (src/ImMesh_mesh_reconstruction.cpp:328-345, the offline entry of config/offline_pointcloud.yaml):
+// the whole cloud is down-sampled by a pcl::VoxelGrid with leaf = minimum_pts_distance and meshed as ONE frame with the identity pose
+// (Eigen::Quaterniond::Identity(), vec_3::Zero(), frame 0).  Both steps run on the device; the down-sampled cloud never leaves it.
+int immesh_mesh_reconstruct_from_pointcloud(immesh_mesh_t* h, immesh_voxelgrid_t* vg, const float* xyz, int n, int on_device, double minimum_pts_distance, int* n_downsampled) {
+    if (!h || !vg || (!xyz && n > 0) || n < 0 || !(minimum_pts_distance > 0)) return im_fail(IMMESH_E_INVALID, "bad argument");
+    int m = 0, small = 0;
+    int rc = immesh_voxelgrid_filter(vg, xyz, n, on_device, (float)minimum_pts_distance, nullptr, &m, &small);
+    if (rc) return rc;
+    if (n_downsampled) *n_downsampled = m;
+    const double zero[3] = {0.0, 0.0, 0.0};
+    return immesh_mesh_push_frame_dev(h, immesh_voxelgrid_device_points(vg), m, zero, 0);
 }
 
 int immesh_mesh_last_timing(immesh_mesh_t* h, double* ms) {

@@ -195,6 +195,26 @@ int immesh_mesh_snapshot(immesh_mesh_t* h, float* vertices /*[nv][3] or NULL*/, 
  * per vertex, one face per triangle oriented by the reference's rule (m_index_flip != 0: p0 p1 p2, else p0 p2 p1).  Host-side only. */
 int immesh_write_ply(const char* path, const float* vertices /*[nv][3]*/, int nv, const int32_t* triangles /*[nt][3]*/,
                      const int32_t* flips /*[nt] or NULL*/, int nt);
+/* pcl::io::savePCDFileBinary of the vertex cloud, written by save_to_ply_file next to the PLY (mesh_rec_geometry.cpp:129).  Host-side only. */
+int immesh_write_pcd(const char* path, const float* vertices /*[nv][3]*/, int nv);
+/* smooth_all_pts(smooth_factor, knn) (src/meshing/mesh_rec_geometry.cpp:60-69) = Global_map::smooth_pts on every vertex
+ * (src/meshing/r3live/pointcloud_rgbd.cpp:932-958, maximum_smooth_dis = g_kd_tree_accept_pt_dis = 1.25 * voxel_resolution): exact knn on the
+ * device, neighbours 1..knn-1 closer than the limit averaged, smoothed = p (1 - f) + mean f.  Updates the vertices' smoothed positions
+ * (set_smooth_pos) and returns them (smoothed may be NULL); save_to_ply_file with smooth_factor != 0 writes exactly these positions. */
+int immesh_mesh_smooth_all(immesh_mesh_t* h, double smooth_factor, int knn /*<= 32*/, double* smoothed /*[n_vertices][3] or NULL*/);
+/* Region-bucketed triangle stream of the viewer (Triangle_manager::insert_triangle_to_list, src/meshing/r3live/triangle.cpp:35-53): every live
+ * triangle belongs to region round(centre / region_size).  Output: regions in ascending key order (region_keys [nr][3], region_offsets
+ * [nr + 1] into `triangles`), triangles [n_live][3] grouped by region, ascending triples inside a region. */
+int immesh_mesh_region_stream(immesh_mesh_t* h, double region_size, int32_t* region_keys /*[cap][3] or NULL*/, int32_t* region_offsets /*[cap+1] or NULL*/,
+                              int cap_regions, int32_t* triangles /*[n_live][3] or NULL*/, int* n_regions);
+/* reconstruct_mesh_from_pointcloud(frame_pts, minimum_pts_distance) (src/ImMesh_mesh_reconstruction.cpp:328-345; the offline whole-cloud
+ * entry of config/offline_pointcloud.yaml): VoxelGrid down-sampling with leaf = minimum_pts_distance, then one
+ * incremental_mesh_reconstruction frame with the identity pose.  xyz: [n][3] host array, or device pointer with on_device = 1. */
+int immesh_mesh_reconstruct_from_pointcloud(immesh_mesh_t* h, immesh_voxelgrid_t* vg, const float* xyz, int n, int on_device, double minimum_pts_distance,
+                                            int* n_downsampled /*or NULL*/);
+/* Voxel_mapping::kitti_log (src/voxel_mapping_common.cpp:43-70): one line "stamp tx ty tz qx qy qz qw\n" of the pose log in the KITTI camera
+ * frame for the pose part (rot_end, pos_end) of a state vector.  Host-side only. */
+int immesh_kitti_pose_line(const double* state /*[>=12]*/, double stamp, char* buf, int cap);
 /* KD_TREE::Nearest_Search(point, k, ..., max_dist) (include/ikd-Tree/ikd_Tree.h:306) over the mesh vertices:
  * exact k nearest by float squared distance, ascending, ties by lower id; idx = -1 / d2 = inf when fewer exist. */
 int immesh_knn(immesh_mesh_t* h, const float* query_xyz /*[nq][3]*/, int nq, int k, double max_dist, int32_t* idx /*[nq][k]*/,

@@ -250,6 +250,18 @@ long orc_mesh_get_voxels(void* h, int* out, long cap) {
             for (int j = 0; j < 4; ++j) out[i * 4 + j] = rows[i][j];
     return (long)rows.size();
 }
+void orc_mesh_smooth_all(void* h, double smooth_factor, int knn, double* out) {
+    std::vector<std::array<double, 3>> r;
+    ((MeshOracle*)h)->smooth_all(smooth_factor, knn, r);
+    for (size_t i = 0; i < r.size(); ++i) { out[3 * i] = r[i][0]; out[3 * i + 1] = r[i][1]; out[3 * i + 2] = r[i][2]; }
+}
+long orc_mesh_region_keys(void* h, double region_size, int* out) {   // one key per live triangle, in ascending-triple order
+    std::vector<std::array<int, 3>> r;
+    ((MeshOracle*)h)->region_keys(region_size, r);
+    if (out)
+        for (size_t i = 0; i < r.size(); ++i) { out[3 * i] = r[i][0]; out[3 * i + 1] = r[i][1]; out[3 * i + 2] = r[i][2]; }
+    return (long)r.size();
+}
 void orc_mesh_knn(void* h, const float* q, int nq, int k, double max_dist, int* idx, float* d2) {
     MeshOracle* m = (MeshOracle*)h;
     std::vector<std::pair<float, int>> nn;

@@ -14,6 +14,7 @@
 //   * Delaunay predicates are exact on coordinates snapped to voxel_resolution * 2^-22
 //     (the reference uses CGAL's inexact Simple_cartesian<double>; CGAL is not vendored).
 #pragma once
+#include <limits>
 #include <algorithm>
 #include <array>
 #include <map>
@@ -350,6 +351,44 @@ class MeshOracle {
             voxels[vi].new_added++;
             voxels[vi].meshing_times = 0;
             frame_new_vertices++;
+        }
+    }
+
+    // smooth_all_pts (mesh_rec_geometry.cpp:60-69) = Global_map::smooth_pts on every vertex (pointcloud_rgbd.cpp:932-958) with
+    // maximum_smooth_dis = g_kd_tree_accept_pt_dis = 1.25 * res (mesh_rec_geometry.cpp:343): knn nearest vertices (the first one is
+    // the vertex itself and is skipped), those with sqrt(d2) < the limit are averaged (double sums in neighbour order),
+    //   smoothed = p (1 - f) + sum f / valid        (valid == 0 divides by zero exactly like the reference)
+    // The result is stored as the vertex's smoothed position (set_smooth_pos) and returned.
+    void smooth_all(double smooth_factor, int knn_k, std::vector<std::array<double, 3>>& out) {
+        const double maxdis = cfg.voxel_resolution * 1.25;
+        const int nv = (int)vpos.size();
+        out.assign(nv, {0, 0, 0});
+        std::vector<std::pair<float, int>> nn;
+        for (int v = 0; v < nv; ++v) {
+            const float q[3] = {vpos[v][0], vpos[v][1], vpos[v][2]};
+            knn(q, knn_k, std::numeric_limits<double>::infinity(), nn);
+            double sv[3] = {0, 0, 0}, valid = 0.0;
+            for (size_t k = 1; k < nn.size(); ++k) {
+                if ((double)std::sqrt(nn[k].first) < maxdis) {
+                    for (int j = 0; j < 3; ++j) sv[j] = sv[j] + (double)vpos[nn[k].second][j];
+                    valid += 1.0;
+                }
+            }
+            for (int j = 0; j < 3; ++j) out[v][j] = (double)vpos[v][j] * (1.0 - smooth_factor) + sv[j] * smooth_factor / valid;
+            vsmooth[v] = out[v];
+        }
+    }
+    // Triangle_manager::insert_triangle_to_list (triangle.cpp:35-53): every live triangle belongs to the region
+    // round(centre / region_size), centre = mean of its three vertex positions (Triangle_manager::get_triangle_center)
+    void region_keys(double region_size, std::vector<std::array<int, 3>>& out) const {
+        out.clear();
+        for (const Tri& t : live) {
+            std::array<int, 3> k;
+            for (int j = 0; j < 3; ++j) {
+                const double c = (((double)vpos[t[0]][j] + (double)vpos[t[1]][j]) + (double)vpos[t[2]][j]) / 3.0;
+                k[j] = (int)std::round(c / region_size);
+            }
+            out.push_back(k);
         }
     }
 

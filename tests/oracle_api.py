@@ -159,6 +159,21 @@ class OracleMesh:
         keys = ["n_vertices", "n_triangles", "frame_new_vertices", "frame_voxels_meshed", "frame_added", "frame_removed", "n_voxels", "n_activated"]
         return dict(zip(keys, (int(v) for v in o)))
 
+    def smooth_all(self, smooth_factor=0.1, knn=20):
+        out = np.zeros((self.counts()["n_vertices"], 3))
+        self.L.orc_mesh_smooth_all.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p]
+        self.L.orc_mesh_smooth_all(self.h, smooth_factor, knn, _p(out))
+        return out
+
+    def region_keys(self, region_size=10.0):
+        """region key of every live triangle, in the snapshot's (ascending triple) order"""
+        self.L.orc_mesh_region_keys.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        self.L.orc_mesh_region_keys.restype = C.c_long
+        n = self.L.orc_mesh_region_keys(self.h, region_size, None)
+        out = np.zeros((n, 3), dtype=np.int32)
+        self.L.orc_mesh_region_keys(self.h, region_size, _p(out))
+        return out
+
     def snapshot(self):
         c = self.counts()
         v = np.zeros((c["n_vertices"], 3), dtype=np.float32)

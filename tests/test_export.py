@@ -32,3 +32,42 @@ def test_write_ply_roundtrip(tmp_path):
         assert False
     except RuntimeError:
         pass
+
+
+def test_write_pcd_layout(tmp_path):
+    lib = api.load_library()
+    rng = np.random.default_rng(1)
+    v = rng.normal(0, 5, (77, 3)).astype(np.float32)
+    path = str(tmp_path / "mesh.ply.pcd")
+    api.write_pcd(path, v, lib=lib)
+    raw = open(path, "rb").read()
+    head, body = raw.split(b"DATA binary\n", 1)
+    lines = head.decode().splitlines()
+    assert lines[0].startswith("# .PCD v0.7") and "FIELDS x y z" in lines and "SIZE 4 4 4" in lines and "TYPE F F F" in lines
+    assert "WIDTH 77" in lines and "HEIGHT 1" in lines and "POINTS 77" in lines
+    assert np.array_equal(np.frombuffer(body, dtype="<f4").reshape(-1, 3), v)
+
+
+def test_kitti_pose_line_matches_numpy():
+    """Voxel_mapping::kitti_log (voxel_mapping_common.cpp:43-70): T_cam = T_l2c [R t] T_l2c^-1 and its quaternion, against numpy / scipy."""
+    from scipy.spatial.transform import Rotation
+    lib = api.load_library()
+    L = np.array([[0.00554604, -0.999971, -0.00523653, 0.0316362], [-0.000379382, 0.00523451, -0.999986, 0.0380934],
+                  [0.999985, 0.00554795, -0.000350341, 0.409066], [0, 0, 0, 1.0]])
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        R = Rotation.from_rotvec(rng.normal(0, 1.5, 3)).as_matrix()
+        t = rng.normal(0, 50, 3)
+        s = np.zeros(348)
+        s[:9] = R.reshape(9)
+        s[9:12] = t
+        line = api.kitti_pose_line(s, 12.5, lib=lib)
+        f = [float(x) for x in line.split()]
+        assert len(f) == 8 and line.endswith("\n") and f[0] == 12.5
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = R, t
+        B = L @ T @ np.linalg.inv(L)
+        assert np.allclose(f[1:4], B[:3, 3], atol=2e-6)
+        q = Rotation.from_matrix(B[:3, :3]).as_quat()     # x y z w
+        got = np.array(f[4:8])
+        assert min(np.abs(got - q).max(), np.abs(got + q).max()) < 2e-5     # %lf = 6 decimals; T_l2c is orthonormal to ~1e-6 only

@@ -110,3 +110,46 @@ def test_pipelined_equals_sequential(cuda_lib):
     for a, b in zip(res[0][2], res[1][2]):
         assert np.array_equal(a, b)
     assert len(res[0][2][1]) > 1000
+
+
+def test_smooth_all_pts_and_region_stream(cuda_lib):
+    """smooth_all_pts (mesh_rec_geometry.cpp:60-69 -> Global_map::smooth_pts, pointcloud_rgbd.cpp:932-958) and the viewer's
+    region-bucketed triangle sets (triangle.cpp:35-53) on the device against the oracle."""
+    g, o, _ = run_mesh_parity(cuda_lib, "avia", 4, seed=14)
+    for sf, k in ((0.1, 20), (0.5, 8)):
+        sg, so = g.smooth_all(sf, k), o.smooth_all(sf, k)
+        assert sg.shape == so.shape and len(sg) > 3000
+        same = (sg == so) | (np.isnan(sg) & np.isnan(so))      # a vertex without a neighbour inside the limit divides by zero on both sides
+        assert same.all()
+    keys, offs, tris = g.region_stream(10.0)
+    _, to, _ = o.snapshot()
+    ko = o.region_keys(10.0)
+    assert len(ko) == len(to) == len(tris)
+    order = np.lexsort((to[:, 2], to[:, 1], to[:, 0], ko[:, 2], ko[:, 1], ko[:, 0]))
+    assert np.array_equal(tris, to[order])
+    ref_keys, first = np.unique(ko[order], axis=0, return_index=True)
+    assert np.array_equal(keys, ref_keys) and np.array_equal(offs[:-1], np.sort(first)) and offs[-1] == len(to)
+    assert len(keys) >= 2
+    # a finer region size
+    keys2, offs2, tris2 = g.region_stream(2.0)
+    assert len(keys2) > len(keys) and offs2[-1] == len(to)
+
+
+def test_offline_reconstruct_from_pointcloud(cuda_lib):
+    """reconstruct_mesh_from_pointcloud (ImMesh_mesh_reconstruction.cpp:328-345): whole cloud -> VoxelGrid(minimum_pts_distance) -> one frame,
+    identity pose, against the same two oracle steps."""
+    import oracle_api as oa
+    from oracle_api import OracleMesh
+    clouds = [w for w, _ in world_scans("avia", 3, seed=15)]
+    cloud = np.concatenate(clouds, axis=0)
+    cfg = api.MeshConfig(**{**SMALL, "number_of_pts_append_to_map": 1 << 30})     # offline_pointcloud.yaml: every point is an append candidate
+    g, o = api.Mesh(cfg, lib=cuda_lib), OracleMesh(cfg)
+    vg = api.VoxelGrid(1 << 18, lib=cuda_lib)
+    m = g.reconstruct_from_pointcloud(vg, cloud, 0.1)
+    ds, small, _ = oa.voxel_grid(cloud, 0.1)
+    assert m == len(ds) and not small
+    o.push_frame(ds, np.zeros(3), 0)
+    assert g.counts() == o.counts()
+    for a, b in zip(g.snapshot(), o.snapshot()):
+        assert np.array_equal(a, b)
+    assert g.counts()["n_triangles"] > 5000
