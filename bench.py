@@ -630,7 +630,12 @@ def run_gpu(args, rank, world):
     # whole-step roofline: algorithmic bytes of every modelled kernel of a scan / the pipelined time per scan
     step_bytes = sum(bb for bb in (algorithmic_bytes(n2, info) for n2 in kern_ms) if bb)
     # ---- max over ranks, aggregate
+    per_rank_ms = None
     if world > 1:
+        mine = torch.tensor([total_ms / K], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank_ms = [round(float(x[0]), 4) for x in allr]
         t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_s = float(t[0]), float(t[1])
@@ -655,6 +660,7 @@ def run_gpu(args, rank, world):
                           "serial_ms_per_scan_blocking": round(float(np.mean(dev_ms)), 4),
                           "serial_ms_per_scan_blocking_median_p95": [round(float(np.median(dev_ms)), 4), round(float(np.percentile(dev_ms, 95)), 4)],
                           "host_enqueue_ms_per_scan": round(host_enqueue_ms, 4),
+                          "ms_per_step_of_every_rank": per_rank_ms,
                           "host_enqueue_wall_ms_per_scan_incl_backpressure": round(enq_wall_ms / K, 4),
                           "cuda_graphs": api.graph_stats(lio, mesh),
                           "transport": None if world == 1 or args.independent_streams else {"voxelmap": lio.shard_transport(), "mesher": mesh.shard_transport()}},

@@ -1,12 +1,15 @@
 // immesh_shim.hpp -- header-only C++ shim that gives the reference ROS node the SAME free-function signatures it
 // already calls (src/voxel_mapping.hpp:80-105, src/ImMesh_mesh_reconstruction.cpp:92, include/ikd-Tree/ikd_Tree.h:306)
 // and forwards them to the C ABI of libimmesh_b200.so.  It is compiled inside the reference tree (it needs the
-// reference's own headers: Eigen, PCL point types, voxel_loc.hpp), so it cannot be built in this repository's
-// sandbox; INTEGRATION.md shows where it is included.  Nothing here touches CUDA.
+// reference's own headers: Eigen, PCL point types, voxel_loc.hpp); INTEGRATION.md shows where it is included.  In this
+// repository it is type-checked and linked against minimal stand-ins of those headers (tests/shim_stubs/, tests/test_shim_compile.py).
+// Nothing here touches CUDA.
 //
 // Usage in the reference:  #define IMMESH_B200_SHIM before including voxel_mapping.hpp, link -limmesh_b200.
 #pragma once
 #ifdef IMMESH_B200_SHIM
+#include <cmath>
+#include <cstdint>
 #include <unordered_map>
 #include <vector>
 
@@ -98,5 +101,67 @@ inline void BuildResidualListOMP(const std::unordered_map<VOXEL_LOC, OctoTree*>&
         for (int r = 0; r < 6; ++r)
             for (int c = r; c < 6; ++c, ++e) { o.plane_var(r, c) = v[e]; o.plane_var(c, r) = v[e]; }
     }
+}
+
+// ---- mesher seams -----------------------------------------------------------------------------------------------
+// The reference keeps the mesher's parameters in globals set by main() (src/ImMesh_node.cpp:93-98, :255-257):
+extern double minimum_pts;            // m_meshing_points_minimum_scale * distance_scale
+extern double g_meshing_voxel_size;   // m_meshing_voxel_resolution * distance_scale
+extern int appending_pts_frame;       // m_meshing_number_of_pts_append_to_map
+namespace immesh_shim {
+inline immesh_mesh_t*& mesh_handle() {
+    static immesh_mesh_t* h = nullptr;
+    return h;
+}
+inline immesh_mesh_t* mesh_handle_or_create() {
+    if (!mesh_handle()) {
+        immesh_mesh_config c{};
+        c.points_minimum_scale = minimum_pts;
+        c.voxel_resolution = g_meshing_voxel_size;
+        c.number_of_pts_append_to_map = appending_pts_frame;
+        if (immesh_mesh_create(&c, &mesh_handle()) != IMMESH_OK) mesh_handle() = nullptr;
+    }
+    return mesh_handle();
+}
+// KD_TREE<ikdTree_PointType>::Nearest_Search(point, k_nearest, Nearest_Points, Point_Distance, max_dist) (include/ikd-Tree/ikd_Tree.h:306)
+// over the mesher's vertices: same outputs -- the k nearest vertices in ascending distance with their m_pt_idx, squared float distances.
+template <class PointType, class PointVector>
+inline void Nearest_Search(PointType point, int k_nearest, PointVector& Nearest_Points, std::vector<float>& Point_Distance, double max_dist = INFINITY) {
+    Nearest_Points.clear();
+    Point_Distance.clear();
+    immesh_mesh_t* h = mesh_handle_or_create();
+    if (!h || k_nearest < 1) return;
+    const float q[3] = {point.x, point.y, point.z};
+    std::vector<int32_t> idx((size_t)k_nearest);
+    std::vector<float> d2((size_t)k_nearest);
+    std::vector<float> pos;
+    if (immesh_knn(h, q, 1, k_nearest, max_dist, idx.data(), d2.data()) != IMMESH_OK) return;
+    int64_t cnt[8];
+    immesh_mesh_counts(h, cnt);
+    pos.resize((size_t)cnt[0] * 3);
+    immesh_mesh_snapshot(h, pos.data(), nullptr, nullptr);
+    for (int i = 0; i < k_nearest && idx[i] >= 0; ++i) {
+        PointType p(pos[(size_t)idx[i] * 3], pos[(size_t)idx[i] * 3 + 1], pos[(size_t)idx[i] * 3 + 2]);
+        p.m_pt_idx = idx[i];
+        Nearest_Points.push_back(p);
+        Point_Distance.push_back(d2[i]);
+    }
+}
+}  // namespace immesh_shim
+
+// src/ImMesh_mesh_reconstruction.cpp:92: one frame of the voxel-wise incremental mesher.  frame_pts is the full-resolution scan already in
+// the world frame (transformLidar's output, float xyz + intensity); pose_q is only logged by the reference (:99-105), pose_t is the
+// sensor position used by the facet orientation (correct_triangle_index).
+inline void incremental_mesh_reconstruction(pcl::PointCloud<pcl::PointXYZI>::Ptr frame_pts, Eigen::Quaterniond pose_q, Eigen::Vector3d pose_t, int frame_idx) {
+    (void)pose_q;
+    immesh_mesh_t* h = immesh_shim::mesh_handle_or_create();
+    if (!h || !frame_pts) return;
+    const size_t n = frame_pts->points.size();
+    std::vector<float> xyz(n * 3);
+    for (size_t i = 0; i < n; ++i) {
+        xyz[i * 3 + 0] = frame_pts->points[i].x; xyz[i * 3 + 1] = frame_pts->points[i].y; xyz[i * 3 + 2] = frame_pts->points[i].z;
+    }
+    const double t[3] = {pose_t[0], pose_t[1], pose_t[2]};
+    immesh_mesh_push_frame(h, xyz.data(), (int)n, t, frame_idx);
 }
 #endif  // IMMESH_B200_SHIM
