@@ -136,6 +136,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         ("immesh_mesh_last_timing", [vp, dp]),
         ("immesh_write_ply", [C.c_char_p, fp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
         ("immesh_write_pcd", [C.c_char_p, fp, C.c_int]),
+        ("immesh_mesh_render_depth", [vp, dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp, fp, fp, C.POINTER(C.c_int32), ip]),
         ("immesh_mesh_reconstruct_from_pointcloud", [vp, vp, vp, C.c_int, C.c_int, C.c_double, ip]),
         ("immesh_mesh_smooth_all", [vp, C.c_double, C.c_int, dp]),
         ("immesh_mesh_region_stream", [vp, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), ip]),
@@ -466,6 +467,21 @@ class Mesh:
         m = C.c_int(0)
         _check(self.lib, self.lib.immesh_mesh_reconstruct_from_pointcloud(self._h, vg._h, C.cast(p, C.c_void_p), a.shape[0], 0, minimum_pts_distance, C.byref(m)), "mesh_reconstruct_from_pointcloud")
         return m.value
+
+    def render_depth(self, intrinsics, width, height, z_near, z_far, cam_R, cam_t):
+        """(depth float32[h,w] (-1 = empty), points float32[n,3], pixel int32[n]) -- depth rasterisation of the live mesh."""
+        K = np.ascontiguousarray(intrinsics, dtype=np.float64)
+        R = np.ascontiguousarray(cam_R, dtype=np.float64).reshape(9)
+        t = np.ascontiguousarray(cam_t, dtype=np.float64)
+        depth = np.zeros((height, width), dtype=np.float32)
+        pts = np.zeros((height * width, 3), dtype=np.float32)
+        pix = np.zeros(height * width, dtype=np.int32)
+        n = C.c_int(0)
+        dp = C.POINTER(C.c_double)
+        _check(self.lib, self.lib.immesh_mesh_render_depth(self._h, K.ctypes.data_as(dp), width, height, z_near, z_far, R.ctypes.data_as(dp), t.ctypes.data_as(dp),
+                                                           depth.ctypes.data_as(C.POINTER(C.c_float)), pts.ctypes.data_as(C.POINTER(C.c_float)),
+                                                           pix.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n)), "mesh_render_depth")
+        return depth, pts[:n.value].copy(), pix[:n.value].copy()
 
     def smooth_all(self, smooth_factor=0.1, knn=20):
         """smooth_all_pts: returns the smoothed positions float64[nv,3] (and stores them as the vertices' smoothed positions)."""

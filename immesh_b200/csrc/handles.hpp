@@ -19,7 +19,7 @@ struct immesh_lio {
     LioCtrl* d_ctrl = nullptr;
     int* d_counters = nullptr;  // node_count, chunk_bump, avail_top, pending_n, err, n_roots, n_touched, seg_top, work_counter
     int* d_sorted = nullptr;
-    int* d_complex = nullptr;   // touched root voxels left to the warp-per-voxel kernel (the others are finished by k_grow_simple)
+    int* d_complex = nullptr;   // touched root voxels left to the general warp-per-voxel kernel (the others are finished by k_grow_simple)
     double* d_ptpl = nullptr;
     float* d_body_own = nullptr;  // scan buffers owned by the handle, 2 slots of max_scan*3 (sb.body points into them unless the caller passed a device pointer)
     cudaStream_t stream_up = nullptr;   // upload stream: the H2D copy of scan k+1 overlaps the kernels of scan k

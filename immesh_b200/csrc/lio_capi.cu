@@ -306,24 +306,32 @@ __global__ void __launch_bounds__(128) k_grow_scatter(ScanBuf sb_) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) grow_scatter(sb, i);
 }
 // Most touched root voxels receive one or two points of a scan and stay in an append-only regime (a node still collecting its
-// first points, or a planar node between two refits): no plane fit, no split, no descent.  Those are finished by ONE THREAD each
-// -- same appends, same order (ascending (var_contrast, index)), same arithmetic as update_octo_tree -- and only the others go to
-// the warp-per-voxel kernel below through a compact list.  (At the 1M-point / 0.2 m configuration 175 k voxels are touched per
-// scan and nearly all of them are of the first kind: a warp each left 31 lanes idle.)
+// first points, or a planar node between two refits): no plane fit, no split, no descent.  k_grow_simple finishes those -- same
+// appends, same order (ascending (var_contrast, index)), same arithmetic as update_octo_tree -- with a warp per voxel in a lean
+// kernel (few registers: many more warps in flight than the general kernel below, which carries the plane fit and the octree
+// split); only the other voxels go on to k_grow_voxel through a compact list.  At the 1M-point / 0.2 m configuration 175 k voxels
+// are touched per scan and nearly all are of the first kind.  (A THREAD per simple voxel was measured and rejected: one thread's
+// 60 dependent moment read-modify-writes take ~5x longer than the warp's two per lane, profiles/README.md.)
 #define GROW_SIMPLE_MAX 4
 __global__ void __launch_bounds__(128) k_grow_simple(VoxelMapDev map, LioParams P, ScanBuf sb, int mode, int* complex_list, int* n_complex) {
+    const int lane = threadIdx.x & 31;
     const int nt = *sb.n_touched;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nt; t += nwarps) {
         const int slot = sb.touched[t];
         const int cnt = sb.slot_count[slot], off = sb.slot_offset[slot];
         const int root = map.root_node[slot];
-        int kind = 0;   // 0: warp path, 1: append all, 2: drop all (frozen planar node)
+        int kind = 0;   // 0: general kernel, 1: append all, 2: drop all (frozen planar node)
         if (root >= 0 && (mode & 1) == 0 && cnt <= GROW_SIMPLE_MAX) {
             const NodeRec& n = map.nodes[root];
             if (!n.init_octo) kind = (n.n_pts + cnt <= P.layer_init[n.layer]) ? 1 : 0;
             else if (map.planes[root].is_plane) kind = !n.update_enable ? 2 : ((n.new_points + cnt <= 5 && n.n_pts + cnt < P.max_points) ? 1 : 0);
         }
-        if (kind == 0) { complex_list[atomicAdd(n_complex, 1)] = t; continue; }
+        kind = __shfl_sync(0xffffffffu, kind, 0);
+        if (kind == 0) {
+            if (lane == 0) complex_list[atomicAdd(n_complex, 1)] = t;
+            continue;
+        }
         if (kind == 1) {
             int idx[GROW_SIMPLE_MAX];
             double key[GROW_SIMPLE_MAX];
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(128) k_grow_simple(VoxelMapDev map, LioParams 
                 if (a < cnt) { idx[a] = sb.seg[off + a]; key[a] = sb.sortkey[idx[a]]; }
             }
 #pragma unroll
-            for (int a = 1; a < GROW_SIMPLE_MAX; ++a)       // insertion sort on (key, index), the order std::sort(var_contrast) + ties by index gives
+            for (int a = 1; a < GROW_SIMPLE_MAX; ++a)       // insertion sort on (key, index): the order std::sort(var_contrast) with ties by index gives
 #pragma unroll
                 for (int b = a; b > 0; --b) {
                     const bool lt = b < cnt && (key[b] < key[b - 1] || (key[b] == key[b - 1] && idx[b] < idx[b - 1]));
@@ -344,13 +352,18 @@ __global__ void __launch_bounds__(128) k_grow_simple(VoxelMapDev map, LioParams 
                 if (a >= cnt) break;
                 const int i = idx[a];
                 const float px = sb.pw[(size_t)i * 3 + 0], py = sb.pw[(size_t)i * 3 + 1], pz = sb.pw[(size_t)i * 3 + 2];
-                map.nodes[root].new_points += 1;
-                node_append(map, root, px, py, pz, sb.var + (size_t)i * 6);
-                node_moments_add(map, root, px, py, pz, sb.var + (size_t)i * 6, 0, 1);
+                if (lane == 0) {
+                    map.nodes[root].new_points += 1;
+                    node_append(map, root, px, py, pz, sb.var + (size_t)i * 6);
+                }
+                node_moments_add(map, root, px, py, pz, sb.var + (size_t)i * 6, lane, 32);
+                __syncwarp();
             }
         }
-        sb.slot_count[slot] = 0;
-        sb.slot_cursor[slot] = 0;
+        if (lane == 0) {
+            sb.slot_count[slot] = 0;
+            sb.slot_cursor[slot] = 0;
+        }
     }
 }
 // one warp per remaining touched root voxel, voxels claimed dynamically (their cost varies by orders of magnitude)
@@ -700,7 +713,7 @@ static void launch_grow(immesh_lio* h, int mode) {
     IM_LAUNCH(k_grow_point, g, 128, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, mode);
     IM_LAUNCH(k_grow_segment, grid_fixed(h, 128, 2), 128, 0, h->stream, h->sb);
     IM_LAUNCH(k_grow_scatter, g, 128, 0, h->stream, h->sb);
-    IM_LAUNCH(k_grow_simple, g, 128, 0, h->stream, h->map, h->P, h->sb, mode, h->d_complex, h->d_counters + 11);
+    IM_LAUNCH(k_grow_simple, h->n_sm * 16, 128, 0, h->stream, h->map, h->P, h->sb, mode, h->d_complex, h->d_counters + 11);
     IM_LAUNCH(k_grow_voxel, h->n_sm * h->bps, 128, 0, h->stream, h->map, h->P, h->sb, mode, h->d_sorted, h->d_counters + 8, (const int*)h->d_complex, (const int*)(h->d_counters + 11));
     IM_LAUNCH(k_grow_finish, 1, 256, 0, h->stream, h->map, h->sb, h->d_counters + 8, h->d_ctrl, (const int*)h->d_counters);
 }

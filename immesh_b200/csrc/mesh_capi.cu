@@ -319,6 +319,72 @@ __global__ void __launch_bounds__(128) k_region_keys(MeshDev M, int n_alloc, dou
     }
 }
 
+// ---- depth rasterisation of the live mesh ("LiDAR point-cloud reinforcement", src/ImMesh_node.cpp:305-329: draw_triangle into a depth
+// camera, Cam_view::read_depth, convert_depth_buffer_to_truth_depth + unproject_point, src/tools/openGL_libs/openGL_camera_view.cpp:316-
+// 418).  The reference lets OpenGL rasterise; here a CUDA rasteriser with a defined sampling rule produces the metric depth directly:
+// camera frame x right / y down / z forward (the frame unproject_point inverts: world = R diag(1,-1,-1) p + t), pixel (u, v) =
+// (fx x / z + cx, fy y / z + cy), samples at integer pixel coordinates, a sample is covered when the three edge functions have one
+// sign (zero included), depth interpolated perspective-correctly (1/z is affine in the image), nearest surface wins (atomicMin on the
+// float bits).  Triangles with a vertex outside (z_near, z_far) are skipped (GL would clip them).
+struct DepthCam { double fx, fy, cx, cy, z_near, z_far; double R[9], t[3]; int w, h; };
+__device__ __forceinline__ void depth_project(const DepthCam& C, const float4& p, double* u, double* v, double* z) {
+    const double d[3] = {(double)p.x - C.t[0], (double)p.y - C.t[1], (double)p.z - C.t[2]};
+    const double xc = (C.R[0] * d[0] + C.R[3] * d[1]) + C.R[6] * d[2];     // R^T d
+    const double yc = -((C.R[1] * d[0] + C.R[4] * d[1]) + C.R[7] * d[2]);
+    const double zc = -((C.R[2] * d[0] + C.R[5] * d[1]) + C.R[8] * d[2]);
+    *z = zc;
+    *u = C.fx * xc / zc + C.cx;
+    *v = C.fy * yc / zc + C.cy;
+}
+__global__ void __launch_bounds__(128) k_depth_clear(unsigned int* depth, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) depth[i] = 0x7f800000u;   // +inf
+}
+__global__ void __launch_bounds__(128) k_depth_raster(MeshDev M, int n_alloc, DepthCam C, unsigned int* depth) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_alloc; t += gridDim.x * blockDim.x) {
+        const int4 r = M.tri[t];
+        if (!r.w) continue;
+        double u0, v0, z0, u1, v1, z1, u2, v2, z2;
+        depth_project(C, M.vpos[r.x], &u0, &v0, &z0);
+        depth_project(C, M.vpos[r.y], &u1, &v1, &z1);
+        depth_project(C, M.vpos[r.z], &u2, &v2, &z2);
+        if (!(z0 > C.z_near && z0 < C.z_far && z1 > C.z_near && z1 < C.z_far && z2 > C.z_near && z2 < C.z_far)) continue;
+        const double area = (u1 - u0) * (v2 - v0) - (v1 - v0) * (u2 - u0);
+        if (area == 0.0) continue;
+        const int x_lo = max(0, (int)ceil(fmin(u0, fmin(u1, u2)))), x_hi = min(C.w - 1, (int)floor(fmax(u0, fmax(u1, u2))));
+        const int y_lo = max(0, (int)ceil(fmin(v0, fmin(v1, v2)))), y_hi = min(C.h - 1, (int)floor(fmax(v0, fmax(v1, v2))));
+        const double iz0 = 1.0 / z0, iz1 = 1.0 / z1, iz2 = 1.0 / z2;
+        for (int y = y_lo; y <= y_hi; ++y)
+            for (int x = x_lo; x <= x_hi; ++x) {
+                const double px = (double)x, py = (double)y;
+                const double e0 = (u2 - u1) * (py - v1) - (v2 - v1) * (px - u1);   // weight of vertex 0
+                const double e1 = (u0 - u2) * (py - v2) - (v0 - v2) * (px - u2);
+                const double e2 = (u1 - u0) * (py - v0) - (v1 - v0) * (px - u0);
+                if (!((e0 >= 0 && e1 >= 0 && e2 >= 0) || (e0 <= 0 && e1 <= 0 && e2 <= 0))) continue;
+                const double iz = ((e0 * iz0 + e1 * iz1) + e2 * iz2) / area;
+                const float zf = (float)(1.0 / iz);
+                if (zf > 0.f) atomicMin(&depth[(size_t)y * C.w + x], __float_as_uint(zf));
+            }
+    }
+}
+// convert_depth_buffer_to_truth_depth's validity rule (val < 0.99 z_far, else -1) + unproject_point (openGL_camera_view.cpp:407-414)
+__global__ void __launch_bounds__(128) k_depth_finish(DepthCam C, const unsigned int* depth, float* out_depth, float* out_pts, int* n_pts) {
+    const int n = C.w * C.h;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float val = __uint_as_float(depth[i]);
+        const bool ok = (double)val < C.z_far * 0.99;
+        out_depth[i] = ok ? val : -1.0f;
+        if (ok && out_pts) {
+            const int x = i % C.w, y = i / C.w;
+            // m_camera_intrinsic_inv * (x, y, 1), scaled to depth val, GL camera axes (x, -y, -z), then R p + t
+            const double sx = ((double)x - C.cx) / C.fx, sy = ((double)y - C.cy) / C.fy;
+            const double g[3] = {sx * (double)val, -(sy * (double)val), -(double)val};
+            const int k = atomicAdd(n_pts, 1);
+            for (int a = 0; a < 3; ++a) out_pts[(size_t)k * 4 + a] = (float)(((C.R[a * 3 + 0] * g[0] + C.R[a * 3 + 1] * g[1]) + C.R[a * 3 + 2] * g[2]) + C.t[a]);
+            out_pts[(size_t)k * 4 + 3] = __int_as_float(i);   // the pixel the point came from (the order of the list is arbitrary)
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host side
 
 template <class T>
@@ -1088,6 +1154,58 @@ int immesh_mesh_reconstruct_from_pointcloud(immesh_mesh_t* h, immesh_voxelgrid_t
     if (n_downsampled) *n_downsampled = m;
     const double zero[3] = {0.0, 0.0, 0.0};
     return immesh_mesh_push_frame_dev(h, immesh_voxelgrid_device_points(vg), m, zero, 0);
+}
+
+int immesh_mesh_render_depth(immesh_mesh_t* h, const double* intrinsics, int width, int height, double z_near, double z_far, const double* cam_R, const double* cam_t,
+                             float* depth, float* points, int32_t* point_pixel, int* n_points) {
+    if (!h || !intrinsics || !cam_R || !cam_t || !depth || width < 1 || height < 1 || (long long)width * height > (1 << 26) || !(z_near > 0) || !(z_far > z_near))
+        return im_fail(IMMESH_E_INVALID, "bad argument");
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    int cnt[32];
+    IM_CUDA(cudaMemcpy(cnt, h->M.cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
+    const int nalloc = std::min(cnt[1], h->M.max_t);
+    DepthCam C;
+    C.fx = intrinsics[0]; C.fy = intrinsics[1]; C.cx = intrinsics[2]; C.cy = intrinsics[3]; C.z_near = z_near; C.z_far = z_far;
+    for (int i = 0; i < 9; ++i) C.R[i] = cam_R[i];
+    for (int i = 0; i < 3; ++i) C.t[i] = cam_t[i];
+    C.w = width; C.h = height;
+    const int n = width * height;
+    unsigned int* d_depth = nullptr;
+    float *d_out = nullptr, *d_pts = nullptr;
+    int* d_n = nullptr;
+    IM_CUDA(cudaMalloc(&d_depth, (size_t)n * 4));
+    IM_CUDA(cudaMalloc(&d_out, (size_t)n * 4));
+    if (points) IM_CUDA(cudaMalloc(&d_pts, (size_t)n * 16));
+    IM_CUDA(cudaMalloc(&d_n, 4));
+    IM_CUDA(cudaMemsetAsync(d_n, 0, 4, h->stream));
+    IM_LAUNCH(k_depth_clear, mesh_grid(h, n, 128), 128, 0, h->stream, d_depth, n);
+    if (nalloc > 0) IM_LAUNCH(k_depth_raster, mesh_grid(h, nalloc, 128), 128, 0, h->stream, h->M, nalloc, C, d_depth);
+    IM_LAUNCH(k_depth_finish, mesh_grid(h, n, 128), 128, 0, h->stream, C, (const unsigned int*)d_depth, d_out, d_pts, d_n);
+    IM_CUDA(cudaGetLastError());
+    int np = 0;
+    IM_CUDA(cudaMemcpyAsync(depth, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaMemcpyAsync(&np, d_n, 4, cudaMemcpyDeviceToHost, h->stream));
+    IM_CUDA(cudaStreamSynchronize(h->stream));
+    if (points && np > 0) {
+        std::vector<float> tmp((size_t)np * 4);
+        IM_CUDA(cudaMemcpy(tmp.data(), d_pts, (size_t)np * 16, cudaMemcpyDeviceToHost));
+        // deterministic order: ascending pixel index (the image scan order of convert_depth_buffer_to_truth_depth)
+        std::vector<int> order(np);
+        for (int i = 0; i < np; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int a, int b) {
+            int pa, pb;
+            std::memcpy(&pa, &tmp[(size_t)a * 4 + 3], 4); std::memcpy(&pb, &tmp[(size_t)b * 4 + 3], 4);
+            return pa < pb;
+        });
+        for (int i = 0; i < np; ++i) {
+            const float* q = &tmp[(size_t)order[i] * 4];
+            points[(size_t)i * 3] = q[0]; points[(size_t)i * 3 + 1] = q[1]; points[(size_t)i * 3 + 2] = q[2];
+            if (point_pixel) std::memcpy(&point_pixel[i], &q[3], 4);
+        }
+    }
+    if (n_points) *n_points = np;
+    cudaFree(d_depth); cudaFree(d_out); if (d_pts) cudaFree(d_pts); cudaFree(d_n);
+    return IMMESH_OK;
 }
 
 int immesh_mesh_last_timing(immesh_mesh_t* h, double* ms) {

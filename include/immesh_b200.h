@@ -212,6 +212,16 @@ int immesh_mesh_region_stream(immesh_mesh_t* h, double region_size, int32_t* reg
  * incremental_mesh_reconstruction frame with the identity pose.  xyz: [n][3] host array, or device pointer with on_device = 1. */
 int immesh_mesh_reconstruct_from_pointcloud(immesh_mesh_t* h, immesh_voxelgrid_t* vg, const float* xyz, int n, int on_device, double minimum_pts_distance,
                                             int* n_downsampled /*or NULL*/);
+/* Depth rasterisation of the live mesh from a camera -- the reference's "LiDAR point-cloud reinforcement" (src/ImMesh_node.cpp:305-329:
+ * draw_triangle into the depth camera, Cam_view::read_depth, convert_depth_buffer_to_truth_depth + unproject_point,
+ * src/tools/openGL_libs/openGL_camera_view.cpp:316-418) as a CUDA rasteriser over the device-resident triangle store.
+ *   intrinsics = fx, fy, cx, cy;  cam_R (row-major) / cam_t = m_camera_rot / m_camera_pos of Cam_view (world = R diag(1,-1,-1) p_cam + t)
+ *   depth  [height][width]: metric depth along the optical axis of the nearest surface, -1 where none is closer than 0.99 z_far
+ *   points [n][3] (+ point_pixel [n] = y * width + x): unproject_point of every valid pixel, ascending pixel order; may be NULL
+ * Sampling rule (defined here; the reference leaves it to the GL implementation): samples at integer pixel coordinates, covered when
+ * the three edge functions share a sign, 1/z interpolated affinely, triangles with a vertex outside (z_near, z_far) skipped. */
+int immesh_mesh_render_depth(immesh_mesh_t* h, const double* intrinsics /*[4]*/, int width, int height, double z_near, double z_far,
+                             const double* cam_R /*[9]*/, const double* cam_t /*[3]*/, float* depth, float* points, int32_t* point_pixel, int* n_points);
 /* Voxel_mapping::kitti_log (src/voxel_mapping_common.cpp:43-70): one line "stamp tx ty tz qx qy qz qw\n" of the pose log in the KITTI camera
  * frame for the pose part (rot_end, pos_end) of a state vector.  Host-side only. */
 int immesh_kitti_pose_line(const double* state /*[>=12]*/, double stamp, char* buf, int cap);

@@ -262,6 +262,15 @@ long orc_mesh_region_keys(void* h, double region_size, int* out) {   // one key 
         for (size_t i = 0; i < r.size(); ++i) { out[3 * i] = r[i][0]; out[3 * i + 1] = r[i][1]; out[3 * i + 2] = r[i][2]; }
     return (long)r.size();
 }
+long orc_mesh_render_depth(void* h, const double* K4, int w, int ht, double z_near, double z_far, const double* R, const double* t, float* depth, float* pts, int* pix) {
+    std::vector<float> d;
+    std::vector<std::array<float, 3>> p;
+    std::vector<int> px;
+    ((MeshOracle*)h)->render_depth(K4, w, ht, z_near, z_far, R, t, d, p, px);
+    std::memcpy(depth, d.data(), d.size() * 4);
+    for (size_t i = 0; i < p.size(); ++i) { pts[3 * i] = p[i][0]; pts[3 * i + 1] = p[i][1]; pts[3 * i + 2] = p[i][2]; pix[i] = px[i]; }
+    return (long)p.size();
+}
 void orc_mesh_knn(void* h, const float* q, int nq, int k, double max_dist, int* idx, float* d2) {
     MeshOracle* m = (MeshOracle*)h;
     std::vector<std::pair<float, int>> nn;

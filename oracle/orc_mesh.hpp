@@ -392,6 +392,60 @@ class MeshOracle {
         }
     }
 
+    // Depth image of the live mesh from a camera (ImMesh_node.cpp:305-329 + openGL_camera_view.cpp:316-418; the sampling rule that the
+    // reference leaves to OpenGL is the one stated in include/immesh_b200.h: immesh_mesh_render_depth).  depth[h*w]: -1 where empty.
+    void render_depth(const double* K4, int w, int h, double z_near, double z_far, const double* R, const double* t, std::vector<float>& depth,
+                      std::vector<std::array<float, 3>>& pts, std::vector<int>& pix) const {
+        std::vector<float> zb((size_t)w * h, INFINITY);
+        auto project = [&](const std::array<float, 3>& p, double* u, double* v, double* z) {
+            const double d[3] = {(double)p[0] - t[0], (double)p[1] - t[1], (double)p[2] - t[2]};
+            const double xc = (R[0] * d[0] + R[3] * d[1]) + R[6] * d[2];
+            const double yc = -((R[1] * d[0] + R[4] * d[1]) + R[7] * d[2]);
+            const double zc = -((R[2] * d[0] + R[5] * d[1]) + R[8] * d[2]);
+            *z = zc;
+            *u = K4[0] * xc / zc + K4[2];
+            *v = K4[1] * yc / zc + K4[3];
+        };
+        for (const Tri& tr : live) {
+            double u0, v0, z0, u1, v1, z1, u2, v2, z2;
+            project(vpos[tr[0]], &u0, &v0, &z0);
+            project(vpos[tr[1]], &u1, &v1, &z1);
+            project(vpos[tr[2]], &u2, &v2, &z2);
+            if (!(z0 > z_near && z0 < z_far && z1 > z_near && z1 < z_far && z2 > z_near && z2 < z_far)) continue;
+            const double area = (u1 - u0) * (v2 - v0) - (v1 - v0) * (u2 - u0);
+            if (area == 0.0) continue;
+            const int x_lo = std::max(0, (int)std::ceil(std::fmin(u0, std::fmin(u1, u2)))), x_hi = std::min(w - 1, (int)std::floor(std::fmax(u0, std::fmax(u1, u2))));
+            const int y_lo = std::max(0, (int)std::ceil(std::fmin(v0, std::fmin(v1, v2)))), y_hi = std::min(h - 1, (int)std::floor(std::fmax(v0, std::fmax(v1, v2))));
+            const double iz0 = 1.0 / z0, iz1 = 1.0 / z1, iz2 = 1.0 / z2;
+            for (int y = y_lo; y <= y_hi; ++y)
+                for (int x = x_lo; x <= x_hi; ++x) {
+                    const double px = (double)x, py = (double)y;
+                    const double e0 = (u2 - u1) * (py - v1) - (v2 - v1) * (px - u1);
+                    const double e1 = (u0 - u2) * (py - v2) - (v0 - v2) * (px - u2);
+                    const double e2 = (u1 - u0) * (py - v0) - (v1 - v0) * (px - u0);
+                    if (!((e0 >= 0 && e1 >= 0 && e2 >= 0) || (e0 <= 0 && e1 <= 0 && e2 <= 0))) continue;
+                    const double iz = ((e0 * iz0 + e1 * iz1) + e2 * iz2) / area;
+                    const float zf = (float)(1.0 / iz);
+                    if (zf > 0.f && zf < zb[(size_t)y * w + x]) zb[(size_t)y * w + x] = zf;
+                }
+        }
+        depth.assign((size_t)w * h, -1.0f);
+        pts.clear();
+        pix.clear();
+        for (int i = 0; i < w * h; ++i) {
+            const float val = zb[i];
+            if (!((double)val < z_far * 0.99)) continue;
+            depth[i] = val;
+            const int x = i % w, y = i / w;
+            const double sx = ((double)x - K4[2]) / K4[0], sy = ((double)y - K4[3]) / K4[1];
+            const double g[3] = {sx * (double)val, -(sy * (double)val), -(double)val};
+            std::array<float, 3> p;
+            for (int a = 0; a < 3; ++a) p[a] = (float)(((R[a * 3 + 0] * g[0] + R[a * 3 + 1] * g[1]) + R[a * 3 + 2] * g[2]) + t[a]);
+            pts.push_back(p);
+            pix.push_back(i);
+        }
+    }
+
     // retrieve_neighbor_pts_kdtree, mesh_rec_geometry.cpp:336-377
     void dilate(const std::vector<int>& in_voxel, std::set<long>& out_ids, std::vector<std::pair<int, std::array<double, 3>>>& smooth_out) const {
         const double accept = cfg.voxel_resolution * 1.25;

@@ -159,6 +159,18 @@ class OracleMesh:
         keys = ["n_vertices", "n_triangles", "frame_new_vertices", "frame_voxels_meshed", "frame_added", "frame_removed", "n_voxels", "n_activated"]
         return dict(zip(keys, (int(v) for v in o)))
 
+    def render_depth(self, intrinsics, width, height, z_near, z_far, cam_R, cam_t):
+        K = np.ascontiguousarray(intrinsics, dtype=np.float64)
+        R = np.ascontiguousarray(cam_R, dtype=np.float64).reshape(9)
+        t = np.ascontiguousarray(cam_t, dtype=np.float64)
+        depth = np.zeros((height, width), dtype=np.float32)
+        pts = np.zeros((height * width, 3), dtype=np.float32)
+        pix = np.zeros(height * width, dtype=np.int32)
+        self.L.orc_mesh_render_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.orc_mesh_render_depth.restype = C.c_long
+        n = self.L.orc_mesh_render_depth(self.h, _p(K), width, height, z_near, z_far, _p(R), _p(t), _p(depth), _p(pts), _p(pix))
+        return depth, pts[:n].copy(), pix[:n].copy()
+
     def smooth_all(self, smooth_factor=0.1, knn=20):
         out = np.zeros((self.counts()["n_vertices"], 3))
         self.L.orc_mesh_smooth_all.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p]

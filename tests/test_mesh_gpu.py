@@ -153,3 +153,30 @@ def test_offline_reconstruct_from_pointcloud(cuda_lib):
     for a, b in zip(g.snapshot(), o.snapshot()):
         assert np.array_equal(a, b)
     assert g.counts()["n_triangles"] > 5000
+
+
+def test_depth_rasterisation_of_the_mesh(cuda_lib):
+    """immesh_mesh_render_depth (the reference's depth view of the mesh, ImMesh_node.cpp:305-329 / openGL_camera_view.cpp:316-418, as a CUDA
+    rasteriser) against the oracle's rasteriser with the same sampling rule: depth image and unprojected points identical; and a
+    geometric sanity check -- every unprojected point lies on the mesh surface it was rendered from (within the local facet size)."""
+    from lio_common import init_velocity  # noqa: F401
+    from immesh_b200 import synth
+    g, o, _ = run_mesh_parity(cuda_lib, "avia", 4, seed=16)
+    sensor, scans = synth.make_stream("avia", 4, seed=16)
+    Rw, tw = scans[3]["R_true"], scans[3]["t_true"]
+    # Cam_view convention: world = R diag(1,-1,-1) p_cam + t with p_cam in the x-right / y-down / z-forward camera frame.  The sensor looks
+    # along body +x: camera z = body x, camera x = -body y, camera y = -body z.
+    body_from_cam = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
+    cam_R = Rw @ body_from_cam @ np.diag([1.0, -1.0, -1.0])
+    K = (300.0, 300.0, 319.5, 239.5)
+    dg, pg, xg = g.render_depth(K, 640, 480, 0.5, 100.0, cam_R, tw)
+    do, po, xo = o.render_depth(K, 640, 480, 0.5, 100.0, cam_R, tw)
+    assert np.array_equal(dg, do)
+    assert np.array_equal(xg, xo) and np.array_equal(pg, po)
+    valid = dg >= 0
+    assert valid.sum() > 20000 and dg[valid].min() > 0.5 and dg[valid].max() < 99.0
+    # unprojected points are close to mesh vertices (the facets are a few decimetres wide)
+    v = g.snapshot()[0]
+    idx, d2 = g.knn(pg[::50], 1)
+    dist = np.sqrt(d2[:, 0])
+    assert np.median(dist) < 0.3 and np.percentile(dist, 99) < 1.5
