@@ -52,6 +52,9 @@ __global__ void __launch_bounds__(RES_THREADS) k_residual(VoxelMapDev map, LioPa
     const ScanBuf sb = scan_load_dyn(sb_);
     const int n = sb.n;
     if (n <= 0) return;   // empty scan: no iteration runs (iters_run stays 0), as with an empty map
+    // the grid is sized for the largest scan (constant launch sequence); blocks without points leave at once and are not counted
+    const int nb_active = min((int)gridDim.x, (n + RES_THREADS - 1) / RES_THREADS);
+    if ((int)blockIdx.x >= nb_active) return;
     // stage rot/pos and the 6x6 pose block of the covariance (the only parts of the state this pass reads)
     for (int i = threadIdx.x; i < 24 + 6 * 18; i += blockDim.x) s_state[i] = ctrl->state[i];
     __syncthreads();
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_residual(VoxelMapDev map, LioPa
     __shared__ int s_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl->blocks_done[iter], 1) == (int)gridDim.x - 1) ? 1 : 0;
+    if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl->blocks_done[iter], 1) == nb_active - 1) ? 1 : 0;
     __syncthreads();
     if (s_last) {
         __shared__ SolveScratch S;
