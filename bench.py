@@ -29,6 +29,11 @@ import time
 
 import numpy as np
 
+# Seven CUDA streams per scan pipeline (localization + upload, mesh + 2 side + upload, front-end) next to torch's and NCCL's own:
+# with the default of 8 hardware work queues two of them can alias and serialise the localization and the mesh pipeline of a rank
+# (seen as one rank of eight running at the blocking-call rate).  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

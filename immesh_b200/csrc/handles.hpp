@@ -96,6 +96,8 @@ struct immesh_mesh {
     int use_graph = 1;
     int bps = 4;              // (mesh: 3 by default, see immesh_mesh_create) resident blocks per SM of the persistent per-voxel kernels (headroom for the other stream)
     int frame_counter = 0;
+    int dilate_bps = 3;       // resident blocks per SM of the dilation kernel
+    int warp_nmax = 96;       // largest dilated set triangulated by a single warp
     int n_sm = 148;
     size_t ccap = 0;
     double last_ms[4] = {0, 0, 0, 0};

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128) k_voxel_dilate(MeshDev M, MeshParams P, F
 }
 // stage B, small dilated sets: one warp per voxel (four independent voxels per block), voxels claimed dynamically
 #define IM_WARP_NMAX 96
-__global__ void __launch_bounds__(128) k_voxel_tri_warp(MeshDev M, MeshParams P, FrameBuf F_) {
+__global__ void __launch_bounds__(128) k_voxel_tri_warp(MeshDev M, MeshParams P, FrameBuf F_, int n_max) {
     const FrameBuf F = frame_load_dyn(F_);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(128) k_voxel_tri_warp(MeshDev M, MeshParams P,
         if (lane == 0) i = atomicAdd(&M.cnt[19], 1);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= nw) break;
-        voxel_mesh_warp<128>(M, P, F, work_slot(M, F, i), S, lane, 32, IM_WARP_NMAX);
+        voxel_mesh_warp<128>(M, P, F, work_slot(M, F, i), S, lane, 32, n_max);
         __syncwarp();
     }
 }
@@ -413,6 +413,12 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     immesh_mesh* h = new immesh_mesh();
     h->F.shard_rank = 0; h->F.shard_n = 1; h->F.x_cap = 0;
     h->bps = std::getenv("IMMESH_MESH_BPS") ? std::atoi(std::getenv("IMMESH_MESH_BPS")) : 3;
+    h->dilate_bps = std::getenv("IMMESH_DILATE_BPS") ? std::atoi(std::getenv("IMMESH_DILATE_BPS")) : h->bps;
+    // dilated sets up to warp_nmax vertices are triangulated by one warp each (side stream), larger ones by a thread block each
+    // (main stream, concurrently): the split balances the two kernels' longest serial insertion chains
+    h->warp_nmax = std::getenv("IMMESH_WARP_NMAX") ? std::atoi(std::getenv("IMMESH_WARP_NMAX")) : IM_WARP_NMAX;
+    if (h->warp_nmax < 3) h->warp_nmax = 3;
+    if (h->warp_nmax > 128) h->warp_nmax = 128;
     h->use_graph = std::getenv("IMMESH_GRAPH") ? std::atoi(std::getenv("IMMESH_GRAPH")) : 1;
     MeshParams& P = h->P;
     P.xi = cfg->points_minimum_scale;
@@ -818,7 +824,7 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         IM_LAUNCH(k_cand_place, g_cand, 128, 0, st, h->M, F);
         IM_LAUNCH(k_voxel_select, g_cand, 128, 0, st, h->M, F);
         if (timing) cudaEventRecord(h->ev[2], st);
-        IM_LAUNCH(k_voxel_dilate, h->n_sm * h->bps, 128, 0, st, h->M, P, F);
+        IM_LAUNCH(k_voxel_dilate, h->n_sm * h->dilate_bps, 128, 0, st, h->M, P, F);
         if (F.shard_n > 1 && h->win.ok) {   // smoothed positions of the other ranks' voxels, pushed into their windows
             IM_LAUNCH(k_xpush, h->n_sm, 256, 0, st, h->M, F, (const unsigned char*)h->d_seg1, 0, pe, h->d_xdone);
             IM_LAUNCH(k_apply_smooth, h->n_sm * 2, 256, 0, st, h->M, F, (const unsigned char*)h->d_recv1, h->seg1_bytes, pe);
@@ -832,11 +838,11 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         cudaEventRecord(h->ev_fork, st);
         cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
         cudaStreamWaitEvent(h->stream3, h->ev_fork, 0);
-        IM_LAUNCH(k_voxel_tri_warp, h->n_sm * h->bps, 128, 4 * sizeof(MeshWarpSmem<128>), h->stream2, h->M, P, F);
+        IM_LAUNCH(k_voxel_tri_warp, h->n_sm * h->bps, 128, 4 * sizeof(MeshWarpSmem<128>), h->stream2, h->M, P, F, h->warp_nmax);
         cudaEventRecord(h->ev_join, h->stream2);
         IM_LAUNCH(k_pull_vertices, h->n_sm * 8, 128, 0, h->stream3, h->M, P, F);   // incidence-list walk: only needs the dilation
         cudaEventRecord(h->ev_join3, h->stream3);
-        IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * h->bps, 128, sizeof(MeshSmem<256>), st, h->M, P, F, IM_WARP_NMAX, 1);
+        IM_LAUNCH((k_voxel_mesh<256>), h->n_sm * h->bps, 128, sizeof(MeshSmem<256>), st, h->M, P, F, h->warp_nmax, 1);
         cudaStreamWaitEvent(st, h->ev_join, 0);
         cudaStreamWaitEvent(st, h->ev_join3, 0);
         IM_LAUNCH((k_voxel_mesh<1024>), h->n_sm * 2, 128, sizeof(MeshSmem<1024>), st, h->M, P, F, 256, 0);
