@@ -211,7 +211,7 @@ struct immesh_voxelgrid {
     int max_points = 0, nblocks_max = 0, n_sm = 148;
     cudaStream_t stream = nullptr;
     float* d_in = nullptr;       // staging for host input / packed (calibrated) cloud of immesh_frontend_prepare: the current slot of
-    float* d_in_ring[4] = {nullptr, nullptr, nullptr, nullptr};   // a ring of 4 (a mesh frame may still be reading the cloud of 2-3 scans ago)
+    float* d_in_ring[8] = {};   // a ring of 8 (a mesh frame may still be reading the cloud of up to IM_SLOTS + 1 scans ago)
     int in_idx = 0;
     float* d_raw = nullptr;      // [max_points][4] strided input of immesh_frontend_prepare
     float* h_raw = nullptr;      // pinned staging for it
@@ -243,7 +243,7 @@ int immesh_voxelgrid_create(int max_points, immesh_voxelgrid_t** out) {
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
     IM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     const size_t n = (size_t)max_points;
-    for (int i = 0; i < 4; ++i) IM_CUDA(cudaMalloc((void**)&h->d_in_ring[i], n * 3 * sizeof(float)));
+    for (int i = 0; i < 8; ++i) IM_CUDA(cudaMalloc((void**)&h->d_in_ring[i], n * 3 * sizeof(float)));
     h->d_in = h->d_in_ring[0];
     IM_CUDA(cudaMalloc((void**)&h->d_out, n * 3 * sizeof(float)));
     IM_CUDA(cudaMalloc((void**)&h->d_raw, n * 4 * sizeof(float)));
@@ -267,7 +267,7 @@ int immesh_voxelgrid_create(int max_points, immesh_voxelgrid_t** out) {
 int immesh_voxelgrid_destroy(immesh_voxelgrid_t* h) {
     if (!h) return IMMESH_OK;
     cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < 4; ++i) cudaFree(h->d_in_ring[i]);
+    for (int i = 0; i < 8; ++i) cudaFree(h->d_in_ring[i]);
     cudaFree(h->d_out); cudaFree(h->d_raw); cudaFreeHost(h->h_raw);
     if (h->ev_raw) cudaEventDestroy(h->ev_raw);
     for (int i = 0; i < 2; ++i) { cudaFree(h->d_k[i]); cudaFree(h->d_v[i]); }
@@ -343,7 +343,7 @@ int immesh_voxelgrid_filter(immesh_voxelgrid_t* h, const float* xyz, int n, int 
 
 // upload (host input) + pack / calibrate into d_in on stream st
 static int frontend_pack(immesh_voxelgrid* h, const float* pts, int n, int stride, int on_device, int calib_laser, cudaStream_t st) {
-    h->in_idx = (h->in_idx + 1) & 3;
+    h->in_idx = (h->in_idx + 1) & 7;
     h->d_in = h->d_in_ring[h->in_idx];
     const float* d_src = pts;
     if (!on_device) {

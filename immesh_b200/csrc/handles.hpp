@@ -12,6 +12,11 @@
 using immesh::LioParams; using immesh::VoxelMapDev; using immesh::ScanBuf; using immesh::LioCtrl;
 using immesh::MeshParams; using immesh::MeshDev; using immesh::FrameBuf; using immesh::FramePose;
 
+// staging depth of the pipelined entry points: the host may queue this many scans / frames ahead of the device before it has to wait
+// (2 was enough for the device, but a host hiccup of ~1 ms then drained the pipeline: seen as single ranks of an 8-rank run falling
+// back to the blocking-call rate)
+#define IM_SLOTS 4
+
 struct immesh_lio {
     LioParams P;
     VoxelMapDev map;
@@ -23,11 +28,11 @@ struct immesh_lio {
     double* d_ptpl = nullptr;
     float* d_body_own = nullptr;  // scan buffers owned by the handle, 2 slots of max_scan*3 (sb.body points into them unless the caller passed a device pointer)
     cudaStream_t stream_up = nullptr;   // upload stream: the H2D copy of scan k+1 overlaps the kernels of scan k
-    cudaEvent_t ev_up[2] = {nullptr, nullptr};
-    float* h_body = nullptr;   // pinned staging, 2 slots
+    cudaEvent_t ev_up[IM_SLOTS] = {};
+    float* h_body = nullptr;   // pinned staging, IM_SLOTS slots
     double* h_state = nullptr; // pinned, 2 slots of (IM_STATE_DOUBLES + 64)
-    cudaEvent_t ev_slot[2] = {nullptr, nullptr};  // completion of the step that used staging slot s
-    int slot_busy[2] = {0, 0};
+    cudaEvent_t ev_slot[IM_SLOTS] = {};  // completion of the step that used staging slot s
+    int slot_busy[IM_SLOTS] = {};
     int step_counter = 0;
     immesh::ScanDyn* h_dyn = nullptr;   // pinned, 2 slots: per-scan inputs of the launch sequence (one H2D per scan)
     immesh::ScanDyn dyn_last = {};         // host copy of the block last uploaded
@@ -73,14 +78,14 @@ struct immesh_mesh {
     immesh::FrameDyn* d_dyn = nullptr;  // device copy read by every kernel of the frame (F.dyn)
     int timed_last = 0;
     double host_wait_ms = 0;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr};    // inputs of slot s ready (recorded on the producer stream)
-    cudaEvent_t ev_done[2] = {nullptr, nullptr};  // frame of slot s finished (mesh stream)
-    int inflight[2] = {0, 0};
+    cudaEvent_t ev_in[IM_SLOTS] = {};    // inputs of slot s ready (recorded on the producer stream)
+    cudaEvent_t ev_done[IM_SLOTS] = {};  // frame of slot s finished (mesh stream)
+    int inflight[IM_SLOTS] = {};
     cudaEvent_t ev_mark = nullptr, ev_sync = nullptr;  // pipeline timing mark (end) / cross-stream join
     cudaStream_t stream2 = nullptr;   // side stream: warp-level triangulation, concurrent with the block-level one
     cudaStream_t stream3 = nullptr;   // side stream: pull (incidence-list walk), concurrent with the triangulation
     cudaStream_t stream_up = nullptr; // upload stream: the H2D copy of frame k+1 overlaps the kernels of frame k
-    cudaEvent_t ev_up[2] = {nullptr, nullptr};
+    cudaEvent_t ev_up[IM_SLOTS] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
     int pending_rc = 0;
     void* nccl_comm = nullptr;        // ncclComm_t when the per-voxel stage is sharded over several GPUs

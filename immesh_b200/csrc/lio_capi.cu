@@ -503,7 +503,7 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
     IM_CREATE(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, im_stream_priority("IMMESH_LIO_PRIO")));
     for (auto& e : h->ev) IM_CREATE(cudaEventCreate(&e));
-    for (int i = 0; i < 2; ++i) IM_CREATE(cudaEventCreateWithFlags(&h->ev_slot[i], cudaEventDisableTiming));
+    for (int i = 0; i < IM_SLOTS; ++i) IM_CREATE(cudaEventCreateWithFlags(&h->ev_slot[i], cudaEventDisableTiming));
     IM_CREATE(cudaEventCreateWithFlags(&h->ev_pose, cudaEventDisableTiming));
     VoxelMapDev& m = h->map;
     IM_CREATE(dev_alloc(h, &m.keys, h->cap, 0xFF));
@@ -521,9 +521,9 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     ScanBuf& sb = h->sb;
     const size_t ms = (size_t)h->max_scan;
     float* d_body = nullptr;
-    IM_CREATE(dev_alloc(h, &d_body, 2 * ms * 3));
+    IM_CREATE(dev_alloc(h, &d_body, IM_SLOTS * ms * 3));
     IM_CREATE(cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) IM_CREATE(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
+    for (int i = 0; i < IM_SLOTS; ++i) IM_CREATE(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
     sb.body = d_body;
     h->d_body_own = d_body;
     IM_CREATE(dev_alloc(h, &sb.body_cov, ms * 6));
@@ -546,12 +546,12 @@ int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
     sb.n = 0;
     IM_CREATE(dev_alloc(h, &h->d_ctrl, 1, 0));
     sb.dyn = &h->d_ctrl->dyn;
-    IM_CREATE(cudaMallocHost((void**)&h->h_body, 2 * ms * 3 * sizeof(float)));
+    IM_CREATE(cudaMallocHost((void**)&h->h_body, IM_SLOTS * ms * 3 * sizeof(float)));
     IM_CREATE(cudaMallocHost((void**)&h->h_state, (IM_STATE_DOUBLES + 64) * sizeof(double)));
     IM_CREATE(cudaMallocHost((void**)&h->h_ints, 64 * sizeof(int)));
-    IM_CREATE(cudaMallocHost((void**)&h->h_dyn, 2 * sizeof(ScanDyn)));
-    IM_CREATE(cudaMallocHost((void**)&h->h_out, 2 * sizeof(LioOut)));
-    std::memset(h->h_out, 0, 2 * sizeof(LioOut));
+    IM_CREATE(cudaMallocHost((void**)&h->h_dyn, IM_SLOTS * sizeof(ScanDyn)));
+    IM_CREATE(cudaMallocHost((void**)&h->h_out, IM_SLOTS * sizeof(LioOut)));
+    std::memset(h->h_out, 0, IM_SLOTS * sizeof(LioOut));
     // StatesGroup(): identity rotation, cov = INIT_COV * I  (include/common_lib.h:201-211)
     std::memset(h->h_state, 0, IM_STATE_DOUBLES * sizeof(double));
     h->h_state[0] = h->h_state[4] = h->h_state[8] = 1.0;
@@ -577,11 +577,11 @@ int immesh_lio_destroy(immesh_lio_t* h) {
     if (h->h_out) cudaFreeHost(h->h_out);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->ev_pose) cudaEventDestroy(h->ev_pose);
-    for (int i = 0; i < 2; ++i) if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
+    for (int i = 0; i < IM_SLOTS; ++i) if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
     if (h->stream_up) cudaStreamDestroy(h->stream_up);
     if (h->ev_mark) cudaEventDestroy(h->ev_mark);
     if (h->stream) cudaStreamDestroy(h->stream);
-    for (int i = 0; i < 2; ++i) if (h->ev_slot[i]) cudaEventDestroy(h->ev_slot[i]);
+    for (int i = 0; i < IM_SLOTS; ++i) if (h->ev_slot[i]) cudaEventDestroy(h->ev_slot[i]);
     cudaGetLastError();
     delete h;
     return IMMESH_OK;
@@ -807,7 +807,7 @@ int immesh_voxelmap_update(immesh_lio_t* h) {
 // ONE cudaGraphLaunch (no node is touched) + ONE D2H of the LioOut block + one event.
 static int lio_enqueue(immesh_lio_t* h, const float* body, int n, int on_device, double dt, double cov_gyr, double cov_acc, bool allow_graph) {
     if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
-    const int s = (++h->step_counter) & 1;
+    const int s = (++h->step_counter) & (IM_SLOTS - 1);
     if (h->slot_busy[s]) {
         const auto t0 = std::chrono::steady_clock::now();
         IM_CUDA(cudaEventSynchronize(h->ev_slot[s]));
@@ -854,9 +854,9 @@ static int lio_enqueue(immesh_lio_t* h, const float* body, int n, int on_device,
 }
 static int lio_wait_impl(immesh_lio_t* h, double* state_out, int* iters_run, bool timings) {
     if (!h) return im_fail(IMMESH_E_INVALID, "null handle");
-    const int s = h->step_counter & 1;
+    const int s = h->step_counter & (IM_SLOTS - 1);
     IM_CUDA(cudaStreamSynchronize(h->stream));
-    h->slot_busy[0] = h->slot_busy[1] = 0;
+    for (int i = 0; i < IM_SLOTS; ++i) h->slot_busy[i] = 0;
     if (profiler().enabled) profiler().collect();
     const LioOut& o = h->h_out[s];
     if (state_out) std::memcpy(state_out, o.state, IM_STATE_DOUBLES * sizeof(double));
@@ -899,7 +899,7 @@ int immesh_lio_enqueue_memset(immesh_lio_t* h, void* d_buf, size_t bytes) {
 // work counters of the last step (roofline byte model): [n, touched root voxels are not kept, plane refits, points read by the refits]
 int immesh_lio_work_stats(immesh_lio_t* h, int64_t* out /*[4]*/) {
     if (!h || !out) return im_fail(IMMESH_E_INVALID, "null argument");
-    const LioOut& o = h->h_out[h->step_counter & 1];
+    const LioOut& o = h->h_out[h->step_counter & (IM_SLOTS - 1)];
     out[0] = h->last_n; out[1] = o.counters[5]; out[2] = o.counters[9]; out[3] = o.counters[10];
     return IMMESH_OK;
 }

@@ -477,10 +477,10 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     F.max_work = max_vox < (1 << 16) ? max_vox : (1 << 16);
     F.max_act = (int)std::min<size_t>((size_t)max_vox, mc);
     F.max_list = 4 << 20;
-    IM_CUDA(mdev_alloc(h, &h->d_pts, 2 * mc * 3));
+    IM_CUDA(mdev_alloc(h, &h->d_pts, IM_SLOTS * mc * 3));
     F.pts = h->d_pts;
-    IM_CUDA(mdev_alloc(h, &h->d_fp, 2));
-    for (int i = 0; i < 2; ++i) { IM_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming)); IM_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming)); }
+    IM_CUDA(mdev_alloc(h, &h->d_fp, IM_SLOTS));
+    for (int i = 0; i < IM_SLOTS; ++i) { IM_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming)); IM_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming)); }
     IM_CUDA(mdev_alloc(h, &F.cand_gkey, mc));
     IM_CUDA(mdev_alloc(h, &F.cand_vslot, mc));
     IM_CUDA(mdev_alloc(h, &F.cand_status, mc));
@@ -513,10 +513,10 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(mdev_alloc(h, &F.add_tri, (size_t)F.max_list * 3));
     IM_CUDA(mdev_alloc(h, &F.add_flip, (size_t)F.max_list));
     IM_CUDA(mdev_alloc(h, &F.rem_tri, (size_t)F.max_list));
-    IM_CUDA(cudaMallocHost((void**)&h->h_pts, 2 * mc * 3 * sizeof(float)));
-    IM_CUDA(cudaMallocHost((void**)&h->h_cnt, 2 * 32 * sizeof(int)));
-    IM_CUDA(cudaMallocHost((void**)&h->h_fp, 2 * sizeof(FramePose)));
-    IM_CUDA(cudaMallocHost((void**)&h->h_dyn, 2 * sizeof(FrameDyn)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_pts, IM_SLOTS * mc * 3 * sizeof(float)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_cnt, IM_SLOTS * 32 * sizeof(int)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_fp, IM_SLOTS * sizeof(FramePose)));
+    IM_CUDA(cudaMallocHost((void**)&h->h_dyn, IM_SLOTS * sizeof(FrameDyn)));
     IM_CUDA(mdev_alloc(h, &h->d_dyn, 1, 0));
     F.dyn = h->d_dyn;
     F.epoch = 0;
@@ -526,7 +526,7 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     IM_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
     IM_CUDA(cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
     IM_CUDA(cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) IM_CUDA(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
+    for (int i = 0; i < IM_SLOTS; ++i) IM_CUDA(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     IM_CUDA(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
@@ -547,13 +547,13 @@ int immesh_mesh_destroy(immesh_mesh_t* h) {
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     if (h->h_fp) cudaFreeHost(h->h_fp);
     if (h->h_dyn) cudaFreeHost(h->h_dyn);
-    for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
+    for (int i = 0; i < IM_SLOTS; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]); }
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->stream_up) cudaStreamDestroy(h->stream_up);
-    for (int i = 0; i < 2; ++i) if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
+    for (int i = 0; i < IM_SLOTS; ++i) if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_join3) cudaEventDestroy(h->ev_join3);
@@ -739,8 +739,8 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
     F.step = step;
     F.m = n > 0 ? (n + step - 1) / step : 0;
     F.frame = ++h->frame_counter;
-    const int s = F.frame & 1;
-    int rc = mesh_harvest(h, s);  // the frame two calls ago used this slot
+    const int s = F.frame & (IM_SLOTS - 1);
+    int rc = mesh_harvest(h, s);  // the frame IM_SLOTS calls ago used this slot
     (void)rc;
     const size_t slot_pts = (size_t)h->max_frame_points * 3;
     float* d_pts = h->d_pts + s * slot_pts;
@@ -773,7 +773,7 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
         // the body-frame scan does not depend on the localization: it is uploaded on the mesh stream right away
         d_body = xyz;
         if (src_mode == 2 && n > 0) {
-            if (!h->d_body) IM_CUDA(mdev_alloc(h, &h->d_body, 2 * slot_pts));
+            if (!h->d_body) IM_CUDA(mdev_alloc(h, &h->d_body, IM_SLOTS * slot_pts));
             const float* src = xyz;
             if (!mesh_host_ptr_is_pinned(xyz)) { std::memcpy(h_pts, xyz, (size_t)n * 3 * sizeof(float)); src = h_pts; }
             // upload stream: overlaps the kernels of the frame before (slot s was released by mesh_harvest above)
@@ -881,9 +881,7 @@ static int mesh_enqueue(immesh_mesh_t* h, const float* xyz, int n, const double*
 }
 // drain the queue; returns the status of the frames harvested since the last call
 static int mesh_wait_impl(immesh_mesh_t* h, bool timings) {
-    const int cur = h->frame_counter & 1;
-    mesh_harvest(h, cur ^ 1);
-    mesh_harvest(h, cur);
+    for (int i = 1; i <= IM_SLOTS; ++i) mesh_harvest(h, (h->frame_counter + i) & (IM_SLOTS - 1));   // oldest frame first: last_cnt ends as the newest frame's
     if (profiler().enabled) {
         cudaStreamSynchronize(h->stream);
         profiler().collect();
