@@ -405,12 +405,19 @@ static size_t pow2_at_least(size_t v) {
 
 extern "C" {
 
+int immesh_mesh_destroy(immesh_mesh_t* h);
 int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     if (!cfg || !out) return im_fail(IMMESH_E_INVALID, "null argument");
     if (!(cfg->points_minimum_scale > 0) || !(cfg->voxel_resolution > 0) || cfg->number_of_pts_append_to_map < 1) return im_fail(IMMESH_E_INVALID, "bad mesh configuration");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return im_fail(IMMESH_E_NO_DEVICE, "no CUDA device: immesh_b200 has no CPU path");
     immesh_mesh* h = new immesh_mesh();
+    // every failure below releases what has been created so far (immesh_mesh_destroy copes with a partially built handle)
+#define IM_CREATE_M(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t im_e_ = (expr);                                                         \
+        if (im_e_ != cudaSuccess) { immesh_mesh_destroy(h); return immesh::im_fail_cuda(im_e_, __FILE__, __LINE__); } \
+    } while (0)
     h->F.shard_rank = 0; h->F.shard_n = 1; h->F.x_cap = 0;
     h->bps = std::getenv("IMMESH_MESH_BPS") ? std::atoi(std::getenv("IMMESH_MESH_BPS")) : 3;
     h->dilate_bps = std::getenv("IMMESH_DILATE_BPS") ? std::atoi(std::getenv("IMMESH_DILATE_BPS")) : h->bps;
@@ -434,111 +441,113 @@ int immesh_mesh_create(const immesh_mesh_config* cfg, immesh_mesh_t** out) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
-    IM_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
-    for (auto& e : h->ev) IM_CUDA(cudaEventCreate(&e));
+    IM_CREATE_M(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
+    for (auto& e : h->ev) IM_CREATE_M(cudaEventCreate(&e));
     MeshDev& M = h->M;
     M.max_v = max_v;
     M.max_t = max_t;
-    IM_CUDA(mdev_alloc(h, &M.vpos, (size_t)max_v));
-    IM_CUDA(mdev_alloc(h, &M.vsmooth, (size_t)max_v * 3));
-    IM_CUDA(mdev_alloc(h, &M.v_tri_head, (size_t)max_v, 0xFF));
+    IM_CREATE_M(mdev_alloc(h, &M.vpos, (size_t)max_v));
+    IM_CREATE_M(mdev_alloc(h, &M.vsmooth, (size_t)max_v * 3));
+    IM_CREATE_M(mdev_alloc(h, &M.v_tri_head, (size_t)max_v, 0xFF));
     const size_t gcap = pow2_at_least((size_t)max_v * 2);
-    IM_CUDA(mdev_alloc(h, &M.gkeys, gcap, 0xFF));
-    IM_CUDA(mdev_alloc(h, &M.gval, gcap, 0xFF));
+    IM_CREATE_M(mdev_alloc(h, &M.gkeys, gcap, 0xFF));
+    IM_CREATE_M(mdev_alloc(h, &M.gval, gcap, 0xFF));
     M.gmask = (unsigned)(gcap - 1);
     const size_t vcap = pow2_at_least((size_t)max_vox * 2);
-    IM_CUDA(mdev_alloc(h, &M.vkeys, vcap, 0xFF));
+    IM_CREATE_M(mdev_alloc(h, &M.vkeys, vcap, 0xFF));
     M.vmask = (unsigned)(vcap - 1);
-    IM_CUDA(mdev_alloc(h, &M.vox_chunk, vcap * IM_VCHUNKS, 0xFF));
+    IM_CREATE_M(mdev_alloc(h, &M.vox_chunk, vcap * IM_VCHUNKS, 0xFF));
     M.max_vchunks = max_v / 4 + 1024;
-    IM_CUDA(mdev_alloc(h, &M.vchunk_pts, (size_t)M.max_vchunks * 16));
-    IM_CUDA(mdev_alloc(h, &M.vox_count, vcap, 0));
-    IM_CUDA(mdev_alloc(h, &M.vox_meshing_times, vcap, 0));
-    IM_CUDA(mdev_alloc(h, &M.vox_new_added, vcap, 0));
-    IM_CUDA(mdev_alloc(h, &M.vox_frame, vcap, 0xFF));
+    IM_CREATE_M(mdev_alloc(h, &M.vchunk_pts, (size_t)M.max_vchunks * 16));
+    IM_CREATE_M(mdev_alloc(h, &M.vox_count, vcap, 0));
+    IM_CREATE_M(mdev_alloc(h, &M.vox_meshing_times, vcap, 0));
+    IM_CREATE_M(mdev_alloc(h, &M.vox_new_added, vcap, 0));
+    IM_CREATE_M(mdev_alloc(h, &M.vox_frame, vcap, 0xFF));
     M.vox_short_axis = nullptr;
-    IM_CUDA(mdev_alloc(h, &M.tri, (size_t)max_t));
-    IM_CUDA(mdev_alloc(h, &M.tri_next, (size_t)max_t * 3));
-    IM_CUDA(mdev_alloc(h, &M.tri_flip, (size_t)max_t));
+    IM_CREATE_M(mdev_alloc(h, &M.tri, (size_t)max_t));
+    IM_CREATE_M(mdev_alloc(h, &M.tri_next, (size_t)max_t * 3));
+    IM_CREATE_M(mdev_alloc(h, &M.tri_flip, (size_t)max_t));
     const size_t tcap = pow2_at_least((size_t)max_t * 2);
-    IM_CUDA(mdev_alloc(h, &M.thash, tcap, 0xFF));
+    IM_CREATE_M(mdev_alloc(h, &M.thash, tcap, 0xFF));
     M.tmask = (unsigned)(tcap - 1);
-    IM_CUDA(mdev_alloc(h, &M.cnt, 64, 0));
+    IM_CREATE_M(mdev_alloc(h, &M.cnt, 64, 0));
     {
         int init[32];
         std::memset(init, 0, sizeof(init));
         init[11] = init[12] = init[13] = 0x7fffffff;
         init[14] = init[15] = init[16] = -0x7fffffff;
-        IM_CUDA(cudaMemcpy(M.cnt, init, sizeof(init), cudaMemcpyHostToDevice));
+        IM_CREATE_M(cudaMemcpy(M.cnt, init, sizeof(init), cudaMemcpyHostToDevice));
     }
     FrameBuf& F = h->F;
     const size_t mc = (size_t)h->max_frame_points;  // candidates <= points
     F.max_cand = (int)mc;
-    F.max_work = max_vox < (1 << 16) ? max_vox : (1 << 16);
+    F.max_work = max_vox < (1 << 16) ? max_vox : std::min(std::max(max_vox / 16, 1 << 16), 1 << 18);   // voxels (re)meshed per frame; 4 KB of id list each
     F.max_act = (int)std::min<size_t>((size_t)max_vox, mc);
     F.max_list = 4 << 20;
-    IM_CUDA(mdev_alloc(h, &h->d_pts, IM_SLOTS * mc * 3));
+    IM_CREATE_M(mdev_alloc(h, &h->d_pts, IM_SLOTS * mc * 3));
+    IM_CREATE_M(mdev_alloc(h, &h->d_body, IM_SLOTS * mc * 3));   // staging of body-frame scans handed over by the localization handle (not allocated lazily: a cudaMalloc inside a frame stalls the pipeline)
     F.pts = h->d_pts;
-    IM_CUDA(mdev_alloc(h, &h->d_fp, IM_SLOTS));
-    for (int i = 0; i < IM_SLOTS; ++i) { IM_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming)); IM_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming)); }
-    IM_CUDA(mdev_alloc(h, &F.cand_gkey, mc));
-    IM_CUDA(mdev_alloc(h, &F.cand_vslot, mc));
-    IM_CUDA(mdev_alloc(h, &F.cand_status, mc));
-    IM_CUDA(mdev_alloc(h, &F.cand_scan, mc));
-    IM_CUDA(mdev_alloc(h, &F.cand_conf, mc * IM_CONF_K));
-    IM_CUDA(mdev_alloc(h, &F.cand_nconf, mc));
-    IM_CUDA(mdev_alloc(h, &F.cand_next, mc));
-    IM_CUDA(mdev_alloc(h, &F.cand_pos, mc));
+    IM_CREATE_M(mdev_alloc(h, &h->d_fp, IM_SLOTS));
+    for (int i = 0; i < IM_SLOTS; ++i) { IM_CREATE_M(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming)); IM_CREATE_M(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming)); }
+    IM_CREATE_M(mdev_alloc(h, &F.cand_gkey, mc));
+    IM_CREATE_M(mdev_alloc(h, &F.cand_vslot, mc));
+    IM_CREATE_M(mdev_alloc(h, &F.cand_status, mc));
+    IM_CREATE_M(mdev_alloc(h, &F.cand_scan, mc));
+    IM_CREATE_M(mdev_alloc(h, &F.cand_conf, mc * IM_CONF_K));
+    IM_CREATE_M(mdev_alloc(h, &F.cand_nconf, mc));
+    IM_CREATE_M(mdev_alloc(h, &F.cand_next, mc));
+    IM_CREATE_M(mdev_alloc(h, &F.cand_pos, mc));
     h->ccap = pow2_at_least(mc * 2);
-    IM_CUDA(mdev_alloc(h, &F.ckeys, h->ccap));
-    IM_CUDA(mdev_alloc(h, &F.chead, h->ccap));
+    IM_CREATE_M(mdev_alloc(h, &F.ckeys, h->ccap));
+    IM_CREATE_M(mdev_alloc(h, &F.chead, h->ccap));
     F.scan_block = nullptr;
-    IM_CUDA(mdev_alloc(h, &F.act, (size_t)F.max_act));
-    IM_CUDA(mdev_alloc(h, &F.work, (size_t)F.max_work));
-    IM_CUDA(mdev_alloc(h, &F.work_n_ids, (size_t)F.max_work));
-    IM_CUDA(mdev_alloc(h, &F.work_ids, (size_t)F.max_work * IM_MAXD));
-    IM_CUDA(mdev_alloc(h, &F.work_nfaces, (size_t)F.max_work));
-    IM_CUDA(mdev_alloc(h, &F.work_bits, (size_t)F.max_work * (IM_MAXG / 32), 0));
-    IM_CUDA(mdev_alloc(h, &F.work_ring, (size_t)F.max_work, 0));
-    IM_CUDA(mdev_alloc(h, &F.work_done, (size_t)F.max_work, 0));
+    IM_CREATE_M(mdev_alloc(h, &F.act, (size_t)F.max_act));
+    IM_CREATE_M(mdev_alloc(h, &F.work, (size_t)F.max_work));
+    IM_CREATE_M(mdev_alloc(h, &F.work_n_ids, (size_t)F.max_work));
+    IM_CREATE_M(mdev_alloc(h, &F.work_ids, (size_t)F.max_work * IM_MAXD));
+    IM_CREATE_M(mdev_alloc(h, &F.work_nfaces, (size_t)F.max_work));
+    IM_CREATE_M(mdev_alloc(h, &F.work_bits, (size_t)F.max_work * (IM_MAXG / 32), 0));
+    IM_CREATE_M(mdev_alloc(h, &F.work_ring, (size_t)F.max_work, 0));
+    IM_CREATE_M(mdev_alloc(h, &F.work_done, (size_t)F.max_work, 0));
     F.max_ditem = F.max_work * 4;
-    IM_CUDA(mdev_alloc(h, &F.ditem, (size_t)F.max_ditem));
+    IM_CREATE_M(mdev_alloc(h, &F.ditem, (size_t)F.max_ditem));
     F.max_vref = 8 << 20;
-    IM_CUDA(mdev_alloc(h, &F.all_faces, (size_t)F.max_list));
-    IM_CUDA(mdev_alloc(h, &F.all_vref, (size_t)F.max_vref));
-    IM_CUDA(mdev_alloc(h, &F.pulled, (size_t)F.max_list * 2));
+    IM_CREATE_M(mdev_alloc(h, &F.all_faces, (size_t)F.max_list));
+    IM_CREATE_M(mdev_alloc(h, &F.all_vref, (size_t)F.max_vref));
+    IM_CREATE_M(mdev_alloc(h, &F.pulled, (size_t)F.max_list * 2));
     F.fset_mask = (1u << 21) - 1;
-    IM_CUDA(mdev_alloc(h, &F.fset, (size_t)F.fset_mask + 1, 0xFF));
-    IM_CUDA(mdev_alloc(h, &F.work_axes, (size_t)F.max_work * 9));
-    IM_CUDA(mdev_alloc(h, &F.add_tri, (size_t)F.max_list * 3));
-    IM_CUDA(mdev_alloc(h, &F.add_flip, (size_t)F.max_list));
-    IM_CUDA(mdev_alloc(h, &F.rem_tri, (size_t)F.max_list));
-    IM_CUDA(cudaMallocHost((void**)&h->h_pts, IM_SLOTS * mc * 3 * sizeof(float)));
-    IM_CUDA(cudaMallocHost((void**)&h->h_cnt, IM_SLOTS * 32 * sizeof(int)));
-    IM_CUDA(cudaMallocHost((void**)&h->h_fp, IM_SLOTS * sizeof(FramePose)));
-    IM_CUDA(cudaMallocHost((void**)&h->h_dyn, IM_SLOTS * sizeof(FrameDyn)));
-    IM_CUDA(mdev_alloc(h, &h->d_dyn, 1, 0));
+    IM_CREATE_M(mdev_alloc(h, &F.fset, (size_t)F.fset_mask + 1, 0xFF));
+    IM_CREATE_M(mdev_alloc(h, &F.work_axes, (size_t)F.max_work * 9));
+    IM_CREATE_M(mdev_alloc(h, &F.add_tri, (size_t)F.max_list * 3));
+    IM_CREATE_M(mdev_alloc(h, &F.add_flip, (size_t)F.max_list));
+    IM_CREATE_M(mdev_alloc(h, &F.rem_tri, (size_t)F.max_list));
+    IM_CREATE_M(cudaMallocHost((void**)&h->h_pts, IM_SLOTS * mc * 3 * sizeof(float)));
+    IM_CREATE_M(cudaMallocHost((void**)&h->h_cnt, IM_SLOTS * 32 * sizeof(int)));
+    IM_CREATE_M(cudaMallocHost((void**)&h->h_fp, IM_SLOTS * sizeof(FramePose)));
+    IM_CREATE_M(cudaMallocHost((void**)&h->h_dyn, IM_SLOTS * sizeof(FrameDyn)));
+    IM_CREATE_M(mdev_alloc(h, &h->d_dyn, 1, 0));
     F.dyn = h->d_dyn;
     F.epoch = 0;
-    IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<1024>)));
-    IM_CUDA(cudaFuncSetAttribute(k_voxel_tri_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(MeshWarpSmem<128>))));
-    IM_CUDA(cudaFuncSetAttribute(k_voxel_mesh<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<256>)));
-    IM_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
-    IM_CUDA(cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
-    IM_CUDA(cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
-    for (int i = 0; i < IM_SLOTS; ++i) IM_CUDA(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
-    IM_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    IM_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-    IM_CUDA(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
+    IM_CREATE_M(cudaFuncSetAttribute(k_voxel_mesh<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<1024>)));
+    IM_CREATE_M(cudaFuncSetAttribute(k_voxel_tri_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(MeshWarpSmem<128>))));
+    IM_CREATE_M(cudaFuncSetAttribute(k_voxel_mesh<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem<256>)));
+    IM_CREATE_M(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
+    IM_CREATE_M(cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, im_stream_priority("IMMESH_MESH_PRIO")));
+    IM_CREATE_M(cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking));
+    for (int i = 0; i < IM_SLOTS; ++i) IM_CREATE_M(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
+    IM_CREATE_M(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    IM_CREATE_M(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    IM_CREATE_M(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
     std::memset(h->last_cnt, 0, sizeof(h->last_cnt));
-    IM_CUDA(cudaDeviceSynchronize());
+    IM_CREATE_M(cudaDeviceSynchronize());
+#undef IM_CREATE_M
     *out = h;
     return IMMESH_OK;
 }
 
 int immesh_mesh_destroy(immesh_mesh_t* h) {
     if (!h) return IMMESH_OK;
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     h->graph.destroy();
     if (h->win.local) immesh::peer_window_close(h->win);
     if (h->nccl_comm && immesh::nccl().CommDestroy) immesh::nccl().CommDestroy(h->nccl_comm);
