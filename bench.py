@@ -259,14 +259,19 @@ def cpu_baseline_block(wl, scans, n_warm, n_timed, what):
 
 # --------------------------------------------------------------------------------------------- GPU arm
 def algorithmic_bytes(kernel, info):
-    """Compulsory bytes per launch of `kernel` from the work counters of the profiled scans."""
+    """Compulsory bytes PER SCAN of `kernel` from the work counters of the profiled scans; the caller divides
+    by the kernel's launches per scan."""
     n = info["n_ds"]
     if kernel == "k_residual":
-        # 12 B body xyz + 16 B hash slot (key + root index) per point, 240 B per distinct matched plane record, 232 B out
-        return 28.0 * n + 240.0 * info["planes_unique"] + 232.0
+        # per IESKF iteration (= per launch): 12 B body xyz + 16 B hash slot (key + root index) per point, 240 B per distinct matched
+        # plane record, 232 B out; times the iterations run per scan
+        return (28.0 * n + 240.0 * info["planes_unique"] + 232.0) * info.get("launches", {}).get("k_residual", 1.0)
     if kernel == "k_grow_voxel":
         # SURVEY 8d: 12 N + 16 N + sum over dirty nodes (96 B per stored point read by the refit + 456 B plane record written)
         return 28.0 * n + 96.0 * info["refit_points"] + 456.0 * info["refits"]
+    if kernel == "k_grow_simple":
+        # append-only voxels: 28 B in per point, 96 B point record + 480 B of moments read-modify-written
+        return n * (28.0 + 96.0 + 2 * 480.0)
     if kernel == "k_voxel_dilate":
         # float4 per gathered kNN candidate, 27 voxel-hash probes (16 B) per voxel, smoothed position write per query, ids out
         return 16.0 * info["gathered"] + 27 * 16.0 * info["voxels_meshed"] + 24.0 * info["queries"] + 4.0 * info["dilated"]
@@ -607,11 +612,12 @@ def run_gpu(args, rank, world):
         k += 1
     api.profile_enable(False, lib)
     prof = api.profile_report(lib)
-    for key in info:
+    for key in list(info):
         info[key] /= n_prof            # per scan
     kern_ms = {name: ms / n_prof for name, (ms, cnt) in prof.items()}              # per scan
     kern_launch_ms = {name: ms / cnt for name, (ms, cnt) in prof.items() if cnt}
     kern_launches_per_scan = {name: cnt / n_prof for name, (ms, cnt) in prof.items()}
+    info["launches"] = kern_launches_per_scan
     dominant = max(kern_ms, key=kern_ms.get)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -684,7 +690,7 @@ def run_gpu(args, rank, world):
                      "mesh_append": round(float(np.mean([s[1][1] for s in stage])), 4), "mesh_voxels": round(float(np.mean([s[1][2] for s in stage])), 4),
                      "mesh_push": round(float(np.mean([s[1][3] for s in stage])), 4)},
         "kernel_ms_per_scan": {k2: round(v, 5) for k2, v in sorted(kern_ms.items(), key=lambda kv: -kv[1])},
-        "work_per_scan": {k2: round(v, 1) for k2, v in info.items()},
+        "work_per_scan": {k2: round(v, 1) for k2, v in info.items() if k2 != "launches"},
         "roofline": roof,
         "roofline_top_kernels": roof_all,
         "roofline_whole_step": {"algorithmic_bytes_per_scan": round(step_bytes), "achieved_gbs": round(step_bytes / (total_ms / K * 1e-3) / 1e9, 3),
