@@ -266,6 +266,12 @@ def algorithmic_bytes(kernel, info):
         # per IESKF iteration (= per launch): 12 B body xyz + 16 B hash slot (key + root index) per point, 240 B per distinct matched
         # plane record, 232 B out; times the iterations run per scan
         return (28.0 * n + 240.0 * info["planes_unique"] + 232.0) * info.get("launches", {}).get("k_residual", 1.0)
+    if kernel == "k_match":
+        # per IESKF iteration: 12 B body xyz + 16 B hash slot per point, 240 B per distinct matched plane record, 8 B match out
+        return (36.0 * n + 240.0 * info["planes_unique"]) * info.get("launches", {}).get("k_match", 1.0)
+    if kernel == "k_terms":
+        # per IESKF iteration: 12 B body xyz + 8 B match per point, 240 B per distinct matched plane record, 232 B of sums out
+        return (20.0 * n + 240.0 * info["planes_unique"] + 232.0) * info.get("launches", {}).get("k_terms", 1.0)
     if kernel == "k_grow_voxel":
         # 12 N + 16 N + sum over dirty nodes (96 B per stored point read by the refit + 456 B plane record written)
         return 28.0 * n + 96.0 * info["refit_points"] + 456.0 * info["refits"]

@@ -18,6 +18,21 @@
 #define IM_HDN
 #endif
 
+// Latency budget of a kernel, measured in place (debug variant of the library only: tools/debug/build_stamps.sh, -DIM_DEBUG_STAMPS):
+// thread 0 of block 0 -- for the IESKF update, thread 0 of whichever block runs it -- stores clock64 at phase boundaries; `dep` is a value
+// the phase before produced, so that the stamp is not taken before that value exists.  Empty in the product build and on the host.
+#if defined(IM_DEBUG_STAMPS) && defined(__CUDACC__)
+namespace immesh { static __device__ long long g_stamps[64]; }
+#endif
+#if defined(IM_DEBUG_STAMPS) && defined(__CUDA_ARCH__)
+__device__ __forceinline__ void immesh_stamp_store(int k, long long v) { immesh::g_stamps[k] = v; }
+#define IM_STAMP_IF(cond, k, dep) do { if ((cond) && (long long)(dep) != 0x7ffffffffffffLL) immesh::g_stamps[k] = clock64(); } while (0)
+#define IM_STAMP(k, dep) IM_STAMP_IF(blockIdx.x == 0 && threadIdx.x == 0, k, dep)
+#else
+#define IM_STAMP_IF(cond, k, dep) do { } while (0)
+#define IM_STAMP(k, dep) do { } while (0)
+#endif
+
 namespace immesh {
 
 // ------------------------------------------------------------------ deterministic libm subset

@@ -42,32 +42,91 @@ __global__ void k_reset_scan(ScanBuf sb, LioCtrl* ctrl, int copy_prop) {
     }
 }
 
-// K2+K3: one thread per scan point; the block's 30 fixed-point sums are reduced with warp shuffles
-// (integer adds: exact, order-free) and folded into the iteration's global accumulators with 60 atomics.
+// K2+K3.  Default (one GPU): two kernels per IESKF iteration.
+//   k_match : 8 lanes per scan point.  The walk over a root voxel's octree (build_single_residual visits EVERY plane below the root,
+//             up to 1 + 8 + 64 for max_layer 2, each a dependent chain of ~150 double operations behind a record load) is split by
+//             first-level child over the 8 lanes and merged with three shuffles, in the serial walk's order (match_in_voxel_lane).
+//   k_terms : one thread per scan point: the 29 fixed-point normal-equation terms of the matched points; the block's sums are reduced
+//             with warp shuffles (integer adds: exact, order-free) and folded into the iteration's global accumulators with 60
+//             atomics; the last block to finish runs the 6x6 IESKF update (ieskf_solve).
+// k_residual is the two steps in one thread per point (used by immesh_lio_residual_build; IMMESH_LIO_SPLIT=0 selects it everywhere).
 #define RES_THREADS 128
-__global__ void __launch_bounds__(RES_THREADS) k_residual(VoxelMapDev map, LioParams P, ScanBuf sb_, LioCtrl* ctrl, int iter, int fused_solve) {
+#define MATCH_THREADS 128
+#define MATCH_LANES 8
+struct MatchCombine8 {
+    unsigned int mask;   // the 8 lanes of this point inside the warp; 0: one lane per point
+    __device__ void operator()(bool* ok, MatchResult* best) const {
+        if (mask == 0u) return;   // one lane per point: nothing to merge
+        const int lane = threadIdx.x & 31;
+        *ok = (__ballot_sync(mask, *ok) & mask) != 0u;
+        double prob = best->prob;
+        int src = lane;
+#pragma unroll
+        for (int o = MATCH_LANES / 2; o > 0; o >>= 1) {
+            const double op = __shfl_xor_sync(mask, prob, o);
+            const int os = __shfl_xor_sync(mask, src, o);
+            if (op > prob || (op == prob && os < src)) { prob = op; src = os; }   // first lane, in lane order, holding the largest probability
+        }
+        best->node = __shfl_sync(mask, best->node, src);
+        best->layer = __shfl_sync(mask, best->layer, src);
+        best->prob = prob;
+    }
+};
+__global__ void __launch_bounds__(MATCH_THREADS, 8) k_match(VoxelMapDev map, LioParams P, ScanBuf sb_, LioCtrl* ctrl) {
+    __shared__ double s_state[24 + 6 * 18];
+    IM_STAMP(0, 0);
+    // the stop flag, the scan's device-resident description and the state are loaded together (one trip to L2 instead of three)
+    const int stop = ctrl->stop;
+    const ScanBuf sb = scan_load_dyn(sb_);
+    for (int i = threadIdx.x; i < 24 + 6 * 18; i += blockDim.x) s_state[i] = ctrl->state[i];
+    const int n = sb.n;
+    if (stop || n <= 0) return;
+    IM_STAMP(1, n);
+    // 8 lanes per point while the scan fits the machine about twice over (the grid is one resident wave); beyond that every SM has
+    // more than enough points to hide the walk's latency and the lanes would only multiply the instruction count: one thread per point
+    const long long threads = (long long)gridDim.x * blockDim.x;
+    const int lanes = ((long long)n * MATCH_LANES <= 2 * threads) ? MATCH_LANES : 1;
+    const int per_block = MATCH_THREADS / lanes;
+    if ((long long)blockIdx.x * per_block >= n) return;   // block-uniform; the grid is sized for the machine, not for the scan
+    __syncthreads();
+    IM_STAMP(2, 0);
+    const int sub = threadIdx.x & (lanes - 1);
+    MatchCombine8 comb;
+    comb.mask = (lanes == 1) ? 0u : 0xFFu << ((threadIdx.x & 31) & ~(MATCH_LANES - 1));
+    for (int i = blockIdx.x * per_block + (threadIdx.x / lanes); i < n; i += gridDim.x * per_block)
+        residual_match_lanes(map, P, sb, s_state, i, sub, lanes, comb);
+    IM_STAMP(7, 0);
+}
+
+template <bool MATCHED>
+__device__ __forceinline__ void residual_block(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb_, LioCtrl* ctrl, int iter, int fused_solve) {
     __shared__ double s_state[24 + 6 * 18];
     __shared__ long long s_part[RES_THREADS / 32][IM_NTERMS];
-    if (ctrl->stop) return;
+    IM_STAMP(10, 0);
+    // the stop flag, the scan's device-resident description and the state -- rot/pos and the 6x6 pose block of the covariance, the only
+    // parts this pass reads -- are loaded together (one trip to L2 instead of three)
+    const int stop = ctrl->stop;
     const ScanBuf sb = scan_load_dyn(sb_);
+    for (int i = threadIdx.x; i < 24 + 6 * 18; i += blockDim.x) s_state[i] = ctrl->state[i];
     const int n = sb.n;
-    if (n <= 0) return;   // empty scan: no iteration runs (iters_run stays 0), as with an empty map
+    if (stop || n <= 0) return;   // empty scan: no iteration runs (iters_run stays 0), as with an empty map
     // the grid is sized for the largest scan (constant launch sequence); blocks without points leave at once and are not counted
     const int nb_active = min((int)gridDim.x, (n + RES_THREADS - 1) / RES_THREADS);
     if ((int)blockIdx.x >= nb_active) return;
-    // stage rot/pos and the 6x6 pose block of the covariance (the only parts of the state this pass reads)
-    for (int i = threadIdx.x; i < 24 + 6 * 18; i += blockDim.x) s_state[i] = ctrl->state[i];
     __syncthreads();
+    IM_STAMP(11, 0);
     long long acc[IM_NTERMS];
 #pragma unroll
     for (int k = 0; k < IM_NTERMS; ++k) acc[k] = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         long long t[IM_NTERMS];
-        if (residual_point(map, P, sb, s_state, i, t, map.err)) {
+        const bool hit = MATCHED ? residual_point_matched(map, P, sb, s_state, i, t, map.err) : residual_point(map, P, sb, s_state, i, t, map.err);
+        if (hit) {
 #pragma unroll
             for (int k = 0; k < IM_NTERMS; ++k) acc[k] += t[k];
         }
     }
+    IM_STAMP(12, acc[0] + acc[27]);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < IM_NTERMS - 1; ++k) {
@@ -85,6 +144,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_residual(VoxelMapDev map, LioPa
             atomicAdd(&ctrl->acc[iter][2 * threadIdx.x + 1], (unsigned long long)(v & 0xffffffffLL));
         }
     }
+    IM_STAMP(13, 0);
     if (!fused_solve) return;
     // the last block to publish its sums runs the IESKF update of this iteration (6x6 form, lio_core.cuh: ieskf_solve)
     __shared__ int s_last;
@@ -92,11 +152,18 @@ __global__ void __launch_bounds__(RES_THREADS) k_residual(VoxelMapDev map, LioPa
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl->blocks_done[iter], 1) == nb_active - 1) ? 1 : 0;
     __syncthreads();
+    IM_STAMP(14, s_last);
     if (s_last) {
         __shared__ SolveScratch S;
         __threadfence();
         ieskf_solve(P, ctrl, iter, &S, threadIdx.x, blockDim.x);
     }
+}
+__global__ void __launch_bounds__(RES_THREADS) k_residual(VoxelMapDev map, LioParams P, ScanBuf sb_, LioCtrl* ctrl, int iter, int fused_solve) {
+    residual_block<false>(map, P, sb_, ctrl, iter, fused_solve);
+}
+__global__ void __launch_bounds__(RES_THREADS) k_terms(VoxelMapDev map, LioParams P, ScanBuf sb_, LioCtrl* ctrl, int iter, int fused_solve) {
+    residual_block<true>(map, P, sb_, ctrl, iter, fused_solve);
 }
 
 // sharded VoxelMap: pass 1 (match where this rank owns the voxel, publish bits) and pass 2 (terms + integer reduction)
@@ -470,6 +537,12 @@ static int grid_fixed(const immesh_lio* h, int threads, int max_waves = 8) {
     return (int)g;
 }
 
+#if defined(IM_DEBUG_STAMPS)
+extern "C" int immesh_debug_stamps(long long* out64) {   // debug variant only (tools/debug/build_stamps.sh); not declared in include/
+    return cudaMemcpyFromSymbol(out64, immesh::g_stamps, 64 * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 extern "C" {
 
 int immesh_lio_create(const immesh_lio_config* cfg, immesh_lio_t** out) {
@@ -751,7 +824,16 @@ static int launch_estimate(immesh_lio* h) {
         }
         return IMMESH_OK;
     }
-    for (int it = 0; it < h->P.max_iter; ++it) IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, 1);
+    static const int split = std::getenv("IMMESH_LIO_SPLIT") ? std::atoi(std::getenv("IMMESH_LIO_SPLIT")) : 1;
+    if (!split) {
+        for (int it = 0; it < h->P.max_iter; ++it) IM_LAUNCH(k_residual, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, 1);
+        return IMMESH_OK;
+    }
+    const int gm = h->n_sm * 8;   // one resident wave of k_match blocks (__launch_bounds__(128, 8)); k_match picks the lanes per point from n
+    for (int it = 0; it < h->P.max_iter; ++it) {
+        IM_LAUNCH(k_match, gm, MATCH_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl);
+        IM_LAUNCH(k_terms, g, RES_THREADS, 0, h->stream, h->map, h->P, h->sb, h->d_ctrl, it, 1);
+    }
     return IMMESH_OK;
 }
 

@@ -212,6 +212,28 @@ IM_HDN inline bool residual_point(const VoxelMapDev& map, const LioParams& P, co
     return residual_terms(map, P, sb, state, i, mr.node, pwd, terms, err);
 }
 
+// The same in two steps (one GPU, k_match + k_terms): the match with each root voxel's walk split over nl lanes (8 or 1), then the terms of
+// the matched points.  match_point_lanes returns what match_point returns (voxelmap.cuh), the second step repeats residual_point's tail.
+template <class Combine>
+IM_HDN inline void residual_match_lanes(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, int lane, int nl, Combine combine) {
+    double pwd[3], pw[3], var6[6];
+    residual_world(P, sb, state, i, pwd, pw, var6);
+    IM_STAMP(3, __double_as_longlong(var6[5] + pw[2]));
+    const MatchResult mr = match_point_lanes(map, P, pw, var6, lane, nl, combine);
+    if (lane == 0) {
+        sb.match_node[i] = mr.node;
+        sb.match_layer[i] = mr.layer;
+    }
+}
+IM_HDN inline bool residual_point_matched(const VoxelMapDev& map, const LioParams& P, const ScanBuf& sb, const double* state, int i, long long* terms, int* err) {
+    const int node = sb.match_node[i];
+    if (node < 0) return false;
+    const double pb[3] = {(double)sb.body[i * 3 + 0], (double)sb.body[i * 3 + 1], (double)sb.body[i * 3 + 2]};
+    double pwd[3];
+    body_to_world(P, state, state + 9, pb, pwd);
+    return residual_terms(map, P, sb, state, i, node, pwd, terms, err);
+}
+
 // ------------------------------------------------------------------ sharded VoxelMap (multi-GPU): split residual pass
 // The scan is replicated, root voxels are owned by voxel_owner(key).  Pass 1: the owner of a point's root voxel matches it
 // there and publishes two bits (root voxel exists / matched there); the owner of the point's retry neighbour voxel
@@ -326,27 +348,55 @@ struct SolveScratch {
     int flags[2];
 };
 
-// 6x6 partial-pivot LU (one thread) + substitution (one thread per column); same operation order as orc::lu_inverse<6>
-IM_HDN inline void lu_factor6(double* a, int* piv) {
-    for (int i = 0; i < 6; ++i) piv[i] = i;
-    for (int k = 0; k < 6; ++k) {
-        int best = k;
-        double bv = fabs(a[k * 6 + k]);
-        for (int i = k + 1; i < 6; ++i) {
-            const double v = fabs(a[i * 6 + k]);
-            if (v > bv) { bv = v; best = i; }
-        }
-        if (best != k) {
-            for (int j = 0; j < 6; ++j) { const double tv = a[k * 6 + j]; a[k * 6 + j] = a[best * 6 + j]; a[best * 6 + j] = tv; }
-            const int tp = piv[k]; piv[k] = piv[best]; piv[best] = tp;
-        }
-        const double pivv = a[k * 6 + k];
-        for (int i = k + 1; i < 6; ++i) a[i * 6 + k] = a[i * 6 + k] / pivv;
-        for (int i = k + 1; i < 6; ++i) {
-            const double lik = a[i * 6 + k];
-            for (int j = k + 1; j < 6; ++j) a[i * 6 + j] = a[i * 6 + j] - lik * a[k * 6 + j];
-        }
+// 6x6 partial-pivot LU (one thread) + substitution (one thread per column); same operation order as orc::lu_inverse<6>.
+// The factorisation runs on a register copy, every loop unrolled through the step template (a row exchange is a chain of selects, no
+// indexed access -- plain `#pragma unroll` loops with a conditional swap left the copy in local memory):
+// through shared memory, as first written, the one thread's dependent load/store chain took 7.8 k cycles (4 us) per IESKF update
+// (profiles/stamps_r02s_*.txt), a quarter of the whole iteration.
+template <int K>
+IM_HD void lu_step6(double (&a)[36], int (&piv)[6]) {
+    int best = K;
+    double bv = fabs(a[K * 6 + K]);
+#pragma unroll
+    for (int i = K + 1; i < 6; ++i) {
+        const double v = fabs(a[i * 6 + K]);
+        if (v > bv) { bv = v; best = i; }
     }
+#pragma unroll
+    for (int i = K + 1; i < 6; ++i) {   // exchange rows K and `best`
+        const bool sw = (best == i);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const double x = a[K * 6 + j], y = a[i * 6 + j];
+            a[K * 6 + j] = sw ? y : x;
+            a[i * 6 + j] = sw ? x : y;
+        }
+        const int p = piv[K], q = piv[i];
+        piv[K] = sw ? q : p;
+        piv[i] = sw ? p : q;
+    }
+    const double pivv = a[K * 6 + K];
+#pragma unroll
+    for (int i = K + 1; i < 6; ++i) a[i * 6 + K] = a[i * 6 + K] / pivv;
+#pragma unroll
+    for (int i = K + 1; i < 6; ++i) {
+        const double lik = a[i * 6 + K];
+#pragma unroll
+        for (int j = K + 1; j < 6; ++j) a[i * 6 + j] = a[i * 6 + j] - lik * a[K * 6 + j];
+    }
+}
+IM_HDN inline void lu_factor6(double* a_io, int* piv_io) {
+    double a[36];
+    int piv[6];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) a[i] = a_io[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) piv[i] = i;
+    lu_step6<0>(a, piv); lu_step6<1>(a, piv); lu_step6<2>(a, piv); lu_step6<3>(a, piv); lu_step6<4>(a, piv); lu_step6<5>(a, piv);
+#pragma unroll
+    for (int i = 0; i < 36; ++i) a_io[i] = a[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) piv_io[i] = piv[i];
 }
 IM_HDN inline void lu_solve_col6(const double* a, const int* piv, int c, double* inv) {
     double y[6];
@@ -409,8 +459,10 @@ IM_HDN inline void ieskf_solve(const LioParams& P, LioCtrl* ctrl, int iter, Solv
         }
     }
     // v = state_propagat (-) state: independent of the gain, done by the last thread while thread 0 factorises
+    IM_STAMP_IF(tid == 0, 20, 0);
     if (tid == nthreads - 1) state_minus(ctrl->state_prop, state, S->vec);
     IM_SYNCBLOCK();
+    IM_STAMP_IF(tid == 0, 21, 0);
     for (int idx = tid; idx < 36; idx += nthreads) {
         const int i = idx / 6, j = idx % 6;
         double s = (i == j) ? 1.0 : 0.0;
@@ -418,10 +470,13 @@ IM_HDN inline void ieskf_solve(const LioParams& P, LioCtrl* ctrl, int iter, Solv
         S->B[idx] = s;
     }
     IM_SYNCBLOCK();
+    IM_STAMP_IF(tid == 0, 22, 0);
     if (tid == 0) lu_factor6(S->B, S->piv);
     IM_SYNCBLOCK();
+    IM_STAMP_IF(tid == 0, 23, 0);
     for (int c = tid; c < 6; c += nthreads) lu_solve_col6(S->B, S->piv, c, S->S);
     IM_SYNCBLOCK();
+    IM_STAMP_IF(tid == 0, 24, 0);
     for (int idx = tid; idx < 108; idx += nthreads) {
         const int i = idx / 6, j = idx % 6;
         double s = 0.0;
@@ -443,6 +498,7 @@ IM_HDN inline void ieskf_solve(const LioParams& P, LioCtrl* ctrl, int iter, Solv
         S->sol[i] = (s1 + S->vec[i]) - s2;
     }
     IM_SYNCBLOCK();
+    IM_STAMP_IF(tid == 0, 25, 0);
     if (tid == 0) {
         const double* sol = S->sol;
         const double rn = sqrt((sol[0] * sol[0] + sol[1] * sol[1]) + sol[2] * sol[2]);
@@ -454,30 +510,37 @@ IM_HDN inline void ieskf_solve(const LioParams& P, LioCtrl* ctrl, int iter, Solv
         ctrl->iters_run = iter + 1;
         S->flags[0] = (rematch >= 2 || iter == P.max_iter - 1) ? 1 : 0;
         S->flags[1] = converged;
-        state_plus(state, S->sol);
-    }
-    // diagnostics of the iteration (parity tests)
-    {
-        IterStats& st = ctrl->stats[iter];
-        for (int i = tid; i < 36; i += nthreads) st.HTH[i] = S->HTH[i];
-        for (int i = tid; i < 6; i += nthreads) st.HTz[i] = S->HTz[i];
-        for (int i = tid; i < 18; i += nthreads) st.solution[i] = S->sol[i];
     }
     IM_SYNCBLOCK();
-    if (tid == 0) ctrl->stats[iter].converged = S->flags[1];
-    if (S->flags[0]) {
-        // cov = (I - G) cov = cov - G[:, :6] cov[:6, :]  (rows 0-5 of cov are operands of every element: staged, then stored)
-        for (int idx = tid; idx < 324; idx += nthreads) {
-            const int i = idx / 18, j = idx % 18;
-            double s = 0.0;
-            for (int k = 0; k < 6; ++k) s = s + S->G6[i * 6 + k] * cov[k * 18 + j];
-            S->ncov[idx] = cov[idx] - s;
+    IM_STAMP_IF(tid == 0, 26, 0);
+    // state (+)= solution by thread 0 while the other warps (all threads when the block is a single warp / the host emulation) do the
+    // covariance update and the diagnostics: neither reads the state vector's first 24 entries
+    const bool split_tail = nthreads > 32;
+    if (tid == 0) state_plus(state, S->sol);
+    if (!split_tail || tid >= 32) {
+        const int t2 = split_tail ? tid - 32 : tid, n2 = split_tail ? nthreads - 32 : nthreads;
+        IterStats& st = ctrl->stats[iter];   // diagnostics of the iteration (parity tests)
+        for (int i = t2; i < 36; i += n2) st.HTH[i] = S->HTH[i];
+        for (int i = t2; i < 6; i += n2) st.HTz[i] = S->HTz[i];
+        for (int i = t2; i < 18; i += n2) st.solution[i] = S->sol[i];
+        if (t2 == 0) st.converged = S->flags[1];
+        if (S->flags[0]) {
+            // cov = (I - G) cov = cov - G[:, :6] cov[:6, :]  (rows 0-5 of cov are operands of every element: staged, then stored)
+            for (int idx = t2; idx < 324; idx += n2) {
+                const int i = idx / 18, j = idx % 18;
+                double s = 0.0;
+                for (int k = 0; k < 6; ++k) s = s + S->G6[i * 6 + k] * cov[k * 18 + j];
+                S->ncov[idx] = cov[idx] - s;
+            }
         }
-        IM_SYNCBLOCK();
+    }
+    IM_SYNCBLOCK();
+    if (S->flags[0]) {
         for (int idx = tid; idx < 324; idx += nthreads) cov[idx] = S->ncov[idx];
         if (tid == 0) ctrl->stop = 1;
     }
     IM_SYNCBLOCK();
+    IM_STAMP_IF(tid == 0, 27, 0);
 }
 
 // Forward_without_imu (constant-velocity prediction), src/IMU_Processing.cpp:486-553

@@ -136,6 +136,8 @@ __global__ void __launch_bounds__(128) k_voxel_tri_warp(MeshDev M, MeshParams P,
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     MeshWarpSmem<128>* S = reinterpret_cast<MeshWarpSmem<128>*>(smem_raw) + warp;
     const int nw = work_total(M, F);
+    IM_STAMP(30, nw);
+    int n_done = 0;
     while (true) {
         int i = 0;
         if (lane == 0) i = atomicAdd(&M.cnt[19], 1);
@@ -143,7 +145,10 @@ __global__ void __launch_bounds__(128) k_voxel_tri_warp(MeshDev M, MeshParams P,
         if (i >= nw) break;
         voxel_mesh_warp<128>(M, P, F, work_slot(M, F, i), S, lane, 32, n_max);
         __syncwarp();
+        ++n_done;
     }
+    IM_STAMP(31, n_done);
+    IM_STAMP_IF(blockIdx.x == 0 && threadIdx.x == 0 && (immesh_stamp_store(41, n_done), true), 42, nw);
 }
 // stage C (flat): after every voxel's smoothing is final
 __global__ void __launch_bounds__(128) k_commit_faces(MeshDev M, MeshParams P, FrameBuf F_) {
@@ -402,6 +407,12 @@ static size_t pow2_at_least(size_t v) {
     while (p < v) p <<= 1;
     return p;
 }
+
+#if defined(IM_DEBUG_STAMPS)
+extern "C" int immesh_debug_stamps_mesh(long long* out64) {   // debug variant only (tools/debug/build_stamps.sh); not declared in include/
+    return cudaMemcpyFromSymbol(out64, immesh::g_stamps, 64 * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" {
 

@@ -684,6 +684,7 @@ template <int MAXD>
 IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int w, MeshWarpSmem<MAXD>* S, int lane, int nlanes, int n_max) {
     const int n = F.work_n_ids[w];
     if (n < 3 || n > n_max || n > MAXD) return;
+    IM_STAMP_IF(blockIdx.x == 0 && threadIdx.x == 0, 32, n);
     float (*pos)[3] = S->circ;  // alias: positions are dead once projected
     for (int i = lane; i < n; i += nlanes) {
         const int id = F.work_ids[(size_t)w * IM_MAXD + i];
@@ -693,6 +694,7 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
     }
     if (lane == 0) S->nface = 0;
     IM_SYNCWARP();
+    IM_STAMP_IF(blockIdx.x == 0 && threadIdx.x == 0, 33, 0);
     if (lane == 0) {
         double c[3] = {0, 0, 0};
         for (int i = 0; i < n; ++i)
@@ -725,6 +727,7 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
         S->centre[0] = c[0]; S->centre[1] = c[1]; S->centre[2] = c[2];
     }
     IM_SYNCWARP();
+    IM_STAMP_IF(blockIdx.x == 0 && threadIdx.x == 0, 34, 0);
     for (int i = lane; i < n; i += nlanes) {
         const double d[3] = {(double)pos[i][0] - S->centre[0], (double)pos[i][1] - S->centre[1], (double)pos[i][2] - S->centre[2]};
         const double u = dot3(d, S->axes + 6), v = dot3(d, S->axes + 3);
@@ -763,6 +766,7 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
     }
     IM_SYNCWARP();
     if (!s_seed[2]) return;
+    IM_STAMP_IF(blockIdx.x == 0 && threadIdx.x == 0, 35, 0);
     const int i1 = s_seed[0], i2 = s_seed[1];
     // per insertion: (1) conflict scan, compacted with ballots; (2) directed edge list of the cavity; (3) boundary edges
     // (those whose reverse is not in the list) ranked with ballots, each writes its new triangle -- cavity slots first,
@@ -883,6 +887,7 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
     }
     if (lane == 0) *s_ovf = ovf ? 1 : 0;
     IM_SYNCWARP();
+    IM_STAMP_IF(blockIdx.x == 0 && threadIdx.x == 0, 36, 0);
     if (*s_ovf) {  // hand this voxel to the block-level stage
         if (lane == 0) F.work_n_ids[w] = -n;
         return;
@@ -906,6 +911,7 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
     }
     IM_SYNCWARP();
     const int nf = S->nface;
+    IM_STAMP_IF(blockIdx.x == 0 && threadIdx.x == 0, 37, nf);
     // facets + principal axes to the frame-wide lists; commit / orientation / pull run in the flat stage-C kernels
     if (lane == 0) {
         im_atomic_add(&M.cnt[23], nf);
@@ -920,6 +926,9 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
     }
     for (int k = lane; k < 9; k += nlanes) F.work_axes[(size_t)w * 9 + k] = S->axes[k];
     if (lane == 0) F.work_nfaces[w] = nf;
+#if defined(IM_DEBUG_STAMPS) && defined(__CUDA_ARCH__)
+    if (blockIdx.x == 0 && threadIdx.x == 0) { immesh::g_stamps[38] = clock64(); immesh::g_stamps[39] = n; immesh::g_stamps[40] = nf; }
+#endif
 }
 
 // ------------------------------------------------------------------ stage C, flat: one thread per new facet / per dilated vertex

@@ -660,39 +660,44 @@ struct MatchResult {
     double prob;
 };
 
-// build_single_residual over one root voxel (voxel_mapping.cpp:247-318); recursion -> explicit stack
-IM_HDN inline void match_in_voxel(const VoxelMapDev& m, const LioParams& P, int root, const double* pw, const double* var6, bool* ok, MatchResult* best) {
+// one plane candidate of build_single_residual (voxel_mapping.cpp:252-283): range gate, 3-sigma gate, keep the most probable plane
+IM_HDN inline void match_eval_plane(const PlaneRec& pl, int nd, int layer, const double* pw, const double* var6, bool* ok, MatchResult* best) {
+    const float dis_to_plane = (float)fabs(((pl.normal[0] * pw[0] + pl.normal[1] * pw[1]) + pl.normal[2] * pw[2]) + (double)pl.d);
+    const float dis_to_center = (float)(((pl.center[0] - pw[0]) * (pl.center[0] - pw[0]) + (pl.center[1] - pw[1]) * (pl.center[1] - pw[1])) +
+                                        (pl.center[2] - pw[2]) * (pl.center[2] - pw[2]));
+    const float range_dis = sqrtf(dis_to_center - dis_to_plane * dis_to_plane);
+    if ((double)range_dis <= 3.0 * (double)pl.radius) {
+        double sigma_l = plane_sigma(pw, pl.center, pl.normal, pl.pv);
+        sigma_l = sigma_l + quad6(pl.normal, var6);
+        const double sq = sqrt(sigma_l);
+        if ((double)dis_to_plane < 3.0 * sq) {  // sigma_num is the literal 3.0 (voxel_mapping.cpp:1365)
+            *ok = true;
+            const double dd = (double)dis_to_plane;
+            const double this_prob = 1.0 / sq * im_exp(-0.5 * dd * dd / sigma_l);
+            if (this_prob > best->prob) {
+                best->prob = this_prob;
+                best->node = nd;
+                best->layer = layer;
+            }
+        }
+    }
+}
+
+// build_single_residual below node `start` at octree layer `depth0` (voxel_mapping.cpp:247-318); recursion -> explicit stack
+IM_HDN inline void match_subtree(const VoxelMapDev& m, const LioParams& P, int start, int depth0, const double* pw, const double* var6, bool* ok, MatchResult* best) {
     int st_node[8], st_child[8];
     int sp = 1;
-    st_node[0] = root; st_child[0] = -1;
+    st_node[0] = start; st_child[0] = -1;
     while (sp > 0) {
         const int nd = st_node[sp - 1];
         if (st_child[sp - 1] < 0) {
             const PlaneRec& pl = m.planes[nd];
             if (pl.is_plane) {
-                const float dis_to_plane = (float)fabs(((pl.normal[0] * pw[0] + pl.normal[1] * pw[1]) + pl.normal[2] * pw[2]) + (double)pl.d);
-                const float dis_to_center = (float)(((pl.center[0] - pw[0]) * (pl.center[0] - pw[0]) + (pl.center[1] - pw[1]) * (pl.center[1] - pw[1])) +
-                                                    (pl.center[2] - pw[2]) * (pl.center[2] - pw[2]));
-                const float range_dis = sqrtf(dis_to_center - dis_to_plane * dis_to_plane);
-                if ((double)range_dis <= 3.0 * (double)pl.radius) {
-                    double sigma_l = plane_sigma(pw, pl.center, pl.normal, pl.pv);
-                    sigma_l = sigma_l + quad6(pl.normal, var6);
-                    const double sq = sqrt(sigma_l);
-                    if ((double)dis_to_plane < 3.0 * sq) {  // sigma_num is the literal 3.0 (voxel_mapping.cpp:1365)
-                        *ok = true;
-                        const double dd = (double)dis_to_plane;
-                        const double this_prob = 1.0 / sq * im_exp(-0.5 * dd * dd / sigma_l);
-                        if (this_prob > best->prob) {
-                            best->prob = this_prob;
-                            best->node = nd;
-                            best->layer = sp - 1;
-                        }
-                    }
-                }
+                match_eval_plane(pl, nd, depth0 + sp - 1, pw, var6, ok, best);
                 --sp;
                 continue;
             }
-            if (sp - 1 >= P.max_layer) { --sp; continue; }
+            if (depth0 + sp - 1 >= P.max_layer) { --sp; continue; }
             st_child[sp - 1] = 0;
         }
         bool pushed = false;
@@ -707,6 +712,26 @@ IM_HDN inline void match_in_voxel(const VoxelMapDev& m, const LioParams& P, int 
             }
         }
         if (!pushed) --sp;
+    }
+}
+IM_HDN inline void match_in_voxel(const VoxelMapDev& m, const LioParams& P, int root, const double* pw, const double* var6, bool* ok, MatchResult* best) {
+    match_subtree(m, P, root, 0, pw, var6, ok, best);
+}
+// One lane's share of match_in_voxel when `nl` lanes (8, or 1 = the whole walk) work on the same point: the root itself (lane 0) when it
+// is a plane, else the subtrees below the lane's 8/nl first-level children.  The serial walk finishes child 0's subtree before it enters
+// child 1's and replaces the best plane only on a strictly larger probability, so taking, over the lanes in order, the first lane that
+// holds the largest probability reproduces its choice (MatchCombine8 in lio_capi.cu; the replay over the lanes in the host emulation).
+IM_HDN inline void match_in_voxel_lane(const VoxelMapDev& m, const LioParams& P, int root, int lane, int nl, const double* pw, const double* var6, bool* ok, MatchResult* best) {
+    const PlaneRec& pl = m.planes[root];
+    if (pl.is_plane) {
+        if (lane == 0) match_eval_plane(pl, root, 0, pw, var6, ok, best);
+        return;
+    }
+    if (0 >= P.max_layer) return;
+    const int per = 8 / nl;
+    for (int c = lane * per; c < (lane + 1) * per; ++c) {
+        const int child = m.nodes[root].children[c];
+        if (child >= 0) match_subtree(m, P, child, 1, pw, var6, ok, best);
     }
 }
 
@@ -743,6 +768,39 @@ IM_HDN inline MatchResult match_point(const VoxelMapDev& m, const LioParams& P, 
             const int s2 = hash_find(m, pack_key(nk[0], nk[1], nk[2]));
             if (s2 >= 0 && m.root_node[s2] >= 0) match_in_voxel(m, P, m.root_node[s2], pw, var6, &ok, &best);
         }
+    }
+    if (!ok) best.node = -1;
+    return best;
+}
+// The same with the walk of each root voxel split over nl lanes.  `combine(ok, best)` merges the lanes' results (in lane order, see
+// match_in_voxel_lane) and hands every lane the merged pair; the lanes of a point always call it together (nl = 1: it does nothing).
+template <class Combine>
+IM_HDN inline MatchResult match_point_lanes(const VoxelMapDev& m, const LioParams& P, const double* pw, const double* var6, int lane, int nl, Combine combine) {
+    MatchResult best;
+    best.node = -1; best.layer = 0; best.prob = 0.0;
+    bool ok = false;
+    long long k[3] = {0, 0, 0};
+    float loc[3] = {0.f, 0.f, 0.f};
+    int root = -1;
+    if (voxel_key3_loc(pw, P.voxel_size, k, loc)) {
+        const int slot = hash_find(m, pack_key(k[0], k[1], k[2]));
+        if (slot >= 0) root = m.root_node[slot];
+    }
+    IM_STAMP(4, root);
+    if (root >= 0) match_in_voxel_lane(m, P, root, lane, nl, pw, var6, &ok, &best);
+    IM_STAMP(5, best.node);
+    combine(&ok, &best);
+    IM_STAMP(6, best.node);
+    if (root >= 0 && !ok) {   // the same decision in all 8 lanes
+        long long nk[3];
+        neighbour_key(P, k, loc, nk);
+        int root2 = -1;
+        if (nk[0] > -1048000 && nk[0] < 1048000 && nk[1] > -1048000 && nk[1] < 1048000 && nk[2] > -1048000 && nk[2] < 1048000) {
+            const int s2 = hash_find(m, pack_key(nk[0], nk[1], nk[2]));
+            if (s2 >= 0) root2 = m.root_node[s2];
+        }
+        if (root2 >= 0) match_in_voxel_lane(m, P, root2, lane, nl, pw, var6, &ok, &best);
+        combine(&ok, &best);
     }
     if (!ok) best.node = -1;
     return best;

@@ -121,6 +121,134 @@ int immesh_voxelmap_build(immesh_lio_t* h, const float* body, int n) {
     grow(h, 1);
     return (*h->map.err) ? IMMESH_E_CAPACITY : 0;
 }
+}  // extern "C"
+
+// ---- host emulation of the 8-lanes-per-point match (k_match).  The lanes of a point meet at `combine`; the emulation replays the
+// lane function: every pass runs the 8 lanes up to the first merge point that is not known yet (their results are recorded and the
+// lane is told `ok` so that it stops), merges the records in lane order with the strict '>' -- the rule the device's shuffle
+// butterfly implements (MatchCombine8, lio_capi.cu) -- and hands the merged pairs to the next pass.
+namespace {
+struct LaneReplay {
+    int n_known = 0;
+    bool known_ok[2] = {false, false};
+    MatchResult known_best[2];
+    int call = 0;
+    bool recorded = false;
+    bool rec_ok = false;
+    MatchResult rec_best;
+};
+struct LaneCombine {
+    LaneReplay* r;
+    void operator()(bool* ok, MatchResult* best) const {
+        const int c = r->call++;
+        if (c < r->n_known) { *ok = r->known_ok[c]; *best = r->known_best[c]; return; }
+        if (c == r->n_known) { r->recorded = true; r->rec_ok = *ok; r->rec_best = *best; }
+        *ok = true;   // nothing after this merge point is evaluated in this pass
+    }
+};
+void match_lanes_point(immesh_lio* h, const double* state, int i) {
+    LaneReplay known;
+    for (int pass = 0; pass < 3; ++pass) {
+        bool any_rec = false, m_ok = false;
+        MatchResult m_best;
+        m_best.node = -1; m_best.layer = 0; m_best.prob = 0.0;
+        for (int lane = 0; lane < 8; ++lane) {   // lane 0 stores the match of the point; the store of the last pass is the final one
+            LaneReplay r = known;
+            r.call = 0; r.recorded = false;
+            residual_match_lanes(h->map, h->P, h->sb, state, i, lane, 8, LaneCombine{&r});
+            if (!r.recorded) continue;
+            any_rec = true;
+            if (r.rec_ok) m_ok = true;
+            if (r.rec_best.prob > m_best.prob) m_best = r.rec_best;
+        }
+        if (!any_rec) return;   // every merge point was known already
+        known.known_ok[known.n_known] = m_ok;
+        known.known_best[known.n_known] = m_best;
+        known.n_known++;
+    }
+}
+int g_split = 1;
+}  // namespace
+
+extern "C" {
+int emu_lio_set_split(int mode) { g_split = mode; return 0; }   // 0: k_residual body, 1: k_match with 8 lanes + k_terms, 2: k_match with 1 lane + k_terms
+// The same per first-level child (the 8-lane split of k_match): out[i*24 + j*3 + {0,1,2}] = nodes visited, planes evaluated, planes
+// past the range gate in the subtree below child j of the point's root voxel (zeros for plane roots: lane 0 evaluates the root).
+int emu_match_lane_stats(immesh_lio_t* h, int* out, int n) {
+    const VoxelMapDev& m = h->map;
+    for (int i = 0; i < n && i < h->sb.n; ++i) {
+        int* o = out + (size_t)i * 24;
+        for (int q = 0; q < 24; ++q) o[q] = 0;
+        double pwd[3], pw[3], var6[6];
+        residual_world(h->P, h->sb, h->ctrl.state, i, pwd, pw, var6);
+        long long k[3];
+        float loc[3];
+        if (!voxel_key3_loc(pw, h->P.voxel_size, k, loc)) continue;
+        const int slot = hash_find(m, pack_key(k[0], k[1], k[2]));
+        if (slot < 0 || m.root_node[slot] < 0) continue;
+        const int root = m.root_node[slot];
+        if (m.planes[root].is_plane) { o[0] = 1; o[1] = 1; o[2] = 1; continue; }
+        if (h->P.max_layer < 1) continue;
+        for (int j = 0; j < 8; ++j) {
+            if (m.nodes[root].children[j] < 0) continue;
+            std::vector<std::pair<int, int>> st{{m.nodes[root].children[j], 1}};
+            while (!st.empty()) {
+                const auto [nd, layer] = st.back();
+                st.pop_back();
+                ++o[j * 3];
+                const PlaneRec& pl = m.planes[nd];
+                if (pl.is_plane) {
+                    ++o[j * 3 + 1];
+                    const float dp = (float)fabs(((pl.normal[0] * pw[0] + pl.normal[1] * pw[1]) + pl.normal[2] * pw[2]) + (double)pl.d);
+                    const float dc = (float)(((pl.center[0] - pw[0]) * (pl.center[0] - pw[0]) + (pl.center[1] - pw[1]) * (pl.center[1] - pw[1])) + (pl.center[2] - pw[2]) * (pl.center[2] - pw[2]));
+                    if ((double)sqrtf(dc - dp * dp) <= 3.0 * (double)pl.radius) ++o[j * 3 + 2];
+                    continue;
+                }
+                if (layer >= h->P.max_layer) continue;
+                for (int c = 0; c < 8; ++c)
+                    if (m.nodes[nd].children[c] >= 0) st.push_back({m.nodes[nd].children[c], layer + 1});
+            }
+        }
+    }
+    return 0;
+}
+// Work statistics of the match walk of the loaded scan at the current state (kernel design aid, tools/debug/match_stats.py):
+// per point out[i*4 + {0,1,2,3}] = root kind (0 no voxel, 1 plane root, 2 split root), nodes visited, planes evaluated, planes that
+// pass the range gate (and so run the 6x6 sigma + exp chain); root voxel only (no neighbour retry).
+int emu_match_walk_stats(immesh_lio_t* h, int* out, int n) {
+    const VoxelMapDev& m = h->map;
+    for (int i = 0; i < n && i < h->sb.n; ++i) {
+        int* o = out + (size_t)i * 4;
+        o[0] = o[1] = o[2] = o[3] = 0;
+        double pwd[3], pw[3], var6[6];
+        residual_world(h->P, h->sb, h->ctrl.state, i, pwd, pw, var6);
+        long long k[3];
+        float loc[3];
+        if (!voxel_key3_loc(pw, h->P.voxel_size, k, loc)) continue;
+        const int slot = hash_find(m, pack_key(k[0], k[1], k[2]));
+        if (slot < 0 || m.root_node[slot] < 0) continue;
+        const int root = m.root_node[slot];
+        o[0] = m.planes[root].is_plane ? 1 : 2;
+        std::vector<std::pair<int, int>> st{{root, 0}};
+        while (!st.empty()) {
+            const auto [nd, layer] = st.back();
+            st.pop_back();
+            ++o[1];
+            const PlaneRec& pl = m.planes[nd];
+            if (pl.is_plane) {
+                ++o[2];
+                const float dp = (float)fabs(((pl.normal[0] * pw[0] + pl.normal[1] * pw[1]) + pl.normal[2] * pw[2]) + (double)pl.d);
+                const float dc = (float)(((pl.center[0] - pw[0]) * (pl.center[0] - pw[0]) + (pl.center[1] - pw[1]) * (pl.center[1] - pw[1])) + (pl.center[2] - pw[2]) * (pl.center[2] - pw[2]));
+                if ((double)sqrtf(dc - dp * dp) <= 3.0 * (double)pl.radius) ++o[3];
+                continue;
+            }
+            if (layer >= h->P.max_layer) continue;
+            for (int c = 0; c < 8; ++c)
+                if (m.nodes[nd].children[c] >= 0) st.push_back({m.nodes[nd].children[c], layer + 1});
+        }
+    }
+    return 0;
+}
 int immesh_lio_estimate(immesh_lio_t* h, const float* body, int n, int* iters_run) {
     load_scan(h, body, n);
     LioCtrl& c = h->ctrl;
@@ -132,9 +260,15 @@ int immesh_lio_estimate(immesh_lio_t* h, const float* body, int n, int* iters_ru
     for (int it = 0; it < h->P.max_iter && !c.stop; ++it) {
         long long sum[IM_NTERMS];
         for (int k = 0; k < IM_NTERMS; ++k) sum[k] = 0;
+        if (g_split == 1)
+            for (int i = 0; i < n; ++i) match_lanes_point(h, c.state, i);   // k_match, 8 lanes per point
+        else if (g_split == 2)
+            for (int i = 0; i < n; ++i) residual_match_lanes(h->map, h->P, h->sb, c.state, i, 0, 1, [](bool*, MatchResult*) {});   // k_match, large scans: 1 lane
         for (int i = 0; i < n; ++i) {
             long long t[IM_NTERMS];
-            if (residual_point(h->map, h->P, h->sb, c.state, i, t, h->map.err))
+            const bool hit = g_split ? residual_point_matched(h->map, h->P, h->sb, c.state, i, t, h->map.err)   // k_terms
+                                     : residual_point(h->map, h->P, h->sb, c.state, i, t, h->map.err);            // k_residual
+            if (hit)
                 for (int k = 0; k < IM_NTERMS; ++k) sum[k] += t[k];
         }
         for (int k = 0; k < IM_NTERMS; ++k) {
