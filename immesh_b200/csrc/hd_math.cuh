@@ -277,64 +277,80 @@ IM_HD void so3_log3(const double* R, double* out) {
 // Cyclic Jacobi eigen-decomposition of a symmetric 3x3 (packed in), eigenvalues d[3], eigenvectors in the
 // columns of V (row-major), unsorted.  Replaces Eigen::EigenSolver / SelfAdjointEigenSolver on the path
 // (voxel_loc.cpp:62, mesh_rec_geometry.cpp:199).
-IM_HDN inline void jacobi3(const double* a6, double* d, double* V) {
-    double a00 = a6[0], a01 = a6[1], a02 = a6[2], a11 = a6[3], a12 = a6[4], a22 = a6[5];
-    double v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    for (int sweep = 0; sweep < 60; ++sweep) {
-        const double off = (fabs(a01) + fabs(a02)) + fabs(a12);
-        if (off == 0.0) break;
-        for (int pq = 0; pq < 3; ++pq) {
-            // (p,q) = (0,1), (0,2), (1,2); r is the remaining index
-            const int p = (pq == 2) ? 1 : 0;
-            const int q = (pq == 0) ? 1 : 2;
-            double app, aqq, apq, arp, arq;
-            if (pq == 0) { app = a00; aqq = a11; apq = a01; arp = a02; arq = a12; }
-            else if (pq == 1) { app = a00; aqq = a22; apq = a02; arp = a01; arq = a12; }
-            else { app = a11; aqq = a22; apq = a12; arp = a01; arq = a02; }
-            if (apq == 0.0) continue;
-            const double g = 100.0 * fabs(apq);
-            bool zero_only = false;
-            double t = 0.0;
-            if (sweep > 3 && (fabs(app) + g == fabs(app)) && (fabs(aqq) + g == fabs(aqq))) {
-                zero_only = true;
-            } else {
-                const double h = aqq - app;
-                if (fabs(h) + g == fabs(h)) {
-                    t = apq / h;
-                } else {
-                    const double theta = 0.5 * h / apq;
-                    t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
-                    if (theta < 0.0) t = -t;
-                }
-            }
-            if (zero_only) {
-                apq = 0.0;
-            } else {
-                const double c = 1.0 / sqrt(1.0 + t * t);
-                const double s = t * c;
-                const double tau = s / (1.0 + c);
-                const double hh = t * apq;
-                app = app - hh;
-                aqq = aqq + hh;
-                apq = 0.0;
-                const double nrp = arp - s * (arq + arp * tau);
-                const double nrq = arq + s * (arp - arq * tau);
-                arp = nrp;
-                arq = nrq;
-                for (int k = 0; k < 3; ++k) {
-                    const double vkp = v[k * 3 + p], vkq = v[k * 3 + q];
-                    v[k * 3 + p] = vkp - s * (vkq + vkp * tau);
-                    v[k * 3 + q] = vkq + s * (vkp - vkq * tau);
-                }
-            }
-            if (pq == 0) { a00 = app; a11 = aqq; a01 = apq; a02 = arp; a12 = arq; }
-            else if (pq == 1) { a00 = app; a22 = aqq; a02 = apq; a01 = arp; a12 = arq; }
-            else { a11 = app; a22 = aqq; a12 = apq; a01 = arp; a02 = arq; }
+// One rotation, pair (p,q) = (0,1), (0,2), (1,2) for PQ = 0, 1, 2; the pair is a template parameter so that every index into the
+// packed matrix and the eigenvector array is a constant: with a run-time pair the arrays lived in local memory and each rotation paid a
+// dozen dependent local loads/stores on top of its 4 divisions and 2 square roots (profiles/stamps_r02*: 27 k cycles per 3x3 problem).
+template <int PQ>
+IM_HD void jacobi3_rotate(int sweep, double (&a)[6], double (&v)[9]) {
+    constexpr int p = (PQ == 2) ? 1 : 0, q = (PQ == 0) ? 1 : 2;
+    constexpr int ipp = (PQ == 2) ? 3 : 0, iqq = (PQ == 0) ? 3 : 5, ipq = (PQ == 0) ? 1 : (PQ == 1) ? 2 : 4;
+    constexpr int irp = (PQ == 0) ? 2 : 1, irq = (PQ == 2) ? 2 : 4;   // the two off-diagonal entries that share an index with (p,q)
+    double app = a[ipp], aqq = a[iqq], apq = a[ipq], arp = a[irp], arq = a[irq];
+    if (apq == 0.0) return;
+    const double g = 100.0 * fabs(apq);
+    bool zero_only = false;
+    double t = 0.0;
+    if (sweep > 3 && (fabs(app) + g == fabs(app)) && (fabs(aqq) + g == fabs(aqq))) {
+        zero_only = true;
+    } else {
+        const double h = aqq - app;
+        if (fabs(h) + g == fabs(h)) {
+            t = apq / h;
+        } else {
+            const double theta = 0.5 * h / apq;
+            t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+            if (theta < 0.0) t = -t;
         }
     }
-    d[0] = a00; d[1] = a11; d[2] = a22;
+    if (zero_only) {
+        apq = 0.0;
+    } else {
+        const double c = 1.0 / sqrt(1.0 + t * t);
+        const double s = t * c;
+        const double tau = s / (1.0 + c);
+        const double hh = t * apq;
+        app = app - hh;
+        aqq = aqq + hh;
+        apq = 0.0;
+        const double nrp = arp - s * (arq + arp * tau);
+        const double nrq = arq + s * (arp - arq * tau);
+        arp = nrp;
+        arq = nrq;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double vkp = v[k * 3 + p], vkq = v[k * 3 + q];
+            v[k * 3 + p] = vkp - s * (vkq + vkp * tau);
+            v[k * 3 + q] = vkq + s * (vkp - vkq * tau);
+        }
+    }
+    a[ipp] = app; a[iqq] = aqq; a[ipq] = apq; a[irp] = arp; a[irq] = arq;
+}
+IM_HD void jacobi3(const double* a6, double* d, double* V) {
+    double a[6] = {a6[0], a6[1], a6[2], a6[3], a6[4], a6[5]};   // a00 a01 a02 a11 a12 a22
+    double v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        const double off = (fabs(a[1]) + fabs(a[2])) + fabs(a[4]);
+        if (off == 0.0) break;
+        jacobi3_rotate<0>(sweep, a, v);
+        jacobi3_rotate<1>(sweep, a, v);
+        jacobi3_rotate<2>(sweep, a, v);
+    }
+    d[0] = a[0]; d[1] = a[3]; d[2] = a[5];
+#pragma unroll
     for (int i = 0; i < 9; ++i) V[i] = v[i];
 }
+
+// Ascending order of three eigenvalues exactly as a bubble sort over an index array produces it (equal values keep their order), and
+// the selection of an eigenvector column, both without indexed access (register arrays stay in registers).
+IM_HD void order3(const double* ev, int* o) {
+    double e0 = ev[0], e1 = ev[1], e2 = ev[2];
+    int o0 = 0, o1 = 1, o2 = 2;
+    if (e1 < e0) { const double t = e0; e0 = e1; e1 = t; const int u = o0; o0 = o1; o1 = u; }
+    if (e2 < e1) { const double t = e1; e1 = e2; e2 = t; const int u = o1; o1 = o2; o2 = u; }
+    if (e1 < e0) { const double t = e0; e0 = e1; e1 = t; const int u = o0; o0 = o1; o1 = u; }
+    o[0] = o0; o[1] = o1; o[2] = o2;
+}
+IM_HD double col3(const double* U, int row, int c) { return c == 0 ? U[row * 3] : (c == 1 ? U[row * 3 + 1] : U[row * 3 + 2]); }
 
 // order-free fixed-point accumulation of the normal equations (2^-20 quantum, 32-bit hi/lo split)
 #define IM_FX_SCALE 1048576.0

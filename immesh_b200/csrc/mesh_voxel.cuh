@@ -586,12 +586,10 @@ IM_HDN inline void voxel_mesh(const MeshDev& M, const MeshParams& P, const Frame
         for (int k = 0; k < 6; ++k) cov[k] = cov[k] / (double)n;
         double ev[3], U[9];
         jacobi3(cov, ev, U);
-        int order[3] = {0, 1, 2};  // ascending eigenvalues (SelfAdjointEigenSolver order)
-        for (int a = 0; a < 2; ++a)
-            for (int b = 0; b < 2 - a; ++b)
-                if (ev[order[b + 1]] < ev[order[b]]) { const int t = order[b]; order[b] = order[b + 1]; order[b + 1] = t; }
+        int order[3];  // ascending eigenvalues (SelfAdjointEigenSolver order)
+        order3(ev, order);
         double s[3], m[3];
-        for (int j = 0; j < 3; ++j) { s[j] = U[j * 3 + order[0]]; m[j] = U[j * 3 + order[1]]; }
+        for (int j = 0; j < 3; ++j) { s[j] = col3(U, j, order[0]); m[j] = col3(U, j, order[1]); }
         const double d0[3] = {(double)S->pos[0][0] - c[0], (double)S->pos[0][1] - c[1], (double)S->pos[0][2] - c[2]};
         const double d1[3] = {(double)S->pos[1][0] - c[0], (double)S->pos[1][1] - c[1], (double)S->pos[1][2] - c[2]};
         if (dot3(d0, s) < 0) { s[0] = -s[0]; s[1] = -s[1]; s[2] = -s[2]; }
@@ -709,12 +707,10 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
         for (int k = 0; k < 6; ++k) cov[k] = cov[k] / (double)n;
         double ev[3], U[9];
         jacobi3(cov, ev, U);
-        int order[3] = {0, 1, 2};
-        for (int a = 0; a < 2; ++a)
-            for (int b = 0; b < 2 - a; ++b)
-                if (ev[order[b + 1]] < ev[order[b]]) { const int t = order[b]; order[b] = order[b + 1]; order[b + 1] = t; }
+        int order[3];
+        order3(ev, order);
         double sx[3], m[3];
-        for (int j = 0; j < 3; ++j) { sx[j] = U[j * 3 + order[0]]; m[j] = U[j * 3 + order[1]]; }
+        for (int j = 0; j < 3; ++j) { sx[j] = col3(U, j, order[0]); m[j] = col3(U, j, order[1]); }
         const double d0[3] = {(double)pos[0][0] - c[0], (double)pos[0][1] - c[1], (double)pos[0][2] - c[2]};
         const double d1[3] = {(double)pos[1][0] - c[0], (double)pos[1][1] - c[1], (double)pos[1][2] - c[2]};
         if (dot3(d0, sx) < 0) { sx[0] = -sx[0]; sx[1] = -sx[1]; sx[2] = -sx[2]; }
@@ -776,8 +772,17 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
     (void)s_cav_n; (void)s_edge_n;
     const unsigned lt = im_lanemask_lt();
     bool ovf = false;
+#if defined(IM_DEBUG_STAMPS) && defined(__CUDA_ARCH__)
+    long long ph_a = 0, ph_b = 0, ph_c = 0, ph_d = 0, ph_t = 0, ph_nm = 0, ph_nc = 0, ph_nt = 0;
+#define IM_PH(acc) do { const long long now_ = clock64(); acc += now_ - ph_t; ph_t = now_; } while (0)
+#else
+#define IM_PH(acc) do { } while (0)
+#endif
     for (int p = 1; p < n && !ovf; ++p) {
         if (p == i1 || p == i2) continue;
+#if defined(IM_DEBUG_STAMPS) && defined(__CUDA_ARCH__)
+        ph_t = clock64();
+#endif
         const int nt = S->ntri;
         const float pxf = (float)Pt[p].x, pyf = (float)Pt[p].y;
         // (1a) cheap pass over the whole pool: live triangles whose cached circumcircle does not exclude p (ghosts always
@@ -806,6 +811,7 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
         }
         if (nm > 192) { ovf = true; break; }   // warp-uniform
         IM_SYNCWARP();
+        IM_PH(ph_a);
         int nc = 0;
         for (int j0 = 0; j0 < nm; j0 += nlanes) {
             const int j = j0 + lane;
@@ -824,6 +830,10 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
         }
         if (nc > 64) { ovf = true; break; }   // warp-uniform
         IM_SYNCWARP();
+        IM_PH(ph_b);
+#if defined(IM_DEBUG_STAMPS) && defined(__CUDA_ARCH__)
+        ph_nm += nm; ph_nc += nc; ph_nt += nt;
+#endif
         if (nc == 0) continue;                // duplicate point: skipped (CGAL does the same)
         const int ne3 = nc * 3;
 #if defined(__CUDA_ARCH__)
@@ -877,6 +887,7 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
             }
             nb += im_popc(m);
         }
+        IM_PH(ph_c);
         // every cavity slot is reused (a valid cavity has nc + 2 boundary edges); kill leftovers defensively
         for (int k = nb + lane; k < nc; k += nlanes) tris[s_cav[k]].alive = 0;
         if (nb > nc) {
@@ -884,7 +895,14 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
             else ovf = true;
         }
         IM_SYNCWARP();
+        IM_PH(ph_d);
     }
+#if defined(IM_DEBUG_STAMPS) && defined(__CUDA_ARCH__)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        immesh::g_stamps[44] = ph_a; immesh::g_stamps[45] = ph_b; immesh::g_stamps[46] = ph_c; immesh::g_stamps[47] = ph_d;
+        immesh::g_stamps[48] = ph_nm; immesh::g_stamps[49] = ph_nc; immesh::g_stamps[50] = ph_nt;
+    }
+#endif
     if (lane == 0) *s_ovf = ovf ? 1 : 0;
     IM_SYNCWARP();
     IM_STAMP_IF(blockIdx.x == 0 && threadIdx.x == 0, 36, 0);

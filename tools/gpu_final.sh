@@ -9,5 +9,9 @@ for c in C1 C2 C3 C4 C5; do
 done
 timeout 300 python bench.py --impl reference --steps 30 --warmup 5 > gpurun_out/benchref_$tag.json 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$tag.csv python tools/mini_stream.py 6 > gpurun_out/ncu_l_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_voxel_dilate|k_voxel_tri_warp|k_pull_vertices|k_cand_init|k_grow_voxel|k_grow_simple|k_residual|k_push_add|k_commit_faces" -s 33 -c 15 -o gpurun_out/prof_$tag python tools/mini_stream.py 5 > gpurun_out/ncu_f_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_voxel_dilate|k_voxel_tri_warp|k_pull_vertices|k_cand_init|k_grow_voxel|k_grow_simple|k_match|k_terms|k_push_add|k_commit_faces" -s 33 -c 19 -o gpurun_out/prof_$tag python tools/mini_stream.py 5 > gpurun_out/ncu_f_$tag.log 2>&1
 ls -la gpurun_out/prof_$tag.ncu-rep
+if [ -f tools/debug/libimmesh_stamps.so ]; then
+  for c in C100k C3; do python tools/debug/lio_stamps.py $c 24 > gpurun_out/stamps_${tag}_$c.txt 2>&1; done
+  python tools/debug/mesh_stamps.py C100k 16 > gpurun_out/mstamps_$tag.txt 2>&1
+fi
