@@ -705,8 +705,10 @@ IM_HDN inline void voxel_mesh_warp(const MeshDev& M, const MeshParams& P, const 
             cov[3] += d[1] * d[1]; cov[4] += d[1] * d[2]; cov[5] += d[2] * d[2];
         }
         for (int k = 0; k < 6; ++k) cov[k] = cov[k] / (double)n;
+        IM_STAMP_IF(blockIdx.x == 0 && threadIdx.x == 0, 51, __double_as_longlong(cov[5] + cov[0]));
         double ev[3], U[9];
         jacobi3(cov, ev, U);
+        IM_STAMP_IF(blockIdx.x == 0 && threadIdx.x == 0, 52, __double_as_longlong(ev[0] + U[8]));
         int order[3];
         order3(ev, order);
         double sx[3], m[3];

@@ -31,6 +31,7 @@ for k in range(1, n_scans):
         print(f"frame {k}: warp 0 of block 0: kernel {d(30, 31)} cycles for {s[41]} voxels of {s[42]} | last voxel: n {s[39]} faces {s[40]} total {d(32, 38)} = "
               f"load {d(32, 33)}  PCA(lane 0) {d(33, 34)}  project+seed {d(34, 35)}  Bowyer-Watson {d(35, 36)} ({d(35, 36) // max(1, s[39] - 3)}/insertion)  "
               f"faces {d(36, 37)}  output {d(37, 38)}")
+        print(f"          PCA: centroid + covariance {d(33, 51)}  Jacobi {d(51, 52)}  ordering + axes {d(52, 34)}")
         ins = max(1, s[39] - 3)
         print(f"          per insertion: prefilter scan {s[44] // ins}  exact conflicts {s[45] // ins}  cavity edges + new triangles {s[46] // ins}  tail {s[47] // ins} | "
               f"pool {s[50] / ins:.1f} triangles, {s[48] / ins:.1f} past the prefilter, {s[49] / ins:.1f} in conflict")
