@@ -364,6 +364,7 @@ int orc_voxel_grid(const float* pts, int n, float leaf, float* out, int cap, int
 void orc_kitti_calib(float* pts, int n) { kitti_calib(pts, n); }
 void orc_jacobi_eig3(const double* a6, double* d, double* V) { jacobi_eig3(a6, d, V); }
 void orc_lu_inverse18(const double* A, double* Ainv) { lu_inverse<18>(A, Ainv); }
+void orc_lu_inverse6(const double* A, double* Ainv) { lu_inverse<6>(A, Ainv); }
 void orc_calc_body_var(const double* pb, double dept_err, double beam_err, double* var6) {
     double p[3] = {pb[0], pb[1], pb[2]};
     const double s = std::sin((double)(float)beam_err * 0.017453293);

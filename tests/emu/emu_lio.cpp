@@ -171,6 +171,16 @@ int g_split = 1;
 }  // namespace
 
 extern "C" {
+// small numerical bodies of the kernels, exposed one by one for tests/test_kernel_math_emu.py
+void emu_jacobi3(const double* a6, double* d, double* V) { jacobi3(a6, d, V); }
+void emu_lu_inverse6(const double* A, double* Ainv) {
+    double a[36];
+    int piv[6];
+    for (int i = 0; i < 36; ++i) a[i] = A[i];
+    lu_factor6(a, piv);
+    for (int c = 0; c < 6; ++c) lu_solve_col6(a, piv, c, Ainv);
+}
+void emu_order3(const double* ev, int* o) { order3(ev, o); }
 int emu_lio_set_split(int mode) { g_split = mode; return 0; }   // 0: k_residual body, 1: k_match with 8 lanes + k_terms, 2: k_match with 1 lane + k_terms
 // The same per first-level child (the 8-lane split of k_match): out[i*24 + j*3 + {0,1,2}] = nodes visited, planes evaluated, planes
 // past the range gate in the subtree below child j of the point's root voxel (zeros for plane roots: lane 0 evaluates the root).
