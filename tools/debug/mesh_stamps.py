@@ -32,6 +32,8 @@ for k in range(1, n_scans):
               f"load {d(32, 33)}  PCA(lane 0) {d(33, 34)}  project+seed {d(34, 35)}  Bowyer-Watson {d(35, 36)} ({d(35, 36) // max(1, s[39] - 3)}/insertion)  "
               f"faces {d(36, 37)}  output {d(37, 38)}")
         print(f"          PCA: centroid + covariance {d(33, 51)}  Jacobi {d(51, 52)}  ordering + axes {d(52, 34)}")
+        print(f"          k_cand_init, candidate 0: point load {d(53, 54)}  voxel get-or-create {d(54, 55)}  activation {d(55, 56)}  xi-cell lookup {d(56, 57)}  "
+              f"27 probes + vertex ids {d(57, 58)}  vertex positions {d(58, 59)}  frame grid insert + list push {d(59, 60)}  (stale when the candidate left early)")
         ins = max(1, s[39] - 3)
         print(f"          per insertion: prefilter scan {s[44] // ins}  exact conflicts {s[45] // ins}  cavity edges + new triangles {s[46] // ins}  tail {s[47] // ins} | "
               f"pool {s[50] / ins:.1f} triangles, {s[48] / ins:.1f} past the prefilter, {s[49] / ins:.1f} in conflict")
