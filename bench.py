@@ -537,10 +537,12 @@ def run_gpu(args, rank, world):
     # unaffected: profiles/bench_history.md).  A pass slower than half the device-timed rate is measured ONCE more on the scans that
     # follow; both passes are reported (`attempts_ms_per_step`), the value is the later one.
     def slow_pass(seconds, steps):
-        v = torch.tensor([seconds / steps], dtype=torch.float64, device=dev)
+        # slowest rank's ms/step of this pass against the slowest rank's device-timed ms/step: both reduced, so that every rank takes
+        # the same decision (a second pass contains barriers)
+        v = torch.tensor([seconds / steps * 1e3, total_ms / K], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(v, op=dist.ReduceOp.MAX)          # the same decision on every rank
-        return float(v[0]) * 1e3 > 2.0 * (total_ms / K)
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v[0]) > 2.0 * float(v[1])
     e2e_attempts = []
     for attempt in range(2):
         pinned = [(pin(scans[k + j]["body_ds"]), pin(scans[k + j]["body_full"])) for j in range(K)]
